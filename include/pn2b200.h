@@ -1,0 +1,205 @@
+/*
+ * pn2b200.h -- C ABI of libpn2b200.so: the B200 (sm_100a) implementation of the
+ * PointNet++ SSG set-abstraction / feature-propagation hot path of
+ * KhairilAriffinYahya/Khairil_TUM-Facade_Semantic_Segmentation.
+ *
+ * Every entry point replaces a function (or a step of a module's forward /
+ * backward) of the reference file models/pointnet2_utils.py; the line numbers
+ * quoted below are into that file.  The reference has no FFI of its own (it is
+ * pure PyTorch); the binding a maintainer adds is the ctypes stub shown in
+ * INTEGRATION.md (this repo's khairil_tum-facade_semantic_segmentation_b200/_lib.py).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *  - all calls are asynchronous on `stream`, allocate nothing, keep no mutable
+ *    global state besides the last-error string and a launch counter, and may be
+ *    used from one thread per GPU.
+ *  - return value: PN2_OK (0) or a negative PN2_ERR_* code; pn2_last_error()
+ *    gives the text.  Nothing throws across the ABI.
+ *  - "rows" = point-major activations: a [M, C] matrix with leading dimension ld
+ *    (elements), row m = (cloud b, point/centroid s[, sample k]) flattened.
+ *  - dtype codes: PN2_F32 / PN2_BF16 select the storage type of activation rows
+ *    (accumulation and all statistics are always fp32).
+ *  - index tensors are int64 at this boundary exactly as in the reference.
+ */
+#ifndef PN2B200_H
+#define PN2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_VERSION 100
+
+enum { PN2_OK = 0, PN2_ERR_ARG = -1, PN2_ERR_CUDA = -2, PN2_ERR_UNSUPPORTED = -3 };
+enum { PN2_F32 = 0, PN2_BF16 = 1 };
+
+/* ---- library ---------------------------------------------------------------- */
+int pn2_version(void);
+const char *pn2_last_error(void);
+/* kernels launched by this library since load (bench.py's "gpu_launches") */
+unsigned long long pn2_launch_count(void);
+
+/* ---- a1 square_distance (:19-40) ---------------------------------------------
+ * out[b,i,j] = ((-2*<src_i,dst_j>) + |src_i|^2) + |dst_j|^2 in the reference's
+ * fp32 rounding order.  src [B,N,3], dst [B,M,3], out [B,N,M], all contiguous.
+ * Provided for API parity; the network path never materialises this matrix. */
+int pn2_square_distance(const float *src, const float *dst, int B, int N, int M, float *out,
+                        void *stream);
+
+/* ---- a2 index_points (:43-60) ------------------------------------------------
+ * out[b,j,:] = points[b, idx[b,j], :].  points has element strides (sB,sN,sC),
+ * idx is [B,J] int64 (J = product of the trailing index dims), out is [B,J,C]
+ * contiguous fp32.  Indices outside [0,N) produce zeros. */
+int pn2_index_points(const float *points, int64_t sB, int64_t sN, int64_t sC, int B, int N, int C,
+                     const int64_t *idx, int64_t J, float *out, void *stream);
+/* backward of a2: dpoints[b, idx[b,j], :] += dout[b,j,:]  (dpoints [B,N,C] contiguous, pre-zeroed) */
+int pn2_index_points_bwd(const float *dout, const int64_t *idx, int B, int N, int C, int64_t J,
+                         float *dpoints, void *stream);
+
+/* ---- a3 farthest_point_sample (:63-84) ---------------------------------------
+ * xyz [B,N,3] with element strides (sB,sN,sC); start_idx [B] int64 = the
+ * torch.randint draw of :75 (made by the caller on the CPU generator);
+ * out_idx [B,npoint] int64; out_xyz [B,npoint,3] fp32 (may be NULL) receives
+ * index_points(xyz, out_idx) (:125).  Bit-exact: dist = (dx*dx+dy*dy)+dz*dz with
+ * separately rounded operations, running minimum from 1e10f, first arg-max. */
+int pn2_farthest_point_sample(const float *xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N,
+                              int npoint, const int64_t *start_idx, int64_t *out_idx,
+                              float *out_xyz, void *stream);
+
+/* ---- a4 query_ball_point (:87-107) -------------------------------------------
+ * xyz [B,N,3] strided, new_xyz [B,S,3] strided; r2 = (float)((double)radius*radius);
+ * out_idx [B,S,nsample] int64: ascending indices of the first nsample points with
+ * !(d > r2) (d in the a1 rounding order), remaining slots = first hit, all slots
+ * = N if there is no hit; out_cnt [B,S] int32 (may be NULL) = number of hits kept. */
+int pn2_query_ball_point(const float *xyz, int64_t sB, int64_t sN, int64_t sC,
+                         const float *new_xyz, int64_t qB, int64_t qN, int64_t qC, int B, int N,
+                         int S, float r2, int nsample, int64_t *out_idx, int32_t *out_cnt,
+                         void *stream);
+
+/* ---- a5 sample_and_group, gather half (:127-132) -----------------------------
+ * rows[(b,s,k), 0:3]     = xyz[b, idx[b,s,k], :] - new_xyz[b,s,:]
+ * rows[(b,s,k), 3:3+D]   = feats[b, idx[b,s,k], :]        (feats may be NULL, D = 0)
+ * rows[(b,s,k), 3+D:ld]  = 0
+ * feats [B,N,D] with element strides (fB,fN,fD); rows has dtype `dtype`, M = B*S*nsample. */
+int pn2_group_points(const float *xyz, int64_t sB, int64_t sN, int64_t sC, const float *new_xyz,
+                     const float *feats, int64_t fB, int64_t fN, int64_t fD, const int64_t *idx,
+                     int B, int N, int S, int nsample, int D, void *rows, int ld, int dtype,
+                     void *stream);
+/* backward: dfeats[b, idx, :] += drows[(b,s,k), 3:3+D]  (dfeats [B,N,D] fp32 contiguous, pre-zeroed) */
+int pn2_group_points_bwd(const void *drows, int ld, int dtype, const int64_t *idx, int B, int N,
+                         int S, int nsample, int D, float *dfeats, void *stream);
+
+/* ---- a7/a8 the 1x1-conv MLP on rows -------------------------------------------
+ * One layer:  Z[M,N] = act(X)[M,K] * W[N,K]^T (+ bias)
+ *   act(x)[m,k] = in_scale ? relu(x[m,k]*in_scale[k] + in_shift[k]) : x[m,k]
+ *   (the previous layer's BatchNorm + ReLU, :198 / :314, applied while loading).
+ * W is the Conv2d/Conv1d weight [N,K(,1,1)] fp32 contiguous.  If stat_partials is
+ * non-NULL the kernel also writes per-CTA column sums of Z and Z^2 (bias
+ * excluded) for the train-mode batch statistics: layout [n_partials][2][N],
+ * n_partials = pn2_linear_num_partials(M).
+ * x_dtype/z_dtype: storage of X and Z rows.  With PN2_BF16 rows the product runs
+ * on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM); with
+ * PN2_F32 rows on the fp32 FMA pipes. */
+int pn2_linear_num_partials(int64_t M);
+int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale,
+                   const float *in_shift, const float *W, const float *bias, int64_t M, int K,
+                   int N, void *Z, int ldz, int z_dtype, float *stat_partials, void *stream);
+/* dX[M,K] = dZ[M,N] * W[N,K]   (no activation handling; see pn2_bn_relu_bwd_*) */
+int pn2_linear_bwd_data(const void *dZ, int lddz, int dz_dtype, const float *W, int64_t M, int K,
+                        int N, void *dX, int lddx, int dx_dtype, void *stream);
+/* dW[N,K] = sum_m dZ[m,n] * act(X)[m,k];  scratch holds pn2_linear_wgrad_scratch_bytes() bytes */
+size_t pn2_linear_wgrad_scratch_bytes(int64_t M, int K, int N);
+int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx,
+                          int x_dtype, const float *in_scale, const float *in_shift, int64_t M,
+                          int K, int N, float *dW, void *scratch, void *stream);
+
+/* ---- BatchNorm (train statistics / eval fold) ---------------------------------
+ * Train (:198 with module.training): reduces the stat partials of pn2_linear_fwd
+ * to mean / biased variance over M rows, writes
+ *   scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd
+ * and updates running_mean/var in place with `momentum` (running_mean includes
+ * the conv bias that the GEMM left out; running_var uses the unbiased variance). */
+int pn2_bn_train_finalize(const float *stat_partials, int n_partials, int64_t M, int N,
+                          const float *gamma, const float *beta, const float *conv_bias,
+                          float eps, float momentum, float *running_mean, float *running_var,
+                          float *scale, float *shift, float *save_mean, float *save_invstd,
+                          void *stream);
+/* Eval: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale (the GEMM adds the bias). */
+int pn2_bn_eval_fold(const float *gamma, const float *beta, const float *running_mean,
+                     const float *running_var, float eps, int N, float *scale, float *shift,
+                     void *stream);
+
+/* ---- a7 tail: BN + ReLU + max over nsample (:198-200) --------------------------
+ * out[g,c] = max_k relu(Z[(g,k),c]*scale[c]+shift[c]); arg[g,c] = first maximal k (int32).
+ * G groups of nsample consecutive rows; out fp32 [G,C] contiguous. */
+int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                    int64_t G, int nsample, int C, float *out, int32_t *arg, void *stream);
+/* a8 tail: out[m,c] = relu(Z[m,c]*scale[c]+shift[c])  (fp32 [M,C] contiguous) */
+int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                int64_t M, int C, float *out, void *stream);
+
+/* ---- backward of BN(train)+ReLU -----------------------------------------------
+ * With g = dA * [bn(z) > 0]:  dbeta = sum g, dgamma = sum g*zhat,
+ *   dz = gamma*invstd * (g - dbeta/M - zhat*dgamma/M)          (train)
+ *   dz = scale * g                                              (eval: pass save_mean = NULL)
+ * Two passes: *_reduce writes partial sums [n_partials][2][C] (n_partials =
+ * pn2_linear_num_partials(M)); pn2_bn_bwd_finalize reduces them into dgamma/dbeta;
+ * *_dz writes dZ (dZ may alias dA: the update is element-wise).  The "pool" variants take the pooled gradient dOut[G,C] and the
+ * arg-max map of pn2_bn_relu_max instead of a dense dA (g is non-zero only on the
+ * arg-max row of each (group, channel)). */
+int pn2_bn_relu_bwd_reduce(const void *dA, int ldda, int da_dtype, const void *Z, int ldz,
+                           int z_dtype, const float *scale, const float *shift,
+                           const float *save_mean, const float *save_invstd, int64_t M, int C,
+                           float *partials, void *stream);
+int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg, const void *Z, int ldz,
+                                int z_dtype, const float *scale, const float *shift,
+                                const float *save_mean, const float *save_invstd, int64_t G,
+                                int nsample, int C, float *partials, void *stream);
+int pn2_bn_bwd_finalize(const float *partials, int n_partials, int C, float *dgamma, float *dbeta,
+                        void *stream);
+int pn2_bn_relu_bwd_dz(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
+                       const float *scale, const float *shift, const float *save_mean,
+                       const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M,
+                       int C, void *dZ, int lddz, int dz_dtype, void *stream);
+int pn2_pool_bn_relu_bwd_dz(const float *dOut, const int32_t *arg, const void *Z, int ldz,
+                            int z_dtype, const float *scale, const float *shift,
+                            const float *save_mean, const float *save_invstd, const float *dgamma,
+                            const float *dbeta, int64_t G, int nsample, int C, void *dZ, int lddz,
+                            int dz_dtype, void *stream);
+
+/* ---- a8 head: three nearest neighbours + inverse-distance interpolation (:296-307)
+ * xyz1 [B,N,3] strided (fine), xyz2 [B,S,3] strided (coarse); idx3 [B,N,3] int64 and
+ * w3 [B,N,3] fp32 follow a stable ascending sort of the a1-order distances;
+ * K3 = min(3,S) valid columns (the rest are idx 0 / weight 0). */
+int pn2_three_nn(const float *xyz1, int64_t aB, int64_t aN, int64_t aC, const float *xyz2,
+                 int64_t cB, int64_t cN, int64_t cC, int B, int N, int S, int64_t *idx3, float *w3,
+                 void *stream);
+/* rows[(b,n), 0:D1]      = points1[b,n,:]                 (may be NULL, D1 = 0)
+ * rows[(b,n), D1:D1+D2]  = (p2[i0]*w0 + p2[i1]*w1) + p2[i2]*w2   (products rounded, :303)
+ * rows[(b,n), D1+D2:ld]  = 0.   points1 [B,N,D1] strides (pB,pN,pD); points2 [B,S,D2] strides (qB,qN,qD). */
+int pn2_interp_concat(const float *points1, int64_t pB, int64_t pN, int64_t pD,
+                      const float *points2, int64_t qB, int64_t qN, int64_t qD, const int64_t *idx3,
+                      const float *w3, int B, int N, int S, int D1, int D2, void *rows, int ld,
+                      int dtype, void *stream);
+/* dpoints2[b, idx3[b,n,k], :] += w3[b,n,k] * drows[(b,n), D1:D1+D2]   (dpoints2 [B,S,D2] fp32, pre-zeroed) */
+int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, const float *w3, int B,
+                   int N, int S, int D1, int D2, float *dpoints2, void *stream);
+
+/* ---- layout helpers ------------------------------------------------------------
+ * dst[r, c] (fp32, leading dim ldd) = src[r*sR + c*sC] for r < R, c < C: turns a
+ * channel-major [C,R] slab into point-major rows (batched over B with strides). */
+int pn2_to_rows(const float *src, int64_t sB, int64_t sR, int64_t sC, int B, int64_t R, int C,
+                float *dst, int64_t dB, int ldd, void *stream);
+/* dst fp32 [M,C] contiguous = rows (any dtype) [M, ld] columns c0..c0+C */
+int pn2_rows_to_f32(const void *rows, int ld, int dtype, int64_t M, int c0, int C, float *dst,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2B200_H */

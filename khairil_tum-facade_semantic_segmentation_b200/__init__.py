@@ -1,0 +1,20 @@
+"""pn2-b200: B200-native (sm_100a) PointNet++ SSG set-abstraction / feature-propagation hot path.
+
+Public surface == the names of /root/reference/models/pointnet2_utils.py.  The
+directory name contains a hyphen, so import it with
+``importlib.import_module("khairil_tum-facade_semantic_segmentation_b200")`` or through
+the repo-root alias ``import pn2b200``; ``models/pointnet2_utils.py`` re-exports the same
+names for the reference's unchanged ``models/pointnet2_sem_seg.py``.
+"""
+from ._lib import EXPORTED_SYMBOLS, SO_PATH, Pn2Error, launch_count, load
+from .modules import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
+from .ops import (farthest_point_sample, get_precision, index_points, query_ball_point, sample_and_group,
+                  sample_and_group_all, set_precision, square_distance, three_nn)
+from .sem_seg import get_loss, get_model
+
+__all__ = [
+    "PointNetSetAbstraction", "PointNetSetAbstractionMsg", "PointNetFeaturePropagation",
+    "square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
+    "sample_and_group_all", "three_nn", "set_precision", "get_precision", "get_model", "get_loss",
+    "load", "launch_count", "Pn2Error", "SO_PATH", "EXPORTED_SYMBOLS",
+]

@@ -1,0 +1,111 @@
+"""ctypes binding of libpn2b200.so (the C ABI declared in include/pn2b200.h).
+
+This is the only place that touches the shared library.  There is no CPU or
+PyTorch fallback: if the library is missing or a call fails, an exception is
+raised.  PyTorch is used by the callers of this module for device memory and
+streams only; every pointer handed to the library is a raw ``data_ptr()``.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpn2b200.so")
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class Pn2Error(RuntimeError):
+    """A libpn2b200 call returned a negative status."""
+
+
+_i, _l, _f, _p, _z = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pn2b200.h one to one
+_SIGNATURES = {
+    "pn2_version": (_i, []),
+    "pn2_last_error": (ctypes.c_char_p, []),
+    "pn2_launch_count": (ctypes.c_ulonglong, []),
+    "pn2_square_distance": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "pn2_index_points": (_i, [_p, _l, _l, _l, _i, _i, _i, _p, _l, _p, _p]),
+    "pn2_index_points_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
+    "pn2_farthest_point_sample": (_i, [_p, _l, _l, _l, _i, _i, _i, _p, _p, _p, _p]),
+    "pn2_query_ball_point": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "pn2_group_points": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "pn2_group_points_bwd": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "pn2_linear_num_partials": (_i, [_l]),
+    "pn2_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
+    "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p]),
+    "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
+    "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
+    "pn2_bn_train_finalize": (_i, [_p, _i, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_bn_eval_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
+    "pn2_bn_relu_max": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
+    "pn2_bn_relu": (_i, [_p, _i, _i, _p, _p, _l, _i, _p, _p]),
+    "pn2_bn_relu_bwd_reduce": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _l, _i, _p, _p]),
+    "pn2_pool_bn_relu_bwd_reduce": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
+    "pn2_bn_bwd_finalize": (_i, [_p, _i, _i, _p, _p, _p]),
+    "pn2_bn_relu_bwd_dz": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _p, _i, _i, _p]),
+    "pn2_pool_bn_relu_bwd_dz": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p]),
+    "pn2_three_nn": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p, _p, _p]),
+    "pn2_interp_concat": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "pn2_interp_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "pn2_to_rows": (_i, [_p, _l, _l, _l, _i, _l, _i, _p, _l, _i, _p]),
+    "pn2_rows_to_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load():
+    """Load libpn2b200.so and declare the signatures.  Fails loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise Pn2Error(
+                "libpn2b200.so is not built (%s).  Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or khairil_tum-facade_semantic_segmentation_b200/csrc/build.sh.  There is no CPU fallback." % SO_PATH)
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise Pn2Error with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise Pn2Error("%s failed (%d): %s" % (name, rc, lib.pn2_last_error().decode()))
+
+
+def launch_count():
+    return int(load().pn2_launch_count())
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+def require_cuda(t, name, dtype=torch.float32):
+    """The product path is CUDA only; wrong device/dtype is an error, never a fallback."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (pn2-b200 has no CPU path), got device %s" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t

@@ -1,0 +1,328 @@
+// bn.cu -- BatchNorm (+ReLU, + max over nsample) around the MLP layers, forward and backward.
+// Reference: bn(conv(x)) -> relu -> torch.max(.., 2) in PointNetSetAbstraction.forward
+// (/root/reference/models/pointnet2_utils.py:196-200) and relu(bn(conv(x))) in
+// PointNetFeaturePropagation.forward (:311-314); modules are nn.BatchNorm2d/1d, i.e. batch
+// statistics over every row in train mode (padding duplicates included) with biased variance
+// for the normalisation and unbiased variance for running_var.
+//
+// All of these are streaming (HBM-bound) passes over [M, C] rows; threads walk channels so
+// accesses coalesce; every cross-thread reduction has a fixed order (deterministic).
+#include "common.cuh"
+
+namespace pn2 {
+
+int linear_num_partials(int64_t M);
+
+// ------------------------------------------------------------------ statistics -> scale/shift
+__global__ void bn_train_finalize_kernel(const float *__restrict__ partials, int n_partials, int64_t M, int N,
+                                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                                         const float *__restrict__ conv_bias, float eps, float momentum,
+                                         float *__restrict__ running_mean, float *__restrict__ running_var,
+                                         float *__restrict__ scale, float *__restrict__ shift,
+                                         float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < n_partials; ++p) {
+        s1 += (double)partials[(int64_t)p * 2 * N + c];
+        s2 += (double)partials[(int64_t)p * 2 * N + N + c];
+    }
+    double mean = s1 / (double)M;
+    double var = s2 / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = invstd;
+    if (running_mean) {
+        float full_mean = (float)mean + (conv_bias ? conv_bias[c] : 0.0f);
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * full_mean;
+    }
+    if (running_var) {
+        double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void bn_eval_fold_kernel(const float *__restrict__ gamma, const float *__restrict__ beta,
+                                    const float *__restrict__ running_mean, const float *__restrict__ running_var,
+                                    float eps, int N, float *__restrict__ scale, float *__restrict__ shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float invstd = 1.0f / sqrtf(running_var[c] + eps);
+    float sc = (gamma ? gamma[c] : 1.0f) * invstd;
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.0f) - running_mean[c] * sc;
+}
+
+// ------------------------------------------------------------------ forward tails
+template <typename T>
+__global__ void bn_relu_max_kernel(const T *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                                   const float *__restrict__ shift, int64_t G, int nsample, int C,
+                                   float *__restrict__ out, int32_t *__restrict__ arg) {
+    const int64_t total = G * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(e % C);
+        int64_t g = e / C;
+        const float sc = scale[c], sh = shift[c];
+        const T *z = Z + g * nsample * (int64_t)ldz + c;
+        float best = -1.0f;
+        int bk = 0;
+        for (int k = 0; k < nsample; ++k) {
+            float a = fmaxf(fmaf(ld_act<T>(z + (int64_t)k * ldz), sc, sh), 0.0f);
+            if (a > best) { best = a; bk = k; }
+        }
+        out[e] = best;
+        if (arg) arg[e] = bk;
+    }
+}
+
+template <typename T>
+__global__ void bn_relu_kernel(const T *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                               const float *__restrict__ shift, int64_t M, int C, float *__restrict__ out) {
+    const int64_t total = M * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(e % C);
+        int64_t m = e / C;
+        out[e] = fmaxf(fmaf(ld_act<T>(Z + m * ldz + c), scale[c], shift[c]), 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------ backward: reductions
+// Block layout: 256 threads = 8 row-lanes x 32 column-lanes; a block owns a contiguous slab
+// of rows and writes one partial [2][C].  POOL: "rows" are groups, and the only contributing
+// row of (group, channel) is its arg-max sample.
+template <typename TA, typename TZ, bool POOL>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restrict__ arg,
+                     const TZ *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                     const float *__restrict__ shift, const float *__restrict__ save_mean,
+                     const float *__restrict__ save_invstd, int64_t R, int nsample, int C,
+                     float *__restrict__ partials) {
+    extern __shared__ float red[];   // [8][2][C]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t rows_per_block = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(R, r_begin + rows_per_block);
+    for (int c = lane; c < C; c += 32) {
+        const float sc = scale[c], sh = shift[c];
+        const float mu = save_mean ? save_mean[c] : 0.0f, is = save_invstd ? save_invstd[c] : 0.0f;
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int64_t r = r_begin + w; r < r_end; r += 8) {
+            int64_t zrow = POOL ? r * nsample + arg[r * C + c] : r;
+            float z = ld_act<TZ>(Z + zrow * ldz + c);
+            float g = POOL ? ((const float *)dA)[r * C + c] : ld_act<TA>(dA + r * ldda + c);
+            if (!(fmaf(z, sc, sh) > 0.0f)) g = 0.0f;
+            s1 += g;
+            s2 = fmaf(g, (z - mu) * is, s2);
+        }
+        red[(w * 2 + 0) * C + c] = s1;
+        red[(w * 2 + 1) * C + c] = s2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        int which = i / C, c = i % C;
+        float s = 0.0f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += red[(ww * 2 + which) * C + c];
+        partials[(int64_t)blockIdx.x * 2 * C + i] = s;
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n_partials, int C,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < n_partials; ++p) {
+        s1 += (double)partials[(int64_t)p * 2 * C + c];
+        s2 += (double)partials[(int64_t)p * 2 * C + C + c];
+    }
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+}
+
+// ------------------------------------------------------------------ backward: dz
+template <typename TA, typename TZ, typename TD, bool POOL>
+__global__ void bn_bwd_dz_kernel(const TA *dA, int ldda, const int32_t *__restrict__ arg,
+                                 const TZ *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                                 const float *__restrict__ shift, const float *__restrict__ save_mean,
+                                 const float *__restrict__ save_invstd, const float *__restrict__ dgamma,
+                                 const float *__restrict__ dbeta, int64_t M, int nsample, int C, float inv_m,
+                                 TD *dZ, int lddz) {
+    const int64_t total = M * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(e % C);
+        int64_t m = e / C;
+        float z = ld_act<TZ>(Z + m * ldz + c);
+        float g;
+        if (POOL) {
+            int64_t grp = m / nsample;
+            int k = (int)(m % nsample);
+            g = (arg[grp * C + c] == k) ? ((const float *)dA)[grp * C + c] : 0.0f;
+        } else {
+            g = ld_act<TA>(dA + m * ldda + c);
+        }
+        const float sc = scale[c];
+        if (!(fmaf(z, sc, shift[c]) > 0.0f)) g = 0.0f;
+        float d;
+        if (save_mean) {   // train: dz = gamma*invstd*(g - dbeta/M - zhat*dgamma/M), scale == gamma*invstd
+            float zhat = (z - save_mean[c]) * save_invstd[c];
+            d = sc * (g - dbeta[c] * inv_m - zhat * dgamma[c] * inv_m);
+        } else {
+            d = sc * g;
+        }
+        st_act<TD>(dZ + m * lddz + c, d);
+    }
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_bn_train_finalize(const float *stat_partials, int n_partials, int64_t M, int N,
+                                     const float *gamma, const float *beta, const float *conv_bias, float eps,
+                                     float momentum, float *running_mean, float *running_var, float *scale,
+                                     float *shift, float *save_mean, float *save_invstd, void *stream) {
+    PN2_REQUIRE(stat_partials && scale && shift, "bn_train_finalize: null pointer");
+    PN2_REQUIRE(n_partials > 0 && M > 0 && N > 0, "bn_train_finalize: bad sizes");
+    bn_train_finalize_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stat_partials, n_partials, M, N, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale,
+        shift, save_mean, save_invstd);
+    count_launch();
+    return check_launch("bn_train_finalize");
+}
+
+extern "C" int pn2_bn_eval_fold(const float *gamma, const float *beta, const float *running_mean,
+                                const float *running_var, float eps, int N, float *scale, float *shift,
+                                void *stream) {
+    PN2_REQUIRE(running_mean && running_var && scale && shift, "bn_eval_fold: null pointer");
+    bn_eval_fold_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, N,
+                                                                           scale, shift);
+    count_launch();
+    return check_launch("bn_eval_fold");
+}
+
+extern "C" int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                               int64_t G, int nsample, int C, float *out, int32_t *arg, void *stream) {
+    PN2_REQUIRE(Z && scale && shift && out, "bn_relu_max: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && nsample >= 1 && C >= 1 && ldz >= C, "bn_relu_max: bad arguments");
+    int64_t total = G * C;
+    if (total == 0) return PN2_OK;
+    PN2_DISPATCH_DTYPE(z_dtype, T, (bn_relu_max_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T *)Z, ldz, scale, shift, G, nsample, C, out, arg)));
+    count_launch();
+    return check_launch("bn_relu_max");
+}
+
+extern "C" int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                           int64_t M, int C, float *out, void *stream) {
+    PN2_REQUIRE(Z && scale && shift && out, "bn_relu: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && C >= 1 && ldz >= C, "bn_relu: bad arguments");
+    int64_t total = M * C;
+    if (total == 0) return PN2_OK;
+    PN2_DISPATCH_DTYPE(z_dtype, T, (bn_relu_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T *)Z, ldz, scale, shift, M, C, out)));
+    count_launch();
+    return check_launch("bn_relu");
+}
+
+template <bool POOL>
+static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *arg, const void *Z, int ldz,
+                           int z_dtype, const float *scale, const float *shift, const float *save_mean,
+                           const float *save_invstd, int64_t R, int nsample, int C, float *partials,
+                           int n_partials, cudaStream_t st) {
+    size_t smem = sizeof(float) * 16 * (size_t)C;
+#define PN2_LAUNCH_RED(TA, TZ)                                                                        \
+    bn_bwd_reduce_kernel<TA, TZ, POOL><<<n_partials, 256, smem, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, \
+                                                                      scale, shift, save_mean, save_invstd, R, nsample, C, partials)
+    if (da_dtype == PN2_F32 && z_dtype == PN2_F32) PN2_LAUNCH_RED(float, float);
+    else if (da_dtype == PN2_F32) PN2_LAUNCH_RED(float, __nv_bfloat16);
+    else if (z_dtype == PN2_F32) PN2_LAUNCH_RED(__nv_bfloat16, float);
+    else PN2_LAUNCH_RED(__nv_bfloat16, __nv_bfloat16);
+#undef PN2_LAUNCH_RED
+    count_launch();
+    return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int pn2_bn_relu_bwd_reduce(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
+                                      const float *scale, const float *shift, const float *save_mean,
+                                      const float *save_invstd, int64_t M, int C, float *partials, void *stream) {
+    PN2_REQUIRE(dA && Z && scale && shift && partials, "bn_relu_bwd_reduce: null pointer");
+    PN2_REQUIRE(valid_dtype(da_dtype) && valid_dtype(z_dtype) && C >= 1 && C <= 768, "bn_relu_bwd_reduce: bad arguments (C <= 768)");
+    if (M == 0) return PN2_OK;
+    return reduce_dispatch<false>(dA, ldda, da_dtype, nullptr, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, M,
+                                  1, C, partials, linear_num_partials(M), (cudaStream_t)stream);
+}
+
+extern "C" int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg, const void *Z, int ldz,
+                                           int z_dtype, const float *scale, const float *shift,
+                                           const float *save_mean, const float *save_invstd, int64_t G,
+                                           int nsample, int C, float *partials, void *stream) {
+    PN2_REQUIRE(dOut && arg && Z && scale && shift && partials, "pool_bn_relu_bwd_reduce: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && C >= 1 && C <= 768, "pool_bn_relu_bwd_reduce: bad arguments (C <= 768)");
+    if (G == 0) return PN2_OK;
+    return reduce_dispatch<true>(dOut, C, PN2_F32, arg, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, G, nsample,
+                                 C, partials, linear_num_partials(G * nsample), (cudaStream_t)stream);
+}
+
+extern "C" int pn2_bn_bwd_finalize(const float *partials, int n_partials, int C, float *dgamma, float *dbeta,
+                                   void *stream) {
+    PN2_REQUIRE(partials && dgamma && dbeta && n_partials > 0, "bn_bwd_finalize: bad arguments");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, C, dgamma, dbeta);
+    count_launch();
+    return check_launch("bn_bwd_finalize");
+}
+
+template <bool POOL>
+static int dz_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *arg, const void *Z, int ldz,
+                       int z_dtype, const float *scale, const float *shift, const float *save_mean,
+                       const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M, int nsample,
+                       int C, void *dZ, int lddz, int dz_dtype, cudaStream_t st) {
+    const float inv_m = 1.0f / (float)M;
+    const int grid = grid_for(M * C, 256);
+#define PN2_LAUNCH_DZ(TA, TZ, TD)                                                                                   \
+    bn_bwd_dz_kernel<TA, TZ, TD, POOL><<<grid, 256, 0, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, scale, shift, \
+                                                             save_mean, save_invstd, dgamma, dbeta, M, nsample, C, inv_m, \
+                                                             (TD *)dZ, lddz)
+    const bool af = da_dtype == PN2_F32, zf = z_dtype == PN2_F32, df = dz_dtype == PN2_F32;
+    if (af && zf && df) PN2_LAUNCH_DZ(float, float, float);
+    else if (af && zf) PN2_LAUNCH_DZ(float, float, __nv_bfloat16);
+    else if (af && df) PN2_LAUNCH_DZ(float, __nv_bfloat16, float);
+    else if (af) PN2_LAUNCH_DZ(float, __nv_bfloat16, __nv_bfloat16);
+    else if (zf && df) PN2_LAUNCH_DZ(__nv_bfloat16, float, float);
+    else if (zf) PN2_LAUNCH_DZ(__nv_bfloat16, float, __nv_bfloat16);
+    else if (df) PN2_LAUNCH_DZ(__nv_bfloat16, __nv_bfloat16, float);
+    else PN2_LAUNCH_DZ(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+#undef PN2_LAUNCH_DZ
+    count_launch();
+    return check_launch("bn_bwd_dz");
+}
+
+extern "C" int pn2_bn_relu_bwd_dz(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
+                                  const float *scale, const float *shift, const float *save_mean,
+                                  const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M,
+                                  int C, void *dZ, int lddz, int dz_dtype, void *stream) {
+    PN2_REQUIRE(dA && Z && scale && shift && dZ, "bn_relu_bwd_dz: null pointer");
+    PN2_REQUIRE(!save_mean || (save_invstd && dgamma && dbeta), "bn_relu_bwd_dz: train mode needs invstd/dgamma/dbeta");
+    PN2_REQUIRE(valid_dtype(da_dtype) && valid_dtype(z_dtype) && valid_dtype(dz_dtype), "bn_relu_bwd_dz: bad dtype");
+    if (M == 0) return PN2_OK;
+    return dz_dispatch<false>(dA, ldda, da_dtype, nullptr, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, dgamma,
+                              dbeta, M, 1, C, dZ, lddz, dz_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_pool_bn_relu_bwd_dz(const float *dOut, const int32_t *arg, const void *Z, int ldz, int z_dtype,
+                                       const float *scale, const float *shift, const float *save_mean,
+                                       const float *save_invstd, const float *dgamma, const float *dbeta,
+                                       int64_t G, int nsample, int C, void *dZ, int lddz, int dz_dtype,
+                                       void *stream) {
+    PN2_REQUIRE(dOut && arg && Z && scale && shift && dZ, "pool_bn_relu_bwd_dz: null pointer");
+    PN2_REQUIRE(!save_mean || (save_invstd && dgamma && dbeta), "pool_bn_relu_bwd_dz: train mode needs invstd/dgamma/dbeta");
+    PN2_REQUIRE(valid_dtype(z_dtype) && valid_dtype(dz_dtype), "pool_bn_relu_bwd_dz: bad dtype");
+    if (G == 0) return PN2_OK;
+    return dz_dispatch<true>(dOut, C, PN2_F32, arg, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, dgamma, dbeta,
+                             G * nsample, nsample, C, dZ, lddz, dz_dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,404 @@
+"""The reference's set-abstraction / feature-propagation modules over libpn2b200.
+
+Same constructor and ``forward`` signatures, same channel-first tensor
+conventions and -- because ``mlp_convs`` / ``mlp_bns`` stay ``nn.ModuleList``s of
+real ``nn.Conv2d/Conv1d`` and ``nn.BatchNorm2d/1d`` -- the same ``state_dict``
+as /root/reference/models/pointnet2_utils.py:161-315.  The convolution and
+batch-norm modules only OWN the parameters; their arithmetic is done by the
+CUDA kernels (weights, running statistics, momentum, eps and train/eval mode are
+read from them at call time, running statistics are written back).
+
+One autograd.Function per module: forward = FPS -> ball query -> gather -> MLP
+(-> max over nsample); backward is hand written on the same kernels.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import call, dt, load, ptr, require_cuda, stream
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _row_ld(k, dtype):
+    # 16-byte aligned rows for the bf16 (tensor-core) path; fp32 rows are packed
+    return k if dtype == torch.float32 else _round_up(k, 8)
+
+
+class _LayerState:
+    __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias")
+
+
+def _bn_trains(bn):
+    return bn.training or bn.running_mean is None
+
+
+def mlp_forward(x0, K0, M, convs, bns):
+    """relu(bn(conv(.))) chain on rows (pointnet2_utils.py:196-198 / :311-314) up to the last
+    layer's pre-BN product; the caller applies the last BN+ReLU fused with its tail."""
+    lib = load()
+    dev, dtype = x0.device, x0.dtype
+    x, ldx, K = x0, x0.shape[1], K0
+    in_scale = in_shift = None
+    layers = []
+    for conv, bn in zip(convs, bns):
+        st = _LayerState()
+        N = conv.out_channels
+        W = conv.weight.detach().reshape(N, -1)
+        if not W.is_contiguous():
+            W = W.contiguous()
+        if W.shape[1] != K or W.dtype != torch.float32:
+            raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
+        bias = None if conv.bias is None else conv.bias.detach()
+        gamma = None if bn.weight is None else bn.weight.detach()
+        beta = None if bn.bias is None else bn.bias.detach()
+        ldz = _row_ld(N, dtype)
+        z = torch.empty(M, ldz, device=dev, dtype=dtype)
+        stats = torch.empty(4, N, device=dev, dtype=torch.float32)
+        st.W, st.K, st.N, st.Z, st.has_bias = W, K, N, z, bias is not None
+        st.scale, st.shift, st.mean, st.invstd = stats[0], stats[1], stats[2], stats[3]
+        st.train = _bn_trains(bn)
+        if st.train:
+            nparts = lib.pn2_linear_num_partials(M)
+            partials = torch.empty(nparts, 2, N, device=dev, dtype=torch.float32)
+            call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
+                 ptr(z), ldz, dt(z), ptr(partials), stream())
+            momentum = bn.momentum
+            if bn.num_batches_tracked is not None and bn.training:
+                bn.num_batches_tracked.add_(1)
+            if momentum is None:      # cumulative moving average (nn.BatchNorm semantics)
+                momentum = 1.0 / float(bn.num_batches_tracked.item()) if bn.num_batches_tracked is not None else 0.0
+            update = bn.training and bn.running_mean is not None
+            call("pn2_bn_train_finalize", ptr(partials), nparts, M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
+                 float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), stream())
+        else:
+            call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
+                 ptr(st.scale), ptr(st.shift), stream())
+            call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K, N,
+                 ptr(z), ldz, dt(z), None, stream())
+            # for a backward pass through frozen statistics: zhat = (z - (rm - b)) * invstd_running
+            st.mean = bn.running_mean.detach() - (bias if bias is not None else 0.0)
+            st.invstd = torch.rsqrt(bn.running_var.detach() + bn.eps)
+        layers.append(st)
+        x, ldx, K = z, ldz, N
+        in_scale, in_shift = st.scale, st.shift
+    return layers
+
+
+def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
+    """Backward of mlp_forward + tail.  dout: [G, C] fp32 pooled gradient with arg-max map `arg`
+    (set abstraction) or [M, C] fp32 dense gradient (feature propagation, arg None).
+    Returns (per-layer (dW, dbias, dgamma, dbeta), dX0 or None)."""
+    lib = load()
+    dev, dtype = x0.device, x0.dtype
+    L = len(layers)
+    grads = [None] * L
+    nparts = lib.pn2_linear_num_partials(M)
+
+    def bn_grads(st, dA, ldda):
+        """dgamma/dbeta of layer st from the gradient w.r.t. its activation, then dZ."""
+        C = st.N
+        partials = torch.empty(nparts, 2, C, device=dev, dtype=torch.float32)
+        dgb = torch.empty(2, C, device=dev, dtype=torch.float32)
+        mean_train = ptr(st.mean) if st.train else None
+        if arg is not None and dA is dout:
+            G = M // nsample
+            call("pn2_pool_bn_relu_bwd_reduce", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(partials), stream())
+            call("pn2_bn_bwd_finalize", ptr(partials), nparts, C, ptr(dgb[0]), ptr(dgb[1]), stream())
+            dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
+            call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgb[0]), ptr(dgb[1]), G, nsample, C, ptr(dZ),
+                 dZ.shape[1], dt(dZ), stream())
+        else:
+            call("pn2_bn_relu_bwd_reduce", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(partials), stream())
+            call("pn2_bn_bwd_finalize", ptr(partials), nparts, C, ptr(dgb[0]), ptr(dgb[1]), stream())
+            if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
+                dZ = dA                                   # element-wise update in place (never on autograd's grad)
+            else:
+                dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
+            call("pn2_bn_relu_bwd_dz", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgb[0]), ptr(dgb[1]), M, C, ptr(dZ), dZ.shape[1],
+                 dt(dZ), stream())
+        return dZ, dgb[0], dgb[1]
+
+    dZ, dgamma, dbeta = bn_grads(layers[-1], dout, dout.shape[1])
+    dx0 = None
+    for l in range(L - 1, -1, -1):
+        st = layers[l]
+        if l == 0:
+            xin, ldx, sc, sh = x0, x0.shape[1], None, None
+        else:
+            prev = layers[l - 1]
+            xin, ldx, sc, sh = prev.Z, prev.Z.shape[1], prev.scale, prev.shift
+        dW = torch.empty(st.N, st.K, device=dev, dtype=torch.float32)
+        scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, st.K, st.N), device=dev, dtype=torch.uint8)
+        call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M, st.K,
+             st.N, ptr(dW), ptr(scratch), stream())
+        if not st.has_bias:
+            dbias = None
+        elif st.train:      # batch-norm's mean subtraction cancels the conv bias exactly
+            dbias = torch.zeros(st.N, device=dev, dtype=torch.float32)
+        else:               # frozen statistics: sum_m dz = scale * dbeta
+            dbias = st.scale * dbeta
+        grads[l] = (dW, dbias, dgamma, dbeta)
+        if l > 0 or need_dx0:
+            ldd = _row_ld(st.K, dtype) if l > 0 else x0.shape[1]
+            dA = torch.empty(M, ldd, device=dev, dtype=dtype)
+            if ldd != st.K:
+                dA[:, st.K:].zero_()
+            call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
+                 stream())
+            if l > 0:
+                dZ, dgamma, dbeta = bn_grads(layers[l - 1], dA, ldd)
+            else:
+                dx0 = dA
+    return grads, dx0
+
+
+def _flat_params(convs, bns):
+    out = []
+    for conv, bn in zip(convs, bns):
+        out += [conv.weight, conv.bias, bn.weight, bn.bias]
+    return out
+
+
+def _param_grads(grads, convs, needs):
+    out = []
+    for (dW, dbias, dgamma, dbeta), conv in zip(grads, convs):
+        out += [dW.view_as(conv.weight), dbias, dgamma, dbeta]
+    return tuple(g if need else None for g, need in zip(out, needs))
+
+
+class _SetAbstractionFn(torch.autograd.Function):
+    """sample_and_group + MLP + max (pointnet2_utils.py:185-200).  perm: optional column
+    permutation of the first conv's input channels (the Msg variant concatenates features
+    first, :248, while the gather kernel writes [dxyz | feats])."""
+
+    @staticmethod
+    def forward(ctx, mod, convs, bns, radius, nsample, new_xyz, xyz_r, pts_r, *params):
+        B, N, _ = xyz_r.shape
+        S = new_xyz.shape[1]
+        dtype = ops.rows_dtype()
+        idx = ops.query_ball_point(radius, nsample, xyz_r, new_xyz)
+        feats = None if pts_r is None else ops.as_rows(pts_r)
+        D = 0 if feats is None else feats.shape[2]
+        K0 = 3 + D
+        x0 = ops.group_rows(xyz_r, new_xyz, feats, idx, _row_ld(K0, dtype), dtype)
+        M = B * S * nsample
+        layers = mlp_forward(x0, K0, M, convs, bns)
+        last = layers[-1]
+        out = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.float32)
+        arg = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.int32)
+        call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B * S,
+             nsample, last.N, ptr(out), ptr(arg), stream())
+        ctx.state = (layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs = ctx.state
+        ctx.state = None
+        need_pts = ctx.needs_input_grad[7] and D > 0
+        dout = dout.contiguous().view(B * S, -1)
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, arg.view(B * S, -1), nsample, need_pts)
+        dpts = None
+        if need_pts:
+            dpts = torch.zeros(B, N, D, device=dout.device, dtype=torch.float32)
+            call("pn2_group_points_bwd", ptr(dx0), dx0.shape[1], dt(dx0), ptr(idx), B, N, S, nsample, D, ptr(dpts),
+                 stream())
+        return (None,) * 7 + (dpts,) + _param_grads(grads, convs, ctx.needs_input_grad[8:])
+
+
+class _GroupAllFn(torch.autograd.Function):
+    """group_all=True branch (:141-158, :189-190): one group of all N points, no centring."""
+
+    @staticmethod
+    def forward(ctx, convs, bns, x0_f32, *params):
+        B, N, K0 = x0_f32.shape
+        dtype = ops.rows_dtype()
+        ld = _row_ld(K0, dtype)
+        x0 = torch.zeros(B * N, ld, device=x0_f32.device, dtype=dtype)
+        x0[:, :K0] = x0_f32.reshape(B * N, K0)
+        layers = mlp_forward(x0, K0, B * N, convs, bns)
+        last = layers[-1]
+        out = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.float32)
+        arg = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.int32)
+        call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B, N,
+             last.N, ptr(out), ptr(arg), stream())
+        ctx.state = (layers, x0, K0, arg, (B, N), convs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        layers, x0, K0, arg, (B, N), convs = ctx.state
+        ctx.state = None
+        need = ctx.needs_input_grad[2]
+        grads, dx0 = mlp_backward(layers, x0, K0, B * N, dout.contiguous().view(B, -1), arg.view(B, -1), N, need)
+        dx = dx0[:, :K0].float().view(B, N, K0) if need else None
+        return (None, None, dx) + _param_grads(grads, convs, ctx.needs_input_grad[3:])
+
+
+class _FeaturePropagationFn(torch.autograd.Function):
+    """3-NN inverse-distance interpolation + concat + MLP (pointnet2_utils.py:285-314)."""
+
+    @staticmethod
+    def forward(ctx, convs, bns, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+        B, N, _ = xyz1_r.shape
+        S = xyz2_r.shape[1]
+        dtype = ops.rows_dtype()
+        p2 = ops.as_rows(p2_r)
+        D2 = p2.shape[2]
+        D1 = 0 if p1_r is None else p1_r.shape[2]
+        idx3, w3 = ops.three_nn(xyz1_r, xyz2_r)   # S == 1 degenerates to weight 1 on the only point (:293-294)
+        K0 = D1 + D2
+        M = B * N
+        x0 = torch.empty(M, _row_ld(K0, dtype), device=p2.device, dtype=dtype)
+        pB, pN, pD = (0, 0, 0) if p1_r is None else p1_r.stride()
+        call("pn2_interp_concat", ptr(p1_r), pB, pN, pD, ptr(p2), S * D2, D2, 1, ptr(idx3), ptr(w3), B, N, S, D1, D2,
+             ptr(x0), x0.shape[1], dt(x0), stream())
+        layers = mlp_forward(x0, K0, M, convs, bns)
+        last = layers[-1]
+        out = torch.empty(B, N, last.N, device=p2.device, dtype=torch.float32)
+        call("pn2_bn_relu", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), M, last.N,
+             ptr(out), stream())
+        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs = ctx.state
+        ctx.state = None
+        need1 = ctx.needs_input_grad[4] and D1 > 0
+        need2 = ctx.needs_input_grad[5]
+        dout = dout.contiguous().view(M, -1)
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, None, 1, need1 or need2)
+        dp1 = dp2 = None
+        if need1:
+            dp1 = torch.empty(B, N, D1, device=dout.device, dtype=torch.float32)
+            call("pn2_rows_to_f32", ptr(dx0), dx0.shape[1], dt(dx0), M, 0, D1, ptr(dp1), stream())
+        if need2:
+            dp2 = torch.zeros(B, S, D2, device=dout.device, dtype=torch.float32)
+            call("pn2_interp_bwd", ptr(dx0), dx0.shape[1], dt(dx0), ptr(idx3), ptr(w3), B, N, S, D1, D2, ptr(dp2),
+                 stream())
+        return (None, None, None, None, dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[6:])
+
+
+def _check_module_inputs(xyz, points):
+    require_cuda(xyz, "xyz")
+    if xyz.dim() != 3 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be [B, 3, N], got %s" % (tuple(xyz.shape),))
+    if points is not None:
+        require_cuda(points, "points")
+        if points.dim() != 3 or points.shape[0] != xyz.shape[0] or points.shape[2] != xyz.shape[2]:
+            raise ValueError("points must be [B, D, N] matching xyz, got %s" % (tuple(points.shape),))
+
+
+def _build_mlp(conv_cls, bn_cls, in_channel, widths):
+    convs, bns = nn.ModuleList(), nn.ModuleList()
+    last = in_channel
+    for width in widths:
+        convs.append(conv_cls(last, width, 1))
+        bns.append(bn_cls(width))
+        last = width
+    return convs, bns
+
+
+class PointNetSetAbstraction(nn.Module):
+    """Drop-in for pointnet2_utils.py:161-202."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs, self.mlp_bns = _build_mlp(nn.Conv2d, nn.BatchNorm2d, in_channel, mlp)
+
+    def forward(self, xyz, points):
+        """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
+        _check_module_inputs(xyz, points)
+        xyz_r = xyz.permute(0, 2, 1)
+        pts_r = None if points is None else points.permute(0, 2, 1)
+        params = _flat_params(self.mlp_convs, self.mlp_bns)
+        if self.group_all:
+            new_xyz = torch.zeros(xyz.shape[0], 1, 3, device=xyz.device, dtype=xyz.dtype)
+            x0 = xyz_r if pts_r is None else torch.cat([xyz_r, pts_r], dim=-1)
+            out = _GroupAllFn.apply(self.mlp_convs, self.mlp_bns, x0, *params)
+        else:
+            _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True)
+            out = _SetAbstractionFn.apply(self, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
+                                          xyz_r, pts_r, *params)
+        return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
+
+
+class _PermutedConv(nn.Module):
+    """View of a Conv2d whose input channels are read in a different order (no parameters of its own)."""
+
+    def __init__(self, conv, perm):
+        super().__init__()
+        self.__dict__["_conv"] = conv          # not registered: the owner keeps the parameters
+        self.perm = perm
+        self.out_channels = conv.out_channels
+
+    @property
+    def weight(self):
+        return self._conv.weight[:, self.perm]
+
+    @property
+    def bias(self):
+        return self._conv.bias
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """Drop-in for pointnet2_utils.py:205-262 (multi-scale grouping; not used by SSG sem-seg).
+    Composed from the same kernels; the reference's feature-first concat order (:248) is
+    honoured by reading the first conv's weight columns in permuted order."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks, self.bn_blocks = nn.ModuleList(), nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = _build_mlp(nn.Conv2d, nn.BatchNorm2d, in_channel + 3, widths)
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+
+    def forward(self, xyz, points):
+        _check_module_inputs(xyz, points)
+        xyz_r = xyz.permute(0, 2, 1)
+        pts_r = None if points is None else points.permute(0, 2, 1)
+        D = 0 if points is None else points.shape[1]
+        _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True)
+        outs = []
+        for radius, k, convs, bns in zip(self.radius_list, self.nsample_list, self.conv_blocks, self.bn_blocks):
+            if D:
+                perm = torch.cat([torch.arange(D, D + 3), torch.arange(0, D)]).to(xyz.device)
+                first = _PermutedConv(convs[0], perm)
+                conv_list = [first] + list(convs)[1:]
+                params = [first.weight, first.bias, bns[0].weight, bns[0].bias] + _flat_params(convs, bns)[4:]
+            else:
+                conv_list, params = list(convs), _flat_params(convs, bns)
+            outs.append(_SetAbstractionFn.apply(self, conv_list, list(bns), radius, k, new_xyz, xyz_r, pts_r, *params))
+        return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=2).permute(0, 2, 1)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """Drop-in for pointnet2_utils.py:265-315."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = _build_mlp(nn.Conv1d, nn.BatchNorm1d, in_channel, mlp)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        _check_module_inputs(xyz1, points1)
+        _check_module_inputs(xyz2, points2)
+        if points2 is None:
+            raise ValueError("points2 is required")
+        out = _FeaturePropagationFn.apply(
+            self.mlp_convs, self.mlp_bns, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
+            None if points1 is None else points1.permute(0, 2, 1), points2.permute(0, 2, 1),
+            *_flat_params(self.mlp_convs, self.mlp_bns))
+        return out.permute(0, 2, 1)

@@ -1,0 +1,186 @@
+"""Host side of the hot path: the reference's free functions over the C ABI.
+
+Same names, argument meaning and tensor conventions as
+/root/reference/models/pointnet2_utils.py (point-first ``[B,N,3]`` inputs, int64
+indices), CUDA float32 only.  Every function below is a thin argument-checking
+wrapper around one or two entry points of libpn2b200.so; torch supplies device
+memory and the current stream, nothing else.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, dt, ptr, require_cuda, stream
+
+_PRECISION = {"rows": torch.float32}
+
+
+def set_precision(mode):
+    """'fp32': rows and MLP arithmetic in fp32 (FMA pipes) -- matches the reference's CPU fp32.
+    'bf16': rows stored as bf16, MLP products on the tcgen05 tensor cores with fp32 accumulation."""
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16', got %r" % (mode,))
+    _PRECISION["rows"] = torch.float32 if mode == "fp32" else torch.bfloat16
+
+
+def get_precision():
+    return "fp32" if _PRECISION["rows"] == torch.float32 else "bf16"
+
+
+def rows_dtype():
+    return _PRECISION["rows"]
+
+
+def _xyz3(t, name):
+    require_cuda(t, name)
+    if t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError("%s must be [B, N, 3], got %s" % (name, tuple(t.shape)))
+    return t
+
+
+def square_distance(src, dst):
+    """pointnet2_utils.py:19-40 -- [B,N,3] x [B,M,3] -> [B,N,M] in the reference's rounding order."""
+    _xyz3(src, "src"), _xyz3(dst, "dst")
+    src, dst = src.contiguous(), dst.contiguous()
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty(B, N, M, device=src.device, dtype=torch.float32)
+    call("pn2_square_distance", ptr(src), ptr(dst), B, N, M, ptr(out), stream())
+    return out
+
+
+class _IndexPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        flat = idx.reshape(B, -1).contiguous()
+        J = flat.shape[1]
+        out = torch.empty(B, J, C, device=points.device, dtype=torch.float32)
+        sB, sN, sC = points.stride()
+        call("pn2_index_points", ptr(points), sB, sN, sC, B, N, C, ptr(flat), J, ptr(out), stream())
+        ctx.save_for_backward(flat)
+        ctx.dims = (B, N, C, J)
+        return out.view(*idx.shape, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (flat,) = ctx.saved_tensors
+        B, N, C, J = ctx.dims
+        dout = dout.contiguous().view(B, J, C)
+        dpoints = torch.zeros(B, N, C, device=dout.device, dtype=torch.float32)
+        call("pn2_index_points_bwd", ptr(dout), ptr(flat), B, N, C, J, ptr(dpoints), stream())
+        return dpoints, None
+
+
+def index_points(points, idx):
+    """pointnet2_utils.py:43-60 -- points [B,N,C], idx [B,S] or [B,S,K] (int64) -> [B,S(,K),C]."""
+    require_cuda(points, "points")
+    require_cuda(idx, "idx", torch.int64)
+    if points.dim() != 3 or idx.shape[0] != points.shape[0]:
+        raise ValueError("index_points: points %s / idx %s" % (tuple(points.shape), tuple(idx.shape)))
+    return _IndexPoints.apply(points, idx)
+
+
+def farthest_point_sample(xyz, npoint, start=None, return_xyz=False):
+    """pointnet2_utils.py:63-84 -- xyz [B,N,3] (any strides) -> int64 [B,npoint].
+
+    The start index is drawn exactly as the reference does (:75): one
+    ``torch.randint(0, N, (B,), dtype=torch.long)`` on the CPU default generator,
+    so both stay in lock-step under ``torch.manual_seed``.  ``start`` overrides it.
+    """
+    _xyz3(xyz, "xyz")
+    B, N, _ = xyz.shape
+    npoint = int(npoint)
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    if start.shape != (B,) or start.dtype != torch.int64:
+        raise ValueError("start must be int64 [B]")
+    start = start.to(xyz.device, non_blocking=True)
+    out = torch.empty(B, npoint, device=xyz.device, dtype=torch.int64)
+    new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32) if return_xyz else None
+    sB, sN, sC = xyz.stride()
+    call("pn2_farthest_point_sample", ptr(xyz), sB, sN, sC, B, N, npoint, ptr(start), ptr(out), ptr(new_xyz), stream())
+    return (out, new_xyz) if return_xyz else out
+
+
+def radius_sq(radius):
+    """float32(radius ** 2) as `sqrdists > radius ** 2` (:102) sees it: a Python double squared,
+    then rounded once to fp32 by the tensor/scalar comparison."""
+    return float(torch.tensor(float(radius) ** 2, dtype=torch.float64).to(torch.float32).item())
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz, return_count=False):
+    """pointnet2_utils.py:87-107 -- first nsample in-radius indices in index order, padded with the first."""
+    _xyz3(xyz, "xyz"), _xyz3(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    nsample = int(nsample)
+    out = torch.empty(B, S, nsample, device=xyz.device, dtype=torch.int64)
+    cnt = torch.empty(B, S, device=xyz.device, dtype=torch.int32) if return_count else None
+    sB, sN, sC = xyz.stride()
+    qB, qN, qC = new_xyz.stride()
+    call("pn2_query_ball_point", ptr(xyz), sB, sN, sC, ptr(new_xyz), qB, qN, qC, B, N, S, radius_sq(radius),
+         nsample, ptr(out), ptr(cnt), stream())
+    return (out, cnt) if return_count else out
+
+
+def three_nn(xyz1, xyz2):
+    """pointnet2_utils.py:296-302 -- (idx [B,N,3] int64, weight [B,N,3]) of the three nearest xyz2 points."""
+    _xyz3(xyz1, "xyz1"), _xyz3(xyz2, "xyz2")
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    idx = torch.empty(B, N, 3, device=xyz1.device, dtype=torch.int64)
+    w = torch.empty(B, N, 3, device=xyz1.device, dtype=torch.float32)
+    aB, aN, aC = xyz1.stride()
+    cB, cN, cC = xyz2.stride()
+    call("pn2_three_nn", ptr(xyz1), aB, aN, aC, ptr(xyz2), cB, cN, cC, B, N, S, ptr(idx), ptr(w), stream())
+    return idx, w
+
+
+def as_rows(t):
+    """[B, N, C] fp32 view with arbitrary strides -> contiguous point-major rows (copy only if needed)."""
+    if t.is_contiguous():
+        return t
+    B, N, C = t.shape
+    out = torch.empty(B, N, C, device=t.device, dtype=torch.float32)
+    sB, sN, sC = t.stride()
+    call("pn2_to_rows", ptr(t), sB, sN, sC, B, N, C, ptr(out), N * C, C, stream())
+    return out
+
+
+def group_rows(xyz, new_xyz, feats, idx, ld, dtype):
+    """sample_and_group's gather (:127-132): rows [(b,s,k), ld] = [xyz[idx]-new_xyz | feats[idx] | 0]."""
+    B, N, _ = xyz.shape
+    S, K = idx.shape[1], idx.shape[2]
+    D = 0 if feats is None else feats.shape[2]
+    rows = torch.empty(B * S * K, ld, device=xyz.device, dtype=dtype)
+    sB, sN, sC = xyz.stride()
+    fB, fN, fD = (0, 0, 0) if feats is None else feats.stride()
+    call("pn2_group_points", ptr(xyz), sB, sN, sC, ptr(new_xyz), ptr(feats), fB, fN, fD, ptr(idx), B, N, S, K, D,
+         ptr(rows), ld, dt(rows), stream())
+    return rows
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """pointnet2_utils.py:110-138 (forward only; the modules use the fused autograd path)."""
+    _xyz3(xyz, "xyz")
+    B, N, C = xyz.shape
+    fps_idx, new_xyz = farthest_point_sample(xyz, npoint, return_xyz=True)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    feats = None if points is None else as_rows(require_cuda(points, "points"))
+    D = 0 if feats is None else feats.shape[2]
+    rows = group_rows(xyz, new_xyz, feats, idx, 3 + D, torch.float32)
+    new_points = rows.view(B, npoint, nsample, 3 + D)
+    if returnfps:
+        return new_xyz, new_points, index_points(xyz, idx), fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """pointnet2_utils.py:141-158 -- one group holding every point; pure views/concat."""
+    _xyz3(xyz, "xyz")
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device, dtype=xyz.dtype)
+    grouped = xyz.reshape(B, 1, N, C)
+    if points is not None:
+        grouped = torch.cat([grouped, points.reshape(B, 1, N, -1)], dim=-1)
+    return new_xyz, grouped

@@ -1,0 +1,58 @@
+"""The SSG semantic-segmentation network that calls the hot path.
+
+Architecture and attribute names follow /root/reference/models/pointnet2_sem_seg.py:6-50
+(4 set-abstraction levels, 4 feature-propagation levels, Conv1d/BN/Dropout/Conv1d head,
+log_softmax), so its ``state_dict`` is interchangeable with the reference's ``get_model``.
+The reference file itself also runs unchanged on top of ``models/pointnet2_utils.py``; this
+copy exists because the reference tree is not present on the GPU box.  The head and the loss
+are ordinary PyTorch (they are outside the hot path).
+"""
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import PointNetFeaturePropagation, PointNetSetAbstraction
+
+# (npoint, radius, nsample, mlp) -- pointnet2_sem_seg.py:9-12
+SA_LEVELS = ((1024, 0.1, 32, (32, 32, 64)), (256, 0.2, 32, (64, 64, 128)),
+             (64, 0.4, 32, (128, 128, 256)), (16, 0.8, 32, (256, 256, 512)))
+# (in_channel, mlp) for fp4, fp3, fp2, fp1 -- pointnet2_sem_seg.py:13-16
+FP_LEVELS = ((768, (256, 256)), (384, (256, 256)), (320, (256, 128)), (128, (128, 128, 128)))
+
+
+class get_model(nn.Module):
+    def __init__(self, num_classes, num_extra_features, sa_cls=PointNetSetAbstraction,
+                 fp_cls=PointNetFeaturePropagation):
+        super().__init__()
+        width = 6 + 3 + num_extra_features
+        for level, (npoint, radius, nsample, mlp) in enumerate(SA_LEVELS, start=1):
+            self.add_module("sa%d" % level, sa_cls(npoint, radius, nsample, width, list(mlp), False))
+            width = mlp[-1] + 3
+        for level, (cin, mlp) in zip((4, 3, 2, 1), FP_LEVELS):
+            self.add_module("fp%d" % level, fp_cls(cin, list(mlp)))
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+
+    def forward(self, xyz):
+        feats = [xyz]
+        coords = [xyz[:, :3, :]]
+        for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+            c, f = sa(coords[-1], feats[-1])
+            coords.append(c)
+            feats.append(f)
+        l4_points = feats[4]
+        up = self.fp4(coords[3], coords[4], feats[3], feats[4])
+        up = self.fp3(coords[2], coords[3], feats[2], up)
+        up = self.fp2(coords[1], coords[2], feats[1], up)
+        up = self.fp1(coords[0], coords[1], None, up)
+        x = self.drop1(F.relu(self.bn1(self.conv1(up))))
+        x = F.log_softmax(self.conv2(x), dim=1)
+        return x.permute(0, 2, 1), l4_points
+
+
+class get_loss(nn.Module):
+    """pointnet2_sem_seg.py:44-50: class-weighted NLL on the log-probabilities."""
+
+    def forward(self, pred, target, trans_feat, weight):
+        return F.nll_loss(pred, target, weight=weight)

@@ -1,0 +1,234 @@
+"""Torch-CPU restatement ("port") of the reference's PointNet++ SSG hot path.
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs, never by the product package.
+
+What it restates (all line numbers are /root/reference/models/pointnet2_utils.py
+unless another file is named):
+
+  pairwise_sqdist      square_distance            :19-40
+  take_points          index_points               :43-60
+  fps                  farthest_point_sample      :63-84
+  ball_query           query_ball_point           :87-107
+  group                sample_and_group           :110-138
+  group_all            sample_and_group_all       :141-158
+  OracleSA             PointNetSetAbstraction     :161-202
+  OracleSAMsg          PointNetSetAbstractionMsg  :205-262
+  OracleFP             PointNetFeaturePropagation :265-315
+  OracleSemSeg         get_model   (models/pointnet2_sem_seg.py:6-40)
+  nll                  get_loss    (models/pointnet2_sem_seg.py:44-50)
+
+The arithmetic itself lives in PyTorch (third party, un-pinned by the reference;
+effective pin torch 2.11.0+cu128 of this image), so this port issues the same
+ATen operations in the same order (matmul/sum/sort/max/conv/batch_norm); the
+machine-independent statement of the rounding order is oracle/pn2_oracle.c.
+
+Pinning: tests/test_oracle_golden.py compares this module and the C file with
+fixtures generated from the unmodified reference by tests/golden/make_golden.py
+(run in the authoring container where /root/reference is mounted).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def pairwise_sqdist(src, dst):
+    # :37-39  -2*src@dst^T, then += |src|^2, then += |dst|^2 (this order)
+    out = torch.matmul(src, dst.transpose(1, 2)) * -2
+    out += (src ** 2).sum(-1).unsqueeze(-1)
+    out += (dst ** 2).sum(-1).unsqueeze(-2)
+    return out
+
+
+def take_points(points, idx):
+    # :53-59  points[b, idx[b, ...], :]
+    B = points.shape[0]
+    rows = torch.arange(B, dtype=torch.long, device=points.device)
+    rows = rows.reshape([B] + [1] * (idx.dim() - 1)).expand_as(idx)
+    return points[rows, idx]
+
+
+def fps(xyz, npoint, start=None):
+    # :73-84; the start index is one CPU-generator randint draw (:75)
+    B, N, _ = xyz.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    far = start.to(xyz.device)
+    picked = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    nearest = torch.full((B, N), 1e10, dtype=xyz.dtype, device=xyz.device)
+    rows = torch.arange(B, device=xyz.device)
+    for i in range(npoint):
+        picked[:, i] = far
+        centre = xyz[rows, far].unsqueeze(1)
+        d = ((xyz - centre) ** 2).sum(-1)
+        nearest = torch.where(d < nearest, d, nearest)
+        far = nearest.max(-1)[1]
+    return picked
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    # :96-106  first nsample in-radius indices in ascending order, padded with the first
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    d = pairwise_sqdist(new_xyz, xyz)
+    cand = torch.arange(N, dtype=torch.long, device=xyz.device).expand(B, S, N).clone()
+    cand[d > radius ** 2] = N
+    kept = cand.sort(dim=-1)[0][:, :, :nsample]
+    lead = kept[:, :, :1].expand(-1, -1, kept.shape[-1])
+    return torch.where(kept == N, lead, kept)
+
+
+def group(npoint, radius, nsample, xyz, points, start=None, return_idx=False):
+    # :121-138
+    picked = fps(xyz, npoint, start)
+    new_xyz = take_points(xyz, picked)
+    nbr = ball_query(radius, nsample, xyz, new_xyz)
+    local = take_points(xyz, nbr) - new_xyz.unsqueeze(2)
+    feats = local if points is None else torch.cat([local, take_points(points, nbr)], -1)
+    if return_idx:
+        return new_xyz, feats, picked, nbr
+    return new_xyz, feats
+
+
+def group_all(xyz, points):
+    # :150-158
+    B, N, C = xyz.shape
+    new_xyz = xyz.new_zeros(B, 1, C)
+    feats = xyz.unsqueeze(1)
+    if points is not None:
+        feats = torch.cat([feats, points.unsqueeze(1)], -1)
+    return new_xyz, feats
+
+
+def _mlp_stack(kind, widths, cin):
+    conv = nn.Conv2d if kind == 2 else nn.Conv1d
+    bn = nn.BatchNorm2d if kind == 2 else nn.BatchNorm1d
+    convs, bns = nn.ModuleList(), nn.ModuleList()
+    for w in widths:
+        convs.append(conv(cin, w, 1))
+        bns.append(bn(w))
+        cin = w
+    return convs, bns
+
+
+class OracleSA(nn.Module):
+    """:161-202"""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs, self.mlp_bns = _mlp_stack(2, mlp, in_channel)
+
+    def forward(self, xyz, points):
+        xyz_t = xyz.transpose(1, 2)
+        pts_t = None if points is None else points.transpose(1, 2)
+        if self.group_all:
+            new_xyz, feats = group_all(xyz_t, pts_t)
+        else:
+            new_xyz, feats = group(self.npoint, self.radius, self.nsample, xyz_t, pts_t)
+        h = feats.permute(0, 3, 2, 1)          # [B, C+D, nsample, npoint]  (:195)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            h = F.relu(bn(conv(h)))
+        return new_xyz.transpose(1, 2), h.max(2)[0]
+
+
+class OracleSAMsg(nn.Module):
+    """:205-262 (feature-first concat order, :248)"""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks, self.bn_blocks = nn.ModuleList(), nn.ModuleList()
+        for widths in mlp_list:
+            c, b = _mlp_stack(2, widths, in_channel + 3)
+            self.conv_blocks.append(c)
+            self.bn_blocks.append(b)
+
+    def forward(self, xyz, points):
+        xyz_t = xyz.transpose(1, 2)
+        pts_t = None if points is None else points.transpose(1, 2)
+        new_xyz = take_points(xyz_t, fps(xyz_t, self.npoint))
+        outs = []
+        for r, k, convs, bns in zip(self.radius_list, self.nsample_list, self.conv_blocks, self.bn_blocks):
+            nbr = ball_query(r, k, xyz_t, new_xyz)
+            local = take_points(xyz_t, nbr) - new_xyz.unsqueeze(2)
+            h = local if pts_t is None else torch.cat([take_points(pts_t, nbr), local], -1)
+            h = h.permute(0, 3, 2, 1)
+            for conv, bn in zip(convs, bns):
+                h = F.relu(bn(conv(h)))
+            outs.append(h.max(2)[0])
+        return new_xyz.transpose(1, 2), torch.cat(outs, 1)
+
+
+def three_nn_weights(xyz1, xyz2):
+    # :296-302
+    d, order = pairwise_sqdist(xyz1, xyz2).sort(dim=-1)
+    d, order = d[:, :, :3], order[:, :, :3]
+    recip = 1.0 / (d + 1e-8)
+    return order, recip / recip.sum(dim=2, keepdim=True)
+
+
+class OracleFP(nn.Module):
+    """:265-315"""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = _mlp_stack(1, mlp, in_channel)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        f, c = xyz1.transpose(1, 2), xyz2.transpose(1, 2)
+        coarse = points2.transpose(1, 2)
+        B, N, _ = f.shape
+        if c.shape[1] == 1:
+            up = coarse.repeat(1, N, 1)
+        else:
+            order, w = three_nn_weights(f, c)
+            up = (take_points(coarse, order) * w.unsqueeze(-1)).sum(dim=2)
+        if points1 is not None:
+            up = torch.cat([points1.transpose(1, 2), up], -1)
+        h = up.transpose(1, 2)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            h = F.relu(bn(conv(h)))
+        return h
+
+
+# (npoint, radius, nsample, mlp) per level and FP (in, mlp): models/pointnet2_sem_seg.py:9-16
+SA_SPEC = ((1024, 0.1, 32, (32, 32, 64)), (256, 0.2, 32, (64, 64, 128)),
+           (64, 0.4, 32, (128, 128, 256)), (16, 0.8, 32, (256, 256, 512)))
+FP_SPEC = ((768, (256, 256)), (384, (256, 256)), (320, (256, 128)), (128, (128, 128, 128)))
+
+
+class OracleSemSeg(nn.Module):
+    """models/pointnet2_sem_seg.py:6-40 with the oracle modules."""
+
+    def __init__(self, num_classes, num_extra_features, sa_cls=OracleSA, fp_cls=OracleFP):
+        super().__init__()
+        cin = 6 + 3 + num_extra_features
+        for i, (npoint, radius, nsample, mlp) in enumerate(SA_SPEC, 1):
+            setattr(self, "sa%d" % i, sa_cls(npoint, radius, nsample, cin, list(mlp), False))
+            cin = mlp[-1] + 3
+        for i, (c, mlp) in zip((4, 3, 2, 1), FP_SPEC):
+            setattr(self, "fp%d" % i, fp_cls(c, list(mlp)))
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+
+    def forward(self, x):
+        xyz0, f0 = x[:, :3, :], x
+        xyz1, f1 = self.sa1(xyz0, f0)
+        xyz2, f2 = self.sa2(xyz1, f1)
+        xyz3, f3 = self.sa3(xyz2, f2)
+        xyz4, f4 = self.sa4(xyz3, f3)
+        f3 = self.fp4(xyz3, xyz4, f3, f4)
+        f2 = self.fp3(xyz2, xyz3, f2, f3)
+        f1 = self.fp2(xyz1, xyz2, f1, f2)
+        f0 = self.fp1(xyz0, xyz1, None, f1)
+        h = self.drop1(F.relu(self.bn1(self.conv1(f0))))
+        h = F.log_softmax(self.conv2(h), dim=1)
+        return h.permute(0, 2, 1), f4
+
+
+def nll(pred, target, weight=None):
+    # models/pointnet2_sem_seg.py:47-48
+    return F.nll_loss(pred, target, weight=weight)
