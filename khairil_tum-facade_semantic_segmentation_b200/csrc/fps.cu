@@ -257,9 +257,9 @@ using namespace pn2;
 extern "C" int pn2_farthest_point_sample(const float *xyz, int64_t sB, int64_t sN, int64_t sC, int B,
                                          int N, int npoint, const int64_t *start_idx,
                                          int64_t *out_idx, float *out_xyz, void *stream) {
-    PN2_REQUIRE(xyz && start_idx && out_idx, "fps: null pointer");
     PN2_REQUIRE(B >= 0 && N > 0 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
     if (B == 0 || npoint == 0) return PN2_OK;
+    PN2_REQUIRE(xyz && start_idx && out_idx, "fps: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     // points per thread P, threads T, CTAs per cloud CL (see file header)
     int P, T, CL = 1;

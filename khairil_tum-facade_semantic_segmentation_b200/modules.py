@@ -79,8 +79,9 @@ def mlp_forward(x0, K0, M, convs, bns):
                  ptr(st.scale), ptr(st.shift), stream())
             call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K, N,
                  ptr(z), ldz, dt(z), None, stream())
-            # for a backward pass through frozen statistics: zhat = (z - (rm - b)) * invstd_running
-            st.mean = bn.running_mean.detach() - (bias if bias is not None else 0.0)
+            # for a backward pass through frozen statistics (Z already holds the bias here):
+            # zhat = (z - running_mean) * invstd_running
+            st.mean = bn.running_mean.detach()
             st.invstd = torch.rsqrt(bn.running_var.detach() + bn.eps)
         layers.append(st)
         x, ldx, K = z, ldz, N

@@ -171,16 +171,38 @@ def modules():
     save("modules.npz", out)
 
 
+def _tie_free(x, seeds):
+    """True if, on every 3-NN level the network evaluates for input x [B,C,N], the reference's
+    sort puts equal distances in ascending index order.  torch.sort(stable=False) on CPU leaves
+    the order of exactly tied distances unspecified (it differs from the CUDA path and between
+    CPU generations); fixtures avoid inputs whose result depends on it."""
+    xyz0 = x[:, :3, :].permute(0, 2, 1).contiguous()
+    for seed in seeds:
+        torch.manual_seed(seed)
+        lv = [xyz0]
+        for S in (1024, 256, 64, 16):
+            lv.append(R.index_points(lv[-1], R.farthest_point_sample(lv[-1], S)))
+        for fine, coarse in zip(lv[:-1], lv[1:]):
+            d = R.square_distance(fine, coarse)
+            if not torch.equal(d.sort(dim=-1)[1][:, :, :3], d.sort(dim=-1, stable=True)[1][:, :, :3]):
+                return False
+    return True
+
+
 def model():
     out = {}
     B, N, NC = 2, 2048, 18
+    fseed = next(s for s in range(2, 500) if _tie_free(I.facade_batch(B, N, 9, s).transpose(2, 1), (71, 72)))
+    cseed = next(s for s in range(0, 500) if _tie_free(I.cube_batch(B, N, 9, s), (71,)))
+    print("  tie-free seeds: facade %d cube %d" % (fseed, cseed))
+    out["facade_seed"], out["cube_seed"] = np.int64(fseed), np.int64(cseed)
     net = I.randomize_module_(RM.get_model(NC, 3), 61)
     net.drop1.p = 0.0                                           # dropout off: its mask is generator/device specific
     keys = sorted(net.state_dict().keys())
     out["state_keys"] = np.array(keys)
     out["state_shapes"] = np.array([str(tuple(net.state_dict()[k].shape)) for k in keys])
     out["param_checksum"] = np.float64(sum(I.checksum(v) for v in net.state_dict().values() if v.is_floating_point()))
-    for tag, x in (("facade", I.facade_batch(B, N, 9, 2).transpose(2, 1)), ("cube", I.cube_batch(B, N, 9, 0))):
+    for tag, x in (("facade", I.facade_batch(B, N, 9, fseed).transpose(2, 1)), ("cube", I.cube_batch(B, N, 9, cseed))):
         net.eval()
         torch.manual_seed(71)
         with torch.no_grad():
@@ -188,7 +210,7 @@ def model():
         out[tag + "_eval_pred"] = pred.numpy()
         out[tag + "_eval_l4"] = l4.numpy()
     # one train step's forward/backward on the facade batch
-    x = I.facade_batch(B, N, 9, 2).transpose(2, 1)
+    x = I.facade_batch(B, N, 9, fseed).transpose(2, 1)
     target = I.labels(B, N, NC, 7)
     weights = torch.linspace(0.5, 1.5, NC)
     net.train()

@@ -45,8 +45,9 @@ def test_unchanged_reference_model_runs_on_gpu(pn2, golden):
     import _inputs as I
     mod, _ = _import_reference_model()
     net = I.randomize_module_(mod.get_model(18, 3), 61).cuda().eval()
-    x = I.facade_batch(2, 2048, 9, 2).cuda().transpose(2, 1)
+    g = golden("model")
+    x = I.facade_batch(2, 2048, 9, int(g["facade_seed"])).cuda().transpose(2, 1)
     torch.manual_seed(71)
     with torch.no_grad():
         pred, _ = net(x)
-    assert np.abs(pred.cpu().numpy() - golden("model")["facade_eval_pred"]).max() < 1e-3
+    assert np.abs(pred.cpu().numpy() - g["facade_eval_pred"]).max() < 1e-3

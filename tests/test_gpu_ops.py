@@ -143,6 +143,19 @@ def test_three_nn_matches_c_oracle(pn2, B, N, S):
     assert (w.cpu().numpy()[:, :, k3:] == 0).all()
 
 
+def test_three_nn_exact_ties_take_the_lower_index(pn2):
+    """Equal distances: the reference's torch.sort(stable=False) leaves their order unspecified
+    (its CPU path is an unstable vectorised sort, its CUDA path a stable radix sort).  This
+    implementation and the C oracle define it as the stable order: lower index first."""
+    fine = torch.zeros(1, 1, 3)
+    coarse = torch.tensor([[[0., 0., 2.], [1., 0., 0.], [-1., 0., 0.], [0., 1., 0.], [0., -1., 0.]]])
+    idx, w = pn2.three_nn(fine.to(DEV), coarse.to(DEV))
+    assert idx.cpu().tolist() == [[[1, 2, 3]]]
+    np.testing.assert_allclose(w.cpu().numpy(), 1.0 / 3.0, rtol=1e-6)
+    widx, _, ww = C.three_nn(fine.numpy(), coarse.numpy())
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(w.cpu().numpy(), ww)
+
+
 def test_index_points_forward_backward(pn2):
     g = torch.Generator().manual_seed(0)
     pts = torch.rand(3, 50, 7, generator=g)
