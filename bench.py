@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline measurement: points/sec of one PointNet++ SSG sem_seg
+TRAINING STEP (zero_grad + forward + weighted NLL + backward + Adam) on synthetic
+32 x 4096-point, 9-channel batches per GPU (BASELINE.json configs[1]), bf16 rows.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the meaning of every key.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_PER_GPU, NPOINT, CHANNELS, NUM_CLASSES = 32, 4096, 9, 18
+METRIC, UNIT = "points/sec (PointNet++ SSG sem_seg train step)", "points/s"
+WORKLOAD = "sem_seg train step, synthetic facade blocks %dx%dx%dch per GPU, %d classes" % (B_PER_GPU, NPOINT, CHANNELS, NUM_CLASSES)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_batches(n, seed):
+    """n pinned host batches [B, NPOINT, C] float32 + labels [B*NPOINT] int64 (S2 "facade block")."""
+    import _inputs as I
+    out = []
+    for i in range(n):
+        pts = I.facade_batch(B_PER_GPU, NPOINT, CHANNELS, seed + i)
+        lab = I.labels(B_PER_GPU, NPOINT, NUM_CLASSES, seed + 100 + i)
+        if torch.cuda.is_available():
+            pts, lab = pts.pin_memory(), lab.pin_memory()
+        out.append((pts, lab))
+    return out
+
+
+def cpu_train_step_rate(batch_clouds, steps, warmup, threads, budget_s=150.0):
+    """The oracle port (torch-CPU restatement of the reference modules) timed on the host cores.
+    Stops early once `budget_s` of timed work is spent; returns (points/s from the median step, s/step, steps)."""
+    from oracle import pn2_oracle as O
+    import _inputs as I
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = O.OracleSemSeg(NUM_CLASSES, CHANNELS - 6).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+    w = torch.ones(NUM_CLASSES)
+    x = I.facade_batch(batch_clouds, NPOINT, CHANNELS, 11)
+    y = I.labels(batch_clouds, NPOINT, NUM_CLASSES, 111)
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        opt.zero_grad()
+        pred, feat = net(x.transpose(2, 1))
+        loss = O.nll(pred.contiguous().view(-1, NUM_CLASSES), y, w)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t)
+            if sum(times) > budget_s:
+                break
+    med = sorted(times)[len(times) // 2]
+    return batch_clouds * NPOINT / med, med, len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_clouds = 16
+    rate, sec, done = cpu_train_step_rate(sample_clouds, args.steps, min(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "oracle port of the reference modules (torch CPU ops in the reference's order), "
+                   "fp32, each step a %d-cloud sample of the 32-cloud batch; median step; at most 150 s of timed steps" % sample_clouds},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d x %d-point clouds per step (train step: fwd+bwd+Adam)" % (sample_clouds, NPOINT)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timed-entry", default="pn2_farthest_point_sample",
+                    help="C-ABI entry point whose launches are event-timed for the roofline object")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    pn2 = importlib.import_module("khairil_tum-facade_semantic_segmentation_b200")
+    lib_mod = importlib.import_module("khairil_tum-facade_semantic_segmentation_b200._lib")
+    pn2.load()                                        # fails loudly if the CUDA library is missing
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pn2.set_precision(args.precision)
+
+    torch.manual_seed(1234)                           # identical initial weights on every rank
+    trainer = pn2.SemSegTrainer(NUM_CLASSES, CHANNELS - 6, device=dev)
+    n_batches = 4
+    host = synthetic_batches(n_batches, 1000 * rank + 11)
+    resident = [(p.to(dev), t.to(dev)) for p, t in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value") -------------------------------------------------------
+    for i in range(args.warmup):
+        trainer.step_device(*resident[i % n_batches])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib_mod.time_entry_point(args.timed_entry)
+    launches0 = pn2.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+        starts[i].record()
+        trainer.step_device(*resident[i % n_batches])
+        ends[i].record()
+    barrier()
+    launches = pn2.launch_count() - launches0
+    kernel_ms = lib_mod.timed_durations_ms()
+    lib_mod.time_entry_point(None)
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+
+    # ---- end-to-end arm ("e2e"): host buffers in, loss out, copies inside the timed region ------
+    for i in range(2):
+        trainer.step(*host[i % n_batches])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        trainer.step(*host[i % n_batches])
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    points_per_step = world * B_PER_GPU * NPOINT
+    ms_per_step = total_ms.item() / args.steps
+    value = points_per_step / (ms_per_step * 1e-3)
+    e2e_value = points_per_step / (e2e_ms.item() / args.steps * 1e-3)
+    pk, pk_kind = peaks()
+
+    # ---- roofline of the dominant kernel (K1 FPS, fp32-ALU bound, 9 flop / point-iteration)
+    roof = None
+    if kernel_ms:
+        per_step = len(kernel_ms) // args.steps
+        levels = [(4096, 1024), (1024, 256), (256, 64), (64, 16)][:per_step]
+        by_level = [kernel_ms[i::per_step] for i in range(per_step)] if per_step else []
+        if args.timed_entry == "pn2_farthest_point_sample" and by_level:
+            n_src, n_pick = levels[0]
+            avg_ms = sum(by_level[0]) / len(by_level[0])
+            alg_bytes = B_PER_GPU * (12 * n_src + 8 * n_pick + 12 * n_pick)
+            alg_flop = 9.0 * B_PER_GPU * n_src * n_pick
+            roof = {"kernel": "fps_kernel (sa1: %d -> %d, %d clouds)" % (n_src, n_pick, B_PER_GPU), "bound": "hbm",
+                    "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                    "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": avg_ms,
+                    "share_of_step": sum(sum(l) for l in by_level) / len(by_level[0]) / ms_per_step,
+                    "note": "latency chain: %d dependent iterations on %d of 148 SMs; fp32-ALU view: %.3f TFLOP/s non-FMA"
+                            % (n_pick, B_PER_GPU, alg_flop / (avg_ms * 1e-3) / 1e12)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        rate, sec, done = cpu_train_step_rate(16, 2, 1, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d timed train steps on 16 x %d-point clouds (oracle port of the reference, fp32), %.1f s/step" % (done, NPOINT, sec)}
+
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch_clouds": world * B_PER_GPU, "points_per_cloud": NPOINT,
+                   "parallelism": "dp%d (blocks sharded, flat-gradient NCCL all-reduce)" % world,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush), outside the per-step events",
+                   "optimizer": "Adam(lr 1e-3, wd 1e-4) inside the step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms.item() / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

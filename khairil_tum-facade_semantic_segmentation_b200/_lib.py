@@ -76,10 +76,32 @@ def load():
     return _lib
 
 
+_TIMED = {"name": None, "events": []}
+
+
+def time_entry_point(name):
+    """Bracket every later call of entry point `name` with CUDA events on the launching (current)
+    stream; bench.py uses this to measure the dominant kernel live.  None switches it off."""
+    _TIMED["name"], _TIMED["events"] = name, []
+
+
+def timed_durations_ms():
+    """Per-launch durations (ms) recorded since time_entry_point(); synchronises."""
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in _TIMED["events"]]
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise Pn2Error with the library's message on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if name == _TIMED["name"]:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        _TIMED["events"].append((s, e))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise Pn2Error("%s failed (%d): %s" % (name, rc, lib.pn2_last_error().decode()))
 

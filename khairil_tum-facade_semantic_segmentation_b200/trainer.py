@@ -1,0 +1,91 @@
+"""Host-side drivers around the hot path: one training step and block-sharded inference.
+
+``SemSegTrainer.step`` is the body of the reference's batch loop
+(/root/reference/localfunctions.py:202-218: zero_grad, host->device copy, transpose,
+forward, weighted NLL, backward, optimizer step) with the optimizer the reference builds
+(/root/reference/sem_seg_training.py:576-582: Adam, betas (0.9, 0.999), eps 1e-8, weight
+decay 1e-4).  Multi-GPU is pure data parallelism over point-cloud blocks, one process per
+GPU: inference needs no collective; training all-reduces ONE flat fp32
+gradient buffer (~3.9 MB) over NCCL/NVLink per step.  BatchNorm statistics stay per rank.
+"""
+import torch
+import torch.distributed as dist
+
+from .sem_seg import get_loss, get_model
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block partition: rank r owns [r*ceil(n/world), min(n, (r+1)*ceil(n/world)))."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+class FlatGradients:
+    """All parameter gradients as views into one flat buffer, so data-parallel training needs a
+    single all-reduce per step (no bucketing: the buffer is latency-, not bandwidth-bound)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+class SemSegTrainer:
+    def __init__(self, num_classes=18, num_extra_features=3, lr=1e-3, weight_decay=1e-4, device="cuda",
+                 class_weights=None, model=None, fused_optimizer=True):
+        self.device = torch.device(device)
+        self.num_classes = num_classes
+        self.model = (model if model is not None else get_model(num_classes, num_extra_features)).to(self.device)
+        self.criterion = get_loss()
+        self.grads = FlatGradients(self.model.parameters())
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08,
+                                          weight_decay=weight_decay,
+                                          fused=bool(fused_optimizer and self.device.type == "cuda"))
+        self.class_weights = (torch.ones(num_classes) if class_weights is None else class_weights).to(self.device)
+
+    def step_device(self, points, target):
+        """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
+        self.model.train()
+        self.grads.zero()
+        pred, feat = self.model(points.transpose(2, 1))
+        loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
+        loss.backward()
+        self.grads.all_reduce_mean()
+        self.optimizer.step()
+        return loss
+
+    def step(self, points_host, target_host):
+        """One training step from HOST buffers (pinned memory recommended); returns the loss as a float
+        (a device->host read, like the reference's per-batch `seg_pred.cpu()`)."""
+        points = points_host.to(self.device, non_blocking=True).float()
+        target = target_host.to(self.device, non_blocking=True).long().view(-1)
+        return float(self.step_device(points, target))
+
+
+@torch.no_grad()
+def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="cuda"):
+    """sem_seg_testing-style inference (num_votes=1) over [nb, 4096, C] blocks held on the host:
+    this rank labels its contiguous shard of blocks; no collective is needed (eval-mode BatchNorm
+    uses running statistics, so blocks are independent).  Returns (lo, hi, labels [hi-lo, 4096] on host)."""
+    model.eval()
+    lo, hi = shard_range(blocks_host.shape[0], rank, world)
+    out = torch.empty(hi - lo, blocks_host.shape[1], dtype=torch.int64)
+    for s in range(lo, hi, batch_size):
+        e = min(hi, s + batch_size)
+        x = blocks_host[s:e].to(device, non_blocking=True).float().transpose(2, 1)
+        pred, _ = model(x)
+        out[s - lo:e - lo] = pred.argmax(dim=2).cpu()
+    return lo, hi, out
