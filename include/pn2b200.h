@@ -106,12 +106,18 @@ int pn2_group_points_bwd(const void *drows, int ld, int dtype, const int64_t *id
  * on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM); with
  * PN2_F32 rows on the fp32 FMA pipes. */
 int pn2_linear_num_partials(int64_t M);
+/* wpack: device scratch of pn2_linear_wpack_bytes(K, N) bytes for the bf16, pre-swizzled copy
+ * of W that the tensor-core path streams with TMA (bf16 rows with ld % 8 == 0; may be NULL,
+ * which selects the FMA-pipe kernel, as does PN2_DISABLE_TC=1 in the environment). */
+size_t pn2_linear_wpack_bytes(int K, int N);
 int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale,
                    const float *in_shift, const float *W, const float *bias, int64_t M, int K,
-                   int N, void *Z, int ldz, int z_dtype, float *stat_partials, void *stream);
-/* dX[M,K] = dZ[M,N] * W[N,K]   (no activation handling; see pn2_bn_relu_bwd_*) */
+                   int N, void *Z, int ldz, int z_dtype, float *stat_partials, void *wpack,
+                   void *stream);
+/* dX[M,K] = dZ[M,N] * W[N,K]   (no activation handling; see pn2_bn_relu_bwd_*);
+ * wpack: scratch of pn2_linear_wpack_bytes(N, K) bytes (note the swapped roles) or NULL */
 int pn2_linear_bwd_data(const void *dZ, int lddz, int dz_dtype, const float *W, int64_t M, int K,
-                        int N, void *dX, int lddx, int dx_dtype, void *stream);
+                        int N, void *dX, int lddx, int dx_dtype, void *wpack, void *stream);
 /* dW[N,K] = sum_m dZ[m,n] * act(X)[m,k];  scratch holds pn2_linear_wgrad_scratch_bytes() bytes */
 size_t pn2_linear_wgrad_scratch_bytes(int64_t M, int K, int N);
 int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx,

@@ -36,8 +36,9 @@ _SIGNATURES = {
     "pn2_group_points": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pn2_group_points_bwd": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pn2_linear_num_partials": (_i, [_l]),
-    "pn2_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
-    "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p]),
+    "pn2_linear_wpack_bytes": (_z, [_i, _i]),
+    "pn2_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
     "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
     "pn2_bn_train_finalize": (_i, [_p, _i, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),

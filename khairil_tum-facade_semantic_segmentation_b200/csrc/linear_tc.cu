@@ -1,0 +1,348 @@
+// linear_tc.cu -- K3: the 1x1-conv MLP layers on bf16 rows as tcgen05 (5th-gen tensor core) GEMMs.
+//
+//   Z[M,N] = act(X)[M,K] . W[N,K]^T (+bias)        forward  (pointnet2_utils.py:196-198, :311-314)
+//   dX[M,K] = dZ[M,N] . W[N,K]                     data gradient (same kernel, W packed transposed)
+//
+// Shape of the problem: M is huge (up to 2^20 rows = clouds x centroids x samples), K and N are
+// tiny (12..768), so every layer is a stream over rows: HBM-bound, not tensor-bound.  The
+// kernel is therefore organised around the row stream:
+//   * one CTA = 128 threads owns 128-row tiles (UMMA M = 128, cta_group::1), persistent over tiles,
+//     several CTAs per SM so that one CTA's loads overlap another's MMA/epilogue;
+//   * A operand: rows are read with coalesced 16-byte loads, the previous layer's BatchNorm+ReLU
+//     is applied in registers (scale/shift/relu, fp32), the result is rounded to bf16 and written
+//     into shared memory in the canonical K-major 128-byte-swizzle UMMA layout;
+//   * B operand: the weight is pre-packed once per call (fp32 -> bf16, already swizzled, one
+//     image per 64-wide K chunk) and fetched with cp.async.bulk (TMA) onto an mbarrier; when K
+//     fits one chunk it stays resident in shared memory for the CTA's whole life;
+//   * D accumulates in tensor memory (fp32, N columns); one elected thread issues tcgen05.mma and
+//     commits to an mbarrier; chunks are double buffered so loads overlap the MMA;
+//   * epilogue: tcgen05.ld -> (+bias) -> bf16 -> staging tile in shared memory -> coalesced 16-byte
+//     stores; the train-mode BatchNorm column sums (sum z, sum z^2 of the STORED values) are
+//     accumulated from the staging tile with lanes walking columns (bank-conflict free) and
+//     kept in registers across tiles; one partial per CTA is written at the end (deterministic).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pn2 {
+
+using namespace tc;
+
+constexpr int kTcThreads = 128;
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int kTcAStage = kTcBM * kTcBK * 2;    // 16 KB
+
+// ---- weight packing: fp32 W (any strides) -> bf16 chunk images in UMMA K-major SW128 layout ----
+// image kc: n_pad rows x 128 bytes; element (n, kc*64 + c*8 + e) at sw128_offset(n, c) + 2e.
+__global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, int64_t w_sk, int N, int K, int n_pad,
+                                   int KC, uint8_t *__restrict__ img) {
+    const int total = KC * n_pad * 8;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const int c = q & 7, n = (q >> 3) % n_pad, kc = (q >> 3) / n_pad;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kc * kTcBK + c * 8 + e;
+            v[e] = (n < N && k < K) ? W[(int64_t)n * w_sn + (int64_t)k * w_sk] : 0.0f;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(img + (size_t)kc * n_pad * 128 + sw128_offset(n, c)) = o;
+    }
+}
+
+struct TcLinearArgs {
+    const __nv_bfloat16 *X;
+    int ldx;
+    const float *in_scale, *in_shift;
+    const uint8_t *Wimg;
+    const float *bias;
+    int64_t M;
+    int K, N, n_pad, n_store, KC;
+    __nv_bfloat16 *Z;
+    int ldz;
+    float *stat_partials;   // [grid][2][stat_ld], this call fills columns stat_off .. stat_off+N
+    int stat_ld, stat_off;
+    int w_resident;
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(kTcThreads) linear_tc_kernel(const TcLinearArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_mma[2], bar_w[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_part[4][2][256];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned (SW128 atoms)
+    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
+    uint8_t *const A_st[2] = {smem, smem + kTcAStage};
+    // B stage 1 first so that a resident W (stage 0) sits behind everything the epilogue staging may use
+    uint8_t *const B_st[2] = {smem + 2 * kTcAStage + b_bytes, smem + 2 * kTcAStage};
+    uint8_t *const staging = smem;
+    const int st_stride = a.n_store * 2 + 16;
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.n_pad) tmem_cols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_init(&bar_w[0], 1);
+        mbar_init(&bar_w[1], 1);
+        mbar_init_fence();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
+
+    uint32_t par_mma[2] = {0, 0}, par_w[2] = {0, 0};
+    if (a.w_resident) {
+        if (tid == 0) {
+            mbar_expect_tx(&bar_w[0], b_bytes);
+            bulk_g2s(B_st[0], a.Wimg, b_bytes, &bar_w[0]);
+        }
+        mbar_wait(&bar_w[0], 0);
+        par_w[0] ^= 1;
+    }
+
+    float sum1[8], sum2[8];   // STATS: this lane's column pairs p = lane + 32 j  (columns 2p, 2p+1)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum1[i] = sum2[i] = 0.0f;
+
+    const int64_t m_tiles = (a.M + kTcBM - 1) / kTcBM;
+    const int c16 = tid & 7;          // this thread's 16-byte column chunk inside a K chunk
+    const int r_base = tid >> 3;      // rows r_base + 16 i
+
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        const int64_t m0 = tile * kTcBM;
+        for (int kc = 0; kc < a.KC; ++kc) {
+            const int s = kc & 1;
+            if (kc >= 2) {   // the MMA of chunk kc-2 must have drained this stage
+                mbar_wait(&bar_mma[s], par_mma[s]);
+                par_mma[s] ^= 1;
+            }
+            // ---- B chunk: TMA bulk copy of the pre-swizzled image ----
+            if (!a.w_resident && tid == 0) {
+                mbar_expect_tx(&bar_w[s], b_bytes);
+                bulk_g2s(B_st[s], a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w[s]);
+            }
+            // ---- A chunk: coalesced 16-byte loads, BN+ReLU of the previous layer, swizzled store ----
+            const int k = kc * kTcBK + c16 * 8;
+            float sc[8], sh[8];
+            if (a.in_scale) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool ok = k + e < a.K;
+                    sc[e] = ok ? a.in_scale[k + e] : 0.0f;
+                    sh[e] = ok ? a.in_shift[k + e] : 0.0f;
+                }
+            }
+            uint4 raw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t m = m0 + r_base + 16 * i;
+                raw[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (m < a.M && k < a.ldx) raw[i] = *reinterpret_cast<const uint4 *>(a.X + m * a.ldx + k);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 v = raw[i];
+                if (a.in_scale) {
+                    const bool row_ok = (m0 + r_base + 16 * i) < a.M;
+                    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        float2 f = unpack_bf16x2(w[e2]);
+                        f.x = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.0f);
+                        f.y = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f);
+                        w[e2] = row_ok ? pack_bf16x2(f.x, f.y) : 0u;
+                    }
+                }
+                *reinterpret_cast<uint4 *>(A_st[s] + sw128_offset(r_base + 16 * i, c16)) = v;
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                if (!a.w_resident) mbar_wait(&bar_w[s], par_w[s]);
+                fence_after_sync();
+                const int k_left = a.K - kc * kTcBK;
+                const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
+                const uint32_t a_base = smem_addr(A_st[s]);
+                const uint32_t b_base = smem_addr(a.w_resident ? B_st[0] : B_st[s]);
+                for (int j = 0; j < nk; ++j)
+                    umma_bf16(tmem, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024), idesc,
+                              (uint32_t)((kc | j) != 0));
+                umma_commit(&bar_mma[s]);
+            }
+            if (!a.w_resident) par_w[s] ^= 1;
+        }
+        // ---- wait for the accumulator (consume the outstanding commits in order) ----
+        if (a.KC >= 2) {
+            const int s2 = (a.KC - 2) & 1;
+            mbar_wait(&bar_mma[s2], par_mma[s2]);
+            par_mma[s2] ^= 1;
+        }
+        {
+            const int s1 = (a.KC - 1) & 1;
+            mbar_wait(&bar_mma[s1], par_mma[s1]);
+            par_mma[s1] ^= 1;
+        }
+        fence_after_sync();
+
+        // ---- epilogue 1: TMEM -> registers -> (+bias) -> bf16 -> staging row `tid` ----
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        uint8_t *my_row = staging + (size_t)tid * st_stride;
+        for (int c0 = 0; c0 < a.n_store; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            if (a.bias) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < a.N) v[i] += a.bias[c0 + i];
+            }
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
+            lo.z = pack_bf16x2(v[4], v[5]);   lo.w = pack_bf16x2(v[6], v[7]);
+            hi.x = pack_bf16x2(v[8], v[9]);   hi.y = pack_bf16x2(v[10], v[11]);
+            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            *reinterpret_cast<uint4 *>(my_row + c0 * 2) = lo;
+            if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(my_row + c0 * 2 + 16) = hi;
+        }
+        fence_before_sync();
+        __syncthreads();
+
+        // ---- epilogue 2: coalesced store + column statistics of the stored values ----
+        const int cpr = a.n_store >> 3;
+        for (int q = tid; q < kTcBM * cpr; q += kTcThreads) {
+            const int r = q / cpr, c = q - r * cpr;
+            const int64_t m = m0 + r;
+            if (m < a.M)
+                *reinterpret_cast<uint4 *>(a.Z + m * a.ldz + c * 8) =
+                    *reinterpret_cast<const uint4 *>(staging + (size_t)r * st_stride + c * 16);
+        }
+        if (STATS) {
+            const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p = lane + 32 * j;
+                if (2 * p < a.N) {
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                    for (int r = 0; r < rows; ++r) {
+                        const float2 f = unpack_bf16x2(
+                            *reinterpret_cast<const uint32_t *>(staging + (size_t)(warp * 32 + r) * st_stride + p * 4));
+                        s1a += f.x; s1b += f.y;
+                        s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+                    }
+                    sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
+                    sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
+                }
+            }
+        }
+        fence_proxy_async();   // generic-proxy accesses of the staging tile before the next TMA write into it
+        __syncthreads();       // staging consumed before the next tile's operands overwrite it
+    }
+
+    if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = lane + 32 * j;
+            if (2 * p < 256) {
+                s_part[warp][0][2 * p] = sum1[2 * j];     s_part[warp][0][2 * p + 1] = sum1[2 * j + 1];
+                s_part[warp][1][2 * p] = sum2[2 * j];     s_part[warp][1][2 * p + 1] = sum2[2 * j + 1];
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < a.N; c += kTcThreads) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
+            float *out = a.stat_partials + (size_t)blockIdx.x * 2 * a.stat_ld + a.stat_off;
+            out[c] = t1;
+            out[a.stat_ld + c] = t2;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+int linear_num_partials(int64_t M);
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+size_t tc_wpack_bytes(int K, int N) {
+    // images for every 256-column block of N, each [KC][n_pad][128 B]
+    size_t KC = (size_t)(K + kTcBK - 1) / kTcBK, total = 0;
+    for (int n0 = 0; n0 < N; n0 += 256) total += KC * (size_t)round_up(N - n0 < 256 ? N - n0 : 256, 16) * 128;
+    return total;
+}
+
+// Z[M,N] = act(X) . W^T with W element (n,k) at W[n*w_sn + k*w_sk]
+int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_shift, const float *W, int64_t w_sn,
+                 int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, float *stat_partials,
+                 void *wpack, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, linear_tc_kernel<true>);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, linear_tc_kernel<false>);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) {
+            set_error("linear_tc: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return PN2_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    const int KC = (K + kTcBK - 1) / kTcBK;
+    uint8_t *img = (uint8_t *)wpack;
+    for (int n0 = 0; n0 < N; n0 += 256) {
+        const int nb = N - n0 < 256 ? N - n0 : 256;
+        const int n_pad = round_up(nb, 16);
+        int n_store = round_up(nb, 8);
+        if (n0 + n_store > ldz) n_store = ldz - n0;      // ldz is a multiple of 8 on this path
+        const size_t img_bytes = (size_t)KC * n_pad * 128;
+        const int total = KC * n_pad * 8;
+        pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, img);
+        count_launch();
+        TcLinearArgs a;
+        a.X = (const __nv_bfloat16 *)X;
+        a.ldx = ldx;
+        a.in_scale = in_scale;
+        a.in_shift = in_shift;
+        a.Wimg = img;
+        a.bias = bias ? bias + n0 : nullptr;
+        a.M = M; a.K = K; a.N = nb; a.n_pad = n_pad; a.n_store = n_store; a.KC = KC;
+        a.Z = (__nv_bfloat16 *)Z + n0;
+        a.ldz = ldz;
+        a.stat_partials = stat_partials;
+        a.stat_ld = N;
+        a.stat_off = n0;
+        const size_t staging = (size_t)kTcBM * (n_store * 2 + 16);
+        a.w_resident = (KC == 1 && staging <= (size_t)2 * kTcAStage + (size_t)n_pad * 128) ? 1 : 0;
+        const size_t dyn = 1024 + 2 * kTcAStage + 2 * (size_t)n_pad * 128;
+        const int grid = linear_num_partials(M);
+        if (stat_partials)
+            linear_tc_kernel<true><<<grid, kTcThreads, dyn, st>>>(a);
+        else
+            linear_tc_kernel<false><<<grid, kTcThreads, dyn, st>>>(a);
+        count_launch();
+        int rc = check_launch("linear_tc");
+        if (rc != PN2_OK) return rc;
+        img += img_bytes;
+    }
+    return PN2_OK;
+}
+
+}  // namespace pn2

@@ -60,11 +60,14 @@ def mlp_forward(x0, K0, M, convs, bns):
         st.W, st.K, st.N, st.Z, st.has_bias = W, K, N, z, bias is not None
         st.scale, st.shift, st.mean, st.invstd = stats[0], stats[1], stats[2], stats[3]
         st.train = _bn_trains(bn)
+        wpack = None
+        if dtype == torch.bfloat16:     # scratch for the bf16, pre-swizzled weight image the tensor-core path streams
+            wpack = torch.empty(lib.pn2_linear_wpack_bytes(K, N), device=dev, dtype=torch.uint8)
         if st.train:
             nparts = lib.pn2_linear_num_partials(M)
             partials = torch.empty(nparts, 2, N, device=dev, dtype=torch.float32)
             call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
-                 ptr(z), ldz, dt(z), ptr(partials), stream())
+                 ptr(z), ldz, dt(z), ptr(partials), ptr(wpack), stream())
             momentum = bn.momentum
             if bn.num_batches_tracked is not None and bn.training:
                 bn.num_batches_tracked.add_(1)
@@ -78,7 +81,7 @@ def mlp_forward(x0, K0, M, convs, bns):
             call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
                  ptr(st.scale), ptr(st.shift), stream())
             call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K, N,
-                 ptr(z), ldz, dt(z), None, stream())
+                 ptr(z), ldz, dt(z), None, ptr(wpack), stream())
             # for a backward pass through frozen statistics (Z already holds the bias here):
             # zhat = (z - running_mean) * invstd_running
             st.mean = bn.running_mean.detach()
@@ -152,8 +155,11 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
             dA = torch.empty(M, ldd, device=dev, dtype=dtype)
             if ldd != st.K:
                 dA[:, st.K:].zero_()
+            wpack = None
+            if dtype == torch.bfloat16:
+                wpack = torch.empty(lib.pn2_linear_wpack_bytes(st.N, st.K), device=dev, dtype=torch.uint8)
             call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
-                 stream())
+                 ptr(wpack), stream())
             if l > 0:
                 dZ, dgamma, dbeta = bn_grads(layers[l - 1], dA, ldd)
             else:

@@ -51,7 +51,7 @@ def test_argument_errors_do_not_need_a_gpu(pn2):
     with pytest.raises(pn2.Pn2Error, match="null pointer"):
         lib_mod.call("pn2_farthest_point_sample", None, 0, 0, 0, 1, 8, 2, None, None, None, None)
     with pytest.raises(pn2.Pn2Error, match="bad sizes"):
-        lib_mod.call("pn2_linear_fwd", 1, 4, 0, None, None, 1, None, 8, 8, 8, 1, 8, 0, None, None)
+        lib_mod.call("pn2_linear_fwd", 1, 4, 0, None, None, 1, None, 8, 8, 8, 1, 8, 0, None, None, None)
 
 
 def test_product_path_has_no_cpu_fallback(pn2):

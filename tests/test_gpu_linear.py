@@ -1,0 +1,121 @@
+"""The MLP layer kernels through the C ABI against a torch fp32 reference of the same contraction
+(this is the one floating-point kernel family, so it keeps a torch reference next to the oracle):
+tcgen05 path (bf16 rows + weight scratch), FMA-pipe path (fp32 rows, or bf16 rows without scratch).
+
+Tolerance: operands are rounded to bf16 exactly as the kernel does, products accumulate in fp32,
+so the only differences are summation order (1e-5 relative) and the final bf16 rounding of the
+stored output (2^-8 relative)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SHAPES = [(1000, 12, 32), (647, 32, 64), (4096, 67, 64), (3000, 131, 128), (2048, 259, 256), (1024, 256, 512),
+          (777, 768, 256), (513, 320, 256), (640, 64, 16), (130, 128, 128), (1, 32, 32)]
+
+
+def _ld(k):
+    return (k + 7) // 8 * 8
+
+
+def _rows(M, K, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.zeros(M, _ld(K) if dtype == torch.bfloat16 else K)
+    x[:, :K] = torch.randn(M, K, generator=g)
+    return x.to(DEV).to(dtype)
+
+
+@pytest.fixture(scope="module")
+def lib(pn2):
+    return importlib.import_module(pn2.__name__ + "._lib")
+
+
+def _forward(lib, x, K, W, bias, scale, shift, stats, use_tc):
+    M, N = x.shape[0], W.shape[0]
+    ldz = _ld(N) if x.dtype == torch.bfloat16 else N
+    z = torch.full((M, ldz), float("nan"), device=DEV, dtype=x.dtype)
+    nparts = lib.load().pn2_linear_num_partials(M)
+    partials = torch.zeros(nparts, 2, N, device=DEV) if stats else None
+    wpack = torch.empty(lib.load().pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8) if use_tc else None
+    lib.call("pn2_linear_fwd", lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale), lib.ptr(shift), lib.ptr(W), lib.ptr(bias),
+             M, K, N, lib.ptr(z), ldz, lib.dt(z), lib.ptr(partials), lib.ptr(wpack), lib.stream())
+    return z, partials
+
+
+def _reference(x, K, W, bias, scale, shift, bf16):
+    a = x[:, :K].float()
+    if scale is not None:
+        a = torch.relu(a * scale + shift)
+    w = W
+    if bf16:
+        a, w = a.bfloat16().float(), W.bfloat16().float()
+    z = a.double() @ w.double().t()
+    return (z + bias.double() if bias is not None else z)
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+@pytest.mark.parametrize("mode", ["tc", "simt_bf16", "simt_fp32"])
+@pytest.mark.parametrize("prologue", [False, True])
+def test_linear_forward(lib, M, K, N, mode, prologue):
+    dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    g = torch.Generator().manual_seed(M + K + N)
+    x = _rows(M, K, dtype, 1)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV) if not prologue else None
+    scale = (0.5 + torch.rand(K, generator=g)).to(DEV) if prologue else None
+    shift = (torch.randn(K, generator=g) * 0.3).to(DEV) if prologue else None
+    stats = prologue                                    # train mode: no bias, statistics on
+    z, partials = _forward(lib, x, K, W, bias, scale, shift, stats, mode == "tc")
+    want = _reference(x, K, W, bias, scale, shift, mode == "tc")     # only the tensor-core path rounds act(X), W to bf16
+    got = z[:, :N].double()
+    tol = 2.0 ** -8 if dtype == torch.bfloat16 else 1e-5
+    err = ((got - want).abs() / (want.abs() + 1.0)).max().item()
+    assert err <= tol, (mode, err)
+    if z.shape[1] > N and mode == "tc":
+        assert float(z[:, N:].float().abs().max()) == 0.0        # row padding is written as zeros
+    if stats:
+        s = partials.double().sum(0)
+        ref_vals = got if mode == "tc" else want                # the tensor-core path sums the stored values
+        np.testing.assert_allclose(s[0].cpu().numpy(), ref_vals.sum(0).cpu().numpy(), rtol=2e-3, atol=2e-3 * M ** 0.5)
+        np.testing.assert_allclose(s[1].cpu().numpy(), (ref_vals ** 2).sum(0).cpu().numpy(), rtol=2e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+@pytest.mark.parametrize("mode", ["tc", "simt_fp32"])
+def test_linear_backward_data(lib, M, K, N, mode):
+    dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    g = torch.Generator().manual_seed(M * 3 + K + N)
+    dz = _rows(M, N, dtype, 2)
+    W = (torch.randn(N, K, generator=g) / N ** 0.5).to(DEV)
+    ldd = _ld(K) if dtype == torch.bfloat16 else K
+    dx = torch.full((M, ldd), float("nan"), device=DEV, dtype=dtype)
+    wpack = torch.empty(lib.load().pn2_linear_wpack_bytes(N, K), device=DEV, dtype=torch.uint8) if mode == "tc" else None
+    lib.call("pn2_linear_bwd_data", lib.ptr(dz), dz.shape[1], lib.dt(dz), lib.ptr(W), M, K, N, lib.ptr(dx), ldd, lib.dt(dx),
+             lib.ptr(wpack), lib.stream())
+    a, w = dz[:, :N].float(), W
+    if dtype == torch.bfloat16:
+        a, w = a.bfloat16().float(), W.bfloat16().float()
+    want = a.double() @ w.double()
+    err = ((dx[:, :K].double() - want).abs() / (want.abs() + 1.0)).max().item()
+    assert err <= (2.0 ** -8 if dtype == torch.bfloat16 else 1e-5), (mode, err)
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_backward_weight(lib, M, K, N, dtype):
+    g = torch.Generator().manual_seed(M + 7 * K + N)
+    x, dz = _rows(M, K, dtype, 3), _rows(M, N, dtype, 4)
+    scale = (0.5 + torch.rand(K, generator=g)).to(DEV)
+    shift = (torch.randn(K, generator=g) * 0.3).to(DEV)
+    dW = torch.full((N, K), float("nan"), device=DEV)
+    scratch = torch.empty(lib.load().pn2_linear_wgrad_scratch_bytes(M, K, N), device=DEV, dtype=torch.uint8)
+    lib.call("pn2_linear_bwd_weight", lib.ptr(dz), dz.shape[1], lib.dt(dz), lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale),
+             lib.ptr(shift), M, K, N, lib.ptr(dW), lib.ptr(scratch), lib.stream())
+    a = torch.relu(x[:, :K].float() * scale + shift)
+    want = dz[:, :N].double().t() @ a.double()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2        # bf16: the tensor-core path rounds act(X) to bf16
+    err = ((dW.double() - want).abs().max() / (want.abs().max() + 1e-9)).item()
+    assert err <= tol, err
