@@ -42,6 +42,10 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
                  int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, float *stat_partials,
                  void *wpack, cudaStream_t st);
 
+size_t tc_wgrad_scratch_bytes(int64_t M, int K, int N);
+int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const float *in_scale, const float *in_shift,
+                    int64_t M, int K, int N, float *dW, void *scratch, cudaStream_t st);
+
 static bool tc_enabled() {
     static int state = -1;
     if (state < 0) {
@@ -97,7 +101,10 @@ extern "C" int pn2_linear_bwd_data(const void *dZ, int lddz, int dz_dtype, const
 
 extern "C" size_t pn2_linear_wpack_bytes(int K, int N) { return tc_wpack_bytes(K, N); }
 
-extern "C" size_t pn2_linear_wgrad_scratch_bytes(int64_t M, int K, int N) { return simt_wgrad_scratch_bytes(M, K, N); }
+extern "C" size_t pn2_linear_wgrad_scratch_bytes(int64_t M, int K, int N) {
+    size_t a = simt_wgrad_scratch_bytes(M, K, N), b = tc_wgrad_scratch_bytes(M, K, N);
+    return a > b ? a : b;
+}
 
 extern "C" int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx, int x_dtype,
                                      const float *in_scale, const float *in_shift, int64_t M, int K, int N,
@@ -106,6 +113,8 @@ extern "C" int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, con
     PN2_REQUIRE(M >= 1 && K >= 1 && N >= 1 && lddz >= N && ldx >= K, "linear_bwd_weight: bad sizes");
     PN2_REQUIRE(valid_dtype(dz_dtype) && valid_dtype(x_dtype), "linear_bwd_weight: bad dtype");
     PN2_REQUIRE(!in_scale == !in_shift, "linear_bwd_weight: in_scale and in_shift go together");
+    if (tc_eligible(dz_dtype, lddz, x_dtype, ldx, scratch))
+        return tc_linear_wgrad(dZ, lddz, X, ldx, in_scale, in_shift, M, K, N, dW, scratch, (cudaStream_t)stream);
     return simt_linear_wgrad(dZ, lddz, dz_dtype, X, ldx, x_dtype, in_scale, in_shift, M, K, N, dW, scratch,
                              (cudaStream_t)stream);
 }

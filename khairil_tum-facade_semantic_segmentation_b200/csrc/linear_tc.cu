@@ -346,3 +346,224 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
 }
 
 }  // namespace pn2
+
+// =================================================================================================
+// Weight gradient  dW[N,K] = sum_m dZ[m,n] * act(X)[m,k]   on the tensor cores.
+//
+// The reduction runs over ROWS, so both operands are "MN-major" in UMMA terms: a stage holds R
+// consecutive rows of dZ and of act(X) copied straight from their row-major storage (16-byte
+// chunks, 128-byte swizzle); a 64-column slab of a row is one 128-byte swizzle row, slabs are
+// LBO = R*128 bytes apart, groups of 8 rows SBO = 1024 bytes apart, and each tcgen05.mma consumes
+// 16 rows (advance the descriptor start by 16*128 bytes).  A CTA owns one (128 x <=256) block of
+// dW and a contiguous range of rows, accumulates it in tensor memory over all its stages, and
+// writes one fp32 partial block; wgrad_reduce_kernel sums the partials in a fixed order.
+// =================================================================================================
+namespace pn2 {
+
+struct TcWgradArgs {
+    const __nv_bfloat16 *dZ;
+    int lddz;
+    const __nv_bfloat16 *X;
+    int ldx;
+    const float *in_scale, *in_shift;
+    int64_t M, rows_per_split;
+    int K, N;
+    int n0, nb;        // dW row block (<= 128 rows)
+    int k0, kb;        // dW column block (<= 256 columns), kb_pad = UMMA N
+    int kb_pad, a_slabs, b_slabs, R;
+    float *scratch;    // [splits][N][K]
+};
+
+__global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_mma[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_scale[256], s_shift[256];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const uint32_t slab_bytes = (uint32_t)a.R * 128u;
+    const uint32_t stage_bytes = slab_bytes * (uint32_t)(a.a_slabs + a.b_slabs);
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.kb_pad) tmem_cols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_init_fence();
+    }
+    if (a.in_scale)
+        for (int i = tid; i < a.kb; i += kTcThreads) {
+            s_scale[i] = a.in_scale[a.k0 + i];
+            s_shift[i] = a.in_shift[a.k0 + i];
+        }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = make_idesc_bf16(128, a.kb_pad, 1, 1);
+
+    const int64_t r_begin = (int64_t)blockIdx.x * a.rows_per_split;
+    const int64_t r_end = min(a.M, r_begin + a.rows_per_split);
+    const int a_cpr = a.a_slabs * 8, b_cpr = a.b_slabs * 8;      // 16-byte chunks per row
+    uint32_t par[2] = {0, 0};
+    int it = 0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
+        const int s = it & 1;
+        uint8_t *stA = smem + (size_t)s * stage_bytes;
+        uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
+        if (it >= 2) {
+            mbar_wait(&bar_mma[s], par[s]);
+            par[s] ^= 1;
+        }
+        const int rows = (int)min((int64_t)a.R, r_end - r0);
+        const int rows16 = (rows + 15) & ~15;                      // rows the MMAs will read
+        // ---- A = dZ[r0 .. , n0 .. n0+nb) ----
+        for (int q = tid; q < rows16 * a_cpr; q += kTcThreads) {
+            const int r = q / a_cpr, cc = q - r * a_cpr;
+            const int n = a.n0 + cc * 8;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < rows && n < a.lddz && cc * 8 < a.nb) v = *reinterpret_cast<const uint4 *>(a.dZ + (r0 + r) * a.lddz + n);
+            *reinterpret_cast<uint4 *>(stA + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7)) = v;
+        }
+        // ---- B = act(X)[r0 .. , k0 .. k0+kb) ----
+        for (int q = tid; q < rows16 * b_cpr; q += kTcThreads) {
+            const int r = q / b_cpr, cc = q - r * b_cpr;
+            const int kk = cc * 8, k = a.k0 + kk;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < rows && k < a.ldx && kk < a.kb) {
+                v = *reinterpret_cast<const uint4 *>(a.X + (r0 + r) * a.ldx + k);
+                if (a.in_scale) {
+                    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        float2 f = unpack_bf16x2(w[e2]);
+                        const int i0 = kk + 2 * e2;
+                        f.x = i0 < a.kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
+                        f.y = i0 + 1 < a.kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
+                        w[e2] = pack_bf16x2(f.x, f.y);
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(stB + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7)) = v;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t a_base = smem_addr(stA), b_base = smem_addr(stB);
+            for (int j = 0; j < rows16 / 16; ++j)
+                umma_bf16(tmem, make_desc(a_base + 2048 * j, slab_bytes, 1024), make_desc(b_base + 2048 * j, slab_bytes, 1024),
+                          idesc, (uint32_t)((it | j) != 0));
+            umma_commit(&bar_mma[s]);
+        }
+    }
+    // drain: the outstanding commits, oldest first
+    if (it >= 2) {
+        const int s2 = it & 1;           // stage of iteration it-2
+        mbar_wait(&bar_mma[s2], par[s2]);
+        par[s2] ^= 1;
+    }
+    if (it >= 1) {
+        const int s1 = (it - 1) & 1;
+        mbar_wait(&bar_mma[s1], par[s1]);
+        par[s1] ^= 1;
+    }
+    fence_after_sync();
+    // ---- epilogue: this thread's dW row n0 + tid, fp32 partial ----
+    const int n = a.n0 + tid;
+    float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K + a.k0;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < a.kb_pad; c0 += 16) {
+        float v[16];
+        if (it > 0) tmem_ld16(taddr + c0, v);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        if (tid < a.nb) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < a.kb) out[c0 + i] = v[i];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+__global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int splits, int64_t NK, float *__restrict__ dW) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < NK; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int z = 0; z < splits; ++z) s += scratch[(int64_t)z * NK + e];
+        dW[e] = s;
+    }
+}
+
+static void tc_wgrad_plan(int64_t M, int K, int N, int &splits, int64_t &rows_per_split) {
+    const int blocks = ((N + 127) / 128) * ((K + 255) / 256);
+    int64_t s = (2 * kNumSMs + blocks - 1) / blocks;          // about two CTAs per SM in total
+    const int64_t max_s = (M + 255) / 256;                    // at least 256 rows per split
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    rows_per_split = ((M + s - 1) / s + 15) / 16 * 16;
+    splits = (int)((M + rows_per_split - 1) / rows_per_split);
+}
+
+size_t tc_wgrad_scratch_bytes(int64_t M, int K, int N) {
+    int splits;
+    int64_t rps;
+    tc_wgrad_plan(M, K, N, splits, rps);
+    return sizeof(float) * (size_t)splits * (size_t)N * (size_t)K;
+}
+
+int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const float *in_scale, const float *in_shift,
+                    int64_t M, int K, int N, float *dW, void *scratch, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, wgrad_tc_kernel);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) {
+            set_error("wgrad_tc: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return PN2_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    int splits;
+    int64_t rps;
+    tc_wgrad_plan(M, K, N, splits, rps);
+    for (int n0 = 0; n0 < N; n0 += 128)
+        for (int k0 = 0; k0 < K; k0 += 256) {
+            TcWgradArgs a;
+            a.dZ = (const __nv_bfloat16 *)dZ; a.lddz = lddz;
+            a.X = (const __nv_bfloat16 *)X;   a.ldx = ldx;
+            a.in_scale = in_scale; a.in_shift = in_shift;
+            a.M = M; a.rows_per_split = rps; a.K = K; a.N = N;
+            a.n0 = n0; a.nb = N - n0 < 128 ? N - n0 : 128;
+            a.k0 = k0; a.kb = K - k0 < 256 ? K - k0 : 256;
+            a.kb_pad = round_up(a.kb, 16);
+            a.a_slabs = (a.nb + 63) / 64;
+            a.b_slabs = (a.kb + 63) / 64;
+            const int per_row = 128 * (a.a_slabs + a.b_slabs);
+            int R = (48 * 1024 / per_row) / 64 * 64;
+            if (R > 256) R = 256;
+            if (R < 64) R = 64;
+            a.R = R;
+            a.scratch = (float *)scratch;
+            const size_t dyn = 1024 + 2 * (size_t)R * per_row;
+            wgrad_tc_kernel<<<splits, kTcThreads, dyn, st>>>(a);
+            count_launch();
+            int rc = check_launch("wgrad_tc");
+            if (rc != PN2_OK) return rc;
+        }
+    const int64_t NK = (int64_t)N * K;
+    wgrad_reduce_kernel2<<<grid_for(NK, 256), 256, 0, st>>>((const float *)scratch, splits, NK, dW);
+    count_launch();
+    return check_launch("wgrad_reduce");
+}
+
+}  // namespace pn2

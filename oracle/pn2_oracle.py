@@ -32,6 +32,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# When set (tests only), index-producing geometry runs in this dtype even if the features are
+# evaluated in another one, e.g. an fp64 evaluation of the network on the reference's fp32
+# sampling / grouping / neighbour indices (used to tell rounding noise from real differences).
+GEOMETRY_DTYPE = None
+
+
+def _geo(t):
+    return t if GEOMETRY_DTYPE is None else t.to(GEOMETRY_DTYPE)
+
+
 def pairwise_sqdist(src, dst):
     # :37-39  -2*src@dst^T, then += |src|^2, then += |dst|^2 (this order)
     out = torch.matmul(src, dst.transpose(1, 2)) * -2
@@ -50,6 +60,7 @@ def take_points(points, idx):
 
 def fps(xyz, npoint, start=None):
     # :73-84; the start index is one CPU-generator randint draw (:75)
+    xyz = _geo(xyz)
     B, N, _ = xyz.shape
     if start is None:
         start = torch.randint(0, N, (B,), dtype=torch.long)
@@ -68,6 +79,7 @@ def fps(xyz, npoint, start=None):
 
 def ball_query(radius, nsample, xyz, new_xyz):
     # :96-106  first nsample in-radius indices in ascending order, padded with the first
+    xyz, new_xyz = _geo(xyz), _geo(new_xyz)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     d = pairwise_sqdist(new_xyz, xyz)
@@ -162,10 +174,11 @@ class OracleSAMsg(nn.Module):
 
 def three_nn_weights(xyz1, xyz2):
     # :296-302
-    d, order = pairwise_sqdist(xyz1, xyz2).sort(dim=-1)
+    out_dtype = xyz1.dtype
+    d, order = pairwise_sqdist(_geo(xyz1), _geo(xyz2)).sort(dim=-1)
     d, order = d[:, :, :3], order[:, :, :3]
     recip = 1.0 / (d + 1e-8)
-    return order, recip / recip.sum(dim=2, keepdim=True)
+    return order, (recip / recip.sum(dim=2, keepdim=True)).to(out_dtype)
 
 
 class OracleFP(nn.Module):

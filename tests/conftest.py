@@ -12,6 +12,12 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# Parity tests compare with the reference's CPU fp32 path: keep the PyTorch-owned head of the
+# network (Conv1d/BatchNorm1d, outside the hot path) in true fp32 instead of cuDNN's default TF32.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
