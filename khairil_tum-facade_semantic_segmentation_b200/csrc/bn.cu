@@ -20,13 +20,20 @@ __global__ void bn_train_finalize_kernel(const float *__restrict__ partials, int
                                          float *__restrict__ running_mean, float *__restrict__ running_var,
                                          float *__restrict__ scale, float *__restrict__ shift,
                                          float *__restrict__ save_mean, float *__restrict__ save_invstd) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per channel: lanes stride over the partials, fixed-order butterfly in fp64
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= N) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int p = 0; p < n_partials; ++p) {
+    for (int p = lane; p < n_partials; p += 32) {
         s1 += (double)partials[(int64_t)p * 2 * N + c];
         s2 += (double)partials[(int64_t)p * 2 * N + N + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     double mean = s1 / (double)M;
     double var = s2 / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -134,13 +141,19 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
 
 __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n_partials, int C,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int p = 0; p < n_partials; ++p) {
+    for (int p = lane; p < n_partials; p += 32) {
         s1 += (double)partials[(int64_t)p * 2 * C + c];
         s2 += (double)partials[(int64_t)p * 2 * C + C + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
 }
@@ -189,7 +202,7 @@ extern "C" int pn2_bn_train_finalize(const float *stat_partials, int n_partials,
                                      float *shift, float *save_mean, float *save_invstd, void *stream) {
     PN2_REQUIRE(stat_partials && scale && shift, "bn_train_finalize: null pointer");
     PN2_REQUIRE(n_partials > 0 && M > 0 && N > 0, "bn_train_finalize: bad sizes");
-    bn_train_finalize_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    bn_train_finalize_kernel<<<(N + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         stat_partials, n_partials, M, N, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale,
         shift, save_mean, save_invstd);
     count_launch();
@@ -272,7 +285,7 @@ extern "C" int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg
 extern "C" int pn2_bn_bwd_finalize(const float *partials, int n_partials, int C, float *dgamma, float *dbeta,
                                    void *stream) {
     PN2_REQUIRE(partials && dgamma && dbeta && n_partials > 0, "bn_bwd_finalize: bad arguments");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, C, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, C, dgamma, dbeta);
     count_launch();
     return check_launch("bn_bwd_finalize");
 }

@@ -13,6 +13,8 @@
 // Bit-exactness contract: dist = (dx*dx + dy*dy) + dz*dz with separately
 // rounded sub/mul/add (no FMA), distance = dist < distance ? dist : distance starting from
 // float32(1e10), next centroid = LOWEST index among the maxima (torch.max semantics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pn2 {
@@ -54,8 +56,8 @@ __device__ __forceinline__ int warp_argmax(unsigned d, unsigned idx, unsigned &w
     return __ffs(__ballot_sync(0xffffffffu, cand == wi)) - 1;
 }
 
-template <int P, bool CLUSTER>
-__global__ void __launch_bounds__(1024, 1)
+template <int P, bool CLUSTER, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_kernel(const float *__restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, int N, int npoint,
            const int64_t *__restrict__ start_idx, int64_t *__restrict__ out_idx,
            float *__restrict__ out_xyz) {
@@ -215,11 +217,11 @@ fps_kernel(const float *__restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, in
     if (CLUSTER) cluster_sync_all();   // nobody may exit while a peer can still write into it
 }
 
-template <int P, bool CLUSTER>
+template <int P, bool CLUSTER, int MAXT>
 static int launch_fps(const float *xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                       const int64_t *start, int64_t *out_idx, float *out_xyz, int T, int CL,
                       cudaStream_t st) {
-    auto kern = fps_kernel<P, CLUSTER>;
+    auto kern = fps_kernel<P, CLUSTER, MAXT>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CL));
     cfg.blockDim = dim3((unsigned)T);
@@ -266,7 +268,9 @@ extern "C" int pn2_farthest_point_sample(const float *xyz, int64_t sB, int64_t s
     auto r32 = [](int v) { return (v + 31) / 32 * 32; };
     if (N <= 32) { P = 1; T = 32; }
     else if (N <= 64) { P = 2; T = 32; }
-    else if (N <= 4096) { P = 4; T = r32((N + 3) / 4); }
+    else if (N < 512) { P = 4; T = r32((N + 3) / 4); }
+    else if (N < 2048) { P = 8; T = r32((N + 7) / 8); }
+    else if (N <= 4096) { P = 16; T = r32((N + 15) / 16); }   // measured on B200: 0.62 ms vs 0.94 ms (P=4) for 4096->1024
     else if (N <= 8192) { P = 8; T = 1024; }
     else {
         P = 8; T = 1024;
@@ -277,11 +281,23 @@ extern "C" int pn2_farthest_point_sample(const float *xyz, int64_t sB, int64_t s
             return PN2_ERR_UNSUPPORTED;
         }
     }
-    if (CL > 1) return launch_fps<8, true>(xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T, CL, st);
-    switch (P) {
-        case 1: return launch_fps<1, false>(xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T, 1, st);
-        case 2: return launch_fps<2, false>(xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T, 1, st);
-        case 4: return launch_fps<4, false>(xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T, 1, st);
-        default: return launch_fps<8, false>(xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T, 1, st);
+    // tuning knob (profiles/microbench.py): PN2_FPS_P=8|16 trades warps per CTA for points per thread
+    if (CL == 1 && N > 64) {
+        const char *e = getenv("PN2_FPS_P");
+        int want = e ? atoi(e) : 0;
+        if ((want == 8 && N <= 8192) || (want == 16 && N <= 4096) || (want == 4 && N <= 4096)) {
+            P = want;
+            T = r32((N + P - 1) / P);
+        }
     }
+#define PN2_FPS_ARGS xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, out_xyz, T
+    if (CL > 1) return launch_fps<8, true, 1024>(PN2_FPS_ARGS, CL, st);
+    switch (P) {
+        case 1: return launch_fps<1, false, 1024>(PN2_FPS_ARGS, 1, st);
+        case 2: return launch_fps<2, false, 1024>(PN2_FPS_ARGS, 1, st);
+        case 4: return launch_fps<4, false, 1024>(PN2_FPS_ARGS, 1, st);
+        case 16: return launch_fps<16, false, 256>(PN2_FPS_ARGS, 1, st);
+        default: return launch_fps<8, false, 1024>(PN2_FPS_ARGS, 1, st);
+    }
+#undef PN2_FPS_ARGS
 }

@@ -17,7 +17,7 @@
 namespace pn2 {
 
 constexpr int kLinBM = 128, kLinBK = 16, kLinThreads = 256, kLinTM = 8;
-constexpr int kMaxPartials = 2 * kNumSMs;
+constexpr int kMaxPartials = 4 * kNumSMs;   // up to four resident CTAs per SM for the row-streaming kernels
 
 static int num_partials(int64_t M) {
     int64_t t = (M + kLinBM - 1) / kLinBM;

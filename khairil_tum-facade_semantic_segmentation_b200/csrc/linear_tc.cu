@@ -418,34 +418,67 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
         }
         const int rows = (int)min((int64_t)a.R, r_end - r0);
         const int rows16 = (rows + 15) & ~15;                      // rows the MMAs will read
+        // Loads are issued in batches of kU independent 16-byte requests per thread before any of them
+        // is consumed, so the HBM latency is paid once per batch, not once per chunk.
+        constexpr int kU = 8;
         // ---- A = dZ[r0 .. , n0 .. n0+nb) ----
-        for (int q = tid; q < rows16 * a_cpr; q += kTcThreads) {
-            const int r = q / a_cpr, cc = q - r * a_cpr;
-            const int n = a.n0 + cc * 8;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < rows && n < a.lddz && cc * 8 < a.nb) v = *reinterpret_cast<const uint4 *>(a.dZ + (r0 + r) * a.lddz + n);
-            *reinterpret_cast<uint4 *>(stA + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7)) = v;
+        for (int q0 = tid; q0 < rows16 * a_cpr; q0 += kTcThreads * kU) {
+            uint4 v[kU];
+            uint32_t off[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int q = q0 + u * kTcThreads;
+                const int r = q / a_cpr, cc = q - r * a_cpr;
+                const int n = a.n0 + cc * 8;
+                v[u] = make_uint4(0u, 0u, 0u, 0u);
+                off[u] = 0xffffffffu;
+                if (q < rows16 * a_cpr) {
+                    off[u] = (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7);
+                    if (r < rows && n < a.lddz && cc * 8 < a.nb)
+                        v[u] = *reinterpret_cast<const uint4 *>(a.dZ + (r0 + r) * a.lddz + n);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (off[u] != 0xffffffffu) *reinterpret_cast<uint4 *>(stA + off[u]) = v[u];
         }
         // ---- B = act(X)[r0 .. , k0 .. k0+kb) ----
-        for (int q = tid; q < rows16 * b_cpr; q += kTcThreads) {
-            const int r = q / b_cpr, cc = q - r * b_cpr;
-            const int kk = cc * 8, k = a.k0 + kk;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (r < rows && k < a.ldx && kk < a.kb) {
-                v = *reinterpret_cast<const uint4 *>(a.X + (r0 + r) * a.ldx + k);
-                if (a.in_scale) {
-                    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+        for (int q0 = tid; q0 < rows16 * b_cpr; q0 += kTcThreads * kU) {
+            uint4 v[kU];
+            uint32_t off[kU];
+            int kks[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int q = q0 + u * kTcThreads;
+                const int r = q / b_cpr, cc = q - r * b_cpr;
+                const int kk = cc * 8, k = a.k0 + kk;
+                v[u] = make_uint4(0u, 0u, 0u, 0u);
+                off[u] = 0xffffffffu;
+                kks[u] = -1;
+                if (q < rows16 * b_cpr) {
+                    off[u] = (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7);
+                    if (r < rows && k < a.ldx && kk < a.kb) {
+                        v[u] = *reinterpret_cast<const uint4 *>(a.X + (r0 + r) * a.ldx + k);
+                        kks[u] = kk;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (off[u] == 0xffffffffu) continue;
+                if (a.in_scale && kks[u] >= 0) {
+                    uint32_t *w = reinterpret_cast<uint32_t *>(&v[u]);
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
                         float2 f = unpack_bf16x2(w[e2]);
-                        const int i0 = kk + 2 * e2;
+                        const int i0 = kks[u] + 2 * e2;
                         f.x = i0 < a.kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
                         f.y = i0 + 1 < a.kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
                         w[e2] = pack_bf16x2(f.x, f.y);
                     }
                 }
+                *reinterpret_cast<uint4 *>(stB + off[u]) = v[u];
             }
-            *reinterpret_cast<uint4 *>(stB + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7)) = v;
         }
         fence_proxy_async();
         __syncthreads();

@@ -6,7 +6,12 @@ Tolerances (stated per SURVEY.md 7.3-6, set from measured error):
              log-probs atol 1e-3, train-mode log-probs atol 1e-2: measured 2.3e-3 on the B200,
              where the reference's own fp32 CPU result is 1.9e-3 away from an fp64 evaluation of
              the same network and its own CUDA path (TF32 convolutions) is 1.1 away;
-             gradients rtol 2e-3 of the tensor's max magnitude.
+             module-level gradients rtol 2e-3 of the tensor's max magnitude; whole-network
+             gradients by relative L2 error <= 3e-2 and cosine >= 0.999: ReLU masks and
+             max-pool arg-maxes flip where a pre-activation is within rounding noise of the
+             threshold, so the gradient error goes like the square root of the forward noise --
+             the reference's own fp32 CPU gradients are 1.0e-2 away from an fp64 evaluation
+             of the same network on this input (ours: 1.6e-2).
   bf16 rows: activations within 2 % of the reference's max magnitude (bf16 has an 8-bit
              mantissa; three chained layers); eval log-probs atol 0.15 with >= 97 % arg-max
              agreement; train-mode log-probs by relative RMS error <= 0.2 (measured 0.09 with
@@ -230,11 +235,14 @@ def test_model_train_step_gradients(pn2, golden, precision):
         l2 = float(p.grad.double().pow(2).sum().sqrt())
         if precision == "bf16":
             continue       # whole-network bf16 gradients: covered by finiteness here, by cosine at module level
-        assert abs(l2 - s[2]) <= 5e-3 * max(s[2], 1e-6) + 1e-7, (n, l2, s[2])
+        assert abs(l2 - s[2]) <= 3e-2 * max(s[2], 1e-6) + 1e-7, (n, l2, s[2])
         if "grad/" + n in g.files:
-            c = _cos(p.grad.cpu().numpy(), g["grad/" + n])
+            want = g["grad/" + n]
+            c = _cos(p.grad.cpu().numpy(), want)
             worst = min(worst, c)
-            assert c > 0.9999, (n, c)
+            assert c > 0.999, (n, c)
+            rel = np.linalg.norm(p.grad.cpu().numpy().ravel() - want.ravel()) / max(np.linalg.norm(want.ravel()), 1e-12)
+            assert rel <= 3e-2, (n, rel)
     if precision == "fp32":
         for n, b in net.named_buffers():
             if "buf_after/" + n in g.files and b.is_floating_point():
