@@ -374,9 +374,16 @@ struct TcWgradArgs {
     float *scratch;    // [splits][N][K]
 };
 
+constexpr int kWgStages = 3;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+    // 16-byte asynchronous global->shared copy (LDGSTS); src-size 0 writes zeros without touching memory
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+
 __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_mma[kWgStages];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_scale[256], s_shift[256];
 
@@ -388,8 +395,7 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     while ((int)tmem_cols < a.kb_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
-        mbar_init(&bar_mma[0], 1);
-        mbar_init(&bar_mma[1], 1);
+        for (int i = 0; i < kWgStages; ++i) mbar_init(&bar_mma[i], 1);
         mbar_init_fence();
     }
     if (a.in_scale)
@@ -405,79 +411,74 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
 
     const int64_t r_begin = (int64_t)blockIdx.x * a.rows_per_split;
     const int64_t r_end = min(a.M, r_begin + a.rows_per_split);
-    const int a_cpr = a.a_slabs * 8, b_cpr = a.b_slabs * 8;      // 16-byte chunks per row
-    uint32_t par[2] = {0, 0};
-    int it = 0;
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
-        const int s = it & 1;
+    const int n_it = r_end > r_begin ? (int)((r_end - r_begin + a.R - 1) / a.R) : 0;
+    // valid 16-byte chunks per row of each operand (the rest of a 64-column slab is never read back
+    // into a stored output element, so it is left untouched)
+    const int a_cpr = (min(a.nb, a.lddz - a.n0) + 7) >> 3, b_cpr = (min(a.kb, a.ldx - a.k0) + 7) >> 3;
+    uint32_t par[kWgStages];
+    for (int i = 0; i < kWgStages; ++i) par[i] = 0;
+
+    // issue the asynchronous copies of iteration `it` into its ring slot
+    auto issue = [&](int it) {
+        const int s = it % kWgStages;
+        const int64_t r0 = r_begin + (int64_t)it * a.R;
+        const int rows = (int)min((int64_t)a.R, r_end - r0);
+        const int rows16 = (rows + 15) & ~15;
+        const uint32_t stA = smem_addr(smem + (size_t)s * stage_bytes);
+        const uint32_t stB = stA + (uint32_t)a.a_slabs * slab_bytes;
+        for (int q = tid; q < rows16 * a_cpr; q += kTcThreads) {
+            const int r = q / a_cpr, cc = q - r * a_cpr;
+            const bool ok = r < rows;
+            cp_async16(stA + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
+                       a.dZ + (ok ? (r0 + r) * a.lddz + a.n0 + cc * 8 : 0), ok);
+        }
+        for (int q = tid; q < rows16 * b_cpr; q += kTcThreads) {
+            const int r = q / b_cpr, cc = q - r * b_cpr;
+            const bool ok = r < rows;
+            cp_async16(stB + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
+                       a.X + (ok ? (r0 + r) * a.ldx + a.k0 + cc * 8 : 0), ok);
+        }
+    };
+
+    for (int p = 0; p < kWgStages - 1; ++p) {
+        if (p < n_it) issue(p);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int it = 0; it < n_it; ++it) {
+        const int s = it % kWgStages;
+        // refill the slot that iteration it-1 used (its MMA must have drained it) with iteration it+S-1
+        const int nxt = it + kWgStages - 1;
+        if (nxt < n_it) {
+            if (it >= 1) {
+                const int sp = (it - 1) % kWgStages;
+                mbar_wait(&bar_mma[sp], par[sp]);
+                par[sp] ^= 1;
+            }
+            issue(nxt);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWgStages - 1) : "memory");   // iteration `it` has landed
+
+        const int64_t r0 = r_begin + (int64_t)it * a.R;
+        const int rows = (int)min((int64_t)a.R, r_end - r0);
+        const int rows16 = (rows + 15) & ~15;
         uint8_t *stA = smem + (size_t)s * stage_bytes;
         uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
-        if (it >= 2) {
-            mbar_wait(&bar_mma[s], par[s]);
-            par[s] ^= 1;
-        }
-        const int rows = (int)min((int64_t)a.R, r_end - r0);
-        const int rows16 = (rows + 15) & ~15;                      // rows the MMAs will read
-        // Loads are issued in batches of kU independent 16-byte requests per thread before any of them
-        // is consumed, so the HBM latency is paid once per batch, not once per chunk.
-        constexpr int kU = 8;
-        // ---- A = dZ[r0 .. , n0 .. n0+nb) ----
-        for (int q0 = tid; q0 < rows16 * a_cpr; q0 += kTcThreads * kU) {
-            uint4 v[kU];
-            uint32_t off[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int q = q0 + u * kTcThreads;
-                const int r = q / a_cpr, cc = q - r * a_cpr;
-                const int n = a.n0 + cc * 8;
-                v[u] = make_uint4(0u, 0u, 0u, 0u);
-                off[u] = 0xffffffffu;
-                if (q < rows16 * a_cpr) {
-                    off[u] = (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7);
-                    if (r < rows && n < a.lddz && cc * 8 < a.nb)
-                        v[u] = *reinterpret_cast<const uint4 *>(a.dZ + (r0 + r) * a.lddz + n);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u)
-                if (off[u] != 0xffffffffu) *reinterpret_cast<uint4 *>(stA + off[u]) = v[u];
-        }
-        // ---- B = act(X)[r0 .. , k0 .. k0+kb) ----
-        for (int q0 = tid; q0 < rows16 * b_cpr; q0 += kTcThreads * kU) {
-            uint4 v[kU];
-            uint32_t off[kU];
-            int kks[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int q = q0 + u * kTcThreads;
+        if (a.in_scale) {   // act(X) = relu(bn(.)) of the previous layer, in place on the chunks this thread copied
+            for (int q = tid; q < rows * b_cpr; q += kTcThreads) {
                 const int r = q / b_cpr, cc = q - r * b_cpr;
-                const int kk = cc * 8, k = a.k0 + kk;
-                v[u] = make_uint4(0u, 0u, 0u, 0u);
-                off[u] = 0xffffffffu;
-                kks[u] = -1;
-                if (q < rows16 * b_cpr) {
-                    off[u] = (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7);
-                    if (r < rows && k < a.ldx && kk < a.kb) {
-                        v[u] = *reinterpret_cast<const uint4 *>(a.X + (r0 + r) * a.ldx + k);
-                        kks[u] = kk;
-                    }
-                }
-            }
+                uint4 *ptr = reinterpret_cast<uint4 *>(stB + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7));
+                uint4 v = *ptr;
+                uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (off[u] == 0xffffffffu) continue;
-                if (a.in_scale && kks[u] >= 0) {
-                    uint32_t *w = reinterpret_cast<uint32_t *>(&v[u]);
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        float2 f = unpack_bf16x2(w[e2]);
-                        const int i0 = kks[u] + 2 * e2;
-                        f.x = i0 < a.kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
-                        f.y = i0 + 1 < a.kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
-                        w[e2] = pack_bf16x2(f.x, f.y);
-                    }
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    float2 f = unpack_bf16x2(w[e2]);
+                    const int i0 = cc * 8 + 2 * e2;
+                    f.x = i0 < a.kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
+                    f.y = i0 + 1 < a.kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
+                    w[e2] = pack_bf16x2(f.x, f.y);
                 }
-                *reinterpret_cast<uint4 *>(stB + off[u]) = v[u];
+                *ptr = v;
             }
         }
         fence_proxy_async();
@@ -491,16 +492,13 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
             umma_commit(&bar_mma[s]);
         }
     }
-    // drain: the outstanding commits, oldest first
-    if (it >= 2) {
-        const int s2 = it & 1;           // stage of iteration it-2
-        mbar_wait(&bar_mma[s2], par[s2]);
-        par[s2] ^= 1;
-    }
-    if (it >= 1) {
-        const int s1 = (it - 1) & 1;
-        mbar_wait(&bar_mma[s1], par[s1]);
-        par[s1] ^= 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // drain the commits nobody waited for yet, oldest first: iteration j was consumed in the loop
+    // iff a refill followed it, i.e. iff j + kWgStages < n_it
+    for (int j = max(0, n_it - kWgStages); j < n_it; ++j) {
+        const int sj = j % kWgStages;
+        mbar_wait(&bar_mma[sj], par[sj]);
+        par[sj] ^= 1;
     }
     fence_after_sync();
     // ---- epilogue: this thread's dW row n0 + tid, fp32 partial ----
@@ -509,7 +507,7 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < a.kb_pad; c0 += 16) {
         float v[16];
-        if (it > 0) tmem_ld16(taddr + c0, v);
+        if (n_it > 0) tmem_ld16(taddr + c0, v);
         else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.0f;
@@ -535,7 +533,7 @@ __global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int spli
 
 static void tc_wgrad_plan(int64_t M, int K, int N, int &splits, int64_t &rows_per_split) {
     const int blocks = ((N + 127) / 128) * ((K + 255) / 256);
-    int64_t s = (2 * kNumSMs + blocks - 1) / blocks;          // about two CTAs per SM in total
+    int64_t s = (kNumSMs + blocks - 1) / blocks;              // about one CTA (three 64 KB ring slots) per SM
     const int64_t max_s = (M + 255) / 256;                    // at least 256 rows per split
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
@@ -582,12 +580,12 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
             a.a_slabs = (a.nb + 63) / 64;
             a.b_slabs = (a.kb + 63) / 64;
             const int per_row = 128 * (a.a_slabs + a.b_slabs);
-            int R = (48 * 1024 / per_row) / 64 * 64;
+            int R = (64 * 1024 / per_row) / 16 * 16;       // <= 64 KB per ring slot, three slots in flight
             if (R > 256) R = 256;
-            if (R < 64) R = 64;
+            if (R < 16) R = 16;
             a.R = R;
             a.scratch = (float *)scratch;
-            const size_t dyn = 1024 + 2 * (size_t)R * per_row;
+            const size_t dyn = 1024 + kWgStages * (size_t)R * per_row;
             wgrad_tc_kernel<<<splits, kTcThreads, dyn, st>>>(a);
             count_launch();
             int rc = check_launch("wgrad_tc");

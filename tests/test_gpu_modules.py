@@ -229,8 +229,8 @@ def test_model_train_step_gradients(pn2, golden, precision):
     worst = 1.0
     for n, p in net.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
-        if "mlp_convs" in n and n.endswith("bias"):
-            continue
+        if ("mlp_convs" in n and n.endswith("bias")) or n == "conv1.bias":
+            continue       # conv bias in front of a train-mode BatchNorm: its gradient is pure rounding noise
         s = g["grad_stat/" + n]
         l2 = float(p.grad.double().pow(2).sum().sqrt())
         if precision == "bf16":
