@@ -98,21 +98,22 @@ int pn2_group_points_bwd(const void *drows, int ld, int dtype, const int64_t *id
  * One layer:  Z[M,N] = act(X)[M,K] * W[N,K]^T (+ bias)
  *   act(x)[m,k] = in_scale ? relu(x[m,k]*in_scale[k] + in_shift[k]) : x[m,k]
  *   (the previous layer's BatchNorm + ReLU, :198 / :314, applied while loading).
- * W is the Conv2d/Conv1d weight [N,K(,1,1)] fp32 contiguous.  If stat_partials is
- * non-NULL the kernel also writes per-CTA column sums of Z and Z^2 (bias
- * excluded) for the train-mode batch statistics: layout [n_partials][2][N],
- * n_partials = pn2_linear_num_partials(M).
+ * W is the Conv2d/Conv1d weight [N,K(,1,1)] fp32 contiguous.  If stat_accum is
+ * non-NULL the kernel also adds the column sums of Z and Z^2 (bias excluded)
+ * into it for the train-mode batch statistics: layout [2][N] fp64, one fp64
+ * atomicAdd per column and CTA (order-independent to ~1e-16 relative, so the
+ * fp32 statistics derived from it are run-to-run stable).  The accumulator must
+ * be ZERO on entry; pn2_bn_train_finalize consumes it and zeroes it again.
  * x_dtype/z_dtype: storage of X and Z rows.  With PN2_BF16 rows the product runs
  * on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM); with
  * PN2_F32 rows on the fp32 FMA pipes. */
-int pn2_linear_num_partials(int64_t M);
 /* wpack: device scratch of pn2_linear_wpack_bytes(K, N) bytes for the bf16, pre-swizzled copy
  * of W that the tensor-core path streams with TMA (bf16 rows with ld % 8 == 0; may be NULL,
  * which selects the FMA-pipe kernel, as does PN2_DISABLE_TC=1 in the environment). */
 size_t pn2_linear_wpack_bytes(int K, int N);
 int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale,
                    const float *in_shift, const float *W, const float *bias, int64_t M, int K,
-                   int N, void *Z, int ldz, int z_dtype, float *stat_partials, void *wpack,
+                   int N, void *Z, int ldz, int z_dtype, double *stat_accum, void *wpack,
                    void *stream);
 /* dX[M,K] = dZ[M,N] * W[N,K]   (no activation handling; see pn2_bn_relu_bwd_*);
  * wpack: scratch of pn2_linear_wpack_bytes(N, K) bytes (note the swapped roles) or NULL */
@@ -125,12 +126,12 @@ int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X,
                           int K, int N, float *dW, void *scratch, void *stream);
 
 /* ---- BatchNorm (train statistics / eval fold) ---------------------------------
- * Train (:198 with module.training): reduces the stat partials of pn2_linear_fwd
- * to mean / biased variance over M rows, writes
+ * Train (:198 with module.training): turns the [2][N] fp64 sums of pn2_linear_fwd
+ * into mean / biased variance over M rows (and zeroes the accumulator), writes
  *   scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd
  * and updates running_mean/var in place with `momentum` (running_mean includes
  * the conv bias that the GEMM left out; running_var uses the unbiased variance). */
-int pn2_bn_train_finalize(const float *stat_partials, int n_partials, int64_t M, int N,
+int pn2_bn_train_finalize(double *stat_accum, int64_t M, int N,
                           const float *gamma, const float *beta, const float *conv_bias,
                           float eps, float momentum, float *running_mean, float *running_var,
                           float *scale, float *shift, float *save_mean, float *save_invstd,
@@ -153,21 +154,20 @@ int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const f
  * With g = dA * [bn(z) > 0]:  dbeta = sum g, dgamma = sum g*zhat,
  *   dz = gamma*invstd * (g - dbeta/M - zhat*dgamma/M)          (train)
  *   dz = scale * g                                              (eval: pass save_mean = NULL)
- * Two passes: *_reduce writes partial sums [n_partials][2][C] (n_partials =
- * pn2_linear_num_partials(M)); pn2_bn_bwd_finalize reduces them into dgamma/dbeta;
+ * Two passes: *_reduce adds (sum g, sum g*zhat) into a zeroed [2][C] fp64 accumulator (same
+ * contract as stat_accum above); pn2_bn_bwd_finalize turns it into dbeta/dgamma and zeroes it;
  * *_dz writes dZ (dZ may alias dA: the update is element-wise).  The "pool" variants take the pooled gradient dOut[G,C] and the
  * arg-max map of pn2_bn_relu_max instead of a dense dA (g is non-zero only on the
  * arg-max row of each (group, channel)). */
 int pn2_bn_relu_bwd_reduce(const void *dA, int ldda, int da_dtype, const void *Z, int ldz,
                            int z_dtype, const float *scale, const float *shift,
                            const float *save_mean, const float *save_invstd, int64_t M, int C,
-                           float *partials, void *stream);
+                           double *accum, void *stream);
 int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg, const void *Z, int ldz,
                                 int z_dtype, const float *scale, const float *shift,
                                 const float *save_mean, const float *save_invstd, int64_t G,
-                                int nsample, int C, float *partials, void *stream);
-int pn2_bn_bwd_finalize(const float *partials, int n_partials, int C, float *dgamma, float *dbeta,
-                        void *stream);
+                                int nsample, int C, double *accum, void *stream);
+int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *dbeta, void *stream);
 int pn2_bn_relu_bwd_dz(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
                        const float *scale, const float *shift, const float *save_mean,
                        const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M,

@@ -35,19 +35,18 @@ _SIGNATURES = {
     "pn2_query_ball_point": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _f, _i, _p, _p, _p]),
     "pn2_group_points": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pn2_group_points_bwd": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "pn2_linear_num_partials": (_i, [_l]),
     "pn2_linear_wpack_bytes": (_z, [_i, _i]),
     "pn2_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p, _p]),
     "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
     "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
-    "pn2_bn_train_finalize": (_i, [_p, _i, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_bn_train_finalize": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_bn_eval_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "pn2_bn_relu_max": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
     "pn2_bn_relu": (_i, [_p, _i, _i, _p, _p, _l, _i, _p, _p]),
     "pn2_bn_relu_bwd_reduce": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _l, _i, _p, _p]),
     "pn2_pool_bn_relu_bwd_reduce": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
-    "pn2_bn_bwd_finalize": (_i, [_p, _i, _i, _p, _p, _p]),
+    "pn2_bn_bwd_finalize": (_i, [_p, _i, _p, _p, _p]),
     "pn2_bn_relu_bwd_dz": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _p, _i, _i, _p]),
     "pn2_pool_bn_relu_bwd_dz": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p]),
     "pn2_three_nn": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p, _p, _p]),

@@ -31,7 +31,7 @@ int check_launch(const char *what) {
 
 int simt_linear_nt(const void *X, int ldx, int x_dtype, const float *in_scale, const float *in_shift,
                    const float *W, int64_t w_sn, int64_t w_sk, const float *bias, int64_t M, int K, int N,
-                   void *Z, int ldz, int z_dtype, float *stat_partials, cudaStream_t st);
+                   void *Z, int ldz, int z_dtype, double *stat_accum, cudaStream_t st);
 int simt_linear_wgrad(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx, int x_dtype,
                       const float *in_scale, const float *in_shift, int64_t M, int K, int N, float *dW,
                       void *scratch, cudaStream_t st);
@@ -39,7 +39,7 @@ size_t simt_wgrad_scratch_bytes(int64_t M, int K, int N);
 int linear_num_partials(int64_t M);
 size_t tc_wpack_bytes(int K, int N);
 int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_shift, const float *W, int64_t w_sn,
-                 int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, float *stat_partials,
+                 int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, double *stat_accum,
                  void *wpack, cudaStream_t st);
 
 size_t tc_wgrad_scratch_bytes(int64_t M, int K, int N);
@@ -66,22 +66,20 @@ extern "C" int pn2_version(void) { return PN2_VERSION; }
 extern "C" const char *pn2_last_error(void) { return g_err; }
 extern "C" unsigned long long pn2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int pn2_linear_num_partials(int64_t M) { return linear_num_partials(M); }
-
 extern "C" int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale, const float *in_shift,
                               const float *W, const float *bias, int64_t M, int K, int N, void *Z, int ldz,
-                              int z_dtype, float *stat_partials, void *wpack, void *stream) {
+                              int z_dtype, double *stat_accum, void *wpack, void *stream) {
     PN2_REQUIRE(X && W && Z, "linear_fwd: null pointer");
     PN2_REQUIRE(M >= 0 && K >= 1 && N >= 1 && ldx >= K && ldz >= N, "linear_fwd: bad sizes M=%lld K=%d N=%d ldx=%d ldz=%d",
                 (long long)M, K, N, ldx, ldz);
     PN2_REQUIRE(valid_dtype(x_dtype) && valid_dtype(z_dtype), "linear_fwd: bad dtype");
     PN2_REQUIRE(!in_scale == !in_shift, "linear_fwd: in_scale and in_shift go together");
-    PN2_REQUIRE(!stat_partials || N <= 4096, "linear_fwd: N=%d too wide for the statistics epilogue", N);
+    PN2_REQUIRE(!stat_accum || N <= 4096, "linear_fwd: N=%d too wide for the statistics epilogue", N);
     if (M == 0) return PN2_OK;
     if (tc_eligible(x_dtype, ldx, z_dtype, ldz, wpack) && N <= 4096)
-        return tc_linear_nt(X, ldx, in_scale, in_shift, W, K, 1, bias, M, K, N, Z, ldz, stat_partials, wpack,
+        return tc_linear_nt(X, ldx, in_scale, in_shift, W, K, 1, bias, M, K, N, Z, ldz, stat_accum, wpack,
                             (cudaStream_t)stream);
-    return simt_linear_nt(X, ldx, x_dtype, in_scale, in_shift, W, K, 1, bias, M, K, N, Z, ldz, z_dtype, stat_partials,
+    return simt_linear_nt(X, ldx, x_dtype, in_scale, in_shift, W, K, 1, bias, M, K, N, Z, ldz, z_dtype, stat_accum,
                           (cudaStream_t)stream);
 }
 

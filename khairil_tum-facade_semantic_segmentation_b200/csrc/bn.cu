@@ -14,26 +14,17 @@ namespace pn2 {
 int linear_num_partials(int64_t M);
 
 // ------------------------------------------------------------------ statistics -> scale/shift
-__global__ void bn_train_finalize_kernel(const float *__restrict__ partials, int n_partials, int64_t M, int N,
+__global__ void bn_train_finalize_kernel(double *__restrict__ accum, int64_t M, int N,
                                          const float *__restrict__ gamma, const float *__restrict__ beta,
                                          const float *__restrict__ conv_bias, float eps, float momentum,
                                          float *__restrict__ running_mean, float *__restrict__ running_var,
                                          float *__restrict__ scale, float *__restrict__ shift,
                                          float *__restrict__ save_mean, float *__restrict__ save_invstd) {
-    // one warp per channel: lanes stride over the partials, fixed-order butterfly in fp64
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int p = lane; p < n_partials; p += 32) {
-        s1 += (double)partials[(int64_t)p * 2 * N + c];
-        s2 += (double)partials[(int64_t)p * 2 * N + N + c];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane != 0) return;
+    const double s1 = accum[c], s2 = accum[N + c];
+    accum[c] = 0.0;          // self-cleaning: ready for the next call of this layer
+    accum[N + c] = 0.0;
     double mean = s1 / (double)M;
     double var = s2 / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -108,7 +99,7 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
                      const TZ *__restrict__ Z, int ldz, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ save_mean,
                      const float *__restrict__ save_invstd, int64_t R, int nsample, int C,
-                     float *__restrict__ partials) {
+                     double *__restrict__ accum) {
     extern __shared__ float red[];   // [8][2][C]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t rows_per_block = (R + gridDim.x - 1) / gridDim.x;
@@ -135,25 +126,17 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
         float s = 0.0f;
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) s += red[(ww * 2 + which) * C + c];
-        partials[(int64_t)blockIdx.x * 2 * C + i] = s;
+        atomicAdd(accum + i, (double)s);
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n_partials, int C,
-                                       float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void bn_bwd_finalize_kernel(double *__restrict__ accum, int C, float *__restrict__ dgamma,
+                                       float *__restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int p = lane; p < n_partials; p += 32) {
-        s1 += (double)partials[(int64_t)p * 2 * C + c];
-        s2 += (double)partials[(int64_t)p * 2 * C + C + c];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane != 0) return;
+    const double s1 = accum[c], s2 = accum[C + c];
+    accum[c] = 0.0;
+    accum[C + c] = 0.0;
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
 }
@@ -192,18 +175,93 @@ __global__ void bn_bwd_dz_kernel(const TA *dA, int ldda, const int32_t *__restri
     }
 }
 
+// bf16 rows, C % 8 == 0, all leading dimensions % 8 == 0: one thread per 16-byte chunk (8 channels).
+// dz = sc*g + a*z + b with a = -sc*dgamma*invstd/M, b = -sc*dbeta/M - a*mean (train) or a = b = 0 (frozen
+// statistics); the four per-channel coefficient vectors are staged in shared memory once per CTA.
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+bn_bwd_dz_vec8_kernel(const __nv_bfloat16 *dA, int ldda, const float *__restrict__ dOut,
+                      const int32_t *__restrict__ arg, const __nv_bfloat16 *__restrict__ Z, int ldz,
+                      const float *__restrict__ scale, const float *__restrict__ shift,
+                      const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                      const float *__restrict__ dgamma, const float *__restrict__ dbeta, int64_t M, int nsample,
+                      int C, float inv_m, __nv_bfloat16 *dZ, int lddz) {
+    extern __shared__ float coef[];   // [4][C]: sc, sh, a, b
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = scale[c];
+        float a = 0.0f, b = 0.0f;
+        if (save_mean) {
+            a = -sc * dgamma[c] * save_invstd[c] * inv_m;
+            b = -sc * dbeta[c] * inv_m - a * save_mean[c];
+        }
+        coef[c] = sc;
+        coef[C + c] = shift[c];
+        coef[2 * C + c] = a;
+        coef[3 * C + c] = b;
+    }
+    __syncthreads();
+    const int cpr = C >> 3;
+    const int64_t total = M * cpr;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(q % cpr) << 3;
+        const int64_t m = q / cpr;
+        const uint4 zr = *reinterpret_cast<const uint4 *>(Z + m * ldz + c0);
+        float g[8];
+        if (POOL) {
+            const int64_t grp = m / nsample;
+            const int k = (int)(m - grp * nsample);
+            const int4 a0 = *reinterpret_cast<const int4 *>(arg + grp * C + c0);
+            const int4 a1 = *reinterpret_cast<const int4 *>(arg + grp * C + c0 + 4);
+            const float4 d0 = *reinterpret_cast<const float4 *>(dOut + grp * C + c0);
+            const float4 d1 = *reinterpret_cast<const float4 *>(dOut + grp * C + c0 + 4);
+            g[0] = a0.x == k ? d0.x : 0.f; g[1] = a0.y == k ? d0.y : 0.f; g[2] = a0.z == k ? d0.z : 0.f; g[3] = a0.w == k ? d0.w : 0.f;
+            g[4] = a1.x == k ? d1.x : 0.f; g[5] = a1.y == k ? d1.y : 0.f; g[6] = a1.z == k ? d1.z : 0.f; g[7] = a1.w == k ? d1.w : 0.f;
+        } else {
+            const uint4 gr = *reinterpret_cast<const uint4 *>(dA + m * ldda + c0);
+            const uint32_t *gw = reinterpret_cast<const uint32_t *>(&gr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&gw[i]);
+                float2 f = __bfloat1622float2(h);
+                g[2 * i] = f.x;
+                g[2 * i + 1] = f.y;
+            }
+        }
+        const uint32_t *zw = reinterpret_cast<const uint32_t *>(&zr);
+        uint4 out;
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&zw[i]);
+            float2 z = __bfloat1622float2(h);
+            float d[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = c0 + 2 * i + j;
+                const float zz = j ? z.y : z.x;
+                const float sc = coef[c];
+                const float gg = (fmaf(zz, sc, coef[C + c]) > 0.0f) ? g[2 * i + j] : 0.0f;
+                d[j] = fmaf(sc, gg, fmaf(coef[2 * C + c], zz, coef[3 * C + c]));
+            }
+            __nv_bfloat162 o = __floats2bfloat162_rn(d[0], d[1]);
+            ow[i] = *reinterpret_cast<uint32_t *>(&o);
+        }
+        *reinterpret_cast<uint4 *>(dZ + m * lddz + c0) = out;
+    }
+}
+
 }  // namespace pn2
 
 using namespace pn2;
 
-extern "C" int pn2_bn_train_finalize(const float *stat_partials, int n_partials, int64_t M, int N,
+extern "C" int pn2_bn_train_finalize(double *stat_accum, int64_t M, int N,
                                      const float *gamma, const float *beta, const float *conv_bias, float eps,
                                      float momentum, float *running_mean, float *running_var, float *scale,
                                      float *shift, float *save_mean, float *save_invstd, void *stream) {
-    PN2_REQUIRE(stat_partials && scale && shift, "bn_train_finalize: null pointer");
-    PN2_REQUIRE(n_partials > 0 && M > 0 && N > 0, "bn_train_finalize: bad sizes");
-    bn_train_finalize_kernel<<<(N + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        stat_partials, n_partials, M, N, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale,
+    PN2_REQUIRE(stat_accum && scale && shift, "bn_train_finalize: null pointer");
+    PN2_REQUIRE(M > 0 && N > 0, "bn_train_finalize: bad sizes");
+    bn_train_finalize_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stat_accum, M, N, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale,
         shift, save_mean, save_invstd);
     count_launch();
     return check_launch("bn_train_finalize");
@@ -246,12 +304,12 @@ extern "C" int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *sca
 template <bool POOL>
 static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *arg, const void *Z, int ldz,
                            int z_dtype, const float *scale, const float *shift, const float *save_mean,
-                           const float *save_invstd, int64_t R, int nsample, int C, float *partials,
+                           const float *save_invstd, int64_t R, int nsample, int C, double *accum,
                            int n_partials, cudaStream_t st) {
     size_t smem = sizeof(float) * 16 * (size_t)C;
 #define PN2_LAUNCH_RED(TA, TZ)                                                                        \
     bn_bwd_reduce_kernel<TA, TZ, POOL><<<n_partials, 256, smem, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, \
-                                                                      scale, shift, save_mean, save_invstd, R, nsample, C, partials)
+                                                                      scale, shift, save_mean, save_invstd, R, nsample, C, accum)
     if (da_dtype == PN2_F32 && z_dtype == PN2_F32) PN2_LAUNCH_RED(float, float);
     else if (da_dtype == PN2_F32) PN2_LAUNCH_RED(float, __nv_bfloat16);
     else if (z_dtype == PN2_F32) PN2_LAUNCH_RED(__nv_bfloat16, float);
@@ -263,29 +321,28 @@ static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t
 
 extern "C" int pn2_bn_relu_bwd_reduce(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
                                       const float *scale, const float *shift, const float *save_mean,
-                                      const float *save_invstd, int64_t M, int C, float *partials, void *stream) {
-    PN2_REQUIRE(dA && Z && scale && shift && partials, "bn_relu_bwd_reduce: null pointer");
+                                      const float *save_invstd, int64_t M, int C, double *accum, void *stream) {
+    PN2_REQUIRE(dA && Z && scale && shift && accum, "bn_relu_bwd_reduce: null pointer");
     PN2_REQUIRE(valid_dtype(da_dtype) && valid_dtype(z_dtype) && C >= 1 && C <= 768, "bn_relu_bwd_reduce: bad arguments (C <= 768)");
     if (M == 0) return PN2_OK;
     return reduce_dispatch<false>(dA, ldda, da_dtype, nullptr, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, M,
-                                  1, C, partials, linear_num_partials(M), (cudaStream_t)stream);
+                                  1, C, accum, linear_num_partials(M), (cudaStream_t)stream);
 }
 
 extern "C" int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg, const void *Z, int ldz,
                                            int z_dtype, const float *scale, const float *shift,
                                            const float *save_mean, const float *save_invstd, int64_t G,
-                                           int nsample, int C, float *partials, void *stream) {
-    PN2_REQUIRE(dOut && arg && Z && scale && shift && partials, "pool_bn_relu_bwd_reduce: null pointer");
+                                           int nsample, int C, double *accum, void *stream) {
+    PN2_REQUIRE(dOut && arg && Z && scale && shift && accum, "pool_bn_relu_bwd_reduce: null pointer");
     PN2_REQUIRE(valid_dtype(z_dtype) && C >= 1 && C <= 768, "pool_bn_relu_bwd_reduce: bad arguments (C <= 768)");
     if (G == 0) return PN2_OK;
     return reduce_dispatch<true>(dOut, C, PN2_F32, arg, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, G, nsample,
-                                 C, partials, linear_num_partials(G * nsample), (cudaStream_t)stream);
+                                 C, accum, linear_num_partials(G * nsample), (cudaStream_t)stream);
 }
 
-extern "C" int pn2_bn_bwd_finalize(const float *partials, int n_partials, int C, float *dgamma, float *dbeta,
-                                   void *stream) {
-    PN2_REQUIRE(partials && dgamma && dbeta && n_partials > 0, "bn_bwd_finalize: bad arguments");
-    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, C, dgamma, dbeta);
+extern "C" int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *dbeta, void *stream) {
+    PN2_REQUIRE(accum && dgamma && dbeta && C > 0, "bn_bwd_finalize: bad arguments");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(accum, C, dgamma, dbeta);
     count_launch();
     return check_launch("bn_bwd_finalize");
 }
@@ -296,6 +353,16 @@ static int dz_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *ar
                        const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M, int nsample,
                        int C, void *dZ, int lddz, int dz_dtype, cudaStream_t st) {
     const float inv_m = 1.0f / (float)M;
+    if (z_dtype == PN2_BF16 && dz_dtype == PN2_BF16 && (POOL || da_dtype == PN2_BF16) && C % 8 == 0 && ldz % 8 == 0 &&
+        lddz % 8 == 0 && (POOL || ldda % 8 == 0) && C <= 2048) {
+        const int vgrid = grid_for(M * (C / 8), 256, kNumSMs * 8);
+        bn_bwd_dz_vec8_kernel<POOL><<<vgrid, 256, sizeof(float) * 4 * C, st>>>(
+            POOL ? nullptr : (const __nv_bfloat16 *)dA, ldda, POOL ? (const float *)dA : nullptr, arg,
+            (const __nv_bfloat16 *)Z, ldz, scale, shift, save_mean, save_invstd, dgamma, dbeta, M, nsample, C, inv_m,
+            (__nv_bfloat16 *)dZ, lddz);
+        count_launch();
+        return check_launch("bn_bwd_dz_vec8");
+    }
     const int grid = grid_for(M * C, 256);
 #define PN2_LAUNCH_DZ(TA, TZ, TD)                                                                                   \
     bn_bwd_dz_kernel<TA, TZ, TD, POOL><<<grid, 256, 0, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, scale, shift, \

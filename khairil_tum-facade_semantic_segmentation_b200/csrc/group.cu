@@ -55,6 +55,42 @@ __global__ void group_points_kernel(const float *__restrict__ xyz, int64_t sB, i
     }
 }
 
+// bf16 rows, ld % 8 == 0: one thread per 16-byte chunk of a row (8 columns)
+__global__ void __launch_bounds__(256)
+group_points_vec8_kernel(const float *__restrict__ xyz, int64_t sB, int64_t sN, int64_t sC,
+                         const float *__restrict__ new_xyz, const float *__restrict__ feats, int64_t fB, int64_t fN,
+                         int64_t fD, const int64_t *__restrict__ idx, int N, int S, int nsample, int D,
+                         __nv_bfloat16 *__restrict__ rows, int ld, int64_t total_chunks) {
+    const int cpr = ld >> 3;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_chunks;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(q % cpr) << 3;
+        const int64_t m = q / cpr;
+        const int64_t g = m / nsample, b = g / S;
+        const int64_t i = idx[m];
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+        if (i >= 0 && i < N) {
+            const float *px = xyz + b * sB + i * sN;
+            const float *pf = feats + b * fB + i * fN;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = c0 + e;
+                if (c < 3) v[e] = __fsub_rn(px[c * sC], new_xyz[g * 3 + c]);
+                else if (c < 3 + D) v[e] = pf[(int64_t)(c - 3) * fD];
+            }
+        }
+        uint4 o;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+        *reinterpret_cast<uint4 *>(rows + m * ld + c0) = o;
+    }
+}
+
 template <typename T>
 __global__ void group_points_bwd_kernel(const T *__restrict__ drows, int ld, const int64_t *__restrict__ idx,
                                         int N, int S, int nsample, int D, float *__restrict__ dfeats,
@@ -150,6 +186,13 @@ extern "C" int pn2_group_points(const float *xyz, int64_t sB, int64_t sN, int64_
     PN2_REQUIRE(valid_dtype(dtype), "group_points: bad dtype %d", dtype);
     int64_t total = (int64_t)B * S * nsample * ld;
     if (total == 0) return PN2_OK;
+    if (dtype == PN2_BF16 && ld % 8 == 0) {
+        const int64_t chunks = total / 8;
+        group_points_vec8_kernel<<<grid_for(chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+            xyz, sB, sN, sC, new_xyz, feats, fB, fN, fD, idx, N, S, nsample, D, (__nv_bfloat16 *)rows, ld, chunks);
+        count_launch();
+        return check_launch("group_points_vec8");
+    }
     PN2_DISPATCH_DTYPE(dtype, T, (group_points_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         xyz, sB, sN, sC, new_xyz, feats, fB, fN, fD, idx, N, S, nsample, D, (T *)rows, ld, total)));
     count_launch();

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kLinThreads)
 linear_nt_kernel(const TX *__restrict__ X, int ldx, const float *__restrict__ in_scale,
                  const float *__restrict__ in_shift, const float *__restrict__ W, int64_t w_sn, int64_t w_sk,
                  const float *__restrict__ bias, int64_t M, int K, int N, TZ *__restrict__ Z, int ldz,
-                 float *__restrict__ stat_partials) {
+                 double *__restrict__ stat_accum) {
     constexpr int TN = BN / 16;
     __shared__ __align__(16) float As[kLinBK][kLinBM + 4];
     __shared__ __align__(16) float Bs[kLinBK][BN + 4];
@@ -41,7 +41,7 @@ linear_nt_kernel(const TX *__restrict__ X, int ldx, const float *__restrict__ in
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t m_tiles = (M + kLinBM - 1) / kLinBM;
     const int n_tiles = (N + BN - 1) / BN;
-    if (stat_partials)
+    if (stat_accum)
         for (int i = tid; i < 2 * N; i += kLinThreads) tot[i] = 0.0f;
 
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
@@ -112,7 +112,7 @@ linear_nt_kernel(const TX *__restrict__ X, int ldx, const float *__restrict__ in
                     st_act<TZ>(Z + m * ldz + n, v);
                 }
             }
-            if (stat_partials) {
+            if (stat_accum) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     red[0][ty][tx * TN + j] = s1[j];
@@ -131,9 +131,9 @@ linear_nt_kernel(const TX *__restrict__ X, int ldx, const float *__restrict__ in
             }
         }
     }
-    if (stat_partials) {
+    if (stat_accum) {   // one fp64 atomic per column and CTA: order-independent to ~1e-16, i.e. deterministic in fp32
         __syncthreads();
-        for (int i = tid; i < 2 * N; i += kLinThreads) stat_partials[(int64_t)blockIdx.x * 2 * N + i] = tot[i];
+        for (int i = tid; i < 2 * N; i += kLinThreads) atomicAdd(stat_accum + i, (double)tot[i]);
     }
 }
 
@@ -221,29 +221,29 @@ static void wgrad_plan(int64_t M, int K, int N, int &splits, int64_t &rows_per_s
 template <typename TX, typename TZ>
 static int launch_nt(const void *X, int ldx, const float *in_scale, const float *in_shift, const float *W,
                      int64_t w_sn, int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz,
-                     float *stat_partials, cudaStream_t st) {
+                     double *stat_accum, cudaStream_t st) {
     int grid = num_partials(M);
-    size_t dyn = stat_partials ? sizeof(float) * 2 * (size_t)N : 0;
+    size_t dyn = stat_accum ? sizeof(float) * 2 * (size_t)N : 0;
     if (N <= 32)
         linear_nt_kernel<TX, TZ, 32><<<grid, kLinThreads, dyn, st>>>((const TX *)X, ldx, in_scale, in_shift, W, w_sn, w_sk,
-                                                                     bias, M, K, N, (TZ *)Z, ldz, stat_partials);
+                                                                     bias, M, K, N, (TZ *)Z, ldz, stat_accum);
     else
         linear_nt_kernel<TX, TZ, 64><<<grid, kLinThreads, dyn, st>>>((const TX *)X, ldx, in_scale, in_shift, W, w_sn, w_sk,
-                                                                     bias, M, K, N, (TZ *)Z, ldz, stat_partials);
+                                                                     bias, M, K, N, (TZ *)Z, ldz, stat_accum);
     count_launch();
     return check_launch("linear_nt");
 }
 
 int simt_linear_nt(const void *X, int ldx, int x_dtype, const float *in_scale, const float *in_shift,
                    const float *W, int64_t w_sn, int64_t w_sk, const float *bias, int64_t M, int K, int N,
-                   void *Z, int ldz, int z_dtype, float *stat_partials, cudaStream_t st) {
+                   void *Z, int ldz, int z_dtype, double *stat_accum, cudaStream_t st) {
     if (x_dtype == PN2_F32 && z_dtype == PN2_F32)
-        return launch_nt<float, float>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_partials, st);
+        return launch_nt<float, float>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_accum, st);
     if (x_dtype == PN2_F32 && z_dtype == PN2_BF16)
-        return launch_nt<float, __nv_bfloat16>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_partials, st);
+        return launch_nt<float, __nv_bfloat16>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_accum, st);
     if (x_dtype == PN2_BF16 && z_dtype == PN2_F32)
-        return launch_nt<__nv_bfloat16, float>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_partials, st);
-    return launch_nt<__nv_bfloat16, __nv_bfloat16>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_partials, st);
+        return launch_nt<__nv_bfloat16, float>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_accum, st);
+    return launch_nt<__nv_bfloat16, __nv_bfloat16>(X, ldx, in_scale, in_shift, W, w_sn, w_sk, bias, M, K, N, Z, ldz, stat_accum, st);
 }
 
 template <typename TD, typename TX>

@@ -19,7 +19,7 @@
 //   * epilogue: tcgen05.ld -> (+bias) -> bf16 -> staging tile in shared memory -> coalesced 16-byte
 //     stores; the train-mode BatchNorm column sums (sum z, sum z^2 of the STORED values) are
 //     accumulated from the staging tile with lanes walking columns (bank-conflict free) and
-//     kept in registers across tiles; one partial per CTA is written at the end (deterministic).
+//     kept in registers across tiles; added once per CTA into fp64 accumulators at the end.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -64,7 +64,7 @@ struct TcLinearArgs {
     int K, N, n_pad, n_store, KC;
     __nv_bfloat16 *Z;
     int ldz;
-    float *stat_partials;   // [grid][2][stat_ld], this call fills columns stat_off .. stat_off+N
+    double *stat_accum;     // [2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
     int stat_ld, stat_off;
     int w_resident;
 };
@@ -262,9 +262,8 @@ __global__ void __launch_bounds__(kTcThreads) linear_tc_kernel(const TcLinearArg
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
-            float *out = a.stat_partials + (size_t)blockIdx.x * 2 * a.stat_ld + a.stat_off;
-            out[c] = t1;
-            out[a.stat_ld + c] = t2;
+            atomicAdd(a.stat_accum + a.stat_off + c, (double)t1);
+            atomicAdd(a.stat_accum + a.stat_ld + a.stat_off + c, (double)t2);
         }
     }
     fence_before_sync();
@@ -285,7 +284,7 @@ size_t tc_wpack_bytes(int K, int N) {
 
 // Z[M,N] = act(X) . W^T with W element (n,k) at W[n*w_sn + k*w_sk]
 int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_shift, const float *W, int64_t w_sn,
-                 int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, float *stat_partials,
+                 int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, double *stat_accum,
                  void *wpack, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -326,14 +325,14 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         a.M = M; a.K = K; a.N = nb; a.n_pad = n_pad; a.n_store = n_store; a.KC = KC;
         a.Z = (__nv_bfloat16 *)Z + n0;
         a.ldz = ldz;
-        a.stat_partials = stat_partials;
+        a.stat_accum = stat_accum;
         a.stat_ld = N;
         a.stat_off = n0;
         const size_t staging = (size_t)kTcBM * (n_store * 2 + 16);
         a.w_resident = (KC == 1 && staging <= (size_t)2 * kTcAStage + (size_t)n_pad * 128) ? 1 : 0;
         const size_t dyn = 1024 + 2 * kTcAStage + 2 * (size_t)n_pad * 128;
         const int grid = linear_num_partials(M);
-        if (stat_partials)
+        if (stat_accum)
             linear_tc_kernel<true><<<grid, kTcThreads, dyn, st>>>(a);
         else
             linear_tc_kernel<false><<<grid, kTcThreads, dyn, st>>>(a);
@@ -523,11 +522,21 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+// blockDim (32, 8): 32 consecutive elements per CTA, the 8 warps stride over the splits, then a
+// fixed-order combine through shared memory (deterministic)
 __global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int splits, int64_t NK, float *__restrict__ dW) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < NK; e += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += scratch[(int64_t)z * NK + e];
-        dW[e] = s;
+    __shared__ float red[8][32];
+    const int64_t e = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    float s = 0.0f;
+    if (e < NK)
+        for (int z = threadIdx.y; z < splits; z += 8) s += scratch[(int64_t)z * NK + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < NK) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        dW[e] = t;
     }
 }
 
@@ -592,7 +601,7 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
             if (rc != PN2_OK) return rc;
         }
     const int64_t NK = (int64_t)N * K;
-    wgrad_reduce_kernel2<<<grid_for(NK, 256), 256, 0, st>>>((const float *)scratch, splits, NK, dW);
+    wgrad_reduce_kernel2<<<(unsigned)((NK + 31) / 32), dim3(32, 8), 0, st>>>((const float *)scratch, splits, NK, dW);
     count_launch();
     return check_launch("wgrad_reduce");
 }

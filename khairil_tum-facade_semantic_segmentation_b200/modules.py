@@ -35,6 +35,24 @@ def _bn_trains(bn):
     return bn.training or bn.running_mean is None
 
 
+_ACCUM = {}
+_ACCUM_COLS = 4096
+
+
+def _stat_accum(dev):
+    """[2][C <= 4096] fp64 accumulator of the column-sum epilogues, one per (device, stream).  It is
+    zero whenever no producer/finalize pair is in flight on that stream: allocated zeroed, and every
+    *_finalize entry point zeroes what it consumed (so a step needs no extra memset launches)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ACCUM.get(key)
+    if buf is None or torch.cuda.is_current_stream_capturing():
+        # a buffer created while capturing lives in the graph's pool and is zeroed by a memset node
+        buf = torch.zeros(2 * _ACCUM_COLS, device=dev, dtype=torch.float64)
+        if not torch.cuda.is_current_stream_capturing():
+            _ACCUM[key] = buf
+    return buf
+
+
 def mlp_forward(x0, K0, M, convs, bns):
     """relu(bn(conv(.))) chain on rows (pointnet2_utils.py:196-198 / :311-314) up to the last
     layer's pre-BN product; the caller applies the last BN+ReLU fused with its tail."""
@@ -64,17 +82,16 @@ def mlp_forward(x0, K0, M, convs, bns):
         if dtype == torch.bfloat16:     # scratch for the bf16, pre-swizzled weight image the tensor-core path streams
             wpack = torch.empty(lib.pn2_linear_wpack_bytes(K, N), device=dev, dtype=torch.uint8)
         if st.train:
-            nparts = lib.pn2_linear_num_partials(M)
-            partials = torch.empty(nparts, 2, N, device=dev, dtype=torch.float32)
+            accum = _stat_accum(dev)
             call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
-                 ptr(z), ldz, dt(z), ptr(partials), ptr(wpack), stream())
+                 ptr(z), ldz, dt(z), ptr(accum), ptr(wpack), stream())
             momentum = bn.momentum
             if bn.num_batches_tracked is not None and bn.training:
                 bn.num_batches_tracked.add_(1)
             if momentum is None:      # cumulative moving average (nn.BatchNorm semantics)
                 momentum = 1.0 / float(bn.num_batches_tracked.item()) if bn.num_batches_tracked is not None else 0.0
             update = bn.training and bn.running_mean is not None
-            call("pn2_bn_train_finalize", ptr(partials), nparts, M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
+            call("pn2_bn_train_finalize", ptr(accum), M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
                  float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
                  ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), stream())
         else:
@@ -100,27 +117,26 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
     dev, dtype = x0.device, x0.dtype
     L = len(layers)
     grads = [None] * L
-    nparts = lib.pn2_linear_num_partials(M)
 
     def bn_grads(st, dA, ldda):
         """dgamma/dbeta of layer st from the gradient w.r.t. its activation, then dZ."""
         C = st.N
-        partials = torch.empty(nparts, 2, C, device=dev, dtype=torch.float32)
+        accum = _stat_accum(dev)
         dgb = torch.empty(2, C, device=dev, dtype=torch.float32)
         mean_train = ptr(st.mean) if st.train else None
         if arg is not None and dA is dout:
             G = M // nsample
             call("pn2_pool_bn_relu_bwd_reduce", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(partials), stream())
-            call("pn2_bn_bwd_finalize", ptr(partials), nparts, C, ptr(dgb[0]), ptr(dgb[1]), stream())
+                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(accum), stream())
+            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgb[0]), ptr(dgb[1]), stream())
             dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
             call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
                  ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgb[0]), ptr(dgb[1]), G, nsample, C, ptr(dZ),
                  dZ.shape[1], dt(dZ), stream())
         else:
             call("pn2_bn_relu_bwd_reduce", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(partials), stream())
-            call("pn2_bn_bwd_finalize", ptr(partials), nparts, C, ptr(dgb[0]), ptr(dgb[1]), stream())
+                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(accum), stream())
+            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgb[0]), ptr(dgb[1]), stream())
             if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
                 dZ = dA                                   # element-wise update in place (never on autograd's grad)
             else:
@@ -322,6 +338,19 @@ class PointNetSetAbstraction(nn.Module):
         super().__init__()
         self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
         self.mlp_convs, self.mlp_bns = _build_mlp(nn.Conv2d, nn.BatchNorm2d, in_channel, mlp)
+        self.start_staging = None      # ops.StartIndexStaging when the caller captures CUDA graphs
+
+    def use_static_start_buffers(self, enable=True):
+        """Route the FPS start-index draw through pinned staging buffers (CUDA-graph capture)."""
+        self.start_staging = "pending" if enable else None
+
+    def _staging(self, B, N, device):
+        st = self.start_staging
+        if st is None:
+            return None
+        if st == "pending" or st.B != B or st.N != N:
+            st = self.start_staging = ops.StartIndexStaging(B, N, device)
+        return st
 
     def forward(self, xyz, points):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
@@ -334,7 +363,8 @@ class PointNetSetAbstraction(nn.Module):
             x0 = xyz_r if pts_r is None else torch.cat([xyz_r, pts_r], dim=-1)
             out = _GroupAllFn.apply(self.mlp_convs, self.mlp_bns, x0, *params)
         else:
-            _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True)
+            _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True,
+                                                   staging=self._staging(xyz.shape[0], xyz.shape[2], xyz.device))
             out = _SetAbstractionFn.apply(self, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
                                           xyz_r, pts_r, *params)
         return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)

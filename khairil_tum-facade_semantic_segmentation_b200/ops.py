@@ -80,7 +80,26 @@ def index_points(points, idx):
     return _IndexPoints.apply(points, idx)
 
 
-def farthest_point_sample(xyz, npoint, start=None, return_xyz=False):
+class StartIndexStaging:
+    """Pinned host + device buffers for the FPS start indices of one call site, so that the
+    host->device copy of the torch.randint draw (:75) is a CUDA-graph-capturable memcpy node whose
+    source can be refreshed before every replay (see trainer.SemSegTrainer.enable_cuda_graph)."""
+
+    def __init__(self, B, N, device):
+        self.B, self.N = B, N
+        self.host = torch.empty(B, dtype=torch.int64).pin_memory()
+        self.dev = torch.empty(B, dtype=torch.int64, device=device)
+
+    def draw(self):
+        """One CPU-generator draw, exactly the reference's torch.randint(0, N, (B,), dtype=torch.long)."""
+        self.host.copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
+
+    def upload(self):
+        self.dev.copy_(self.host, non_blocking=True)
+        return self.dev
+
+
+def farthest_point_sample(xyz, npoint, start=None, return_xyz=False, staging=None):
     """pointnet2_utils.py:63-84 -- xyz [B,N,3] (any strides) -> int64 [B,npoint].
 
     The start index is drawn exactly as the reference does (:75): one
@@ -90,11 +109,16 @@ def farthest_point_sample(xyz, npoint, start=None, return_xyz=False):
     _xyz3(xyz, "xyz")
     B, N, _ = xyz.shape
     npoint = int(npoint)
-    if start is None:
-        start = torch.randint(0, N, (B,), dtype=torch.long)
-    if start.shape != (B,) or start.dtype != torch.int64:
-        raise ValueError("start must be int64 [B]")
-    start = start.to(xyz.device, non_blocking=True)
+    if staging is not None and start is None:
+        if not torch.cuda.is_current_stream_capturing():
+            staging.draw()
+        start = staging.upload()
+    else:
+        if start is None:
+            start = torch.randint(0, N, (B,), dtype=torch.long)
+        if start.shape != (B,) or start.dtype != torch.int64:
+            raise ValueError("start must be int64 [B]")
+        start = start.to(xyz.device, non_blocking=True)
     out = torch.empty(B, npoint, device=xyz.device, dtype=torch.int64)
     new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32) if return_xyz else None
     sB, sN, sC = xyz.stride()

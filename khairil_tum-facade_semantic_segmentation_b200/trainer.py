@@ -51,25 +51,86 @@ class SemSegTrainer:
         self.model = (model if model is not None else get_model(num_classes, num_extra_features)).to(self.device)
         self.criterion = get_loss()
         self.grads = FlatGradients(self.model.parameters())
+        on_gpu = self.device.type == "cuda"
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08,
-                                          weight_decay=weight_decay,
-                                          fused=bool(fused_optimizer and self.device.type == "cuda"))
+                                          weight_decay=weight_decay, fused=bool(fused_optimizer and on_gpu),
+                                          capturable=on_gpu)
         self.class_weights = (torch.ones(num_classes) if class_weights is None else class_weights).to(self.device)
+        self._graph = None
 
-    def step_device(self, points, target):
-        """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
-        self.model.train()
+    def _step_impl(self, points, target):
         self.grads.zero()
         pred, feat = self.model(points.transpose(2, 1))
         loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
         loss.backward()
         self.grads.all_reduce_mean()
         self.optimizer.step()
-        return loss
+        return loss.detach()
+
+    def enable_cuda_graph(self, batch_clouds, npoint, channels, warmup=3):
+        """Capture the whole training step (forward, loss, backward, gradient all-reduce, Adam) into ONE
+        CUDA graph replayed per step: the ~420 kernel launches of a step cost no host time any more.
+        Inputs are copied into static buffers; the FPS start indices stay a fresh CPU-generator draw per
+        step (drawn on the host before each replay into pinned buffers the graph's memcpy nodes read).
+        Re-capture after changing BatchNorm momentum or the learning-rate schedule's Python state."""
+        from .modules import PointNetSetAbstraction
+        dev = self.device
+        self.model.train()
+        self._sa = [m for m in self.model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
+        for m in self._sa:
+            m.use_static_start_buffers(True)
+        self._g_points = torch.zeros(batch_clouds, npoint, channels, device=dev)
+        self._g_target = torch.zeros(batch_clouds * npoint, dtype=torch.int64, device=dev)
+        self._g_points.uniform_(-0.5, 0.5)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        saved = [(p.detach().clone()) for p in self.model.state_dict().values()]
+        opt_state = None
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self._g_points, self._g_target)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # the warm-up steps must not count as training: restore parameters/buffers and optimizer moments
+        with torch.no_grad():
+            for t, s in zip(self.model.state_dict().values(), saved):
+                t.copy_(s)
+            for st in self.optimizer.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._g_loss = self._step_impl(self._g_points, self._g_target)
+        with torch.no_grad():                         # capture does not execute, but keep the state pristine anyway
+            for t, s in zip(self.model.state_dict().values(), saved):
+                t.copy_(s)
+        self._graph = graph
+        return self
+
+    def step_device(self, points, target):
+        """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
+        self.model.train()
+        if self._graph is None:
+            return self._step_impl(points, target)
+        self._g_points.copy_(points, non_blocking=True)
+        self._g_target.copy_(target.view(-1), non_blocking=True)
+        for m in self._sa:                            # the reference's per-forward randint draws, in module order
+            m.start_staging.draw()
+        self._graph.replay()
+        return self._g_loss
 
     def step(self, points_host, target_host):
         """One training step from HOST buffers (pinned memory recommended); returns the loss as a float
         (a device->host read, like the reference's per-batch `seg_pred.cpu()`)."""
+        if self._graph is not None:                  # host -> static device buffers directly
+            self.model.train()
+            self._g_points.copy_(points_host, non_blocking=True)
+            self._g_target.copy_(target_host.view(-1), non_blocking=True)
+            for m in self._sa:
+                m.start_staging.draw()
+            self._graph.replay()
+            return float(self._g_loss)
         points = points_host.to(self.device, non_blocking=True).float()
         target = target_host.to(self.device, non_blocking=True).long().view(-1)
         return float(self.step_device(points, target))
