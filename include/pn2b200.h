@@ -37,6 +37,10 @@ extern "C" {
 
 enum { PN2_OK = 0, PN2_ERR_ARG = -1, PN2_ERR_CUDA = -2, PN2_ERR_UNSUPPORTED = -3 };
 enum { PN2_F32 = 0, PN2_BF16 = 1 };
+/* fp64 column-sum accumulators (stat_accum / accum below) hold PN2_STAT_REPLICAS copies of
+ * [2][C] doubles: CTA i adds into copy i % PN2_STAT_REPLICAS (spreads same-address atomics),
+ * the *_finalize entry points add the copies in a fixed order and zero them. */
+#define PN2_STAT_REPLICAS 8
 
 /* ---- library ---------------------------------------------------------------- */
 int pn2_version(void);
@@ -100,7 +104,7 @@ int pn2_group_points_bwd(const void *drows, int ld, int dtype, const int64_t *id
  *   (the previous layer's BatchNorm + ReLU, :198 / :314, applied while loading).
  * W is the Conv2d/Conv1d weight [N,K(,1,1)] fp32 contiguous.  If stat_accum is
  * non-NULL the kernel also adds the column sums of Z and Z^2 (bias excluded)
- * into it for the train-mode batch statistics: layout [2][N] fp64, one fp64
+ * into it for the train-mode batch statistics: layout [PN2_STAT_REPLICAS][2][N] fp64, one fp64
  * atomicAdd per column and CTA (order-independent to ~1e-16 relative, so the
  * fp32 statistics derived from it are run-to-run stable).  The accumulator must
  * be ZERO on entry; pn2_bn_train_finalize consumes it and zeroes it again.
@@ -126,7 +130,7 @@ int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X,
                           int K, int N, float *dW, void *scratch, void *stream);
 
 /* ---- BatchNorm (train statistics / eval fold) ---------------------------------
- * Train (:198 with module.training): turns the [2][N] fp64 sums of pn2_linear_fwd
+ * Train (:198 with module.training): turns the [PN2_STAT_REPLICAS][2][N] fp64 sums of pn2_linear_fwd
  * into mean / biased variance over M rows (and zeroes the accumulator), writes
  *   scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd
  * and updates running_mean/var in place with `momentum` (running_mean includes
@@ -154,7 +158,7 @@ int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const f
  * With g = dA * [bn(z) > 0]:  dbeta = sum g, dgamma = sum g*zhat,
  *   dz = gamma*invstd * (g - dbeta/M - zhat*dgamma/M)          (train)
  *   dz = scale * g                                              (eval: pass save_mean = NULL)
- * Two passes: *_reduce adds (sum g, sum g*zhat) into a zeroed [2][C] fp64 accumulator (same
+ * Two passes: *_reduce adds (sum g, sum g*zhat) into a zeroed [PN2_STAT_REPLICAS][2][C] fp64 accumulator (same
  * contract as stat_accum above); pn2_bn_bwd_finalize turns it into dbeta/dgamma and zeroes it;
  * *_dz writes dZ (dZ may alias dA: the update is element-wise).  The "pool" variants take the pooled gradient dOut[G,C] and the
  * arg-max map of pn2_bn_relu_max instead of a dense dA (g is non-zero only on the

@@ -22,9 +22,15 @@ __global__ void bn_train_finalize_kernel(double *__restrict__ accum, int64_t M, 
                                          float *__restrict__ save_mean, float *__restrict__ save_invstd) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
-    const double s1 = accum[c], s2 = accum[N + c];
-    accum[c] = 0.0;          // self-cleaning: ready for the next call of this layer
-    accum[N + c] = 0.0;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < kStatReplicas; ++r) {   // fixed order; self-cleaning: ready for the next producer
+        double *a = accum + (size_t)r * 2 * N;
+        s1 += a[c];
+        s2 += a[N + c];
+        a[c] = 0.0;
+        a[N + c] = 0.0;
+    }
     double mean = s1 / (double)M;
     double var = s2 / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -126,7 +132,112 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
         float s = 0.0f;
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) s += red[(ww * 2 + which) * C + c];
-        atomicAdd(accum + i, (double)s);
+        atomicAdd(accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * C + i, (double)s);
+    }
+}
+
+// bf16 Z, C % 8 == 0 and 256 % (C/8) == 0: one thread owns 8 channels (16-byte loads) of every
+// (256 / (C/8))-th row, four rows in flight per thread, 16 fp32 accumulators in registers.
+// MODE 0: dense bf16 dA, 1: dense fp32 dA, 2: pooled fp32 dOut + arg-max map ("rows" are groups).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_vec8_kernel(const void *__restrict__ dA_, int ldda, const int32_t *__restrict__ arg,
+                          const __nv_bfloat16 *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                          const float *__restrict__ shift, const float *__restrict__ save_mean,
+                          const float *__restrict__ save_invstd, int64_t R, int nsample, int C,
+                          double *__restrict__ accum) {
+    constexpr int kStride = 264;
+    __shared__ float red[16 * kStride];
+    const int cpr = C >> 3;
+    const int c8 = threadIdx.x % cpr, rl = threadIdx.x / cpr, rstep = 256 / cpr;
+    const int c0 = c8 << 3;
+    float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = scale[c0 + e];
+        sh[e] = shift[c0 + e];
+        mu[e] = save_mean ? save_mean[c0 + e] : 0.0f;
+        is[e] = save_invstd ? save_invstd[c0 + e] : 0.0f;
+        s1[e] = s2[e] = 0.0f;
+    }
+    const int64_t rows_per_block = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(R, r_begin + rows_per_block);
+    constexpr int U = MODE == 2 ? 2 : 4;
+    for (int64_t r = r_begin + rl; r < r_end; r += (int64_t)rstep * U) {
+        float z[U][8], g[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = r + (int64_t)u * rstep;
+            const bool ok = rr < r_end;
+            if (MODE == 2) {
+                int4 a0 = make_int4(0, 0, 0, 0), a1 = a0;
+                float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+                if (ok) {
+                    a0 = *reinterpret_cast<const int4 *>(arg + rr * C + c0);
+                    a1 = *reinterpret_cast<const int4 *>(arg + rr * C + c0 + 4);
+                    d0 = *reinterpret_cast<const float4 *>((const float *)dA_ + rr * C + c0);
+                    d1 = *reinterpret_cast<const float4 *>((const float *)dA_ + rr * C + c0 + 4);
+                }
+                const int ai[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float di[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    g[u][e] = di[e];
+                    z[u][e] = ok ? __bfloat162float(Z[(rr * nsample + ai[e]) * ldz + c0 + e]) : 0.0f;
+                }
+            } else {
+                uint4 zr = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) zr = *reinterpret_cast<const uint4 *>(Z + rr * ldz + c0);
+                const uint32_t *zw = reinterpret_cast<const uint32_t *>(&zr);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&zw[i]));
+                    z[u][2 * i] = f.x;
+                    z[u][2 * i + 1] = f.y;
+                }
+                if (MODE == 0) {
+                    uint4 gr = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) gr = *reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)dA_ + rr * ldda + c0);
+                    const uint32_t *gw = reinterpret_cast<const uint32_t *>(&gr);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[i]));
+                        g[u][2 * i] = f.x;
+                        g[u][2 * i + 1] = f.y;
+                    }
+                } else {
+                    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+                    if (ok) {
+                        d0 = *reinterpret_cast<const float4 *>((const float *)dA_ + rr * ldda + c0);
+                        d1 = *reinterpret_cast<const float4 *>((const float *)dA_ + rr * ldda + c0 + 4);
+                    }
+                    g[u][0] = d0.x; g[u][1] = d0.y; g[u][2] = d0.z; g[u][3] = d0.w;
+                    g[u][4] = d1.x; g[u][5] = d1.y; g[u][6] = d1.z; g[u][7] = d1.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float gg = (fmaf(z[u][e], sc[e], sh[e]) > 0.0f) ? g[u][e] : 0.0f;
+                s1[e] += gg;
+                s2[e] = fmaf(gg, (z[u][e] - mu[e]) * is[e], s2[e]);
+            }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[e * kStride + threadIdx.x] = s1[e];
+        red[(8 + e) * kStride + threadIdx.x] = s2[e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        const int which = i / C, c = i - which * C;
+        const float *p = red + (which * 8 + (c & 7)) * kStride + (c >> 3);
+        float s = 0.0f;
+        for (int q = 0; q < rstep; ++q) s += p[q * cpr];     // fixed order
+        atomicAdd(accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * C + i, (double)s);
     }
 }
 
@@ -134,9 +245,15 @@ __global__ void bn_bwd_finalize_kernel(double *__restrict__ accum, int C, float 
                                        float *__restrict__ dbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double s1 = accum[c], s2 = accum[C + c];
-    accum[c] = 0.0;
-    accum[C + c] = 0.0;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < kStatReplicas; ++r) {
+        double *a = accum + (size_t)r * 2 * C;
+        s1 += a[c];
+        s2 += a[C + c];
+        a[c] = 0.0;
+        a[C + c] = 0.0;
+    }
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
 }
@@ -306,6 +423,24 @@ static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t
                            int z_dtype, const float *scale, const float *shift, const float *save_mean,
                            const float *save_invstd, int64_t R, int nsample, int C, double *accum,
                            int n_partials, cudaStream_t st) {
+    if (z_dtype == PN2_BF16 && C % 8 == 0 && 256 % (C / 8) == 0 && ldz % 8 == 0 &&
+        (POOL || (da_dtype == PN2_BF16 ? ldda % 8 == 0 : ldda % 4 == 0))) {
+        const int rstep = 256 / (C / 8);
+        const int per_pass = rstep * (POOL ? 2 : 4);
+        int64_t want = (R + per_pass - 1) / per_pass;
+        const int grid = (int)(want < 1 ? 1 : (want > 2 * kNumSMs ? 2 * kNumSMs : want));
+        if (POOL)
+            bn_bwd_reduce_vec8_kernel<2><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
+                                                               save_mean, save_invstd, R, nsample, C, accum);
+        else if (da_dtype == PN2_BF16)
+            bn_bwd_reduce_vec8_kernel<0><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
+                                                               save_mean, save_invstd, R, nsample, C, accum);
+        else
+            bn_bwd_reduce_vec8_kernel<1><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
+                                                               save_mean, save_invstd, R, nsample, C, accum);
+        count_launch();
+        return check_launch("bn_bwd_reduce_vec8");
+    }
     size_t smem = sizeof(float) * 16 * (size_t)C;
 #define PN2_LAUNCH_RED(TA, TZ)                                                                        \
     bn_bwd_reduce_kernel<TA, TZ, POOL><<<n_partials, 256, smem, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, \

@@ -133,7 +133,8 @@ linear_nt_kernel(const TX *__restrict__ X, int ldx, const float *__restrict__ in
     }
     if (stat_accum) {   // one fp64 atomic per column and CTA: order-independent to ~1e-16, i.e. deterministic in fp32
         __syncthreads();
-        for (int i = tid; i < 2 * N; i += kLinThreads) atomicAdd(stat_accum + i, (double)tot[i]);
+        for (int i = tid; i < 2 * N; i += kLinThreads)
+            atomicAdd(stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * N + i, (double)tot[i]);
     }
 }
 

@@ -262,8 +262,9 @@ __global__ void __launch_bounds__(kTcThreads) linear_tc_kernel(const TcLinearArg
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll
             for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
-            atomicAdd(a.stat_accum + a.stat_off + c, (double)t1);
-            atomicAdd(a.stat_accum + a.stat_ld + a.stat_off + c, (double)t2);
+            double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
+            atomicAdd(acc + c, (double)t1);
+            atomicAdd(acc + a.stat_ld + c, (double)t2);
         }
     }
     fence_before_sync();
@@ -366,14 +367,14 @@ struct TcWgradArgs {
     int ldx;
     const float *in_scale, *in_shift;
     int64_t M, rows_per_split;
-    int K, N;
-    int n0, nb;        // dW row block (<= 128 rows)
-    int k0, kb;        // dW column block (<= 256 columns), kb_pad = UMMA N
-    int kb_pad, a_slabs, b_slabs, R;
-    float *scratch;    // [splits][N][K]
+    int K, N, K_ld;    // K_ld: row stride of the fp32 partials (K rounded up to 4 -> 16-byte stores)
+    int nblk_k;        // blockIdx.y = (dW row block of 128) * nblk_k + (dW column block of 256)
+    int a_slabs, b_slabs, R;   // ring-slot geometry of the largest block
+    float *scratch;    // [splits][N][K_ld]
 };
 
-constexpr int kWgStages = 3;
+constexpr int kWgStages = 4;           // ring slots
+constexpr int kWgAhead = kWgStages - 2;   // copies run this many iterations ahead; one MMA may still be draining
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
     // 16-byte asynchronous global->shared copy (LDGSTS); src-size 0 writes zeros without touching memory
@@ -387,33 +388,36 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     __shared__ float s_scale[256], s_shift[256];
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int n0 = ((int)blockIdx.y / a.nblk_k) * 128, k0 = ((int)blockIdx.y % a.nblk_k) * 256;
+    const int nb = min(128, a.N - n0), kb = min(256, a.K - k0);
+    const int kb_pad = (kb + 15) & ~15;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const uint32_t slab_bytes = (uint32_t)a.R * 128u;
     const uint32_t stage_bytes = slab_bytes * (uint32_t)(a.a_slabs + a.b_slabs);
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < a.kb_pad) tmem_cols <<= 1;
+    while ((int)tmem_cols < kb_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < kWgStages; ++i) mbar_init(&bar_mma[i], 1);
         mbar_init_fence();
     }
     if (a.in_scale)
-        for (int i = tid; i < a.kb; i += kTcThreads) {
-            s_scale[i] = a.in_scale[a.k0 + i];
-            s_shift[i] = a.in_shift[a.k0 + i];
+        for (int i = tid; i < kb; i += kTcThreads) {
+            s_scale[i] = a.in_scale[k0 + i];
+            s_shift[i] = a.in_shift[k0 + i];
         }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_bf16(128, a.kb_pad, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(128, kb_pad, 1, 1);
 
     const int64_t r_begin = (int64_t)blockIdx.x * a.rows_per_split;
     const int64_t r_end = min(a.M, r_begin + a.rows_per_split);
     const int n_it = r_end > r_begin ? (int)((r_end - r_begin + a.R - 1) / a.R) : 0;
     // valid 16-byte chunks per row of each operand (the rest of a 64-column slab is never read back
     // into a stored output element, so it is left untouched)
-    const int a_cpr = (min(a.nb, a.lddz - a.n0) + 7) >> 3, b_cpr = (min(a.kb, a.ldx - a.k0) + 7) >> 3;
+    const int a_cpr = (min(nb, a.lddz - n0) + 7) >> 3, b_cpr = (min(kb, a.ldx - k0) + 7) >> 3;
     uint32_t par[kWgStages];
     for (int i = 0; i < kWgStages; ++i) par[i] = 0;
 
@@ -429,34 +433,34 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
             const int r = q / a_cpr, cc = q - r * a_cpr;
             const bool ok = r < rows;
             cp_async16(stA + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
-                       a.dZ + (ok ? (r0 + r) * a.lddz + a.n0 + cc * 8 : 0), ok);
+                       a.dZ + (ok ? (r0 + r) * a.lddz + n0 + cc * 8 : 0), ok);
         }
         for (int q = tid; q < rows16 * b_cpr; q += kTcThreads) {
             const int r = q / b_cpr, cc = q - r * b_cpr;
             const bool ok = r < rows;
             cp_async16(stB + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
-                       a.X + (ok ? (r0 + r) * a.ldx + a.k0 + cc * 8 : 0), ok);
+                       a.X + (ok ? (r0 + r) * a.ldx + k0 + cc * 8 : 0), ok);
         }
     };
 
-    for (int p = 0; p < kWgStages - 1; ++p) {
+    for (int p = 0; p < kWgAhead; ++p) {
         if (p < n_it) issue(p);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int it = 0; it < n_it; ++it) {
         const int s = it % kWgStages;
-        // refill the slot that iteration it-1 used (its MMA must have drained it) with iteration it+S-1
-        const int nxt = it + kWgStages - 1;
+        // refill the slot that iteration it-2 used (its MMA was issued a whole iteration ago) with it+kWgAhead
+        const int nxt = it + kWgAhead;
         if (nxt < n_it) {
-            if (it >= 1) {
-                const int sp = (it - 1) % kWgStages;
+            if (nxt >= kWgStages) {
+                const int sp = nxt % kWgStages;
                 mbar_wait(&bar_mma[sp], par[sp]);
                 par[sp] ^= 1;
             }
             issue(nxt);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group %0;" ::"n"(kWgStages - 1) : "memory");   // iteration `it` has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWgAhead) : "memory");   // iteration `it` has landed
 
         const int64_t r0 = r_begin + (int64_t)it * a.R;
         const int rows = (int)min((int64_t)a.R, r_end - r0);
@@ -473,8 +477,8 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
                 for (int e2 = 0; e2 < 4; ++e2) {
                     float2 f = unpack_bf16x2(w[e2]);
                     const int i0 = cc * 8 + 2 * e2;
-                    f.x = i0 < a.kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
-                    f.y = i0 + 1 < a.kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
+                    f.x = i0 < kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
+                    f.y = i0 + 1 < kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
                     w[e2] = pack_bf16x2(f.x, f.y);
                 }
                 *ptr = v;
@@ -493,28 +497,29 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // drain the commits nobody waited for yet, oldest first: iteration j was consumed in the loop
-    // iff a refill followed it, i.e. iff j + kWgStages < n_it
+    // iff a refill of its slot followed, i.e. iff j + kWgStages < n_it
     for (int j = max(0, n_it - kWgStages); j < n_it; ++j) {
         const int sj = j % kWgStages;
         mbar_wait(&bar_mma[sj], par[sj]);
         par[sj] ^= 1;
     }
     fence_after_sync();
-    // ---- epilogue: this thread's dW row n0 + tid, fp32 partial ----
-    const int n = a.n0 + tid;
-    float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K + a.k0;
+    // ---- epilogue: this thread's dW row n0 + tid, fp32 partial, 16-byte stores ----
+    const int n = n0 + tid;
+    float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K_ld + k0;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < a.kb_pad; c0 += 16) {
+    for (int c0 = 0; c0 < kb_pad; c0 += 16) {
         float v[16];
         if (n_it > 0) tmem_ld16(taddr + c0, v);
         else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.0f;
         }
-        if (tid < a.nb) {
+        if (tid < nb) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < a.kb) out[c0 + i] = v[i];
+            for (int i = 0; i < 16; i += 4)
+                if (k0 + c0 + i < a.K_ld)
+                    *reinterpret_cast<float4 *>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
     }
     fence_before_sync();
@@ -524,12 +529,15 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
 
 // blockDim (32, 8): 32 consecutive elements per CTA, the 8 warps stride over the splits, then a
 // fixed-order combine through shared memory (deterministic)
-__global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int splits, int64_t NK, float *__restrict__ dW) {
+__global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int splits, int N, int K, int K_ld,
+                                     float *__restrict__ dW) {
     __shared__ float red[8][32];
-    const int64_t e = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * 32 + threadIdx.x, NK = (int64_t)N * K;
     float s = 0.0f;
-    if (e < NK)
-        for (int z = threadIdx.y; z < splits; z += 8) s += scratch[(int64_t)z * NK + e];
+    if (e < NK) {
+        const int64_t src = (e / K) * K_ld + (e % K), plane = (int64_t)N * K_ld;
+        for (int z = threadIdx.y; z < splits; z += 8) s += scratch[(int64_t)z * plane + src];
+    }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && e < NK) {
@@ -540,21 +548,43 @@ __global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int spli
     }
 }
 
-static void tc_wgrad_plan(int64_t M, int K, int N, int &splits, int64_t &rows_per_split) {
-    const int blocks = ((N + 127) / 128) * ((K + 255) / 256);
-    int64_t s = (kNumSMs + blocks - 1) / blocks;              // about one CTA (three 64 KB ring slots) per SM
-    const int64_t max_s = (M + 255) / 256;                    // at least 256 rows per split
-    if (s > max_s) s = max_s;
+struct WgradPlan {
+    int splits, nblk_n, nblk_k, a_slabs, b_slabs, R, K_ld;
+    int64_t rows_per_split;
+    size_t dyn_smem;
+};
+
+static WgradPlan tc_wgrad_plan(int64_t M, int K, int N) {
+    WgradPlan p;
+    p.nblk_n = (N + 127) / 128;
+    p.nblk_k = (K + 255) / 256;
+    p.K_ld = round_up(K, 4);
+    p.a_slabs = ((N < 128 ? N : 128) + 63) / 64;
+    p.b_slabs = ((K < 256 ? K : 256) + 63) / 64;
+    const int per_row = 128 * (p.a_slabs + p.b_slabs);
+    int R = (26 * 1024 / per_row) / 16 * 16;          // <= 26 KB per ring slot: four slots, two CTAs per SM
+    if (R > 256) R = 256;
+    if (R < 16) R = 16;
+    p.R = R;
+    p.dyn_smem = 1024 + kWgStages * (size_t)R * per_row;
+    // splits: fill the machine (two CTAs per SM), but keep >= 2 ring iterations per CTA, and balance the
+    // per-CTA iteration chain (~1 us each) against writing + re-reading the fp32 partials
+    const int blocks = p.nblk_n * p.nblk_k;
+    int64_t s = (2 * kNumSMs + blocks - 1) / blocks;
+    const int64_t max_rows = (M + 2 * R - 1) / (2 * R);
+    const double chain = (double)M / R * 1e-6, part = 2.0 * N * p.K_ld * 4.0 / 3.0e12;
+    int64_t s_bal = (int64_t)(sqrt(chain / part) + 0.5);
+    if (s > max_rows) s = max_rows;
+    if (s > s_bal) s = s_bal;
     if (s < 1) s = 1;
-    rows_per_split = ((M + s - 1) / s + 15) / 16 * 16;
-    splits = (int)((M + rows_per_split - 1) / rows_per_split);
+    p.rows_per_split = ((M + s - 1) / s + 15) / 16 * 16;
+    p.splits = (int)((M + p.rows_per_split - 1) / p.rows_per_split);
+    return p;
 }
 
 size_t tc_wgrad_scratch_bytes(int64_t M, int K, int N) {
-    int splits;
-    int64_t rps;
-    tc_wgrad_plan(M, K, N, splits, rps);
-    return sizeof(float) * (size_t)splits * (size_t)N * (size_t)K;
+    const WgradPlan p = tc_wgrad_plan(M, K, N);
+    return sizeof(float) * (size_t)p.splits * (size_t)N * (size_t)p.K_ld + 16;
 }
 
 int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const float *in_scale, const float *in_shift,
@@ -573,35 +603,20 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
         }
         attr_done = true;
     }
-    int splits;
-    int64_t rps;
-    tc_wgrad_plan(M, K, N, splits, rps);
-    for (int n0 = 0; n0 < N; n0 += 128)
-        for (int k0 = 0; k0 < K; k0 += 256) {
-            TcWgradArgs a;
-            a.dZ = (const __nv_bfloat16 *)dZ; a.lddz = lddz;
-            a.X = (const __nv_bfloat16 *)X;   a.ldx = ldx;
-            a.in_scale = in_scale; a.in_shift = in_shift;
-            a.M = M; a.rows_per_split = rps; a.K = K; a.N = N;
-            a.n0 = n0; a.nb = N - n0 < 128 ? N - n0 : 128;
-            a.k0 = k0; a.kb = K - k0 < 256 ? K - k0 : 256;
-            a.kb_pad = round_up(a.kb, 16);
-            a.a_slabs = (a.nb + 63) / 64;
-            a.b_slabs = (a.kb + 63) / 64;
-            const int per_row = 128 * (a.a_slabs + a.b_slabs);
-            int R = (64 * 1024 / per_row) / 16 * 16;       // <= 64 KB per ring slot, three slots in flight
-            if (R > 256) R = 256;
-            if (R < 16) R = 16;
-            a.R = R;
-            a.scratch = (float *)scratch;
-            const size_t dyn = 1024 + kWgStages * (size_t)R * per_row;
-            wgrad_tc_kernel<<<splits, kTcThreads, dyn, st>>>(a);
-            count_launch();
-            int rc = check_launch("wgrad_tc");
-            if (rc != PN2_OK) return rc;
-        }
+    const WgradPlan p = tc_wgrad_plan(M, K, N);
+    TcWgradArgs a;
+    a.dZ = (const __nv_bfloat16 *)dZ; a.lddz = lddz;
+    a.X = (const __nv_bfloat16 *)X;   a.ldx = ldx;
+    a.in_scale = in_scale; a.in_shift = in_shift;
+    a.M = M; a.rows_per_split = p.rows_per_split; a.K = K; a.N = N; a.K_ld = p.K_ld;
+    a.nblk_k = p.nblk_k; a.a_slabs = p.a_slabs; a.b_slabs = p.b_slabs; a.R = p.R;
+    a.scratch = (float *)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+    wgrad_tc_kernel<<<dim3((unsigned)p.splits, (unsigned)(p.nblk_n * p.nblk_k)), kTcThreads, p.dyn_smem, st>>>(a);
+    count_launch();
+    int rc = check_launch("wgrad_tc");
+    if (rc != PN2_OK) return rc;
     const int64_t NK = (int64_t)N * K;
-    wgrad_reduce_kernel2<<<(unsigned)((NK + 31) / 32), dim3(32, 8), 0, st>>>((const float *)scratch, splits, NK, dW);
+    wgrad_reduce_kernel2<<<(unsigned)((NK + 31) / 32), dim3(32, 8), 0, st>>>(a.scratch, p.splits, N, K, p.K_ld, dW);
     count_launch();
     return check_launch("wgrad_reduce");
 }

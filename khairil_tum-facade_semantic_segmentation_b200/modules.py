@@ -37,17 +37,18 @@ def _bn_trains(bn):
 
 _ACCUM = {}
 _ACCUM_COLS = 4096
+_ACCUM_REPLICAS = 8          # PN2_STAT_REPLICAS of include/pn2b200.h
 
 
 def _stat_accum(dev):
-    """[2][C <= 4096] fp64 accumulator of the column-sum epilogues, one per (device, stream).  It is
+    """[PN2_STAT_REPLICAS][2][C <= 4096] fp64 accumulator of the column-sum epilogues, one per (device, stream).  It is
     zero whenever no producer/finalize pair is in flight on that stream: allocated zeroed, and every
     *_finalize entry point zeroes what it consumed (so a step needs no extra memset launches)."""
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ACCUM.get(key)
     if buf is None or torch.cuda.is_current_stream_capturing():
         # a buffer created while capturing lives in the graph's pool and is zeroed by a memset node
-        buf = torch.zeros(2 * _ACCUM_COLS, device=dev, dtype=torch.float64)
+        buf = torch.zeros(_ACCUM_REPLICAS * 2 * _ACCUM_COLS, device=dev, dtype=torch.float64)
         if not torch.cuda.is_current_stream_capturing():
             _ACCUM[key] = buf
     return buf

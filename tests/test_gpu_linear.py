@@ -37,7 +37,7 @@ def _forward(lib, x, K, W, bias, scale, shift, stats, use_tc):
     M, N = x.shape[0], W.shape[0]
     ldz = _ld(N) if x.dtype == torch.bfloat16 else N
     z = torch.full((M, ldz), float("nan"), device=DEV, dtype=x.dtype)
-    partials = torch.zeros(2, N, device=DEV, dtype=torch.float64) if stats else None   # fp64 column-sum accumulator
+    partials = torch.zeros(8, 2, N, device=DEV, dtype=torch.float64) if stats else None   # PN2_STAT_REPLICAS fp64 column-sum accumulators
     wpack = torch.empty(lib.load().pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8) if use_tc else None
     lib.call("pn2_linear_fwd", lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale), lib.ptr(shift), lib.ptr(W), lib.ptr(bias),
              M, K, N, lib.ptr(z), ldz, lib.dt(z), lib.ptr(partials), lib.ptr(wpack), lib.stream())
@@ -76,7 +76,7 @@ def test_linear_forward(lib, M, K, N, mode, prologue):
     if z.shape[1] > N and mode == "tc":
         assert float(z[:, N:].float().abs().max()) == 0.0        # row padding is written as zeros
     if stats:
-        s = partials
+        s = partials.sum(0)
         ref_vals = got if mode == "tc" else want                # the tensor-core path sums the stored values
         np.testing.assert_allclose(s[0].cpu().numpy(), ref_vals.sum(0).cpu().numpy(), rtol=2e-3, atol=2e-3 * M ** 0.5)
         np.testing.assert_allclose(s[1].cpu().numpy(), (ref_vals ** 2).sum(0).cpu().numpy(), rtol=2e-3, atol=1e-3)
@@ -118,3 +118,69 @@ def test_linear_backward_weight(lib, M, K, N, dtype):
     tol = 1e-4 if dtype == torch.float32 else 2e-2        # bf16: the tensor-core path rounds act(X) to bf16
     err = ((dW.double() - want).abs().max() / (want.abs().max() + 1e-9)).item()
     assert err <= tol, err
+
+
+@pytest.mark.parametrize("M,C", [(1000, 32), (4096, 64), (333, 128), (5000, 256), (640, 24), (8, 512)])
+@pytest.mark.parametrize("mode", ["bf16", "f32dA", "pool", "fp32rows"])
+@pytest.mark.parametrize("train", [True, False])
+def test_bn_relu_backward_kernels(lib, M, C, mode, train):
+    """dgamma/dbeta reduction (fp64 accumulators) and dz of BN(train or frozen)+ReLU against the formulas of
+    include/pn2b200.h, dense and pooled (arg-max routed) variants, vectorised bf16 and scalar paths."""
+    g = torch.Generator().manual_seed(M + C)
+    ns = 8
+    zt = torch.float32 if mode == "fp32rows" else torch.bfloat16
+    ldz = C if zt == torch.float32 else _ld(C)
+    Z = torch.zeros(M, ldz, dtype=zt, device=DEV)
+    Z[:, :C] = torch.randn(M, C, generator=g).to(DEV).to(zt)
+    scale = (torch.rand(C, generator=g) - 0.3).to(DEV)           # some negative gammas
+    shift = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    mean = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    invstd = (0.5 + torch.rand(C, generator=g)).to(DEV)
+    accum = torch.zeros(8, 2, C, dtype=torch.float64, device=DEV)
+    zf = Z[:, :C].float()
+    mask = (zf * scale + shift) > 0
+    if mode == "pool":
+        G = M // ns
+        M = G * ns
+        Z, zf, mask = Z[:M], zf[:M], mask[:M]
+        dOut = torch.randn(G, C, generator=g).to(DEV)
+        arg = torch.randint(0, ns, (G, C), generator=g, dtype=torch.int32).to(DEV)
+        dense = torch.zeros(G, ns, C, device=DEV)
+        dense.scatter_(1, arg.long().unsqueeze(1), dOut.unsqueeze(1))
+        gfull = dense.view(M, C)
+        lib.call("pn2_pool_bn_relu_bwd_reduce", lib.ptr(dOut), lib.ptr(arg), lib.ptr(Z), ldz, lib.dt(Z), lib.ptr(scale),
+                 lib.ptr(shift), lib.ptr(mean), lib.ptr(invstd), G, ns, C, lib.ptr(accum), lib.stream())
+    else:
+        at = torch.float32 if mode in ("f32dA", "fp32rows") else torch.bfloat16
+        ldda = C if at == torch.float32 else _ld(C)
+        dA = torch.zeros(M, ldda, dtype=at, device=DEV)
+        dA[:, :C] = torch.randn(M, C, generator=g).to(DEV).to(at)
+        gfull = dA[:, :C].float()
+        lib.call("pn2_bn_relu_bwd_reduce", lib.ptr(dA), ldda, lib.dt(dA), lib.ptr(Z), ldz, lib.dt(Z), lib.ptr(scale),
+                 lib.ptr(shift), lib.ptr(mean), lib.ptr(invstd), M, C, lib.ptr(accum), lib.stream())
+    gm = torch.where(mask, gfull, torch.zeros_like(gfull)).double()
+    zhat = ((zf - mean) * invstd).double()
+    want_dbeta, want_dgamma = gm.sum(0), (gm * zhat).sum(0)
+    dgb = torch.empty(2, C, device=DEV)
+    lib.call("pn2_bn_bwd_finalize", lib.ptr(accum), C, lib.ptr(dgb[0]), lib.ptr(dgb[1]), lib.stream())
+    assert float(accum.abs().max()) == 0.0                       # finalize leaves the accumulator clean
+    tol = 1e-3 * max(1.0, M ** 0.5)
+    np.testing.assert_allclose(dgb[1].cpu().numpy(), want_dbeta.cpu().numpy(), rtol=1e-4, atol=tol)
+    np.testing.assert_allclose(dgb[0].cpu().numpy(), want_dgamma.cpu().numpy(), rtol=1e-4, atol=tol)
+    dzt = zt
+    dZ = torch.full((M, ldz), float("nan"), dtype=dzt, device=DEV)
+    mu_p, is_p = (lib.ptr(mean), lib.ptr(invstd)) if train else (None, None)
+    if mode == "pool":
+        lib.call("pn2_pool_bn_relu_bwd_dz", lib.ptr(dOut), lib.ptr(arg), lib.ptr(Z), ldz, lib.dt(Z), lib.ptr(scale),
+                 lib.ptr(shift), mu_p, is_p, lib.ptr(dgb[0]), lib.ptr(dgb[1]), G, ns, C, lib.ptr(dZ), ldz, lib.dt(dZ),
+                 lib.stream())
+    else:
+        lib.call("pn2_bn_relu_bwd_dz", lib.ptr(dA), ldda, lib.dt(dA), lib.ptr(Z), ldz, lib.dt(Z), lib.ptr(scale),
+                 lib.ptr(shift), mu_p, is_p, lib.ptr(dgb[0]), lib.ptr(dgb[1]), M, C, lib.ptr(dZ), ldz, lib.dt(dZ),
+                 lib.stream())
+    if train:
+        want = scale.double() * (gm - dgb[1].double() / M - zhat * dgb[0].double() / M)
+    else:
+        want = scale.double() * gm
+    err = ((dZ[:, :C].double() - want).abs() / (want.abs() + 1.0)).max().item()
+    assert err <= (2.0 ** -7 if dzt == torch.bfloat16 else 1e-5), err
