@@ -27,7 +27,6 @@ namespace pn2 {
 
 using namespace tc;
 
-constexpr int kTcThreads = 128;
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int kTcAStage = kTcBM * kTcBK * 2;    // 16 KB
@@ -55,224 +54,213 @@ __global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, in
 }
 
 struct TcLinearArgs {
-    const __nv_bfloat16 *X;
-    int ldx;
+    CUtensorMap tm_x, tm_z;   // X [M, ldx] (boxes 64 x 128 rows) and this call's Z column block [M, n_store] (row stride ldz)
     const float *in_scale, *in_shift;
     const uint8_t *Wimg;
     const float *bias;
     int64_t M;
     int K, N, n_pad, n_store, KC;
-    __nv_bfloat16 *Z;
-    int ldz;
-    double *stat_accum;     // [2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
+    double *stat_accum;     // [replicas][2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
     int stat_ld, stat_off;
-    int w_resident;
+    int w_resident, stages;
 };
 
+constexpr int kLinTcThreads = 160;   // warps 0-3: A transform, MMA issue (thread 0), epilogue; warp 4: TMA producer
+
+// Shared-memory map (1024-byte aligned): [W image: KC chunks if resident] [staging: ceil(n_store/64) slabs of
+// 128 rows x 128 B] [ring: `stages` slots of {A chunk 16 KB, + W chunk n_pad*128 B when W is streamed}]
 template <bool STATS>
-__global__ void __launch_bounds__(kTcThreads) linear_tc_kernel(const TcLinearArgs a) {
+__global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_constant__ TcLinearArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_mma[2], bar_w[2];
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_w, bar_acc;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_part[4][2][256];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned (SW128 atoms)
     const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
-    uint8_t *const A_st[2] = {smem, smem + kTcAStage};
-    // B stage 1 first so that a resident W (stage 0) sits behind everything the epilogue staging may use
-    uint8_t *const B_st[2] = {smem + 2 * kTcAStage + b_bytes, smem + 2 * kTcAStage};
-    uint8_t *const staging = smem;
-    const int st_stride = a.n_store * 2 + 16;
+    const int z_slabs = (a.n_store + 63) >> 6;
+    uint8_t *const w_res = smem;
+    uint8_t *const staging = smem + (a.w_resident ? (size_t)a.KC * b_bytes : 0);
+    uint8_t *const ring = staging + (size_t)z_slabs * kTcAStage;
+    const uint32_t slot_bytes = kTcAStage + (a.w_resident ? 0u : b_bytes);
 
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < a.n_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
-        mbar_init(&bar_mma[0], 1);
-        mbar_init(&bar_mma[1], 1);
-        mbar_init(&bar_w[0], 1);
-        mbar_init(&bar_w[1], 1);
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+        }
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_acc, 1);
         mbar_init_fence();
     }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
-
-    uint32_t par_mma[2] = {0, 0}, par_w[2] = {0, 0};
-    if (a.w_resident) {
-        if (tid == 0) {
-            mbar_expect_tx(&bar_w[0], b_bytes);
-            bulk_g2s(B_st[0], a.Wimg, b_bytes, &bar_w[0]);
-        }
-        mbar_wait(&bar_w[0], 0);
-        par_w[0] ^= 1;
-    }
-
-    float sum1[8], sum2[8];   // STATS: this lane's column pairs p = lane + 32 j  (columns 2p, 2p+1)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum1[i] = sum2[i] = 0.0f;
-
     const int64_t m_tiles = (a.M + kTcBM - 1) / kTcBM;
-    const int c16 = tid & 7;          // this thread's 16-byte column chunk inside a K chunk
-    const int r_base = tid >> 3;      // rows r_base + 16 i
 
-    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-        const int64_t m0 = tile * kTcBM;
-        for (int kc = 0; kc < a.KC; ++kc) {
-            const int s = kc & 1;
-            if (kc >= 2) {   // the MMA of chunk kc-2 must have drained this stage
-                mbar_wait(&bar_mma[s], par_mma[s]);
-                par_mma[s] ^= 1;
+    if (warp == 4) {
+        // ---- producer: one thread streams the A chunks (and W chunks unless resident) with TMA ----
+        if (lane == 0) {
+            tma_prefetch_desc(&a.tm_x);
+            if (a.w_resident) {
+                mbar_expect_tx(&bar_w, (uint32_t)a.KC * b_bytes);
+                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
             }
-            // ---- B chunk: TMA bulk copy of the pre-swizzled image ----
-            if (!a.w_resident && tid == 0) {
-                mbar_expect_tx(&bar_w[s], b_bytes);
-                bulk_g2s(B_st[s], a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w[s]);
-            }
-            // ---- A chunk: coalesced 16-byte loads, BN+ReLU of the previous layer, swizzled store ----
-            const int k = kc * kTcBK + c16 * 8;
-            float sc[8], sh[8];
-            if (a.in_scale) {
+            uint32_t n = 0;
+            for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x)
+                for (int kc = 0; kc < a.KC; ++kc, ++n) {
+                    const uint32_t s = n % (uint32_t)a.stages, use = n / (uint32_t)a.stages;
+                    if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1u);
+                    uint8_t *slot = ring + (size_t)s * slot_bytes;
+                    mbar_expect_tx(&bar_full[s], slot_bytes);
+                    tma_load_2d(slot, &a.tm_x, kc * kTcBK, (int)(tile * kTcBM), &bar_full[s]);
+                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
+                }
+        }
+        __syncwarp();
+    } else {
+        const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
+        float sum1[8], sum2[8];   // STATS: this lane's column pairs p = lane + 32 j  (columns 2p, 2p+1)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const bool ok = k + e < a.K;
-                    sc[e] = ok ? a.in_scale[k + e] : 0.0f;
-                    sh[e] = ok ? a.in_shift[k + e] : 0.0f;
+        for (int i = 0; i < 8; ++i) sum1[i] = sum2[i] = 0.0f;
+        // transform ownership: physical 16-byte unit q = tid + 128 i of a chunk: row r = q >> 3 (r & 7 is the same
+        // for every i), logical column chunk cc = (q & 7) ^ (r & 7)
+        const int t_cc = (tid & 7) ^ ((tid >> 3) & 7);
+        if (a.w_resident && tid == 0) mbar_wait(&bar_w, 0);
+        uint32_t n = 0, acc_par = 0;
+        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+            const int64_t m0 = tile * kTcBM;
+            for (int kc = 0; kc < a.KC; ++kc, ++n) {
+                const uint32_t s = n % (uint32_t)a.stages, par = (n / (uint32_t)a.stages) & 1u;
+                uint8_t *slot = ring + (size_t)s * slot_bytes;
+                if (a.in_scale) {
+                    // previous layer's BatchNorm + ReLU, in place on the landed chunk
+                    const int k = kc * kTcBK + t_cc * 8;
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const bool ok = k + e < a.K;
+                        sc[e] = ok ? a.in_scale[k + e] : 0.0f;
+                        sh[e] = ok ? a.in_shift[k + e] : 0.0f;
+                    }
+                    mbar_wait(&bar_full[s], par);
+                    if (k < a.K) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint4 *ptr = reinterpret_cast<uint4 *>(slot + (size_t)(tid + 128 * i) * 16);
+                            uint4 v = *ptr;
+                            uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float2 f = unpack_bf16x2(w[e2]);
+                                f.x = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.0f);
+                                f.y = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f);
+                                w[e2] = pack_bf16x2(f.x, f.y);
+                            }
+                            *ptr = v;
+                        }
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                } else if (tid == 0) {
+                    mbar_wait(&bar_full[s], par);
+                }
+                if (tid == 0) {
+                    fence_after_sync();
+                    const int k_left = a.K - kc * kTcBK;
+                    const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
+                    const uint32_t a_base = smem_addr(slot);
+                    const uint32_t b_base = smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage);
+                    for (int j = 0; j < nk; ++j)
+                        umma_bf16(tmem, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024), idesc,
+                                  (uint32_t)((kc | j) != 0));
+                    umma_commit(&bar_empty[s]);
+                    if (kc == a.KC - 1) umma_commit(&bar_acc);
                 }
             }
-            uint4 raw[8];
+            mbar_wait(&bar_acc, acc_par);
+            acc_par ^= 1u;
+            fence_after_sync();
+
+            // ---- epilogue 1: TMEM -> registers -> (+bias) -> bf16 -> staging row `tid` (SW128 box layout) ----
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < a.n_store; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (a.bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t m = m0 + r_base + 16 * i;
-                raw[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (m < a.M && k < a.ldx) raw[i] = *reinterpret_cast<const uint4 *>(a.X + m * a.ldx + k);
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.N) v[i] += a.bias[c0 + i];
+                }
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
+                lo.z = pack_bf16x2(v[4], v[5]);   lo.w = pack_bf16x2(v[6], v[7]);
+                hi.x = pack_bf16x2(v[8], v[9]);   hi.y = pack_bf16x2(v[10], v[11]);
+                hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+                uint8_t *slab = staging + (size_t)(c0 >> 6) * kTcAStage;
+                const int ch = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch)) = lo;
+                if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
             }
+            fence_before_sync();     // TMEM reads done before the next tile's MMA (issued after the barrier below)
+            fence_proxy_async();     // staging writes -> visible to the TMA store
+            named_bar_sync(1, 128);
+
+            // ---- epilogue 2: TMA store of the tile (rows >= M and columns >= n_store are clipped) + column statistics ----
+            if (tid == 0)
+                for (int j = 0; j < z_slabs; ++j) tma_store_2d(&a.tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
+            if (STATS) {
+                const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint4 v = raw[i];
-                if (a.in_scale) {
-                    const bool row_ok = (m0 + r_base + 16 * i) < a.M;
-                    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        float2 f = unpack_bf16x2(w[e2]);
-                        f.x = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.0f);
-                        f.y = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f);
-                        w[e2] = row_ok ? pack_bf16x2(f.x, f.y) : 0u;
+                for (int j = 0; j < 4; ++j) {
+                    const int p = lane + 32 * j;
+                    if (2 * p < a.N) {
+                        const uint8_t *slab = staging + (size_t)(p >> 5) * kTcAStage;
+                        const int ch = (p & 31) >> 2, inb = (p & 3) * 4;
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                        for (int r = 0; r < rows; ++r) {
+                            const float2 f = unpack_bf16x2(
+                                *reinterpret_cast<const uint32_t *>(slab + sw128_offset(warp * 32 + r, ch) + inb));
+                            s1a += f.x; s1b += f.y;
+                            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+                        }
+                        sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
+                        sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
                     }
                 }
-                *reinterpret_cast<uint4 *>(A_st[s] + sw128_offset(r_base + 16 * i, c16)) = v;
             }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
-                if (!a.w_resident) mbar_wait(&bar_w[s], par_w[s]);
-                fence_after_sync();
-                const int k_left = a.K - kc * kTcBK;
-                const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
-                const uint32_t a_base = smem_addr(A_st[s]);
-                const uint32_t b_base = smem_addr(a.w_resident ? B_st[0] : B_st[s]);
-                for (int j = 0; j < nk; ++j)
-                    umma_bf16(tmem, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024), idesc,
-                              (uint32_t)((kc | j) != 0));
-                umma_commit(&bar_mma[s]);
-            }
-            if (!a.w_resident) par_w[s] ^= 1;
+            if (tid == 0) tma_store_wait_read();
+            named_bar_sync(1, 128);   // staging free again (store has read it, statistics have read it)
         }
-        // ---- wait for the accumulator (consume the outstanding commits in order) ----
-        if (a.KC >= 2) {
-            const int s2 = (a.KC - 2) & 1;
-            mbar_wait(&bar_mma[s2], par_mma[s2]);
-            par_mma[s2] ^= 1;
-        }
-        {
-            const int s1 = (a.KC - 1) & 1;
-            mbar_wait(&bar_mma[s1], par_mma[s1]);
-            par_mma[s1] ^= 1;
-        }
-        fence_after_sync();
+        if (tid == 0) tma_store_wait_all();
 
-        // ---- epilogue 1: TMEM -> registers -> (+bias) -> bf16 -> staging row `tid` ----
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        uint8_t *my_row = staging + (size_t)tid * st_stride;
-        for (int c0 = 0; c0 < a.n_store; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            if (a.bias) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < a.N) v[i] += a.bias[c0 + i];
-            }
-            uint4 lo, hi;
-            lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
-            lo.z = pack_bf16x2(v[4], v[5]);   lo.w = pack_bf16x2(v[6], v[7]);
-            hi.x = pack_bf16x2(v[8], v[9]);   hi.y = pack_bf16x2(v[10], v[11]);
-            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
-            *reinterpret_cast<uint4 *>(my_row + c0 * 2) = lo;
-            if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(my_row + c0 * 2 + 16) = hi;
-        }
-        fence_before_sync();
-        __syncthreads();
-
-        // ---- epilogue 2: coalesced store + column statistics of the stored values ----
-        const int cpr = a.n_store >> 3;
-        for (int q = tid; q < kTcBM * cpr; q += kTcThreads) {
-            const int r = q / cpr, c = q - r * cpr;
-            const int64_t m = m0 + r;
-            if (m < a.M)
-                *reinterpret_cast<uint4 *>(a.Z + m * a.ldz + c * 8) =
-                    *reinterpret_cast<const uint4 *>(staging + (size_t)r * st_stride + c * 16);
-        }
         if (STATS) {
-            const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
+            float(*s_part)[2][256] = reinterpret_cast<float(*)[2][256]>(staging);   // 8 KB of the (now idle) staging tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int p = lane + 32 * j;
-                if (2 * p < a.N) {
-                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                    for (int r = 0; r < rows; ++r) {
-                        const float2 f = unpack_bf16x2(
-                            *reinterpret_cast<const uint32_t *>(staging + (size_t)(warp * 32 + r) * st_stride + p * 4));
-                        s1a += f.x; s1b += f.y;
-                        s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
-                    }
-                    sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
-                    sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
-                }
-            }
-        }
-        fence_proxy_async();   // generic-proxy accesses of the staging tile before the next TMA write into it
-        __syncthreads();       // staging consumed before the next tile's operands overwrite it
-    }
-
-    if (STATS) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = lane + 32 * j;
-            if (2 * p < 256) {
                 s_part[warp][0][2 * p] = sum1[2 * j];     s_part[warp][0][2 * p + 1] = sum1[2 * j + 1];
                 s_part[warp][1][2 * p] = sum2[2 * j];     s_part[warp][1][2 * p + 1] = sum2[2 * j + 1];
             }
-        }
-        __syncthreads();
-        for (int c = tid; c < a.N; c += kTcThreads) {
-            float t1 = 0.f, t2 = 0.f;
+            named_bar_sync(1, 128);
+            for (int c = tid; c < a.N; c += 128) {
+                float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
-            double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
-            atomicAdd(acc + c, (double)t1);
-            atomicAdd(acc + a.stat_ld + c, (double)t2);
+                for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
+                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
+                atomicAdd(acc + c, (double)t1);
+                atomicAdd(acc + a.stat_ld + c, (double)t2);
+            }
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
-
-int linear_num_partials(int64_t M);
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -288,9 +276,11 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
                  int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, double *stat_accum,
                  void *wpack, cudaStream_t st) {
     static bool attr_done = false;
+    static int static_smem = 0;
     if (!attr_done) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, linear_tc_kernel<true>);
+        static_smem = (int)fa.sharedSizeBytes;
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024 - (int)fa.sharedSizeBytes);
@@ -307,6 +297,7 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
     }
     const int KC = (K + kTcBK - 1) / kTcBK;
     uint8_t *img = (uint8_t *)wpack;
+    const int64_t m_tiles = (M + kTcBM - 1) / kTcBM;
     for (int n0 = 0; n0 < N; n0 += 256) {
         const int nb = N - n0 < 256 ? N - n0 : 256;
         const int n_pad = round_up(nb, 16);
@@ -317,26 +308,45 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, img);
         count_launch();
         TcLinearArgs a;
-        a.X = (const __nv_bfloat16 *)X;
-        a.ldx = ldx;
+        if (!make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, kTcBM) ||
+            !make_rows_tensor_map(&a.tm_z, (const __nv_bfloat16 *)Z + n0, M, n_store, ldz, kTcBM)) {
+            set_error("linear_tc: cuTensorMapEncodeTiled failed (M=%lld ldx=%d ldz=%d)", (long long)M, ldx, ldz);
+            return PN2_ERR_CUDA;
+        }
         a.in_scale = in_scale;
         a.in_shift = in_shift;
         a.Wimg = img;
         a.bias = bias ? bias + n0 : nullptr;
         a.M = M; a.K = K; a.N = nb; a.n_pad = n_pad; a.n_store = n_store; a.KC = KC;
-        a.Z = (__nv_bfloat16 *)Z + n0;
-        a.ldz = ldz;
         a.stat_accum = stat_accum;
         a.stat_ld = N;
         a.stat_off = n0;
-        const size_t staging = (size_t)kTcBM * (n_store * 2 + 16);
-        a.w_resident = (KC == 1 && staging <= (size_t)2 * kTcAStage + (size_t)n_pad * 128) ? 1 : 0;
-        const size_t dyn = 1024 + 2 * kTcAStage + 2 * (size_t)n_pad * 128;
-        const int grid = linear_num_partials(M);
+        // shared-memory plan: resident W when its image is <= 64 KB; as many ring slots as fit the per-CTA budget
+        // of 3, 2 or 1 CTAs per SM (whichever is the densest that still leaves >= 3 slots, at most 8)
+        a.w_resident = img_bytes <= 64 * 1024 ? 1 : 0;
+        const size_t fixed = 1024 + (a.w_resident ? img_bytes : 0) + (size_t)((n_store + 63) / 64) * kTcAStage;
+        const size_t slot = kTcAStage + (a.w_resident ? 0 : (size_t)n_pad * 128);
+        const size_t budgets[3] = {(size_t)(227 * 1024 / 3 - 1024 - static_smem), (size_t)(227 * 1024 / 2 - 1024 - static_smem),
+                                   (size_t)(227 * 1024 - static_smem)};
+        int stages = 0, per_sm = 1;
+        for (int b = 0; b < 3 && stages == 0; ++b) {
+            if (budgets[b] < fixed + slot * (b < 2 ? 3 : 2)) continue;
+            stages = (int)((budgets[b] - fixed) / slot);
+            per_sm = 3 - b;
+        }
+        if (stages < 2) {
+            set_error("linear_tc: layer K=%d N=%d does not fit shared memory", K, nb);
+            return PN2_ERR_UNSUPPORTED;
+        }
+        if (stages > 8) stages = 8;
+        a.stages = stages;
+        const size_t dyn = fixed + slot * stages;
+        int64_t grid = (int64_t)per_sm * kNumSMs;
+        if (grid > m_tiles) grid = m_tiles;
         if (stat_accum)
-            linear_tc_kernel<true><<<grid, kTcThreads, dyn, st>>>(a);
+            linear_tc_kernel<true><<<(unsigned)grid, kLinTcThreads, dyn, st>>>(a);
         else
-            linear_tc_kernel<false><<<grid, kTcThreads, dyn, st>>>(a);
+            linear_tc_kernel<false><<<(unsigned)grid, kLinTcThreads, dyn, st>>>(a);
         count_launch();
         int rc = check_launch("linear_tc");
         if (rc != PN2_OK) return rc;
@@ -361,29 +371,22 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
 namespace pn2 {
 
 struct TcWgradArgs {
-    const __nv_bfloat16 *dZ;
-    int lddz;
-    const __nv_bfloat16 *X;
-    int ldx;
+    CUtensorMap tm_dz, tm_x;   // [M, lddz] / [M, ldx] bf16, boxes of 64 columns x R rows, 128-byte swizzle
     const float *in_scale, *in_shift;
-    int64_t M, rows_per_split;
+    int64_t M, rows_per_split;   // rows_per_split % R == 0: only the global tail is a partial (zero-filled) box
     int K, N, K_ld;    // K_ld: row stride of the fp32 partials (K rounded up to 4 -> 16-byte stores)
+    int lddz, ldx;
     int nblk_k;        // blockIdx.y = (dW row block of 128) * nblk_k + (dW column block of 256)
     int a_slabs, b_slabs, R;   // ring-slot geometry of the largest block
     float *scratch;    // [splits][N][K_ld]
 };
 
 constexpr int kWgStages = 4;           // ring slots
-constexpr int kWgAhead = kWgStages - 2;   // copies run this many iterations ahead; one MMA may still be draining
+constexpr int kWgThreads = 160;        // warps 0-3: activation transform + epilogue (thread 0 issues the MMAs); warp 4: TMA producer
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
-    // 16-byte asynchronous global->shared copy (LDGSTS); src-size 0 writes zeros without touching memory
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-
-__global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs a) {
+__global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_constant__ TcWgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_mma[kWgStages];
+    __shared__ __align__(8) uint64_t bar_full[kWgStages], bar_empty[kWgStages], bar_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_scale[256], s_shift[256];
 
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     const int n0 = ((int)blockIdx.y / a.nblk_k) * 128, k0 = ((int)blockIdx.y % a.nblk_k) * 256;
     const int nb = min(128, a.N - n0), kb = min(256, a.K - k0);
     const int kb_pad = (kb + 15) & ~15;
+    const int a_sl = (nb + 63) >> 6, b_sl = (kb + 63) >> 6;      // slabs this block really needs
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const uint32_t slab_bytes = (uint32_t)a.R * 128u;
     const uint32_t stage_bytes = slab_bytes * (uint32_t)(a.a_slabs + a.b_slabs);
@@ -398,11 +402,15 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     while ((int)tmem_cols < kb_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
-        for (int i = 0; i < kWgStages; ++i) mbar_init(&bar_mma[i], 1);
+        for (int i = 0; i < kWgStages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+        }
+        mbar_init(&bar_done, 1);
         mbar_init_fence();
     }
     if (a.in_scale)
-        for (int i = tid; i < kb; i += kTcThreads) {
+        for (int i = tid; i < kb; i += kWgThreads) {
             s_scale[i] = a.in_scale[k0 + i];
             s_shift[i] = a.in_shift[k0 + i];
         }
@@ -410,116 +418,97 @@ __global__ void __launch_bounds__(kTcThreads) wgrad_tc_kernel(const TcWgradArgs 
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = make_idesc_bf16(128, kb_pad, 1, 1);
 
     const int64_t r_begin = (int64_t)blockIdx.x * a.rows_per_split;
     const int64_t r_end = min(a.M, r_begin + a.rows_per_split);
     const int n_it = r_end > r_begin ? (int)((r_end - r_begin + a.R - 1) / a.R) : 0;
-    // valid 16-byte chunks per row of each operand (the rest of a 64-column slab is never read back
-    // into a stored output element, so it is left untouched)
-    const int a_cpr = (min(nb, a.lddz - n0) + 7) >> 3, b_cpr = (min(kb, a.ldx - k0) + 7) >> 3;
-    uint32_t par[kWgStages];
-    for (int i = 0; i < kWgStages; ++i) par[i] = 0;
 
-    // issue the asynchronous copies of iteration `it` into its ring slot
-    auto issue = [&](int it) {
-        const int s = it % kWgStages;
-        const int64_t r0 = r_begin + (int64_t)it * a.R;
-        const int rows = (int)min((int64_t)a.R, r_end - r0);
-        const int rows16 = (rows + 15) & ~15;
-        const uint32_t stA = smem_addr(smem + (size_t)s * stage_bytes);
-        const uint32_t stB = stA + (uint32_t)a.a_slabs * slab_bytes;
-        for (int q = tid; q < rows16 * a_cpr; q += kTcThreads) {
-            const int r = q / a_cpr, cc = q - r * a_cpr;
-            const bool ok = r < rows;
-            cp_async16(stA + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
-                       a.dZ + (ok ? (r0 + r) * a.lddz + n0 + cc * 8 : 0), ok);
-        }
-        for (int q = tid; q < rows16 * b_cpr; q += kTcThreads) {
-            const int r = q / b_cpr, cc = q - r * b_cpr;
-            const bool ok = r < rows;
-            cp_async16(stB + (uint32_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7),
-                       a.X + (ok ? (r0 + r) * a.ldx + k0 + cc * 8 : 0), ok);
-        }
-    };
-
-    for (int p = 0; p < kWgAhead; ++p) {
-        if (p < n_it) issue(p);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    for (int it = 0; it < n_it; ++it) {
-        const int s = it % kWgStages;
-        // refill the slot that iteration it-2 used (its MMA was issued a whole iteration ago) with it+kWgAhead
-        const int nxt = it + kWgAhead;
-        if (nxt < n_it) {
-            if (nxt >= kWgStages) {
-                const int sp = nxt % kWgStages;
-                mbar_wait(&bar_mma[sp], par[sp]);
-                par[sp] ^= 1;
+    if (warp == 4) {
+        // ---- producer: one thread streams (dZ, X) row boxes into the ring with tensor-map TMA ----
+        if ((tid & 31) == 0) {
+            tma_prefetch_desc(&a.tm_dz);
+            tma_prefetch_desc(&a.tm_x);
+            const uint32_t tx = slab_bytes * (uint32_t)(a_sl + b_sl);
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % kWgStages;
+                if (it >= kWgStages) mbar_wait(&bar_empty[s], (uint32_t)((it / kWgStages - 1) & 1));
+                const int r0 = (int)(r_begin + (int64_t)it * a.R);
+                uint8_t *stA = smem + (size_t)s * stage_bytes;
+                uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
+                mbar_expect_tx(&bar_full[s], tx);
+                for (int j = 0; j < a_sl; ++j) tma_load_2d(stA + (size_t)j * slab_bytes, &a.tm_dz, n0 + 64 * j, r0, &bar_full[s]);
+                for (int j = 0; j < b_sl; ++j) tma_load_2d(stB + (size_t)j * slab_bytes, &a.tm_x, k0 + 64 * j, r0, &bar_full[s]);
             }
-            issue(nxt);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group %0;" ::"n"(kWgAhead) : "memory");   // iteration `it` has landed
-
-        const int64_t r0 = r_begin + (int64_t)it * a.R;
-        const int rows = (int)min((int64_t)a.R, r_end - r0);
-        const int rows16 = (rows + 15) & ~15;
-        uint8_t *stA = smem + (size_t)s * stage_bytes;
-        uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
-        if (a.in_scale) {   // act(X) = relu(bn(.)) of the previous layer, in place on the chunks this thread copied
-            for (int q = tid; q < rows * b_cpr; q += kTcThreads) {
-                const int r = q / b_cpr, cc = q - r * b_cpr;
-                uint4 *ptr = reinterpret_cast<uint4 *>(stB + (size_t)(cc >> 3) * slab_bytes + sw128_offset(r, cc & 7));
-                uint4 v = *ptr;
-                uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+        __syncwarp();
+    } else {
+        const uint32_t idesc = make_idesc_bf16(128, kb_pad, 1, 1);
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % kWgStages;
+            const uint32_t par = (uint32_t)((it / kWgStages) & 1);
+            const int64_t r0 = r_begin + (int64_t)it * a.R;
+            const int rows = (int)min((int64_t)a.R, r_end - r0);
+            const int rows16 = (rows + 15) & ~15;
+            uint8_t *stA = smem + (size_t)s * stage_bytes;
+            uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
+            if (a.in_scale) {
+                // act(X) = relu(bn(.)) of the previous layer, in place; threads walk PHYSICAL 16-byte units
+                // (conflict-free), the logical column chunk of unit pc in row r is pc ^ (r & 7)
+                mbar_wait(&bar_full[s], par);
+                for (int j = 0; j < b_sl; ++j) {
+                    uint8_t *slab = stB + (size_t)j * slab_bytes;
+                    for (int q = tid; q < rows16 * 8; q += 128) {
+                        const int r = q >> 3, cc = (q & 7) ^ (r & 7);
+                        const int i0 = j * 64 + cc * 8;
+                        if (i0 >= kb) continue;
+                        uint4 *ptr = reinterpret_cast<uint4 *>(slab + (size_t)q * 16);
+                        uint4 v = *ptr;
+                        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    float2 f = unpack_bf16x2(w[e2]);
-                    const int i0 = cc * 8 + 2 * e2;
-                    f.x = i0 < kb ? fmaxf(fmaf(f.x, s_scale[i0], s_shift[i0]), 0.0f) : 0.0f;
-                    f.y = i0 + 1 < kb ? fmaxf(fmaf(f.y, s_scale[i0 + 1], s_shift[i0 + 1]), 0.0f) : 0.0f;
-                    w[e2] = pack_bf16x2(f.x, f.y);
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            float2 f = unpack_bf16x2(w[e2]);
+                            const int i = i0 + 2 * e2;
+                            f.x = i < kb ? fmaxf(fmaf(f.x, s_scale[i], s_shift[i]), 0.0f) : 0.0f;
+                            f.y = i + 1 < kb ? fmaxf(fmaf(f.y, s_scale[i + 1], s_shift[i + 1]), 0.0f) : 0.0f;
+                            w[e2] = pack_bf16x2(f.x, f.y);
+                        }
+                        *ptr = v;
+                    }
                 }
-                *ptr = v;
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+            } else if (tid == 0) {
+                mbar_wait(&bar_full[s], par);
+            }
+            if (tid == 0) {
+                fence_after_sync();
+                const uint32_t a_base = smem_addr(stA), b_base = smem_addr(stB);
+                for (int j = 0; j < rows16 / 16; ++j)
+                    umma_bf16(tmem, make_desc(a_base + 2048 * j, slab_bytes, 1024), make_desc(b_base + 2048 * j, slab_bytes, 1024),
+                              idesc, (uint32_t)((it | j) != 0));
+                umma_commit(&bar_empty[s]);
+                if (it == n_it - 1) umma_commit(&bar_done);
             }
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            fence_after_sync();
-            const uint32_t a_base = smem_addr(stA), b_base = smem_addr(stB);
-            for (int j = 0; j < rows16 / 16; ++j)
-                umma_bf16(tmem, make_desc(a_base + 2048 * j, slab_bytes, 1024), make_desc(b_base + 2048 * j, slab_bytes, 1024),
-                          idesc, (uint32_t)((it | j) != 0));
-            umma_commit(&bar_mma[s]);
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // drain the commits nobody waited for yet, oldest first: iteration j was consumed in the loop
-    // iff a refill of its slot followed, i.e. iff j + kWgStages < n_it
-    for (int j = max(0, n_it - kWgStages); j < n_it; ++j) {
-        const int sj = j % kWgStages;
-        mbar_wait(&bar_mma[sj], par[sj]);
-        par[sj] ^= 1;
-    }
-    fence_after_sync();
-    // ---- epilogue: this thread's dW row n0 + tid, fp32 partial, 16-byte stores ----
-    const int n = n0 + tid;
-    float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K_ld + k0;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < kb_pad; c0 += 16) {
-        float v[16];
-        if (n_it > 0) tmem_ld16(taddr + c0, v);
-        else {
+        if (n_it > 0) mbar_wait(&bar_done, 0);
+        fence_after_sync();
+        // ---- epilogue: this thread's dW row n0 + tid, fp32 partial, 16-byte stores ----
+        const int n = n0 + tid;
+        float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K_ld + k0;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < kb_pad; c0 += 16) {
+            float v[16];
+            if (n_it > 0) tmem_ld16(taddr + c0, v);
+            else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
-        }
-        if (tid < nb) {
+                for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+            }
+            if (tid < nb) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                if (k0 + c0 + i < a.K_ld)
-                    *reinterpret_cast<float4 *>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4)
+                    if (k0 + c0 + i < a.K_ld)
+                        *reinterpret_cast<float4 *>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
     }
     fence_before_sync();
@@ -577,7 +566,7 @@ static WgradPlan tc_wgrad_plan(int64_t M, int K, int N) {
     if (s > max_rows) s = max_rows;
     if (s > s_bal) s = s_bal;
     if (s < 1) s = 1;
-    p.rows_per_split = ((M + s - 1) / s + 15) / 16 * 16;
+    p.rows_per_split = ((M + s - 1) / s + R - 1) / R * R;
     p.splits = (int)((M + p.rows_per_split - 1) / p.rows_per_split);
     return p;
 }
@@ -605,13 +594,16 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
     }
     const WgradPlan p = tc_wgrad_plan(M, K, N);
     TcWgradArgs a;
-    a.dZ = (const __nv_bfloat16 *)dZ; a.lddz = lddz;
-    a.X = (const __nv_bfloat16 *)X;   a.ldx = ldx;
+    if (!make_rows_tensor_map(&a.tm_dz, dZ, M, lddz, lddz, p.R) || !make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, p.R)) {
+        set_error("wgrad_tc: cuTensorMapEncodeTiled failed (M=%lld lddz=%d ldx=%d R=%d)", (long long)M, lddz, ldx, p.R);
+        return PN2_ERR_CUDA;
+    }
+    a.lddz = lddz; a.ldx = ldx;
     a.in_scale = in_scale; a.in_shift = in_shift;
     a.M = M; a.rows_per_split = p.rows_per_split; a.K = K; a.N = N; a.K_ld = p.K_ld;
     a.nblk_k = p.nblk_k; a.a_slabs = p.a_slabs; a.b_slabs = p.b_slabs; a.R = p.R;
     a.scratch = (float *)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
-    wgrad_tc_kernel<<<dim3((unsigned)p.splits, (unsigned)(p.nblk_n * p.nblk_k)), kTcThreads, p.dyn_smem, st>>>(a);
+    wgrad_tc_kernel<<<dim3((unsigned)p.splits, (unsigned)(p.nblk_n * p.nblk_k)), kWgThreads, p.dyn_smem, st>>>(a);
     count_launch();
     int rc = check_launch("wgrad_tc");
     if (rc != PN2_OK) return rc;

@@ -5,7 +5,9 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction
 // descriptor" tables (the same fields CUTLASS names UMMA::SmemDescriptor / InstrDescriptor).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pn2 {
@@ -43,6 +45,35 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                      smem_addr(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
+}
+
+// ---- tensor-map (tiled) TMA: one 2-D box of a row-major bf16 matrix -> shared memory, 128-byte swizzle.
+// c_col / c_row are element coordinates of the box origin; out-of-bounds elements arrive as zeros.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int c_col, int c_row, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_addr(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c_col), "r"(c_row), "r"(smem_addr(bar))
+        : "memory");
+}
+// shared memory (SW128 box layout) -> 2-D box of a row-major bf16 matrix; out-of-bounds elements are not written
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, int c_col, int c_row, const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c_col), "r"(c_row), "r"(smem_addr(src_smem))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the shared-memory source of every committed bulk store has been read (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed bulk store is complete (globally visible at kernel end anyway; used before exit)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// named barrier among `count` threads (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
@@ -115,6 +146,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&u);
     return __bfloat1622float2(v);
+}
+
+// Host: tensor map of the first `cols` columns of a row-major bf16 matrix [rows, ld] (ld % 8 == 0, base 16-byte
+// aligned) with boxes of 64 columns x box_rows
+// rows, 128-byte swizzle: the box lands in shared memory exactly in the canonical SW128 layout
+// (row r at r*128 bytes, 16-byte chunk c at (c ^ (r & 7)) * 16), which is both the K-major and, read
+// along rows, the MN-major UMMA operand layout used by the kernels here.
+inline bool make_rows_tensor_map(CUtensorMap *tm, const void *base, int64_t rows, int cols, int ld, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (EncodeFn)p;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc
