@@ -134,12 +134,13 @@ int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X,
  * into mean / biased variance over M rows (and zeroes the accumulator), writes
  *   scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd
  * and updates running_mean/var in place with `momentum` (running_mean includes
- * the conv bias that the GEMM left out; running_var uses the unbiased variance). */
+ * the conv bias that the GEMM left out; running_var uses the unbiased variance) and, when
+ * num_batches_tracked is non-NULL, increments that int64 counter (nn.BatchNorm's buffer). */
 int pn2_bn_train_finalize(double *stat_accum, int64_t M, int N,
                           const float *gamma, const float *beta, const float *conv_bias,
                           float eps, float momentum, float *running_mean, float *running_var,
                           float *scale, float *shift, float *save_mean, float *save_invstd,
-                          void *stream);
+                          int64_t *num_batches_tracked, void *stream);
 /* Eval: scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale (the GEMM adds the bias). */
 int pn2_bn_eval_fold(const float *gamma, const float *beta, const float *running_mean,
                      const float *running_var, float eps, int N, float *scale, float *shift,

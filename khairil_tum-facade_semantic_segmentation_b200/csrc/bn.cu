@@ -19,8 +19,10 @@ __global__ void bn_train_finalize_kernel(double *__restrict__ accum, int64_t M, 
                                          const float *__restrict__ conv_bias, float eps, float momentum,
                                          float *__restrict__ running_mean, float *__restrict__ running_var,
                                          float *__restrict__ scale, float *__restrict__ shift,
-                                         float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+                                         float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                         long long *__restrict__ num_batches_tracked) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= N) return;
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
@@ -374,12 +376,13 @@ using namespace pn2;
 extern "C" int pn2_bn_train_finalize(double *stat_accum, int64_t M, int N,
                                      const float *gamma, const float *beta, const float *conv_bias, float eps,
                                      float momentum, float *running_mean, float *running_var, float *scale,
-                                     float *shift, float *save_mean, float *save_invstd, void *stream) {
+                                     float *shift, float *save_mean, float *save_invstd,
+                                     int64_t *num_batches_tracked, void *stream) {
     PN2_REQUIRE(stat_accum && scale && shift, "bn_train_finalize: null pointer");
     PN2_REQUIRE(M > 0 && N > 0, "bn_train_finalize: bad sizes");
     bn_train_finalize_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         stat_accum, M, N, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale,
-        shift, save_mean, save_invstd);
+        shift, save_mean, save_invstd, (long long *)num_batches_tracked);
     count_launch();
     return check_launch("bn_train_finalize");
 }

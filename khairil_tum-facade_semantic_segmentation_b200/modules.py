@@ -87,14 +87,16 @@ def mlp_forward(x0, K0, M, convs, bns):
             call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
                  ptr(z), ldz, dt(z), ptr(accum), ptr(wpack), stream())
             momentum = bn.momentum
-            if bn.num_batches_tracked is not None and bn.training:
-                bn.num_batches_tracked.add_(1)
-            if momentum is None:      # cumulative moving average (nn.BatchNorm semantics)
-                momentum = 1.0 / float(bn.num_batches_tracked.item()) if bn.num_batches_tracked is not None else 0.0
+            nbt = bn.num_batches_tracked if (bn.num_batches_tracked is not None and bn.training) else None
+            if momentum is None:      # cumulative moving average (nn.BatchNorm semantics): needs the counter's value
+                if nbt is not None:
+                    nbt.add_(1)
+                momentum = 1.0 / float(nbt.item()) if nbt is not None else 0.0
+                nbt = None
             update = bn.training and bn.running_mean is not None
             call("pn2_bn_train_finalize", ptr(accum), M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
                  float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
-                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), stream())
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt), stream())
         else:
             call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
                  ptr(st.scale), ptr(st.shift), stream())
@@ -110,7 +112,36 @@ def mlp_forward(x0, K0, M, convs, bns):
     return layers
 
 
-def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
+OVERLAP_WGRAD = True      # weight gradients on a side stream, concurrently with the data-gradient / BatchNorm chain
+_SIDE = {}
+_GRAD_SINK = {}           # id(parameter) -> flat fp32 view the parameter's gradient is written into (trainer.FlatGradients)
+
+
+def set_grad_sink(mapping):
+    """mapping: {id(parameter): preallocated fp32 tensor of the parameter's shape} or None.  Backward passes write
+    weight / BatchNorm gradients straight into these buffers and hand autograd views of them (no accumulate kernels)."""
+    _GRAD_SINK.clear()
+    if mapping:
+        _GRAD_SINK.update(mapping)
+
+
+def _sink(param, shape=None):
+    if param is None or not isinstance(param, nn.Parameter):
+        return None
+    v = _GRAD_SINK.get(id(param))
+    if v is None or not v.is_cuda or v.dtype != torch.float32 or v.numel() != param.numel() or not v.is_contiguous():
+        return None
+    return v.view(shape if shape is not None else param.shape)      # a fresh tensor object every time
+
+
+def _side_stream(dev):
+    s = _SIDE.get(dev.index)
+    if s is None:
+        s = _SIDE[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bns=None):
     """Backward of mlp_forward + tail.  dout: [G, C] fp32 pooled gradient with arg-max map `arg`
     (set abstraction) or [M, C] fp32 dense gradient (feature propagation, arg None).
     Returns (per-layer (dW, dbias, dgamma, dbeta), dX0 or None)."""
@@ -118,36 +149,44 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
     dev, dtype = x0.device, x0.dtype
     L = len(layers)
     grads = [None] * L
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if OVERLAP_WGRAD else None
+    keep = []                 # operands of side-stream kernels stay alive until the streams are joined
 
-    def bn_grads(st, dA, ldda):
-        """dgamma/dbeta of layer st from the gradient w.r.t. its activation, then dZ."""
+    def bn_grads(l, dA, ldda):
+        """dgamma/dbeta of layer l from the gradient w.r.t. its activation, then dZ."""
+        st = layers[l]
         C = st.N
         accum = _stat_accum(dev)
-        dgb = torch.empty(2, C, device=dev, dtype=torch.float32)
+        dgamma = _sink(bns[l].weight) if bns is not None else None
+        dbeta = _sink(bns[l].bias) if bns is not None else None
+        if dgamma is None or dbeta is None:
+            dgb = torch.empty(2, C, device=dev, dtype=torch.float32)
+            dgamma, dbeta = dgb[0], dgb[1]
         mean_train = ptr(st.mean) if st.train else None
         if arg is not None and dA is dout:
             G = M // nsample
             call("pn2_pool_bn_relu_bwd_reduce", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
                  ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(accum), stream())
-            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgb[0]), ptr(dgb[1]), stream())
+            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgamma), ptr(dbeta), stream())
             dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
             call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgb[0]), ptr(dgb[1]), G, nsample, C, ptr(dZ),
+                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgamma), ptr(dbeta), G, nsample, C, ptr(dZ),
                  dZ.shape[1], dt(dZ), stream())
         else:
             call("pn2_bn_relu_bwd_reduce", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
                  ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(accum), stream())
-            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgb[0]), ptr(dgb[1]), stream())
+            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgamma), ptr(dbeta), stream())
             if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
                 dZ = dA                                   # element-wise update in place (never on autograd's grad)
             else:
                 dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
             call("pn2_bn_relu_bwd_dz", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgb[0]), ptr(dgb[1]), M, C, ptr(dZ), dZ.shape[1],
+                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgamma), ptr(dbeta), M, C, ptr(dZ), dZ.shape[1],
                  dt(dZ), stream())
-        return dZ, dgb[0], dgb[1]
+        return dZ, dgamma, dbeta
 
-    dZ, dgamma, dbeta = bn_grads(layers[-1], dout, dout.shape[1])
+    dZ, dgamma, dbeta = bn_grads(L - 1, dout, dout.shape[1])
     dx0 = None
     for l in range(L - 1, -1, -1):
         st = layers[l]
@@ -156,14 +195,25 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
         else:
             prev = layers[l - 1]
             xin, ldx, sc, sh = prev.Z, prev.Z.shape[1], prev.scale, prev.shift
-        dW = torch.empty(st.N, st.K, device=dev, dtype=torch.float32)
+        conv = convs[l] if convs is not None else None
+        dW = _sink(getattr(conv, "weight", None), (st.N, st.K))
+        if dW is None:
+            dW = torch.empty(st.N, st.K, device=dev, dtype=torch.float32)
         scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, st.K, st.N), device=dev, dtype=torch.uint8)
-        call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M, st.K,
-             st.N, ptr(dW), ptr(scratch), stream())
+        if side is not None:          # dZ is complete on the main stream here; the side stream picks it up
+            side.wait_stream(main)
+            call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M,
+                 st.K, st.N, ptr(dW), ptr(scratch), side.cuda_stream)
+            keep += [dZ, xin, sc, sh, scratch]
+        else:
+            call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M,
+                 st.K, st.N, ptr(dW), ptr(scratch), stream())
         if not st.has_bias:
             dbias = None
         elif st.train:      # batch-norm's mean subtraction cancels the conv bias exactly
-            dbias = torch.zeros(st.N, device=dev, dtype=torch.float32)
+            dbias = _sink(getattr(conv, "bias", None))        # the sink is zeroed once per step by its owner
+            if dbias is None:
+                dbias = torch.zeros(st.N, device=dev, dtype=torch.float32)
         else:               # frozen statistics: sum_m dz = scale * dbeta
             dbias = st.scale * dbeta
         grads[l] = (dW, dbias, dgamma, dbeta)
@@ -178,9 +228,12 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0):
             call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
                  ptr(wpack), stream())
             if l > 0:
-                dZ, dgamma, dbeta = bn_grads(layers[l - 1], dA, ldd)
+                dZ, dgamma, dbeta = bn_grads(l - 1, dA, ldd)
             else:
                 dx0 = dA
+    if side is not None:
+        main.wait_stream(side)
+    del keep
     return grads, dx0
 
 
@@ -204,11 +257,12 @@ class _SetAbstractionFn(torch.autograd.Function):
     first, :248, while the gather kernel writes [dxyz | feats])."""
 
     @staticmethod
-    def forward(ctx, mod, convs, bns, radius, nsample, new_xyz, xyz_r, pts_r, *params):
+    def forward(ctx, idx, convs, bns, radius, nsample, new_xyz, xyz_r, pts_r, *params):
         B, N, _ = xyz_r.shape
         S = new_xyz.shape[1]
         dtype = ops.rows_dtype()
-        idx = ops.query_ball_point(radius, nsample, xyz_r, new_xyz)
+        if idx is None:
+            idx = ops.query_ball_point(radius, nsample, xyz_r, new_xyz)
         feats = None if pts_r is None else ops.as_rows(pts_r)
         D = 0 if feats is None else feats.shape[2]
         K0 = 3 + D
@@ -220,16 +274,16 @@ class _SetAbstractionFn(torch.autograd.Function):
         arg = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.int32)
         call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B * S,
              nsample, last.N, ptr(out), ptr(arg), stream())
-        ctx.state = (layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs)
+        ctx.state = (layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs = ctx.state
+        layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns = ctx.state
         ctx.state = None
         need_pts = ctx.needs_input_grad[7] and D > 0
         dout = dout.contiguous().view(B * S, -1)
-        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, arg.view(B * S, -1), nsample, need_pts)
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, arg.view(B * S, -1), nsample, need_pts, convs, bns)
         dpts = None
         if need_pts:
             dpts = torch.zeros(B, N, D, device=dout.device, dtype=torch.float32)
@@ -254,15 +308,15 @@ class _GroupAllFn(torch.autograd.Function):
         arg = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.int32)
         call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B, N,
              last.N, ptr(out), ptr(arg), stream())
-        ctx.state = (layers, x0, K0, arg, (B, N), convs)
+        ctx.state = (layers, x0, K0, arg, (B, N), convs, bns)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layers, x0, K0, arg, (B, N), convs = ctx.state
+        layers, x0, K0, arg, (B, N), convs, bns = ctx.state
         ctx.state = None
         need = ctx.needs_input_grad[2]
-        grads, dx0 = mlp_backward(layers, x0, K0, B * N, dout.contiguous().view(B, -1), arg.view(B, -1), N, need)
+        grads, dx0 = mlp_backward(layers, x0, K0, B * N, dout.contiguous().view(B, -1), arg.view(B, -1), N, need, convs, bns)
         dx = dx0[:, :K0].float().view(B, N, K0) if need else None
         return (None, None, dx) + _param_grads(grads, convs, ctx.needs_input_grad[3:])
 
@@ -271,14 +325,15 @@ class _FeaturePropagationFn(torch.autograd.Function):
     """3-NN inverse-distance interpolation + concat + MLP (pointnet2_utils.py:285-314)."""
 
     @staticmethod
-    def forward(ctx, convs, bns, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+    def forward(ctx, nn3, convs, bns, xyz1_r, xyz2_r, p1_r, p2_r, *params):
         B, N, _ = xyz1_r.shape
         S = xyz2_r.shape[1]
         dtype = ops.rows_dtype()
         p2 = ops.as_rows(p2_r)
         D2 = p2.shape[2]
         D1 = 0 if p1_r is None else p1_r.shape[2]
-        idx3, w3 = ops.three_nn(xyz1_r, xyz2_r)   # S == 1 degenerates to weight 1 on the only point (:293-294)
+        # S == 1 degenerates to weight 1 on the only point (:293-294)
+        idx3, w3 = nn3 if nn3 is not None else ops.three_nn(xyz1_r, xyz2_r)
         K0 = D1 + D2
         M = B * N
         x0 = torch.empty(M, _row_ld(K0, dtype), device=p2.device, dtype=dtype)
@@ -290,17 +345,17 @@ class _FeaturePropagationFn(torch.autograd.Function):
         out = torch.empty(B, N, last.N, device=p2.device, dtype=torch.float32)
         call("pn2_bn_relu", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), M, last.N,
              ptr(out), stream())
-        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs)
+        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs = ctx.state
+        layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns = ctx.state
         ctx.state = None
-        need1 = ctx.needs_input_grad[4] and D1 > 0
-        need2 = ctx.needs_input_grad[5]
+        need1 = ctx.needs_input_grad[5] and D1 > 0
+        need2 = ctx.needs_input_grad[6]
         dout = dout.contiguous().view(M, -1)
-        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, None, 1, need1 or need2)
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, None, 1, need1 or need2, convs, bns)
         dp1 = dp2 = None
         if need1:
             dp1 = torch.empty(B, N, D1, device=dout.device, dtype=torch.float32)
@@ -309,7 +364,7 @@ class _FeaturePropagationFn(torch.autograd.Function):
             dp2 = torch.zeros(B, S, D2, device=dout.device, dtype=torch.float32)
             call("pn2_interp_bwd", ptr(dx0), dx0.shape[1], dt(dx0), ptr(idx3), ptr(w3), B, N, S, D1, D2, ptr(dp2),
                  stream())
-        return (None, None, None, None, dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[6:])
+        return (None, None, None, None, None, dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[7:])
 
 
 def _check_module_inputs(xyz, points):
@@ -353,7 +408,18 @@ class PointNetSetAbstraction(nn.Module):
             st = self.start_staging = ops.StartIndexStaging(B, N, device)
         return st
 
-    def forward(self, xyz, points):
+    def geometry(self, xyz):
+        """The index half of sample_and_group (:124-126): FPS centroids and ball-query indices.  They depend on
+        xyz only, so a caller may compute them ahead of (and concurrently with) the feature path and hand
+        them to forward().  Returns (new_xyz [B,S,3], idx [B,S,nsample] int64)."""
+        _check_module_inputs(xyz, None)
+        xyz_r = xyz.permute(0, 2, 1)
+        _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True,
+                                               staging=self._staging(xyz.shape[0], xyz.shape[2], xyz.device))
+        idx = ops.query_ball_point(self.radius, self.nsample, xyz_r, new_xyz)
+        return new_xyz, idx
+
+    def forward(self, xyz, points, geometry=None):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
         _check_module_inputs(xyz, points)
         xyz_r = xyz.permute(0, 2, 1)
@@ -364,9 +430,13 @@ class PointNetSetAbstraction(nn.Module):
             x0 = xyz_r if pts_r is None else torch.cat([xyz_r, pts_r], dim=-1)
             out = _GroupAllFn.apply(self.mlp_convs, self.mlp_bns, x0, *params)
         else:
-            _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True,
-                                                   staging=self._staging(xyz.shape[0], xyz.shape[2], xyz.device))
-            out = _SetAbstractionFn.apply(self, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
+            if geometry is None:
+                _, new_xyz = ops.farthest_point_sample(xyz_r, self.npoint, return_xyz=True,
+                                                       staging=self._staging(xyz.shape[0], xyz.shape[2], xyz.device))
+                idx = None
+            else:
+                new_xyz, idx = geometry
+            out = _SetAbstractionFn.apply(idx, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
                                           xyz_r, pts_r, *params)
         return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
 
@@ -418,7 +488,7 @@ class PointNetSetAbstractionMsg(nn.Module):
                 params = [first.weight, first.bias, bns[0].weight, bns[0].bias] + _flat_params(convs, bns)[4:]
             else:
                 conv_list, params = list(convs), _flat_params(convs, bns)
-            outs.append(_SetAbstractionFn.apply(self, conv_list, list(bns), radius, k, new_xyz, xyz_r, pts_r, *params))
+            outs.append(_SetAbstractionFn.apply(None, conv_list, list(bns), radius, k, new_xyz, xyz_r, pts_r, *params))
         return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=2).permute(0, 2, 1)
 
 
@@ -429,14 +499,22 @@ class PointNetFeaturePropagation(nn.Module):
         super().__init__()
         self.mlp_convs, self.mlp_bns = _build_mlp(nn.Conv1d, nn.BatchNorm1d, in_channel, mlp)
 
-    def forward(self, xyz1, xyz2, points1, points2):
+    @staticmethod
+    def neighbours(xyz1, xyz2):
+        """The index half of forward (:296-302): the three nearest xyz2 points of every xyz1 point and their
+        normalised inverse-distance weights; depends on coordinates only (see PointNetSetAbstraction.geometry)."""
+        _check_module_inputs(xyz1, None)
+        _check_module_inputs(xyz2, None)
+        return ops.three_nn(xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1))
+
+    def forward(self, xyz1, xyz2, points1, points2, neighbours=None):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
         _check_module_inputs(xyz1, points1)
         _check_module_inputs(xyz2, points2)
         if points2 is None:
             raise ValueError("points2 is required")
         out = _FeaturePropagationFn.apply(
-            self.mlp_convs, self.mlp_bns, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
+            neighbours, self.mlp_convs, self.mlp_bns, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
             None if points1 is None else points1.permute(0, 2, 1), points2.permute(0, 2, 1),
             *_flat_params(self.mlp_convs, self.mlp_bns))
         return out.permute(0, 2, 1)

@@ -7,6 +7,7 @@ The reference file itself also runs unchanged on top of ``models/pointnet2_utils
 copy exists because the reference tree is not present on the GPU box.  The head and the loss
 are ordinary PyTorch (they are outside the hot path).
 """
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -17,6 +18,16 @@ SA_LEVELS = ((1024, 0.1, 32, (32, 32, 64)), (256, 0.2, 32, (64, 64, 128)),
              (64, 0.4, 32, (128, 128, 256)), (16, 0.8, 32, (256, 256, 512)))
 # (in_channel, mlp) for fp4, fp3, fp2, fp1 -- pointnet2_sem_seg.py:13-16
 FP_LEVELS = ((768, (256, 256)), (384, (256, 256)), (320, (256, 128)), (128, (128, 128, 128)))
+
+
+_GEO_STREAMS = {}
+
+
+def _geometry_stream(dev):
+    s = _GEO_STREAMS.get(dev.index)
+    if s is None:
+        s = _GEO_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class get_model(nn.Module):
@@ -34,18 +45,55 @@ class get_model(nn.Module):
         self.drop1 = nn.Dropout(0.5)
         self.conv2 = nn.Conv1d(128, num_classes, 1)
 
+    overlap_geometry = True     # run the coordinate-only index pipeline on a side stream, ahead of the MLPs
+
+    def _geometry_ahead(self, xyz0):
+        """FPS -> ball query for the four levels, then the four 3-NN searches, on a side stream: all of it depends
+        on coordinates only, so it runs concurrently with the feature MLPs, which wait per level."""
+        dev = xyz0.device
+        main = torch.cuda.current_stream(dev)
+        side = _geometry_stream(dev)
+        side.wait_stream(main)           # inputs ready; also orders reuse of last step's index buffers
+        geo, nn3, events = [], [], []
+        with torch.cuda.stream(side):
+            coords = [xyz0]
+            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+                g = sa.geometry(coords[-1])
+                geo.append(g)
+                coords.append(g[0].permute(0, 2, 1))
+                events.append(side.record_event())
+            for fine, coarse in ((3, 4), (2, 3), (1, 2), (0, 1)):
+                nn3.append(PointNetFeaturePropagation.neighbours(coords[fine], coords[coarse]))
+                events.append(side.record_event())
+        return geo, nn3, events, main
+
     def forward(self, xyz):
         feats = [xyz]
         coords = [xyz[:, :3, :]]
-        for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
-            c, f = sa(coords[-1], feats[-1])
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        fps = (self.fp4, self.fp3, self.fp2, self.fp1)
+        ahead = xyz.is_cuda and self.overlap_geometry and all(
+            type(m) is PointNetSetAbstraction and not m.group_all for m in sas) and all(
+            type(m) is PointNetFeaturePropagation for m in fps)
+        if ahead:
+            geo, nn3, events, main = self._geometry_ahead(coords[0])
+        for i, sa in enumerate(sas):
+            if ahead:
+                main.wait_event(events[i])
+                c, f = sa(coords[-1], feats[-1], geometry=geo[i])
+            else:
+                c, f = sa(coords[-1], feats[-1])
             coords.append(c)
             feats.append(f)
         l4_points = feats[4]
-        up = self.fp4(coords[3], coords[4], feats[3], feats[4])
-        up = self.fp3(coords[2], coords[3], feats[2], up)
-        up = self.fp2(coords[1], coords[2], feats[1], up)
-        up = self.fp1(coords[0], coords[1], None, up)
+        up = feats[4]
+        for i, (fp, fine) in enumerate(zip(fps, (3, 2, 1, 0))):
+            skip = feats[fine] if fine > 0 else None
+            if ahead:
+                main.wait_event(events[4 + i])
+                up = fp(coords[fine], coords[fine + 1], skip, up, neighbours=nn3[i])
+            else:
+                up = fp(coords[fine], coords[fine + 1], skip, up)
         x = self.drop1(F.relu(self.bn1(self.conv1(up))))
         x = F.log_softmax(self.conv2(x), dim=1)
         return x.permute(0, 2, 1), l4_points

@@ -22,20 +22,38 @@ def shard_range(n_items, rank, world):
 
 
 class FlatGradients:
-    """All parameter gradients as views into one flat buffer, so data-parallel training needs a
-    single all-reduce per step (no bucketing: the buffer is latency-, not bandwidth-bound)."""
+    """One flat fp32 buffer holding every parameter gradient, so data-parallel training needs a single
+    all-reduce per step (no bucketing: the buffer is latency-, not bandwidth-bound).  The buffer is also the
+    gradient SINK of the hot path (modules.set_grad_sink): backward kernels write weight / BatchNorm gradients
+    straight into it and autograd adopts views of it as `.grad` -- no accumulate or fill kernels per parameter.
+    Gradients produced elsewhere (the PyTorch head) are copied in by adopt()."""
 
     def __init__(self, params):
+        from . import modules
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
-        off = 0
+        self.views, off = [], 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        if self.flat.is_cuda:
+            modules.set_grad_sink({id(p): v for p, v in zip(self.params, self.views)})
 
     def zero(self):
+        for p in self.params:
+            p.grad = None              # autograd adopts the incoming gradient tensor instead of adding into an old one
         self.flat.zero_()
+
+    def adopt(self):
+        """After backward: make every .grad a view of the flat buffer (copy the few that were produced elsewhere)."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                p.grad = v             # no gradient this step: the zeroed slice
+            elif g.data_ptr() != v.data_ptr() or g.stride() != v.stride():
+                v.copy_(g)
+                p.grad = v
 
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -63,6 +81,7 @@ class SemSegTrainer:
         pred, feat = self.model(points.transpose(2, 1))
         loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
         loss.backward()
+        self.grads.adopt()
         self.grads.all_reduce_mean()
         self.optimizer.step()
         return loss.detach()
