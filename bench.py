@@ -80,6 +80,81 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _esz(dtype_code):
+    return 2 if dtype_code == 1 else 4
+
+
+# Algorithmic work of one call of a C-ABI entry point, from its arguments (include/pn2b200.h): (HBM bytes, flop or
+# pair-evaluations x 6, bound).  "Algorithmic" = every operand read once and every result written once, in the
+# storage types the call was given -- the figure DESIGN.md section 4 states per kernel.
+KERNEL_MODEL = {
+    "pn2_farthest_point_sample": lambda a: (a[4] * (12 * a[5] + 20 * a[6]), 9.0 * a[4] * a[5] * a[6], "latency"),
+    "pn2_query_ball_point": lambda a: (a[8] * (12 * a[9] + 12 * a[10] + 8 * a[10] * a[12]), 6.0 * a[8] * a[9] * a[10], "alu"),
+    "pn2_three_nn": lambda a: (a[8] * (12 * a[9] + 12 * a[10] + 36 * a[9]), 6.0 * a[8] * a[9] * a[10], "alu"),
+    "pn2_group_points": lambda a: (a[10] * a[12] * a[13] * (8 + (3 + a[14]) * 4 + a[16] * _esz(a[17])), 0.0, "hbm"),
+    "pn2_group_points_bwd": lambda a: (a[4] * a[6] * a[7] * (8 + a[1] * _esz(a[2]) + a[8] * 4), 0.0, "hbm"),
+    "pn2_linear_fwd": lambda a: (a[7] * (a[1] * _esz(a[2]) + a[11] * _esz(a[12])), 2.0 * a[7] * a[8] * a[9], "hbm"),
+    "pn2_linear_bwd_data": lambda a: (a[4] * (a[1] * _esz(a[2]) + a[8] * _esz(a[9])), 2.0 * a[4] * a[5] * a[6], "hbm"),
+    "pn2_linear_bwd_weight": lambda a: (a[8] * (a[1] * _esz(a[2]) + a[4] * _esz(a[5])), 2.0 * a[8] * a[9] * a[10], "hbm"),
+    "pn2_bn_relu_max": lambda a: (a[5] * a[6] * a[7] * _esz(a[2]) + a[5] * a[7] * 8, 0.0, "hbm"),
+    "pn2_bn_relu": lambda a: (a[5] * a[6] * (_esz(a[2]) + 4), 0.0, "hbm"),
+    "pn2_bn_relu_bwd_reduce": lambda a: (a[10] * a[11] * (_esz(a[2]) + _esz(a[5])), 0.0, "hbm"),
+    "pn2_pool_bn_relu_bwd_reduce": lambda a: (a[9] * a[11] * (8 + _esz(a[4])), 0.0, "hbm"),
+    "pn2_bn_relu_bwd_dz": lambda a: (a[12] * a[13] * (_esz(a[2]) + _esz(a[5]) + _esz(a[16])), 0.0, "hbm"),
+    "pn2_pool_bn_relu_bwd_dz": lambda a: (a[11] * a[13] * 8 + a[11] * a[12] * a[13] * (_esz(a[4]) + _esz(a[16])), 0.0, "hbm"),
+    "pn2_interp_concat": lambda a: (a[10] * a[11] * (a[13] * 4 + 3 * a[14] * 4 + 36 + a[16] * _esz(a[17])), 6.0 * a[10] * a[11] * a[14], "hbm"),
+    "pn2_interp_bwd": lambda a: (a[5] * a[6] * (a[1] * _esz(a[2]) + 36 + 3 * a[9] * 4), 6.0 * a[5] * a[6] * a[9], "hbm"),
+    "pn2_to_rows": lambda a: (a[4] * a[5] * a[6] * 8, 0.0, "hbm"),
+    "pn2_rows_to_f32": lambda a: (a[3] * a[5] * (_esz(a[2]) + 4), 0.0, "hbm"),
+}
+
+
+def kernel_table(calls, steps, step_ms, hbm_gbs):
+    """Aggregate the event-timed entry-point calls of `steps` eager training steps (kernels serialised: no stream
+    overlap) into one row per entry point: launches and ms per step, algorithmic GB/s and its fraction of the HBM peak."""
+    agg = {}
+    for name, a, ms in calls:
+        row = agg.setdefault(name, {"entry": name, "calls": 0, "ms": 0.0, "bytes": 0.0, "flop": 0.0, "bound": "-"})
+        row["calls"] += 1
+        row["ms"] += ms
+        model = KERNEL_MODEL.get(name)
+        if model:
+            b, f, bound = model(a)
+            row["bytes"] += b
+            row["flop"] += f
+            row["bound"] = bound
+    total = sum(r["ms"] for r in agg.values()) or 1.0
+    out = []
+    for r in sorted(agg.values(), key=lambda r: -r["ms"]):
+        gbs = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0.0
+        out.append({"entry": r["entry"], "calls_per_step": r["calls"] / steps, "ms_per_step": round(r["ms"] / steps, 4),
+                    "share_of_kernel_time": round(r["ms"] / total, 4), "bound": r["bound"],
+                    "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm_gbs, 4),
+                    "alg_TFLOPs": round(r["flop"] / (r["ms"] * 1e-3) / 1e12, 3) if r["ms"] > 0 else 0.0})
+    return out
+
+
+def forward_points_per_s(model, resident, flush, steps, warmup):
+    """ms per eval-mode forward of one resident batch (median-free mean over `steps`, CUDA events per iteration)."""
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        for i in range(warmup):
+            model(resident[i % len(resident)][0].transpose(2, 1))
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            model(resident[i % len(resident)][0].transpose(2, 1))
+            ends[i].record()
+        torch.cuda.synchronize()
+    model.train(was_training)
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) / steps
+    return torch.tensor([ms], device=resident[0][0].device, dtype=torch.float64)
+
+
 def synthetic_batches(n, seed):
     """n pinned host batches [B, NPOINT, C] float32 + labels [B*NPOINT] int64 (S2 "facade block")."""
     import _inputs as I
@@ -125,7 +200,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_clouds = 16
+    sample_clouds = args.ref_sample_clouds
     rate, sec, done = cpu_train_step_rate(sample_clouds, args.steps, min(args.warmup, 1), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
@@ -149,9 +224,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-clouds", type=int, default=16,
+                    help="clouds per step of the CPU reference arm (a bounded sample of the 32-cloud batch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
-    ap.add_argument("--timed-entry", default="pn2_farthest_point_sample",
-                    help="C-ABI entry point whose launches are event-timed for the roofline object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -188,18 +263,24 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
-    # ---- the dominant kernel, event-timed live on its launching stream (eager pass; a graph replay
-    #      cannot carry events around one node) ---------------------------------------------------
+    # ---- every kernel of the path, event-timed live on its launching stream in an eager pass with the stream
+    #      overlap switched off (a graph replay cannot carry events around one node; overlapping kernels would
+    #      time each other) -------------------------------------------------------------------------------
+    modules_mod = importlib.import_module("khairil_tum-facade_semantic_segmentation_b200.modules")
     for i in range(2):
         trainer.step_device(*resident[i % n_batches])
-    lib_mod.time_entry_point(args.timed_entry)
+    overlap_saved = (modules_mod.OVERLAP_WGRAD, trainer.model.overlap_geometry)
+    modules_mod.OVERLAP_WGRAD, trainer.model.overlap_geometry = False, False
+    trainer.step_device(*resident[0])
+    lib_mod.time_entry_point("*")
     eager0 = pn2.launch_count()
-    for i in range(3):
-        trainer.step_device(*resident[i % n_batches])
-    launches_per_step = (pn2.launch_count() - eager0) // 3
-    kernel_ms = lib_mod.timed_durations_ms()
     kernel_steps = 3
+    for i in range(kernel_steps):
+        trainer.step_device(*resident[i % n_batches])
+    launches_per_step = (pn2.launch_count() - eager0) // kernel_steps
+    timed_calls = lib_mod.timed_calls()
     lib_mod.time_entry_point(None)
+    modules_mod.OVERLAP_WGRAD, trainer.model.overlap_geometry = overlap_saved
 
     graphed = False
     if not args.no_graph:
@@ -240,10 +321,15 @@ def main():
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # ---- inference forward (BASELINE.json's "fwd" half of the metric): eval-mode get_model forward under no_grad on
+    #      the same 32 x 4096 x 9 batch, inputs resident, L2 flushed between iterations ---------------------------
+    fwd_ms = forward_points_per_s(trainer.model, resident, flush, args.steps, args.warmup)
+    barrier()
     clocks = sampler.stop() if sampler else None
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fwd_ms, op=dist.ReduceOp.MAX)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -255,24 +341,22 @@ def main():
     e2e_value = points_per_step / (e2e_ms.item() / args.steps * 1e-3)
     pk, pk_kind = peaks()
 
-    # ---- roofline of the dominant kernel (K1 FPS, fp32-ALU bound, 9 flop / point-iteration)
+    # ---- roofline: per entry point, and the dominant one as the contract's "roofline" object
+    kernels = kernel_table(timed_calls, kernel_steps, ms_per_step, pk["hbm_gbs"])
     roof = None
-    if kernel_ms:
-        per_step = len(kernel_ms) // kernel_steps
-        levels = [(4096, 1024), (1024, 256), (256, 64), (64, 16)][:per_step]
-        by_level = [kernel_ms[i::per_step] for i in range(per_step)] if per_step else []
-        if args.timed_entry == "pn2_farthest_point_sample" and by_level:
-            n_src, n_pick = levels[0]
-            avg_ms = sum(by_level[0]) / len(by_level[0])
-            alg_bytes = B_PER_GPU * (12 * n_src + 8 * n_pick + 12 * n_pick)
-            alg_flop = 9.0 * B_PER_GPU * n_src * n_pick
-            roof = {"kernel": "fps_kernel (sa1: %d -> %d, %d clouds)" % (n_src, n_pick, B_PER_GPU), "bound": "hbm",
-                    "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
-                    "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": avg_ms,
-                    "share_of_step": sum(sum(l) for l in by_level) / len(by_level[0]) / ms_per_step,
-                    "note": "latency chain: %d dependent iterations on %d of 148 SMs; fp32-ALU view: %.3f TFLOP/s non-FMA"
-                            % (n_pick, B_PER_GPU, alg_flop / (avg_ms * 1e-3) / 1e12)}
+    hbm_rows = [k for k in kernels if k["bound"] == "hbm"]
+    if hbm_rows:
+        top = hbm_rows[0]
+        top_calls = [(a, ms) for n, a, ms in timed_calls if n == top["entry"]]
+        alg = sum(KERNEL_MODEL[top["entry"]](a)[0] for a, _ in top_calls)
+        dur = sum(ms for _, ms in top_calls) * 1e-3
+        roof = {"kernel": top["entry"] + " (all %d launches of a step; the largest share of kernel time among the streaming kernels)" % round(top["calls_per_step"]),
+                "bound": "hbm", "achieved": alg / dur / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": alg / dur / 1e9 / pk["hbm_gbs"], "traffic": None,
+                "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": dur * 1e3 / len(top_calls),
+                "bytes_per_launch_avg": alg / len(top_calls), "share_of_step": top["ms_per_step"] / ms_per_step,
+                "note": "achieved = sum of algorithmic bytes / sum of CUDA-event durations over the launches of %d eager steps; "
+                        "the FPS dependency chain (pn2_farthest_point_sample) is latency-bound and listed under kernels" % kernel_steps}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -293,7 +377,9 @@ def main():
                    "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms.item() / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "forward": {"value": points_per_step / (fwd_ms.item() * 1e-3), "unit": UNIT, "ms_per_batch": fwd_ms.item(),
+                    "what": "eval-mode forward (no_grad), same batch shape, device-resident inputs"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -76,13 +76,13 @@ def load():
     return _lib
 
 
-_TIMED = {"name": None, "events": []}
+_TIMED = {"name": None, "events": [], "calls": []}
 
 
 def time_entry_point(name):
-    """Bracket every later call of entry point `name` with CUDA events on the launching (current)
-    stream; bench.py uses this to measure the dominant kernel live.  None switches it off."""
-    _TIMED["name"], _TIMED["events"] = name, []
+    """Bracket every later call of entry point `name` ("*" = every entry point) with CUDA events on the
+    stream the call is launched on; bench.py uses this to measure the kernels live.  None switches it off."""
+    _TIMED["name"], _TIMED["events"], _TIMED["calls"] = name, [], []
 
 
 def timed_durations_ms():
@@ -91,15 +91,23 @@ def timed_durations_ms():
     return [s.elapsed_time(e) for s, e in _TIMED["events"]]
 
 
+def timed_calls():
+    """[(entry point, argument tuple, ms)] recorded since time_entry_point(); synchronises."""
+    return [(n, a, ms) for (n, a), ms in zip(_TIMED["calls"], timed_durations_ms())]
+
+
 def call(name, *args):
-    """Invoke an int-returning entry point; raise Pn2Error with the library's message on failure."""
+    """Invoke an int-returning entry point; raise Pn2Error with the library's message on failure.
+    The last argument of every such entry point is the stream."""
     lib = load()
-    if name == _TIMED["name"]:
+    if _TIMED["name"] is not None and (_TIMED["name"] == name or _TIMED["name"] == "*"):
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.current_stream()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        s.record(st)
         rc = getattr(lib, name)(*args)
-        e.record()
+        e.record(st)
         _TIMED["events"].append((s, e))
+        _TIMED["calls"].append((name, args))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

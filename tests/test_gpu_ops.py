@@ -67,7 +67,7 @@ def test_network_levels_match_reference_fixture(pn2, golden, tag, B):
         assert np.array_equal(w.cpu().numpy(), g["%s_l%d_nn_w" % (tag, lvl)]), lvl
 
 
-@pytest.mark.parametrize("B,N,npoint", [(1, 64, 16), (16, 64, 64), (3, 100, 37), (16, 256, 64), (2, 1000, 333),
+@pytest.mark.parametrize("B,N,npoint", [(1, 1, 1), (2, 7, 7), (2, 7, 12), (3, 33, 20), (1, 64, 16), (16, 64, 64), (3, 100, 37), (16, 256, 64), (2, 1000, 333),
                                          (16, 1024, 256), (16, 4096, 1024), (2, 5000, 500), (2, 8192, 256)])
 @pytest.mark.parametrize("kind", ["cube", "facade"])
 def test_fps_matches_c_oracle(pn2, B, N, npoint, kind):
