@@ -196,6 +196,27 @@ def cpu_train_step_rate(batch_clouds, steps, warmup, threads, budget_s=150.0):
     return batch_clouds * NPOINT / med, med, len(times)
 
 
+def shutdown(world, trainer):
+    """Multi-rank exit.  NCCL requires every CUDA graph that captured a communicator's collectives to be destroyed
+    before the communicator is (otherwise the destroy blocks for ever): drop the captured training step first, give
+    the process-group teardown a bounded time, then leave without running further destructors."""
+    if world <= 1:
+        return
+    import gc
+    import torch.distributed as dist
+    sys.stdout.flush()
+    trainer._graph = None
+    trainer._g_loss = None
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -331,9 +352,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(fwd_ms, op=dist.ReduceOp.MAX)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return shutdown(world, trainer)
 
     points_per_step = world * B_PER_GPU * NPOINT
     ms_per_step = total_ms.item() / args.steps
@@ -382,8 +401,7 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(world, trainer)
 
 
 if __name__ == "__main__":

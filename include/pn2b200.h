@@ -155,6 +155,26 @@ int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, con
 int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
                 int64_t M, int C, float *out, void *stream);
 
+/* ---- a7 inference: one whole set-abstraction level in one kernel (:127-132, :196-200) ------------
+ * out[b,s,:] = max_k MLP([xyz[b,idx[b,s,k]] - new_xyz[b,s] | feats[b,idx[b,s,k]]]) with L layers of
+ * relu(bn_eval(conv1x1)) -- the ball-query gather, the L tensor-core GEMMs (bf16 operands, fp32
+ * accumulation in tensor memory), eval-mode BatchNorm, ReLU and the max over nsample fused; grouped
+ * rows and activations never reach HBM.  Requirements: nsample == 32, L <= 4, every hidden width a
+ * multiple of 16, every width <= 512 (PN2_ERR_UNSUPPORTED otherwise: use the per-layer entry points).
+ * The *_host arrays are HOST arrays of L entries: widths (out channels), and DEVICE pointers to
+ * W_l [N_l, K_l] fp32 (K_0 = 3 + D with the reference's [xyz | feats] column order, K_l = N_{l-1}),
+ * conv bias (entries may be NULL), and the eval-mode scale / shift of pn2_bn_eval_fold.
+ * xyz [B,N,3] strided; new_xyz [B,S,3] contiguous; feats [B,N,D] with row strides (fB,fN), element
+ * stride 1 (NULL when D = 0); idx [B,S,32] int64 (out-of-range entries gather zeros);
+ * out [B,S,N_{L-1}] fp32.  workspace: pn2_sa_fused_eval_workspace_bytes() bytes (0 = unsupported). */
+size_t pn2_sa_fused_eval_workspace_bytes(int D, int L, const int *widths_host);
+int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64_t sC, const float *new_xyz,
+                      const float *feats, int64_t fB, int64_t fN, const int64_t *idx, int B, int N,
+                      int S, int nsample, int D, int L, const int *widths_host,
+                      const float *const *W_host, const float *const *bias_host,
+                      const float *const *scale_host, const float *const *shift_host, float *out,
+                      void *workspace, void *stream);
+
 /* ---- backward of BN(train)+ReLU -----------------------------------------------
  * With g = dA * [bn(z) > 0]:  dbeta = sum g, dgamma = sum g*zhat,
  *   dz = gamma*invstd * (g - dbeta/M - zhat*dgamma/M)          (train)

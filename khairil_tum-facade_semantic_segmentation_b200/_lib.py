@@ -44,6 +44,8 @@ _SIGNATURES = {
     "pn2_bn_eval_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "pn2_bn_relu_max": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
     "pn2_bn_relu": (_i, [_p, _i, _i, _p, _p, _l, _i, _p, _p]),
+    "pn2_sa_fused_eval_workspace_bytes": (_z, [_i, _i, _p]),
+    "pn2_sa_fused_eval": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_bn_relu_bwd_reduce": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _l, _i, _p, _p]),
     "pn2_pool_bn_relu_bwd_reduce": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
     "pn2_bn_bwd_finalize": (_i, [_p, _i, _p, _p, _p]),

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libpn2b200.so
-SRCS="api.cu fps.cu ballquery.cu group.cu threenn.cu linear_simt.cu bn.cu $(ls linear_tc.cu 2>/dev/null || true)"
+SRCS="api.cu fps.cu ballquery.cu group.cu threenn.cu linear_simt.cu bn.cu linear_tc.cu sa_fused.cu"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include ${PN2_NVCC_EXTRA}"
 mkdir -p build
@@ -12,7 +12,7 @@ pids=""
 for s in $SRCS; do
   o=build/${s%.cu}.o
   objs="$objs $o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pn2b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tc_common.cuh -nt "$o" ] || [ ../../include/pn2b200.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$s" -o "$o" &
     pids="$pids $!"
   fi

@@ -33,8 +33,9 @@ constexpr int kTcAStage = kTcBM * kTcBK * 2;    // 16 KB
 
 // ---- weight packing: fp32 W (any strides) -> bf16 chunk images in UMMA K-major SW128 layout ----
 // image kc: n_pad rows x 128 bytes; element (n, kc*64 + c*8 + e) at sw128_offset(n, c) + 2e.
+// k_rot: image column k holds W column (k + k_rot) % K (sa_fused.cu gathers [feats | xyz] while the conv sees [xyz | feats]).
 __global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, int64_t w_sk, int N, int K, int n_pad,
-                                   int KC, uint8_t *__restrict__ img) {
+                                   int KC, int k_rot, uint8_t *__restrict__ img) {
     const int total = KC * n_pad * 8;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         const int c = q & 7, n = (q >> 3) % n_pad, kc = (q >> 3) / n_pad;
@@ -42,7 +43,7 @@ __global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, in
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = kc * kTcBK + c * 8 + e;
-            v[e] = (n < N && k < K) ? W[(int64_t)n * w_sn + (int64_t)k * w_sk] : 0.0f;
+            v[e] = (n < N && k < K) ? W[(int64_t)n * w_sn + (int64_t)((k + k_rot) % K) * w_sk] : 0.0f;
         }
         uint4 o;
         o.x = pack_bf16x2(v[0], v[1]);
@@ -305,7 +306,7 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         if (n0 + n_store > ldz) n_store = ldz - n0;      // ldz is a multiple of 8 on this path
         const size_t img_bytes = (size_t)KC * n_pad * 128;
         const int total = KC * n_pad * 8;
-        pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, img);
+        pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, 0, img);
         count_launch();
         TcLinearArgs a;
         if (!make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, kTcBM) ||

@@ -11,6 +11,8 @@ read from them at call time, running statistics are written back).
 One autograd.Function per module: forward = FPS -> ball query -> gather -> MLP
 (-> max over nsample); backward is hand written on the same kernels.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -237,6 +239,62 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
     return grads, dx0
 
 
+FUSED_EVAL = True         # inference: one fused kernel per set-abstraction level (csrc/sa_fused.cu) when it applies
+
+
+def _fused_eval_applies(convs, bns, nsample, tensors, D=0):
+    if not FUSED_EVAL or ops.rows_dtype() != torch.bfloat16 or nsample != 32 or not 1 <= len(convs) <= 4:
+        return False
+    if any(_bn_trains(bn) for bn in bns):
+        return False
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        return False                      # somebody wants gradients: the per-layer path keeps what backward needs
+    widths = [c.out_channels for c in convs]
+    # the library's own plan decides (widths, shared / tensor memory): 0 bytes = not supported -> per-layer path
+    return load().pn2_sa_fused_eval_workspace_bytes(D, len(widths), (ctypes.c_int * len(widths))(*widths)) > 0
+
+
+def sa_fused_eval(idx, convs, bns, new_xyz, xyz_r, pts_r):
+    """Inference forward of one set-abstraction level in one kernel: gather -> L x relu(bn(conv)) -> max over nsample."""
+    lib = load()
+    dev = xyz_r.device
+    B, N, _ = xyz_r.shape
+    S, nsample = idx.shape[1], idx.shape[2]
+    feats = None if pts_r is None else ops.as_rows(pts_r)
+    D = 0 if feats is None else feats.shape[2]
+    L = len(convs)
+    widths = [c.out_channels for c in convs]
+    c_widths = (ctypes.c_int * L)(*widths)
+    ws_bytes = lib.pn2_sa_fused_eval_workspace_bytes(D, L, c_widths)
+    if ws_bytes == 0:
+        raise ValueError("sa_fused_eval: unsupported level D=%d widths=%s" % (D, widths))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    fold = torch.empty(L, 2, max(widths), device=dev, dtype=torch.float32)
+    Ws, keep = [], []
+    K = 3 + D
+    for l, (conv, bn) in enumerate(zip(convs, bns)):
+        W = conv.weight.detach().reshape(widths[l], -1)
+        W = W if W.is_contiguous() else W.contiguous()
+        if W.shape[1] != K or W.dtype != torch.float32:
+            raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
+        gamma = None if bn.weight is None else bn.weight.detach()
+        beta = None if bn.bias is None else bn.bias.detach()
+        call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
+             widths[l], ptr(fold[l, 0]), ptr(fold[l, 1]), stream())
+        Ws.append(W)
+        keep.append(None if conv.bias is None else conv.bias.detach())
+        K = widths[l]
+    arr = ctypes.c_void_p * L
+    out = torch.empty(B, S, widths[-1], device=dev, dtype=torch.float32)
+    sB, sN, sC = xyz_r.stride()
+    fB, fN = (0, 0) if feats is None else feats.stride()[:2]
+    call("pn2_sa_fused_eval", ptr(xyz_r), sB, sN, sC, ptr(new_xyz), ptr(feats), fB, fN, ptr(idx), B, N, S, nsample, D, L,
+         c_widths, arr(*[w.data_ptr() for w in Ws]), arr(*[None if b is None else b.data_ptr() for b in keep]),
+         arr(*[fold[l, 0].data_ptr() for l in range(L)]), arr(*[fold[l, 1].data_ptr() for l in range(L)]),
+         ptr(out), ptr(ws), stream())
+    return out
+
+
 def _flat_params(convs, bns):
     out = []
     for conv, bn in zip(convs, bns):
@@ -436,8 +494,14 @@ class PointNetSetAbstraction(nn.Module):
                 idx = None
             else:
                 new_xyz, idx = geometry
-            out = _SetAbstractionFn.apply(idx, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
-                                          xyz_r, pts_r, *params)
+            if _fused_eval_applies(self.mlp_convs, self.mlp_bns, self.nsample, [points] + params,
+                                   0 if points is None else points.shape[1]):
+                if idx is None:
+                    idx = ops.query_ball_point(self.radius, self.nsample, xyz_r, new_xyz)
+                out = sa_fused_eval(idx, self.mlp_convs, self.mlp_bns, new_xyz, xyz_r, pts_r)
+            else:
+                out = _SetAbstractionFn.apply(idx, self.mlp_convs, self.mlp_bns, self.radius, self.nsample, new_xyz,
+                                              xyz_r, pts_r, *params)
         return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
 
 
