@@ -11,11 +11,11 @@ from .modules import PointNetFeaturePropagation, PointNetSetAbstraction, PointNe
 from .ops import (farthest_point_sample, get_precision, index_points, query_ball_point, sample_and_group,
                   sample_and_group_all, set_precision, square_distance, three_nn)
 from .sem_seg import get_loss, get_model
-from .trainer import FlatGradients, SemSegTrainer, predict_blocks, shard_range
+from .trainer import FlatGradients, SemSegPredictor, SemSegTrainer, predict_blocks, shard_range
 
 __all__ = [
     "PointNetSetAbstraction", "PointNetSetAbstractionMsg", "PointNetFeaturePropagation",
     "square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
     "sample_and_group_all", "three_nn", "set_precision", "get_precision", "get_model", "get_loss",
-    "SemSegTrainer", "FlatGradients", "predict_blocks", "shard_range", "load", "launch_count", "Pn2Error", "SO_PATH", "EXPORTED_SYMBOLS",
+    "SemSegTrainer", "SemSegPredictor", "FlatGradients", "predict_blocks", "shard_range", "load", "launch_count", "Pn2Error", "SO_PATH", "EXPORTED_SYMBOLS",
 ]

@@ -82,7 +82,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // Shared-memory map (1024-byte aligned): [activation tile: a_slabs x 16 KB] [weight ring: stages x slot_bytes]
-// [scale | shift of every layer: 2 x ss_floats fp32] [gather indices: 128 int32]
+// [scale | shift of every layer: 2 x ss_floats fp32] [gather row offsets: 128 int64]
+template <int kGU>
 __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_constant__ SaFusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kSaMaxChunks], bar_empty[kSaMaxChunks], bar_acc;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_
     uint8_t *const ring = act + (size_t)a.a_slabs * kSaSlab;
     float *const s_scale = reinterpret_cast<float *>(ring + (size_t)a.stages * a.slot_bytes);
     float *const s_shift = s_scale + a.ss_floats;
-    int *const s_idx = reinterpret_cast<int *>(s_shift + a.ss_floats);
+    int64_t *const s_off = reinterpret_cast<int64_t *>(s_shift + a.ss_floats);     // feature-row offsets of the tile's 128 rows
 
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
     if (tid == 0) {
@@ -142,51 +143,99 @@ __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_
     } else {
         const int K0 = a.D + 3;
         const int cpr = ((K0 + 15) >> 4) << 1;          // 16-byte chunks per gathered row, zero-padded to 16 columns
+        const int cpf = a.D >> 3;                       // chunks that hold features only; the rest is the row's tail
+        const int cpf_shift = (cpf > 0 && (cpf & (cpf - 1)) == 0) ? 31 - __clz(cpf) : -1;
         const bool vec_ok = (a.D & 3) == 0 && (a.fN & 3) == 0 && (a.fB & 3) == 0 &&
                             (reinterpret_cast<uintptr_t>(a.feats) & 15) == 0;
         uint32_t n = 0, acc_par = 0;
+        // the source index of this thread's row, fetched one tile ahead (takes one global-memory latency off every tile)
+        int64_t v_next = -1;
+        if (((int64_t)blockIdx.x * kSaTile + tid) >> 5 < a.G) v_next = __ldg(a.idx + (int64_t)blockIdx.x * kSaTile + tid);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            // ---- gather: this tile's 128 source indices, then its input rows into the activation tile ----
+            // ---- gather, phase 1: thread r resolves row r (source index, cloud, feature-row offset) once and
+            //      writes the row's TAIL chunks itself: [last features (D % 8) | xyz[idx] - new_xyz | zeros] ----
             {
                 const int64_t m = tile * kSaTile + tid;
-                int i = -1;
-                if ((m >> 5) < a.G) {
-                    const int64_t v = a.idx[m];
-                    i = (v >= 0 && v < a.N) ? (int)v : -1;
+                const int64_t g = m >> 5;
+                int64_t off = -1;
+                float tail[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) tail[e] = 0.0f;
+                const int64_t v = v_next;
+                {
+                    const int64_t m_next = m + (int64_t)gridDim.x * kSaTile;
+                    v_next = (m_next >> 5) < a.G ? __ldg(a.idx + m_next) : -1;
                 }
-                s_idx[tid] = i;
-            }
-            named_bar_sync(1, 128);
-            for (int q = tid; q < kSaTile * cpr; q += 128) {
-                const int r = q / cpr, c = q - r * cpr;
-                const int i = s_idx[r];
-                const int64_t g = (tile * kSaTile + r) >> 5;
-                float v[8];
+                if (g < a.G) {
+                    if (v >= 0 && v < a.N) {
+                        const int64_t b = g / a.S;
+                        off = b * a.fB + v * a.fN;
+                        const float *px = a.xyz + b * a.sB + v * a.sN;
+                        const float *pc = a.new_xyz + g * 3;
+                        const int nf = a.D & 7;        // features that share the tail's first chunk
+                        const float dx = __fsub_rn(__ldg(px), __ldg(pc));
+                        const float dy = __fsub_rn(__ldg(px + a.sC), __ldg(pc + 1));
+                        const float dz = __fsub_rn(__ldg(px + 2 * a.sC), __ldg(pc + 2));
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-                if (i >= 0) {
-                    const int64_t b = g / a.S;
-                    const int p0 = c << 3;
-                    if (vec_ok && p0 + 8 <= a.D) {
-                        const float4 *src = reinterpret_cast<const float4 *>(a.feats + b * a.fB + (int64_t)i * a.fN + p0);
-                        const float4 lo = src[0], hi = src[1];
-                        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-                        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-                    } else if (p0 < K0) {
-                        const float *pf = a.feats + b * a.fB + (int64_t)i * a.fN;
-                        const float *px = a.xyz + b * a.sB + (int64_t)i * a.sN;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int p = p0 + e;
-                            if (p < a.D) v[e] = pf[p];
-                            else if (p < K0) v[e] = __fsub_rn(px[(int64_t)(p - a.D) * a.sC], a.new_xyz[g * 3 + (p - a.D)]);
+                        for (int j = 0; j < 10; ++j) {     // nf <= 7: the tail's non-zero part ends before column 10
+                            float val = 0.0f;
+                            if (j < nf) val = __ldg(a.feats + off + (cpf << 3) + j);
+                            else if (j == nf) val = dx;
+                            else if (j == nf + 1) val = dy;
+                            else if (j == nf + 2) val = dz;
+                            tail[j] = val;
                         }
                     }
                 }
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4 *>(act + (size_t)(c >> 3) * kSaSlab + sw128_offset(r, c & 7)) = o;
+                s_off[tid] = off;
+                for (int c = cpf, t = 0; c < cpr; ++c, ++t) {
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (t == 0) {
+                        o.x = pack_bf16x2(tail[0], tail[1]); o.y = pack_bf16x2(tail[2], tail[3]);
+                        o.z = pack_bf16x2(tail[4], tail[5]); o.w = pack_bf16x2(tail[6], tail[7]);
+                    } else if (t == 1) {
+                        o.x = pack_bf16x2(tail[8], tail[9]); o.y = pack_bf16x2(tail[10], tail[11]);
+                        o.z = pack_bf16x2(tail[12], tail[13]); o.w = pack_bf16x2(tail[14], tail[15]);
+                    }
+                    *reinterpret_cast<uint4 *>(act + (size_t)(c >> 3) * kSaSlab + sw128_offset(tid, c & 7)) = o;
+                }
+            }
+            named_bar_sync(1, 128);
+            // ---- phase 2: the pure-feature chunks, 8 consecutive lanes per row (coalesced 256-byte segments); kGU
+            //      chunks per thread and pass with all their global loads issued before the first conversion, so a
+            //      thread keeps 2*kGU 16-byte requests in flight (the gather is L2-latency bound otherwise) ----
+            const int n_tasks = kSaTile * cpf;
+            for (int q0 = tid; q0 < n_tasks; q0 += 128 * kGU) {
+                float4 lo[kGU], hi[kGU];
+                int rr[kGU], cc[kGU];
+#pragma unroll
+                for (int u = 0; u < kGU; ++u) {
+                    const int q = q0 + 128 * u;
+                    const int r = cpf_shift >= 0 ? q >> cpf_shift : q / cpf;
+                    const int c = q - r * cpf;
+                    rr[u] = r;
+                    cc[u] = c;
+                    lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q >= n_tasks) continue;
+                    const int64_t off = s_off[r];
+                    if (off < 0) continue;
+                    const float *src = a.feats + off + (c << 3);
+                    if (vec_ok) {
+                        lo[u] = __ldg(reinterpret_cast<const float4 *>(src));
+                        hi[u] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+                    } else {
+                        lo[u] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+                        hi[u] = make_float4(__ldg(src + 4), __ldg(src + 5), __ldg(src + 6), __ldg(src + 7));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kGU; ++u) {
+                    if (q0 + 128 * u >= n_tasks) continue;
+                    uint4 o;
+                    o.x = pack_bf16x2(lo[u].x, lo[u].y); o.y = pack_bf16x2(lo[u].z, lo[u].w);
+                    o.z = pack_bf16x2(hi[u].x, hi[u].y); o.w = pack_bf16x2(hi[u].z, hi[u].w);
+                    *reinterpret_cast<uint4 *>(act + (size_t)(cc[u] >> 3) * kSaSlab + sw128_offset(rr[u], cc[u] & 7)) = o;
+                }
             }
             fence_before_sync();      // the previous tile's TMEM reads are done before this tile's first MMA
             fence_proxy_async();      // generic-proxy writes of the tile -> visible to the tensor core
@@ -331,7 +380,7 @@ static SaPlan sa_plan(int D, int L, const int *widths) {
     if (tc > 512) { p.why = "accumulator exceeds tensor memory"; return p; }
     a.tmem_cols = tc;
     p.wimg_bytes = off;
-    const size_t fixed = 1024 + (size_t)a_slabs * kSaSlab + (size_t)ss * 8 + 128 * 4;
+    const size_t fixed = 1024 + (size_t)a_slabs * kSaSlab + (size_t)ss * 8 + 128 * 8;
     const size_t budget = 227 * 1024 - 2048;       // static shared memory (barriers) stays far below 2 KB
     // resident weights when the whole level fits next to the activation tile (then as many CTAs per SM as fit,
     // tensor memory allowing); otherwise a ring of at least two chunk slots, one CTA per SM
@@ -347,7 +396,7 @@ static SaPlan sa_plan(int D, int L, const int *widths) {
     p.dyn_smem = fixed + (size_t)a.stages * slot;
     int per_sm = (int)((227 * 1024) / (p.dyn_smem + 2048));
     if (per_sm > 512 / tc) per_sm = 512 / tc;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
     p.per_sm = per_sm;
     p.ok = true;
@@ -386,9 +435,12 @@ extern "C" int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, sa_fused_eval_kernel);
+        cudaError_t e = cudaFuncGetAttributes(&fa, sa_fused_eval_kernel<4>);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(sa_fused_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(sa_fused_eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(sa_fused_eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024 - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) {
             set_error("sa_fused_eval: shared-memory opt-in failed: %s", cudaGetErrorString(e));
@@ -431,7 +483,12 @@ extern "C" int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64
     const int64_t n_tiles = (a.G * 32 + kSaTile - 1) / kSaTile;
     int64_t grid = (int64_t)p.per_sm * kNumSMs;
     if (grid > n_tiles) grid = n_tiles;
-    sa_fused_eval_kernel<<<(unsigned)grid, kSaThreads, p.dyn_smem, st>>>(a);
+    // rows in flight per thread during the gather: 8 when shared memory allows at most two CTAs per SM (registers are
+    // plentiful then and nothing else hides the L2 latency), 4 otherwise
+    if (p.per_sm <= 2)
+        sa_fused_eval_kernel<8><<<(unsigned)grid, kSaThreads, p.dyn_smem, st>>>(a);
+    else
+        sa_fused_eval_kernel<4><<<(unsigned)grid, kSaThreads, p.dyn_smem, st>>>(a);
     count_launch();
     return check_launch("sa_fused_eval");
 }

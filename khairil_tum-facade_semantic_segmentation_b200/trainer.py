@@ -155,17 +155,74 @@ class SemSegTrainer:
         return float(self.step_device(points, target))
 
 
+class SemSegPredictor:
+    """Inference forward of the SSG network on fixed-shape batches, captured ONCE as a CUDA graph
+    (the ~100 kernel launches of a forward cost no host time per batch).  The body is the
+    reference's test-time batch step (/root/reference/localfunctions.py:396-400: host->device copy,
+    transpose, `classifier(torch_data)`, arg-max of the log-probabilities); the FPS start indices stay a
+    fresh CPU-generator draw per forward (pointnet2_utils.py:75), staged through pinned buffers."""
+
+    def __init__(self, model, batch_clouds, npoint, channels, device="cuda", warmup=2):
+        from .modules import PointNetSetAbstraction
+        self.model = model.eval()
+        self.device = dev = torch.device(device)
+        self.batch = batch_clouds
+        self._sa = [m for m in model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
+        for m in self._sa:
+            m.use_static_start_buffers(True)
+        self.points = torch.zeros(batch_clouds, npoint, channels, device=dev)
+        self.points.uniform_(-0.5, 0.5)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.model(self.points.transpose(2, 1))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.log_probs, _ = self.model(self.points.transpose(2, 1))       # [B, npoint, classes]
+            self.labels = self.log_probs.argmax(dim=2)
+        self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
+
+    def forward_device(self, points):
+        """points [b <= batch, npoint, C] on the device -> (log_probs, labels) views of the static outputs."""
+        b = points.shape[0]
+        self.points[:b].copy_(points, non_blocking=True)
+        for m in self._sa:
+            m.start_staging.draw()
+        self.graph.replay()
+        return self.log_probs[:b], self.labels[:b]
+
+    def predict_host(self, points_host):
+        """points [b <= batch, npoint, C] on the host (pinned recommended) -> labels [b, npoint] on the host."""
+        b = points_host.shape[0]
+        self.points[:b].copy_(points_host, non_blocking=True)
+        for m in self._sa:
+            m.start_staging.draw()
+        self.graph.replay()
+        self._host_labels.copy_(self.labels, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_labels[:b]
+
+
 @torch.no_grad()
-def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="cuda"):
+def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="cuda", use_graph=True):
     """sem_seg_testing-style inference (num_votes=1) over [nb, 4096, C] blocks held on the host:
     this rank labels its contiguous shard of blocks; no collective is needed (eval-mode BatchNorm
     uses running statistics, so blocks are independent).  Returns (lo, hi, labels [hi-lo, 4096] on host)."""
     model.eval()
     lo, hi = shard_range(blocks_host.shape[0], rank, world)
     out = torch.empty(hi - lo, blocks_host.shape[1], dtype=torch.int64)
+    predictor = None
+    if use_graph and hi - lo >= batch_size:
+        predictor = SemSegPredictor(model, batch_size, blocks_host.shape[1], blocks_host.shape[2], device)
     for s in range(lo, hi, batch_size):
         e = min(hi, s + batch_size)
-        x = blocks_host[s:e].to(device, non_blocking=True).float().transpose(2, 1)
-        pred, _ = model(x)
-        out[s - lo:e - lo] = pred.argmax(dim=2).cpu()
+        if predictor is not None:         # a short tail batch rides in the same fixed-shape graph
+            out[s - lo:e - lo] = predictor.predict_host(blocks_host[s:e].float())
+        else:
+            x = blocks_host[s:e].to(device, non_blocking=True).float().transpose(2, 1)
+            pred, _ = model(x)
+            out[s - lo:e - lo] = pred.argmax(dim=2).cpu()
     return lo, hi, out
