@@ -119,6 +119,31 @@ int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale,
                    const float *in_shift, const float *W, const float *bias, int64_t M, int K,
                    int N, void *Z, int ldz, int z_dtype, double *stat_accum, void *wpack,
                    void *stream);
+/* One launch packs the bf16 images of n weights (every layer of an MLP, both orientations) ahead of the layer calls:
+ * image i is what pn2_linear_fwd streams for W_i [N_i, K_i] (transposed_host[i] == 0, pn2_linear_wpack_bytes(K_i, N_i)
+ * bytes) or what pn2_linear_bwd_data streams (transposed_host[i] != 0, pn2_linear_wpack_bytes(N_i, K_i) bytes).
+ * All five arrays are HOST arrays of n entries (W_host / wpack_host hold device pointers). */
+int pn2_pack_weights(int n, const float *const *W_host, const int *K_host, const int *N_host,
+                     const int *transposed_host, void *const *wpack_host, void *stream);
+/* Train-mode BatchNorm finalize fused into the layer kernel: the CTA that draws the last ticket does what
+ * pn2_bn_train_finalize does (same fields) and leaves stat_accum and *ticket zeroed.  ticket: a zero-initialised
+ * uint32 in device memory, reusable by consecutive calls on one stream. */
+typedef struct pn2_bn_finalize {
+    uint32_t *ticket;
+    const float *gamma, *beta, *conv_bias;
+    float eps, momentum;
+    float *running_mean, *running_var, *scale, *shift, *save_mean, *save_invstd;
+    int64_t *num_batches_tracked;
+} pn2_bn_finalize;
+/* pn2_linear_fwd with wpack ALREADY holding the image (pn2_pack_weights) and, when fin_host (a HOST struct of device
+ * pointers) is non-NULL, the BatchNorm finalize of the layer's statistics fused in (stat_accum required). */
+int pn2_linear_fwd_prepacked(const void *X, int ldx, int x_dtype, const float *in_scale,
+                             const float *in_shift, const float *W, const float *bias, int64_t M, int K,
+                             int N, void *Z, int ldz, int z_dtype, double *stat_accum, const void *wpack,
+                             const pn2_bn_finalize *fin_host, void *stream);
+/* pn2_linear_bwd_data with wpack already holding the transposed image (pn2_pack_weights, transposed = 1) */
+int pn2_linear_bwd_data_prepacked(const void *dZ, int lddz, int dz_dtype, const float *W, int64_t M, int K,
+                                  int N, void *dX, int lddx, int dx_dtype, const void *wpack, void *stream);
 /* dX[M,K] = dZ[M,N] * W[N,K]   (no activation handling; see pn2_bn_relu_bwd_*);
  * wpack: scratch of pn2_linear_wpack_bytes(N, K) bytes (note the swapped roles) or NULL */
 int pn2_linear_bwd_data(const void *dZ, int lddz, int dz_dtype, const float *W, int64_t M, int K,
@@ -193,6 +218,18 @@ int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg, const voi
                                 const float *save_mean, const float *save_invstd, int64_t G,
                                 int nsample, int C, double *accum, void *stream);
 int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *dbeta, void *stream);
+/* The two reductions with pn2_bn_bwd_finalize fused in: the block that draws the last ticket (a zero-initialised
+ * uint32 in device memory, left zero again) writes dgamma / dbeta and zeroes the accumulator. */
+int pn2_bn_relu_bwd_reduce_finalize(const void *dA, int ldda, int da_dtype, const void *Z, int ldz,
+                                    int z_dtype, const float *scale, const float *shift,
+                                    const float *save_mean, const float *save_invstd, int64_t M, int C,
+                                    double *accum, uint32_t *ticket, float *dgamma, float *dbeta,
+                                    void *stream);
+int pn2_pool_bn_relu_bwd_reduce_finalize(const float *dOut, const int32_t *arg, const void *Z, int ldz,
+                                         int z_dtype, const float *scale, const float *shift,
+                                         const float *save_mean, const float *save_invstd, int64_t G,
+                                         int nsample, int C, double *accum, uint32_t *ticket,
+                                         float *dgamma, float *dbeta, void *stream);
 int pn2_bn_relu_bwd_dz(const void *dA, int ldda, int da_dtype, const void *Z, int ldz, int z_dtype,
                        const float *scale, const float *shift, const float *save_mean,
                        const float *save_invstd, const float *dgamma, const float *dbeta, int64_t M,

@@ -36,6 +36,9 @@ _SIGNATURES = {
     "pn2_group_points": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pn2_group_points_bwd": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pn2_linear_wpack_bytes": (_z, [_i, _i]),
+    "pn2_pack_weights": (_i, [_i, _p, _p, _p, _p, _p, _p]),
+    "pn2_linear_fwd_prepacked": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p, _p, _p]),
+    "pn2_linear_bwd_data_prepacked": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p, _p, _p]),
     "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
@@ -49,6 +52,8 @@ _SIGNATURES = {
     "pn2_bn_relu_bwd_reduce": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _l, _i, _p, _p]),
     "pn2_pool_bn_relu_bwd_reduce": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
     "pn2_bn_bwd_finalize": (_i, [_p, _i, _p, _p, _p]),
+    "pn2_bn_relu_bwd_reduce_finalize": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p]),
+    "pn2_pool_bn_relu_bwd_reduce_finalize": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p]),
     "pn2_bn_relu_bwd_dz": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _p, _i, _i, _p]),
     "pn2_pool_bn_relu_bwd_dz": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p]),
     "pn2_three_nn": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p, _p, _p]),
@@ -57,6 +62,15 @@ _SIGNATURES = {
     "pn2_to_rows": (_i, [_p, _l, _l, _l, _i, _l, _i, _p, _l, _i, _p]),
     "pn2_rows_to_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
 }
+
+
+
+class BnFinalize(ctypes.Structure):
+    """pn2_bn_finalize of include/pn2b200.h (a HOST struct of device pointers)."""
+    _fields_ = [("ticket", _p), ("gamma", _p), ("beta", _p), ("conv_bias", _p), ("eps", _f), ("momentum", _f),
+                ("running_mean", _p), ("running_var", _p), ("scale", _p), ("shift", _p), ("save_mean", _p),
+                ("save_invstd", _p), ("num_batches_tracked", _p)]
+
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None

@@ -13,6 +13,35 @@ namespace pn2 {
 
 int linear_num_partials(int64_t M);
 
+// "Last block finalizes": every block has added its partial sums into the fp64 accumulator (L2 atomics); the block
+// that draws the last ticket turns the accumulator into dbeta / dgamma, zeroes it and resets the ticket, which saves
+// the separate finalize launch (and its dependency gap) behind every reduction.  ticket == nullptr: plain reduction.
+__device__ __forceinline__ void bn_bwd_last_block_finalize(double *accum, int C, unsigned *ticket, float *dgamma,
+                                                           float *dbeta) {
+    __shared__ int s_last;
+    if (!ticket) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kStatReplicas; ++r) {   // fixed order
+            double *a = accum + (size_t)r * 2 * C;
+            s1 += __ldcg(a + c);
+            s2 += __ldcg(a + C + c);
+            a[c] = 0.0;
+            a[C + c] = 0.0;
+        }
+        dbeta[c] = (float)s1;
+        dgamma[c] = (float)s2;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // ------------------------------------------------------------------ statistics -> scale/shift
 __global__ void bn_train_finalize_kernel(double *__restrict__ accum, int64_t M, int N,
                                          const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -33,24 +62,8 @@ __global__ void bn_train_finalize_kernel(double *__restrict__ accum, int64_t M, 
         a[c] = 0.0;
         a[N + c] = 0.0;
     }
-    double mean = s1 / (double)M;
-    double var = s2 / (double)M - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
-    float sc = g * invstd;
-    scale[c] = sc;
-    shift[c] = b - (float)mean * sc;
-    if (save_mean) save_mean[c] = (float)mean;
-    if (save_invstd) save_invstd[c] = invstd;
-    if (running_mean) {
-        float full_mean = (float)mean + (conv_bias ? conv_bias[c] : 0.0f);
-        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * full_mean;
-    }
-    if (running_var) {
-        double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
-    }
+    bn_finalize_channel(s1, s2, M, c, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
+                        save_mean, save_invstd);
 }
 
 __global__ void bn_eval_fold_kernel(const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -107,7 +120,7 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
                      const TZ *__restrict__ Z, int ldz, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ save_mean,
                      const float *__restrict__ save_invstd, int64_t R, int nsample, int C,
-                     double *__restrict__ accum) {
+                     double *__restrict__ accum, unsigned *ticket, float *dgamma, float *dbeta) {
     extern __shared__ float red[];   // [8][2][C]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t rows_per_block = (R + gridDim.x - 1) / gridDim.x;
@@ -136,6 +149,7 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
         for (int ww = 0; ww < 8; ++ww) s += red[(ww * 2 + which) * C + c];
         atomicAdd(accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * C + i, (double)s);
     }
+    bn_bwd_last_block_finalize(accum, C, ticket, dgamma, dbeta);
 }
 
 // bf16 Z, C % 8 == 0 and 256 % (C/8) == 0: one thread owns 8 channels (16-byte loads) of every
@@ -147,7 +161,7 @@ bn_bwd_reduce_vec8_kernel(const void *__restrict__ dA_, int ldda, const int32_t 
                           const __nv_bfloat16 *__restrict__ Z, int ldz, const float *__restrict__ scale,
                           const float *__restrict__ shift, const float *__restrict__ save_mean,
                           const float *__restrict__ save_invstd, int64_t R, int nsample, int C,
-                          double *__restrict__ accum) {
+                          double *__restrict__ accum, unsigned *ticket, float *dgamma, float *dbeta) {
     constexpr int kStride = 264;
     __shared__ float red[16 * kStride];
     const int cpr = C >> 3;
@@ -241,6 +255,7 @@ bn_bwd_reduce_vec8_kernel(const void *__restrict__ dA_, int ldda, const int32_t 
         for (int q = 0; q < rstep; ++q) s += p[q * cpr];     // fixed order
         atomicAdd(accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * C + i, (double)s);
     }
+    bn_bwd_last_block_finalize(accum, C, ticket, dgamma, dbeta);
 }
 
 __global__ void bn_bwd_finalize_kernel(double *__restrict__ accum, int C, float *__restrict__ dgamma,
@@ -425,7 +440,8 @@ template <bool POOL>
 static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *arg, const void *Z, int ldz,
                            int z_dtype, const float *scale, const float *shift, const float *save_mean,
                            const float *save_invstd, int64_t R, int nsample, int C, double *accum,
-                           int n_partials, cudaStream_t st) {
+                           int n_partials, cudaStream_t st, unsigned *ticket = nullptr, float *dgamma = nullptr,
+                           float *dbeta = nullptr) {
     if (z_dtype == PN2_BF16 && C % 8 == 0 && 256 % (C / 8) == 0 && ldz % 8 == 0 &&
         (POOL || (da_dtype == PN2_BF16 ? ldda % 8 == 0 : ldda % 4 == 0))) {
         const int rstep = 256 / (C / 8);
@@ -434,20 +450,20 @@ static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t
         const int grid = (int)(want < 1 ? 1 : (want > 2 * kNumSMs ? 2 * kNumSMs : want));
         if (POOL)
             bn_bwd_reduce_vec8_kernel<2><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
-                                                               save_mean, save_invstd, R, nsample, C, accum);
+                                                               save_mean, save_invstd, R, nsample, C, accum, ticket, dgamma, dbeta);
         else if (da_dtype == PN2_BF16)
             bn_bwd_reduce_vec8_kernel<0><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
-                                                               save_mean, save_invstd, R, nsample, C, accum);
+                                                               save_mean, save_invstd, R, nsample, C, accum, ticket, dgamma, dbeta);
         else
             bn_bwd_reduce_vec8_kernel<1><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
-                                                               save_mean, save_invstd, R, nsample, C, accum);
+                                                               save_mean, save_invstd, R, nsample, C, accum, ticket, dgamma, dbeta);
         count_launch();
         return check_launch("bn_bwd_reduce_vec8");
     }
     size_t smem = sizeof(float) * 16 * (size_t)C;
 #define PN2_LAUNCH_RED(TA, TZ)                                                                        \
     bn_bwd_reduce_kernel<TA, TZ, POOL><<<n_partials, 256, smem, st>>>((const TA *)dA, ldda, arg, (const TZ *)Z, ldz, \
-                                                                      scale, shift, save_mean, save_invstd, R, nsample, C, accum)
+                                                                      scale, shift, save_mean, save_invstd, R, nsample, C, accum, ticket, dgamma, dbeta)
     if (da_dtype == PN2_F32 && z_dtype == PN2_F32) PN2_LAUNCH_RED(float, float);
     else if (da_dtype == PN2_F32) PN2_LAUNCH_RED(float, __nv_bfloat16);
     else if (z_dtype == PN2_F32) PN2_LAUNCH_RED(__nv_bfloat16, float);
@@ -476,6 +492,30 @@ extern "C" int pn2_pool_bn_relu_bwd_reduce(const float *dOut, const int32_t *arg
     if (G == 0) return PN2_OK;
     return reduce_dispatch<true>(dOut, C, PN2_F32, arg, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, G, nsample,
                                  C, accum, linear_num_partials(G * nsample), (cudaStream_t)stream);
+}
+
+extern "C" int pn2_bn_relu_bwd_reduce_finalize(const void *dA, int ldda, int da_dtype, const void *Z, int ldz,
+                                               int z_dtype, const float *scale, const float *shift,
+                                               const float *save_mean, const float *save_invstd, int64_t M, int C,
+                                               double *accum, unsigned *ticket, float *dgamma, float *dbeta,
+                                               void *stream) {
+    PN2_REQUIRE(dA && Z && scale && shift && accum && ticket && dgamma && dbeta, "bn_relu_bwd_reduce_finalize: null pointer");
+    PN2_REQUIRE(valid_dtype(da_dtype) && valid_dtype(z_dtype) && C >= 1 && C <= 768 && M >= 1,
+                "bn_relu_bwd_reduce_finalize: bad arguments (C <= 768, M >= 1)");
+    return reduce_dispatch<false>(dA, ldda, da_dtype, nullptr, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, M,
+                                  1, C, accum, linear_num_partials(M), (cudaStream_t)stream, ticket, dgamma, dbeta);
+}
+
+extern "C" int pn2_pool_bn_relu_bwd_reduce_finalize(const float *dOut, const int32_t *arg, const void *Z, int ldz,
+                                                    int z_dtype, const float *scale, const float *shift,
+                                                    const float *save_mean, const float *save_invstd, int64_t G,
+                                                    int nsample, int C, double *accum, unsigned *ticket,
+                                                    float *dgamma, float *dbeta, void *stream) {
+    PN2_REQUIRE(dOut && arg && Z && scale && shift && accum && ticket && dgamma && dbeta,
+                "pool_bn_relu_bwd_reduce_finalize: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && C >= 1 && C <= 768 && G >= 1, "pool_bn_relu_bwd_reduce_finalize: bad arguments (C <= 768, G >= 1)");
+    return reduce_dispatch<true>(dOut, C, PN2_F32, arg, Z, ldz, z_dtype, scale, shift, save_mean, save_invstd, G, nsample,
+                                 C, accum, linear_num_partials(G * nsample), (cudaStream_t)stream, ticket, dgamma, dbeta);
 }
 
 extern "C" int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *dbeta, void *stream) {

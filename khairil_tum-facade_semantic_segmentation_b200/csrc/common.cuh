@@ -52,6 +52,39 @@ template <> __device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16 
     *p = __float2bfloat16_rn(v);
 }
 
+// ---- train-mode BatchNorm statistics -> scale/shift for ONE channel (shared by bn_train_finalize_kernel and the
+// fused "last CTA finalizes" tail of the tensor-core layer kernel).  s1, s2: sum z, sum z^2 over M rows (bias excluded).
+struct BnFinalize {           // device pointers; mirrors pn2_bn_finalize of include/pn2b200.h
+    unsigned *ticket;
+    const float *gamma, *beta, *conv_bias;
+    float eps, momentum;
+    float *running_mean, *running_var, *scale, *shift, *save_mean, *save_invstd;
+    long long *num_batches_tracked;
+};
+__device__ __forceinline__ void bn_finalize_channel(double s1, double s2, int64_t M, int c, const float *gamma,
+                                                    const float *beta, const float *conv_bias, float eps, float momentum,
+                                                    float *running_mean, float *running_var, float *scale, float *shift,
+                                                    float *save_mean, float *save_invstd) {
+    double mean = s1 / (double)M;
+    double var = s2 / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = invstd;
+    if (running_mean) {
+        float full_mean = (float)mean + (conv_bias ? conv_bias[c] : 0.0f);
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * full_mean;
+    }
+    if (running_var) {
+        double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
 inline bool valid_dtype(int d) { return d == PN2_F32 || d == PN2_BF16; }
 
 // dispatch a callable templated on the activation storage type

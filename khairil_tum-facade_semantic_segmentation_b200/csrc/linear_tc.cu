@@ -20,6 +20,8 @@
 //     stores; the train-mode BatchNorm column sums (sum z, sum z^2 of the STORED values) are
 //     accumulated from the staging tile with lanes walking columns (bank-conflict free) and
 //     kept in registers across tiles; added once per CTA into fp64 accumulators at the end.
+#include <string.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -54,6 +56,44 @@ __global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, in
     }
 }
 
+// One launch packs up to kPackJobs weights (every layer of an MLP, both orientations): job j owns blocks
+// [first_block[j], first_block[j+1]); its image is the concatenation over 256-row blocks of N of [KC][n_pad][128 B].
+constexpr int kPackJobs = 16;
+struct PackJobs {
+    int n;
+    const float *W[kPackJobs];
+    int64_t w_sn[kPackJobs], w_sk[kPackJobs];
+    int N[kPackJobs], K[kPackJobs];
+    uint8_t *img[kPackJobs];
+    int first_block[kPackJobs + 1];
+};
+__global__ void pack_weights_multi_kernel(const __grid_constant__ PackJobs a) {
+    int j = 0;
+    while (j + 1 < a.n && (int)blockIdx.x >= a.first_block[j + 1]) ++j;
+    const int N = a.N[j], K = a.K[j], KC = (K + kTcBK - 1) / kTcBK;
+    const int q = ((int)blockIdx.x - a.first_block[j]) * blockDim.x + threadIdx.x;     // 16-byte unit of the job's image
+    const int full = KC * 256 * 8;                                                  // units of one full 256-row block
+    const int blk = q / full, rem = q - blk * full;
+    const int n0 = blk * 256;
+    if (n0 >= N) return;
+    const int nb = N - n0 < 256 ? N - n0 : 256, n_pad = (nb + 15) & ~15;
+    if (rem >= KC * n_pad * 8) return;
+    const int c = rem & 7, n = (rem >> 3) % n_pad, kc = (rem >> 3) / n_pad;
+    const float *W = a.W[j] + (int64_t)n0 * a.w_sn[j];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kc * kTcBK + c * 8 + e;
+        v[e] = (n < nb && k < K) ? W[(int64_t)n * a.w_sn[j] + (int64_t)k * a.w_sk[j]] : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(a.img[j] + (size_t)blk * KC * 256 * 128 + (size_t)kc * n_pad * 128 + sw128_offset(n, c)) = o;
+}
+
 struct TcLinearArgs {
     CUtensorMap tm_x, tm_z;   // X [M, ldx] (boxes 64 x 128 rows) and this call's Z column block [M, n_store] (row stride ldz)
     const float *in_scale, *in_shift;
@@ -64,6 +104,7 @@ struct TcLinearArgs {
     double *stat_accum;     // [replicas][2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
     int stat_ld, stat_off;
     int w_resident, stages;
+    BnFinalize fin;         // fin.ticket != null: the CTA that draws the last ticket turns the sums into scale/shift
 };
 
 constexpr int kLinTcThreads = 160;   // warps 0-3: A transform, MMA issue (thread 0), epilogue; warp 4: TMA producer
@@ -75,6 +116,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_w, bar_acc;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned (SW128 atoms)
@@ -256,6 +298,35 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                 atomicAdd(acc + c, (double)t1);
                 atomicAdd(acc + a.stat_ld + c, (double)t2);
             }
+            if (a.fin.ticket) {
+                // ---- "last CTA finalizes": mean / variance -> scale, shift, running statistics; accumulator and ticket
+                //      are left zeroed for the next layer (saves the finalize launch between two layers) ----
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (tid == 0) s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+                named_bar_sync(1, 128);
+                if (s_last) {
+                    __threadfence();
+                    for (int c = tid; c < a.N; c += 128) {
+                        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                        for (int r = 0; r < kStatReplicas; ++r) {   // fixed order
+                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + a.stat_off;
+                            s1 += __ldcg(acc + c);
+                            s2 += __ldcg(acc + a.stat_ld + c);
+                            acc[c] = 0.0;
+                            acc[a.stat_ld + c] = 0.0;
+                        }
+                        bn_finalize_channel(s1, s2, a.M, a.stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
+                                            a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
+                                            a.fin.save_mean, a.fin.save_invstd);
+                    }
+                    if (tid == 0) {
+                        *a.fin.ticket = 0u;
+                        if (a.fin.num_batches_tracked && a.stat_off == 0) *a.fin.num_batches_tracked += 1;
+                    }
+                }
+            }
         }
     }
     fence_before_sync();
@@ -264,6 +335,35 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int tc_pack_weights(int n, const float *const *W, const int *K, const int *N, const int *transposed, void *const *wpack,
+                    cudaStream_t st) {
+    // job i: the image tc_linear_nt streams for Z = X.W^T (transposed[i] == 0: rows = N out channels, columns = K) or
+    // for dX = dZ.W (transposed[i] != 0: rows = K, columns = N), W row-major [N, K]
+    for (int i0 = 0; i0 < n; i0 += kPackJobs) {
+        PackJobs a;
+        a.n = n - i0 < kPackJobs ? n - i0 : kPackJobs;
+        int blocks = 0;
+        for (int j = 0; j < a.n; ++j) {
+            const int i = i0 + j;
+            const int rows = transposed[i] ? K[i] : N[i], cols = transposed[i] ? N[i] : K[i];
+            a.W[j] = W[i];
+            a.w_sn[j] = transposed[i] ? 1 : K[i];
+            a.w_sk[j] = transposed[i] ? K[i] : 1;
+            a.N[j] = rows;
+            a.K[j] = cols;
+            a.img[j] = (uint8_t *)wpack[i];
+            a.first_block[j] = blocks;
+            const int KC = (cols + kTcBK - 1) / kTcBK;
+            const int units = ((rows + 255) / 256) * KC * 256 * 8;
+            blocks += (units + 255) / 256;
+        }
+        a.first_block[a.n] = blocks;
+        pack_weights_multi_kernel<<<blocks, 256, 0, st>>>(a);
+        count_launch();
+    }
+    return check_launch("pack_weights");
+}
 
 size_t tc_wpack_bytes(int K, int N) {
     // images for every 256-column block of N, each [KC][n_pad][128 B]
@@ -275,7 +375,7 @@ size_t tc_wpack_bytes(int K, int N) {
 // Z[M,N] = act(X) . W^T with W element (n,k) at W[n*w_sn + k*w_sk]
 int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_shift, const float *W, int64_t w_sn,
                  int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, double *stat_accum,
-                 void *wpack, cudaStream_t st) {
+                 void *wpack, cudaStream_t st, bool packed, const BnFinalize *fin) {
     static bool attr_done = false;
     static int static_smem = 0;
     if (!attr_done) {
@@ -306,9 +406,13 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         if (n0 + n_store > ldz) n_store = ldz - n0;      // ldz is a multiple of 8 on this path
         const size_t img_bytes = (size_t)KC * n_pad * 128;
         const int total = KC * n_pad * 8;
-        pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, 0, img);
-        count_launch();
+        if (!packed) {
+            pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, 0, img);
+            count_launch();
+        }
         TcLinearArgs a;
+        memset(&a.fin, 0, sizeof(a.fin));
+        if (fin && stat_accum) a.fin = *fin;
         if (!make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, kTcBM) ||
             !make_rows_tensor_map(&a.tm_z, (const __nv_bfloat16 *)Z + n0, M, n_store, ldz, kTcBM)) {
             set_error("linear_tc: cuTensorMapEncodeTiled failed (M=%lld ldx=%d ldz=%d)", (long long)M, ldx, ldz);

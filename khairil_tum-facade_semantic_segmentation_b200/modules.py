@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import call, dt, load, ptr, require_cuda, stream
+from ._lib import BnFinalize, call, dt, load, ptr, require_cuda, stream
 
 
 def _round_up(v, m):
@@ -30,7 +30,7 @@ def _row_ld(k, dtype):
 
 
 class _LayerState:
-    __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias")
+    __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias", "wpack_bwd")
 
 
 def _bn_trains(bn):
@@ -56,22 +56,64 @@ def _stat_accum(dev):
     return buf
 
 
-def mlp_forward(x0, K0, M, convs, bns):
+_TICKET = {}
+
+
+def _ticket(dev):
+    """Zero-initialised uint32 the "last block finalizes" kernels count on; they leave it zero, so one per
+    (device, stream) serves every layer (same life cycle as _stat_accum)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _TICKET.get(key)
+    if buf is None or torch.cuda.is_current_stream_capturing():
+        buf = torch.zeros(4, device=dev, dtype=torch.int32)
+        if not torch.cuda.is_current_stream_capturing():
+            _TICKET[key] = buf
+    return buf
+
+
+def _pack_weights(Ws, Ks, Ns, transposed, dev):
+    """bf16 tensor-core images of several weights in ONE launch; returns the uint8 image tensors."""
+    lib = load()
+    n = len(Ws)
+    imgs = [torch.empty(lib.pn2_linear_wpack_bytes(*((N, K) if t else (K, N))), device=dev, dtype=torch.uint8)
+            for K, N, t in zip(Ks, Ns, transposed)]
+    vp, ci = ctypes.c_void_p * n, ctypes.c_int * n
+    call("pn2_pack_weights", n, vp(*[w.data_ptr() for w in Ws]), ci(*Ks), ci(*Ns), ci(*transposed),
+         vp(*[i.data_ptr() for i in imgs]), stream())
+    return imgs
+
+
+def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     """relu(bn(conv(.))) chain on rows (pointnet2_utils.py:196-198 / :311-314) up to the last
     layer's pre-BN product; the caller applies the last BN+ReLU fused with its tail."""
-    lib = load()
     dev, dtype = x0.device, x0.dtype
     x, ldx, K = x0, x0.shape[1], K0
     in_scale = in_shift = None
     layers = []
-    for conv, bn in zip(convs, bns):
-        st = _LayerState()
+    Ws, Ks = [], []
+    for conv in convs:
         N = conv.out_channels
         W = conv.weight.detach().reshape(N, -1)
         if not W.is_contiguous():
             W = W.contiguous()
         if W.shape[1] != K or W.dtype != torch.float32:
             raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
+        Ws.append(W)
+        Ks.append(K)
+        K = N
+    Ns = Ks[1:] + [K]
+    K = K0
+    fwd_img = bwd_img = None
+    if dtype == torch.bfloat16:
+        # every layer's weight image (and, for a backward pass, its transposed image for the data gradient) in one launch;
+        # the first layer's data gradient is only needed when the MLP input wants a gradient -- pack it anyway, it is tiny
+        n_l = len(Ws)
+        tr = [0] * n_l + ([1] * n_l if want_bwd else [])
+        imgs = _pack_weights(Ws * (2 if want_bwd else 1), Ks * (2 if want_bwd else 1), Ns * (2 if want_bwd else 1), tr, dev)
+        fwd_img, bwd_img = imgs[:n_l], (imgs[n_l:] if want_bwd else None)
+    for l, (conv, bn) in enumerate(zip(convs, bns)):
+        st = _LayerState()
+        N, W = Ns[l], Ws[l]
         bias = None if conv.bias is None else conv.bias.detach()
         gamma = None if bn.weight is None else bn.weight.detach()
         beta = None if bn.bias is None else bn.bias.detach()
@@ -81,13 +123,10 @@ def mlp_forward(x0, K0, M, convs, bns):
         st.W, st.K, st.N, st.Z, st.has_bias = W, K, N, z, bias is not None
         st.scale, st.shift, st.mean, st.invstd = stats[0], stats[1], stats[2], stats[3]
         st.train = _bn_trains(bn)
-        wpack = None
-        if dtype == torch.bfloat16:     # scratch for the bf16, pre-swizzled weight image the tensor-core path streams
-            wpack = torch.empty(lib.pn2_linear_wpack_bytes(K, N), device=dev, dtype=torch.uint8)
+        st.wpack_bwd = None if bwd_img is None else bwd_img[l]
+        wpack = None if fwd_img is None else fwd_img[l]
         if st.train:
             accum = _stat_accum(dev)
-            call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
-                 ptr(z), ldz, dt(z), ptr(accum), ptr(wpack), stream())
             momentum = bn.momentum
             nbt = bn.num_batches_tracked if (bn.num_batches_tracked is not None and bn.training) else None
             if momentum is None:      # cumulative moving average (nn.BatchNorm semantics): needs the counter's value
@@ -96,18 +135,32 @@ def mlp_forward(x0, K0, M, convs, bns):
                 momentum = 1.0 / float(nbt.item()) if nbt is not None else 0.0
                 nbt = None
             update = bn.training and bn.running_mean is not None
-            call("pn2_bn_train_finalize", ptr(accum), M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
-                 float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
-                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt), stream())
+            if wpack is not None:     # tensor-core rows: statistics -> scale/shift fused into the layer kernel
+                fin = BnFinalize(ptr(_ticket(dev)), ptr(gamma), ptr(beta), ptr(bias), float(bn.eps), float(momentum),
+                                 ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
+                                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt))
+                call("pn2_linear_fwd_prepacked", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
+                     ptr(z), ldz, dt(z), ptr(accum), ptr(wpack), ctypes.addressof(fin), stream())
+            else:
+                call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
+                     ptr(z), ldz, dt(z), ptr(accum), None, stream())
+                call("pn2_bn_train_finalize", ptr(accum), M, N, ptr(gamma), ptr(beta), ptr(bias), float(bn.eps),
+                     float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
+                     ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt), stream())
         else:
             call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
                  ptr(st.scale), ptr(st.shift), stream())
-            call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K, N,
-                 ptr(z), ldz, dt(z), None, ptr(wpack), stream())
-            # for a backward pass through frozen statistics (Z already holds the bias here):
-            # zhat = (z - running_mean) * invstd_running
-            st.mean = bn.running_mean.detach()
-            st.invstd = torch.rsqrt(bn.running_var.detach() + bn.eps)
+            if wpack is not None:
+                call("pn2_linear_fwd_prepacked", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K,
+                     N, ptr(z), ldz, dt(z), None, ptr(wpack), None, stream())
+            else:
+                call("pn2_linear_fwd", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K, N,
+                     ptr(z), ldz, dt(z), None, None, stream())
+            if want_bwd:
+                # for a backward pass through frozen statistics (Z already holds the bias here):
+                # zhat = (z - running_mean) * invstd_running
+                st.mean = bn.running_mean.detach()
+                st.invstd = torch.rsqrt(bn.running_var.detach() + bn.eps)
         layers.append(st)
         x, ldx, K = z, ldz, N
         in_scale, in_shift = st.scale, st.shift
@@ -168,17 +221,17 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
         mean_train = ptr(st.mean) if st.train else None
         if arg is not None and dA is dout:
             G = M // nsample
-            call("pn2_pool_bn_relu_bwd_reduce", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(accum), stream())
-            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgamma), ptr(dbeta), stream())
+            call("pn2_pool_bn_relu_bwd_reduce_finalize", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z),
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(accum),
+                 ptr(_ticket(dev)), ptr(dgamma), ptr(dbeta), stream())
             dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
             call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
                  ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgamma), ptr(dbeta), G, nsample, C, ptr(dZ),
                  dZ.shape[1], dt(dZ), stream())
         else:
-            call("pn2_bn_relu_bwd_reduce", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(accum), stream())
-            call("pn2_bn_bwd_finalize", ptr(accum), C, ptr(dgamma), ptr(dbeta), stream())
+            call("pn2_bn_relu_bwd_reduce_finalize", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z),
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(accum), ptr(_ticket(dev)),
+                 ptr(dgamma), ptr(dbeta), stream())
             if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
                 dZ = dA                                   # element-wise update in place (never on autograd's grad)
             else:
@@ -224,11 +277,15 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
             dA = torch.empty(M, ldd, device=dev, dtype=dtype)
             if ldd != st.K:
                 dA[:, st.K:].zero_()
-            wpack = None
-            if dtype == torch.bfloat16:
-                wpack = torch.empty(lib.pn2_linear_wpack_bytes(st.N, st.K), device=dev, dtype=torch.uint8)
-            call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
-                 ptr(wpack), stream())
+            if st.wpack_bwd is not None:
+                call("pn2_linear_bwd_data_prepacked", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd,
+                     dt(dA), ptr(st.wpack_bwd), stream())
+            else:
+                wpack = None
+                if dtype == torch.bfloat16:
+                    wpack = torch.empty(lib.pn2_linear_wpack_bytes(st.N, st.K), device=dev, dtype=torch.uint8)
+                call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
+                     ptr(wpack), stream())
             if l > 0:
                 dZ, dgamma, dbeta = bn_grads(l - 1, dA, ldd)
             else:
@@ -326,7 +383,7 @@ class _SetAbstractionFn(torch.autograd.Function):
         K0 = 3 + D
         x0 = ops.group_rows(xyz_r, new_xyz, feats, idx, _row_ld(K0, dtype), dtype)
         M = B * S * nsample
-        layers = mlp_forward(x0, K0, M, convs, bns)
+        layers = mlp_forward(x0, K0, M, convs, bns, any(ctx.needs_input_grad))
         last = layers[-1]
         out = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.float32)
         arg = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.int32)
@@ -360,7 +417,7 @@ class _GroupAllFn(torch.autograd.Function):
         ld = _row_ld(K0, dtype)
         x0 = torch.zeros(B * N, ld, device=x0_f32.device, dtype=dtype)
         x0[:, :K0] = x0_f32.reshape(B * N, K0)
-        layers = mlp_forward(x0, K0, B * N, convs, bns)
+        layers = mlp_forward(x0, K0, B * N, convs, bns, any(ctx.needs_input_grad))
         last = layers[-1]
         out = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.float32)
         arg = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.int32)
@@ -398,7 +455,7 @@ class _FeaturePropagationFn(torch.autograd.Function):
         pB, pN, pD = (0, 0, 0) if p1_r is None else p1_r.stride()
         call("pn2_interp_concat", ptr(p1_r), pB, pN, pD, ptr(p2), S * D2, D2, 1, ptr(idx3), ptr(w3), B, N, S, D1, D2,
              ptr(x0), x0.shape[1], dt(x0), stream())
-        layers = mlp_forward(x0, K0, M, convs, bns)
+        layers = mlp_forward(x0, K0, M, convs, bns, any(ctx.needs_input_grad))
         last = layers[-1]
         out = torch.empty(B, N, last.N, device=p2.device, dtype=torch.float32)
         call("pn2_bn_relu", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), M, last.N,

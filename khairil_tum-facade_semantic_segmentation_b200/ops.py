@@ -20,6 +20,9 @@ def set_precision(mode):
     if mode not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32' or 'bf16', got %r" % (mode,))
     _PRECISION["rows"] = torch.float32 if mode == "fp32" else torch.bfloat16
+    # the PyTorch-owned head of the network (two 128-wide matrix products) follows the mode: strict fp32, or TF32
+    # tensor cores next to the bf16 hot path (what the reference's own CUDA path does by default through cuDNN)
+    torch.backends.cuda.matmul.allow_tf32 = mode == "bf16"
 
 
 def get_precision():

@@ -94,13 +94,50 @@ class get_model(nn.Module):
                 up = fp(coords[fine], coords[fine + 1], skip, up, neighbours=nn3[i])
             else:
                 up = fp(coords[fine], coords[fine + 1], skip, up)
-        x = self.drop1(F.relu(self.bn1(self.conv1(up))))
-        x = F.log_softmax(self.conv2(x), dim=1)
-        return x.permute(0, 2, 1), l4_points
+        return self._head(up), l4_points
+
+    rows_head = True      # run the Conv1d/BN/Dropout/Conv1d/log_softmax head on point-major rows (no layout copies)
+
+    def _head(self, up):
+        """pointnet2_sem_seg.py:36-39.  `up` is [B,128,N]; when it comes from PointNetFeaturePropagation it is a
+        permuted view of contiguous point-major rows [B,N,128], and a 1x1 Conv1d on it is a plain matrix product on
+        those rows: same parameters (the nn.Conv1d / nn.BatchNorm1d modules own them), same arithmetic, but no
+        [B,C,N] <-> [B,N,C] copies and the log-probabilities come out as [B,N,classes] directly.  Outside the
+        hot path: ordinary PyTorch kernels."""
+        if not self.rows_head:
+            x = self.drop1(F.relu(self.bn1(self.conv1(up))))
+            x = F.log_softmax(self.conv2(x), dim=1)
+            return x.permute(0, 2, 1)
+        B, C, N = up.shape
+        rows = up.permute(0, 2, 1).reshape(B * N, C)
+        x = F.linear(rows, self.conv1.weight.view(self.conv1.out_channels, C), self.conv1.bias)
+        bn = self.bn1
+        use_batch_stats = bn.training or bn.running_mean is None
+        momentum = bn.momentum
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        with torch.backends.cudnn.flags(enabled=False):     # the native kernels handle [M, C] rows well; cuDNN's 1x1 path does not
+            x = F.batch_norm(x, bn.running_mean if not bn.training or bn.track_running_stats else None,
+                             bn.running_var if not bn.training or bn.track_running_stats else None,
+                             bn.weight, bn.bias, use_batch_stats, 0.0 if momentum is None else momentum, bn.eps)
+        x = self.drop1(F.relu(x))
+        x = F.linear(x, self.conv2.weight.view(self.conv2.out_channels, -1), self.conv2.bias)
+        return F.log_softmax(x, dim=1).view(B, N, -1)
 
 
 class get_loss(nn.Module):
-    """pointnet2_sem_seg.py:44-50: class-weighted NLL on the log-probabilities."""
+    """pointnet2_sem_seg.py:44-50: class-weighted NLL on the log-probabilities (mean over the class weights of
+    the targets, F.nll_loss semantics).  On CUDA it is evaluated as gather / weighted sums -- the same value and
+    gradient as F.nll_loss(pred, target, weight=weight), whose single-block reduction kernels take ~0.2 ms on a
+    32 x 4096-point batch; targets equal to the default ignore_index (-100) contribute nothing, as there."""
 
     def forward(self, pred, target, trans_feat, weight):
-        return F.nll_loss(pred, target, weight=weight)
+        if not pred.is_cuda or pred.dim() != 2:
+            return F.nll_loss(pred, target, weight=weight)
+        keep = target != -100
+        safe = torch.where(keep, target, torch.zeros_like(target))
+        w_t = (weight[safe] if weight is not None else torch.ones_like(pred[:, 0])) * keep
+        picked = pred.gather(1, safe.unsqueeze(1)).squeeze(1)
+        return -(picked * w_t).sum() / w_t.sum()

@@ -184,3 +184,93 @@ def test_bn_relu_backward_kernels(lib, M, C, mode, train):
         want = scale.double() * gm
     err = ((dZ[:, :C].double() - want).abs() / (want.abs() + 1.0)).max().item()
     assert err <= (2.0 ** -7 if dzt == torch.bfloat16 else 1e-5), err
+
+
+# ---- the launch-saving variants: one pack launch for many weights, prepacked layer calls with the train-mode
+#      BatchNorm finalize fused in ("last CTA finalizes"), reductions with their finalize fused in -------------------
+import ctypes
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 12, 32), (4096, 67, 64), (2048, 259, 256), (1024, 256, 512), (777, 768, 256),
+                                   (130000, 32, 64)])
+def test_prepacked_forward_with_fused_finalize_matches_two_step_path(lib, M, K, N):
+    g = torch.Generator().manual_seed(M + K)
+    x = _rows(M, K, torch.bfloat16, 5)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    gamma, beta = (0.5 + torch.rand(N, generator=g)).to(DEV), torch.randn(N, generator=g).to(DEV)
+    scale_in = (0.5 + torch.rand(K, generator=g)).to(DEV)
+    shift_in = (torch.randn(K, generator=g) * 0.3).to(DEV)
+    L = lib.load()
+    ldz = _ld(N)
+
+    def buffers():
+        return dict(z=torch.full((M, ldz), float("nan"), device=DEV, dtype=torch.bfloat16),
+                    accum=torch.zeros(8, 2, N, device=DEV, dtype=torch.float64), out=torch.zeros(4, N, device=DEV),
+                    rm=torch.full((N,), 0.25, device=DEV), rv=torch.full((N,), 2.0, device=DEV),
+                    nbt=torch.tensor(3, device=DEV, dtype=torch.int64))
+
+    a = buffers()           # reference: pn2_linear_fwd (packs inside) + pn2_bn_train_finalize
+    wp = torch.empty(L.pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8)
+    lib.call("pn2_linear_fwd", lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale_in), lib.ptr(shift_in), lib.ptr(W), None, M,
+             K, N, lib.ptr(a["z"]), ldz, 1, lib.ptr(a["accum"]), lib.ptr(wp), lib.stream())
+    lib.call("pn2_bn_train_finalize", lib.ptr(a["accum"]), M, N, lib.ptr(gamma), lib.ptr(beta), lib.ptr(bias), 1e-5, 0.1,
+             lib.ptr(a["rm"]), lib.ptr(a["rv"]), lib.ptr(a["out"][0]), lib.ptr(a["out"][1]), lib.ptr(a["out"][2]),
+             lib.ptr(a["out"][3]), lib.ptr(a["nbt"]), lib.stream())
+    b = buffers()           # one pack launch (both orientations), then the prepacked call with the fused finalize
+    img_f = torch.empty(L.pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8)
+    img_b = torch.empty(L.pn2_linear_wpack_bytes(N, K), device=DEV, dtype=torch.uint8)
+    vp, ci = ctypes.c_void_p * 2, ctypes.c_int * 2
+    lib.call("pn2_pack_weights", 2, vp(W.data_ptr(), W.data_ptr()), ci(K, K), ci(N, N), ci(0, 1),
+             vp(img_f.data_ptr(), img_b.data_ptr()), lib.stream())
+    assert torch.equal(img_f, wp)                                    # same image as the in-call packing
+    ticket = torch.zeros(4, device=DEV, dtype=torch.int32)
+    for rep in range(2):                                             # the ticket and the accumulator are self-cleaning
+        fin = lib.BnFinalize(lib.ptr(ticket), lib.ptr(gamma), lib.ptr(beta), lib.ptr(bias), 1e-5, 0.1, lib.ptr(b["rm"]),
+                             lib.ptr(b["rv"]), lib.ptr(b["out"][0]), lib.ptr(b["out"][1]), lib.ptr(b["out"][2]),
+                             lib.ptr(b["out"][3]), lib.ptr(b["nbt"]))
+        lib.call("pn2_linear_fwd_prepacked", lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale_in), lib.ptr(shift_in),
+                 lib.ptr(W), None, M, K, N, lib.ptr(b["z"]), ldz, 1, lib.ptr(b["accum"]), lib.ptr(img_f),
+                 ctypes.addressof(fin), lib.stream())
+        torch.cuda.synchronize()
+        assert int(ticket[0]) == 0 and float(b["accum"].abs().sum()) == 0.0
+        if rep == 0:
+            assert torch.equal(a["z"], b["z"])
+            for k in ("out", "rm", "rv"):
+                assert torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), k
+            assert int(a["nbt"]) == int(b["nbt"]) == 4
+    assert int(b["nbt"]) == 5
+    # data gradient through the transposed image of the same pack launch
+    dz = _rows(M, N, torch.bfloat16, 6)
+    ldd = _ld(K)
+    d1 = torch.full((M, ldd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    d2 = torch.full((M, ldd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    wp2 = torch.empty(L.pn2_linear_wpack_bytes(N, K), device=DEV, dtype=torch.uint8)
+    lib.call("pn2_linear_bwd_data", lib.ptr(dz), dz.shape[1], 1, lib.ptr(W), M, K, N, lib.ptr(d1), ldd, 1, lib.ptr(wp2), lib.stream())
+    lib.call("pn2_linear_bwd_data_prepacked", lib.ptr(dz), dz.shape[1], 1, lib.ptr(W), M, K, N, lib.ptr(d2), ldd, 1,
+             lib.ptr(img_b), lib.stream())
+    assert torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("M,C,da", [(5000, 32, torch.bfloat16), (4096, 128, torch.float32), (777, 24, torch.float32),
+                                    (60000, 256, torch.bfloat16)])
+def test_bn_backward_reduce_with_fused_finalize(lib, M, C, da):
+    g = torch.Generator().manual_seed(C)
+    ld = _ld(C)
+    z = _rows(M, C, torch.bfloat16, 8)
+    dA = _rows(M, C, da, 9) if da == torch.bfloat16 else torch.randn(M, C, generator=g).to(DEV)
+    scale, shift = (0.5 + torch.rand(C, generator=g)).to(DEV), (torch.randn(C, generator=g) * 0.2).to(DEV)
+    mean, invstd = (torch.randn(C, generator=g) * 0.1).to(DEV), (0.5 + torch.rand(C, generator=g)).to(DEV)
+    acc1, acc2 = (torch.zeros(8, 2, C, device=DEV, dtype=torch.float64) for _ in range(2))
+    want, got = torch.zeros(2, C, device=DEV), torch.zeros(2, C, device=DEV)
+    lib.call("pn2_bn_relu_bwd_reduce", lib.ptr(dA), dA.shape[1], lib.dt(dA), lib.ptr(z), ld, 1, lib.ptr(scale), lib.ptr(shift),
+             lib.ptr(mean), lib.ptr(invstd), M, C, lib.ptr(acc1), lib.stream())
+    lib.call("pn2_bn_bwd_finalize", lib.ptr(acc1), C, lib.ptr(want[0]), lib.ptr(want[1]), lib.stream())
+    ticket = torch.zeros(4, device=DEV, dtype=torch.int32)
+    for _ in range(2):
+        lib.call("pn2_bn_relu_bwd_reduce_finalize", lib.ptr(dA), dA.shape[1], lib.dt(dA), lib.ptr(z), ld, 1, lib.ptr(scale),
+                 lib.ptr(shift), lib.ptr(mean), lib.ptr(invstd), M, C, lib.ptr(acc2), lib.ptr(ticket), lib.ptr(got[0]),
+                 lib.ptr(got[1]), lib.stream())
+        torch.cuda.synchronize()
+        assert int(ticket[0]) == 0 and float(acc2.abs().sum()) == 0.0
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
