@@ -258,6 +258,25 @@ int pn2_interp_concat(const float *points1, int64_t pB, int64_t pN, int64_t pD,
 int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, const float *w3, int B,
                    int N, int S, int D1, int D2, float *dpoints2, void *stream);
 
+/* ---- segmentation head tail on rows (models/pointnet2_sem_seg.py:36-39) -----------
+ * conv1 + bn1 run as one more pn2_linear_fwd layer; these two calls are what follows its pre-BatchNorm
+ * product Z [M, C] (bf16 rows, C % 8 == 0, C <= 256):
+ *   forward : a = dropout(relu(Z*scale + shift)); logp[M, NC] = log_softmax(a.W2^T + b2)   (NC <= 32 classes,
+ *             W2 [NC, C] fp32, b2 may be NULL); act_out (bf16 rows [M, ldo], may be NULL) receives a, which
+ *             conv2's weight gradient needs.
+ *   backward: dlogits = dlogp - exp(logp)*rowsum(dlogp);  dA[M, C] (bf16) = (dlogits.W2) * keep/(1-p), i.e. the
+ *             gradient w.r.t. relu(bn1(.)) that pn2_bn_relu_bwd_* take; db2[NC] = column sums of dlogits (through
+ *             the zeroed fp64 accumulator db2_accum[>= 32], left zero); dlogits_rows (bf16 [M, lddl], lddl % 8 == 0,
+ *             may be NULL) receives dlogits for pn2_linear_bwd_weight (conv2's weight gradient).
+ * Dropout keeps element (m, k) when hash(*seed, m*C + k) >= p (p quantised to 1/256; kept values scaled by
+ * 1/(1-p)); *seed is an int64 in DEVICE memory read at run time; drop_p = 0 (eval mode) ignores it. */
+int pn2_head_tail_fwd(const void *Z, int ldz, const float *scale, const float *shift, const float *W2,
+                      const float *b2, int64_t M, int C, int NC, float drop_p, const int64_t *seed,
+                      float *logp, void *act_out, int ldo, void *stream);
+int pn2_head_tail_bwd(const float *dlogp, const float *logp, const float *W2, int64_t M, int C, int NC,
+                      float drop_p, const int64_t *seed, void *dA, int ldda, void *dlogits_rows, int lddl,
+                      double *db2_accum, float *db2, void *stream);
+
 /* ---- layout helpers ------------------------------------------------------------
  * dst[r, c] (fp32, leading dim ldd) = src[r*sR + c*sC] for r < R, c < C: turns a
  * channel-major [C,R] slab into point-major rows (batched over B with strides). */

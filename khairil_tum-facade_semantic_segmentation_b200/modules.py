@@ -482,6 +482,82 @@ class _FeaturePropagationFn(torch.autograd.Function):
         return (None, None, None, None, None, dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[7:])
 
 
+class _FeaturePropagationHeadFn(torch.autograd.Function):
+    """The last feature-propagation level followed by the segmentation head (pointnet2_sem_seg.py:35-39) as ONE chain
+    of point-major rows: conv1 + bn1 ride as one more layer of the level's MLP (same tensor-core kernels, same fused
+    BatchNorm), then csrc/head.cu does ReLU -> dropout -> conv2 -> log_softmax per point.  Returns log-probabilities
+    [B, N, classes].  SURVEY.md 8(f) n2; the modules keep owning every parameter."""
+
+    @staticmethod
+    def forward(ctx, nn3, convs, bns, conv2, drop_p, seed, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+        B, N, _ = xyz1_r.shape
+        S = xyz2_r.shape[1]
+        dtype = ops.rows_dtype()
+        p2 = ops.as_rows(p2_r)
+        D2 = p2.shape[2]
+        D1 = 0 if p1_r is None else p1_r.shape[2]
+        idx3, w3 = nn3 if nn3 is not None else ops.three_nn(xyz1_r, xyz2_r)
+        K0 = D1 + D2
+        M = B * N
+        x0 = torch.empty(M, _row_ld(K0, dtype), device=p2.device, dtype=dtype)
+        pB, pN, pD = (0, 0, 0) if p1_r is None else p1_r.stride()
+        call("pn2_interp_concat", ptr(p1_r), pB, pN, pD, ptr(p2), S * D2, D2, 1, ptr(idx3), ptr(w3), B, N, S, D1, D2,
+             ptr(x0), x0.shape[1], dt(x0), stream())
+        want_bwd = any(ctx.needs_input_grad)
+        layers = mlp_forward(x0, K0, M, convs, bns, want_bwd)
+        last = layers[-1]
+        NC = conv2.out_channels
+        W2 = conv2.weight.detach().reshape(NC, -1)
+        W2 = W2 if W2.is_contiguous() else W2.contiguous()
+        b2 = None if conv2.bias is None else conv2.bias.detach()
+        logp = torch.empty(B, N, NC, device=p2.device, dtype=torch.float32)
+        act = torch.empty(M, last.Z.shape[1], device=p2.device, dtype=torch.bfloat16) if want_bwd else None
+        call("pn2_head_tail_fwd", ptr(last.Z), last.Z.shape[1], ptr(last.scale), ptr(last.shift), ptr(W2), ptr(b2), M,
+             last.N, NC, float(drop_p), ptr(seed), ptr(logp), ptr(act), 0 if act is None else act.shape[1], stream())
+        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, float(drop_p), seed, logp, act)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, drop_p, seed, logp, act = ctx.state
+        ctx.state = None
+        lib = load()
+        dev = dlogp.device
+        need1 = ctx.needs_input_grad[8] and D1 > 0
+        need2 = ctx.needs_input_grad[9]
+        NC, C = W2.shape
+        dlogp = dlogp.contiguous().view(M, NC)
+        dA = torch.empty(M, act.shape[1], device=dev, dtype=torch.bfloat16)
+        if dA.shape[1] != C:
+            dA[:, C:].zero_()
+        lddl = _round_up(_round_up(NC, 4), 8)
+        dl_rows = torch.empty(M, lddl, device=dev, dtype=torch.bfloat16)
+        db2 = _sink(conv2.bias)
+        if db2 is None:
+            db2 = torch.empty(NC, device=dev, dtype=torch.float32)
+        call("pn2_head_tail_bwd", ptr(dlogp), ptr(logp), ptr(W2), M, C, NC, drop_p, ptr(seed), ptr(dA), dA.shape[1],
+             ptr(dl_rows), lddl, ptr(_stat_accum(dev)), ptr(db2), stream())
+        dW2 = _sink(conv2.weight, (NC, C))
+        if dW2 is None:
+            dW2 = torch.empty(NC, C, device=dev, dtype=torch.float32)
+        scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, C, NC), device=dev, dtype=torch.uint8)
+        call("pn2_linear_bwd_weight", ptr(dl_rows), lddl, dt(dl_rows), ptr(act), act.shape[1], dt(act), None, None, M, C, NC,
+             ptr(dW2), ptr(scratch), stream())
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dA, None, 1, need1 or need2, convs, bns)
+        dp1 = dp2 = None
+        if need1:
+            dp1 = torch.empty(B, N, D1, device=dev, dtype=torch.float32)
+            call("pn2_rows_to_f32", ptr(dx0), dx0.shape[1], dt(dx0), M, 0, D1, ptr(dp1), stream())
+        if need2:
+            dp2 = torch.zeros(B, S, D2, device=dev, dtype=torch.float32)
+            call("pn2_interp_bwd", ptr(dx0), dx0.shape[1], dt(dx0), ptr(idx3), ptr(w3), B, N, S, D1, D2, ptr(dp2),
+                 stream())
+        n_mlp = 4 * len(convs)
+        tail_needs = ctx.needs_input_grad[10 + n_mlp:]
+        tail = (dW2.view_as(conv2.weight) if tail_needs[0] else None, db2 if len(tail_needs) > 1 and tail_needs[1] else None)
+        return (None,) * 8 + (dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[10:10 + n_mlp]) + tail[:len(tail_needs)]
+
+
 def _check_module_inputs(xyz, points):
     require_cuda(xyz, "xyz")
     if xyz.dim() != 3 or xyz.shape[1] != 3:
@@ -627,6 +703,29 @@ class PointNetFeaturePropagation(nn.Module):
         _check_module_inputs(xyz1, None)
         _check_module_inputs(xyz2, None)
         return ops.three_nn(xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1))
+
+    def head_applies(self, conv1, bn1, conv2, points2):
+        """Can forward_with_head run this head?  (bf16 rows on CUDA, <= 32 classes, a 1x1 conv of <= 256 channels)"""
+        return (ops.rows_dtype() == torch.bfloat16 and points2.is_cuda and isinstance(conv1, nn.Conv1d)
+                and isinstance(conv2, nn.Conv1d) and isinstance(bn1, nn.BatchNorm1d) and conv1.kernel_size == (1,)
+                and conv2.kernel_size == (1,) and conv1.in_channels == self.mlp_convs[-1].out_channels
+                and conv1.out_channels % 8 == 0 and conv1.out_channels <= 256 and conv2.in_channels == conv1.out_channels
+                and conv2.out_channels <= 32 and bn1.num_features == conv1.out_channels)
+
+    def forward_with_head(self, xyz1, xyz2, points1, points2, conv1, bn1, dropout, conv2, neighbours=None):
+        """This level followed by `log_softmax(conv2(dropout(relu(bn1(conv1(.))))))` (pointnet2_sem_seg.py:36-38) in one
+        chain of rows; returns the log-probabilities [B, N, classes] (already permuted as :39 does)."""
+        _check_module_inputs(xyz1, points1)
+        _check_module_inputs(xyz2, points2)
+        p = float(dropout.p) if (dropout is not None and dropout.training) else 0.0
+        seed = None
+        if p > 0.0:      # drawn on the device (CUDA generator), read by the kernels at run time: graph replays get fresh masks
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), device=points2.device, dtype=torch.int64)
+        convs, bns = list(self.mlp_convs) + [conv1], list(self.mlp_bns) + [bn1]
+        params = _flat_params(convs, bns) + [conv2.weight] + ([conv2.bias] if conv2.bias is not None else [])
+        return _FeaturePropagationHeadFn.apply(
+            neighbours, convs, bns, conv2, p, seed, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
+            None if points1 is None else points1.permute(0, 2, 1), points2.permute(0, 2, 1), *params)
 
     def forward(self, xyz1, xyz2, points1, points2, neighbours=None):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""

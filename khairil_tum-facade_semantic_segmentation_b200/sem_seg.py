@@ -89,6 +89,14 @@ class get_model(nn.Module):
         up = feats[4]
         for i, (fp, fine) in enumerate(zip(fps, (3, 2, 1, 0))):
             skip = feats[fine] if fine > 0 else None
+            if fine == 0 and self.fused_head and type(fp) is PointNetFeaturePropagation and fp.head_applies(
+                    self.conv1, self.bn1, self.conv2, up):
+                # the last level and the head as one chain of rows (csrc/head.cu); log-probabilities come out [B,N,classes]
+                if ahead:
+                    main.wait_event(events[4 + i])
+                pred = fp.forward_with_head(coords[0], coords[1], skip, up, self.conv1, self.bn1, self.drop1, self.conv2,
+                                            neighbours=nn3[i] if ahead else None)
+                return pred, l4_points
             if ahead:
                 main.wait_event(events[4 + i])
                 up = fp(coords[fine], coords[fine + 1], skip, up, neighbours=nn3[i])
@@ -96,7 +104,8 @@ class get_model(nn.Module):
                 up = fp(coords[fine], coords[fine + 1], skip, up)
         return self._head(up), l4_points
 
-    rows_head = True      # run the Conv1d/BN/Dropout/Conv1d/log_softmax head on point-major rows (no layout copies)
+    fused_head = True     # bf16 mode: fp1 + head as one chain of rows on this library's kernels
+    rows_head = True      # otherwise: the PyTorch head on point-major rows (no layout copies)
 
     def _head(self, up):
         """pointnet2_sem_seg.py:36-39.  `up` is [B,128,N]; when it comes from PointNetFeaturePropagation it is a
