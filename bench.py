@@ -17,6 +17,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -245,6 +246,157 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# =================================================================================================
+# The other configurations of BASELINE.json (run by hand, results under profiles/): same launcher, same JSON keys.
+# =================================================================================================
+def _rank_max(t, world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
+    """BASELINE.json configs[2]: FPS 65536 -> 16384 and ball query r = 0.1 / nsample = 32 on 64 unit-cube clouds (SURVEY
+    8(d) "Cfg 3"), the 64 clouds sharded contiguously over the ranks (strong scaling, no collective).  A step = both
+    kernels over the rank's clouds."""
+    import _inputs as I
+    B_total, N, S = 64, 65536, 16384
+    lo, hi = pn2.shard_range(B_total, rank, world)
+    cube_h = I.cube_xyz(B_total, N, 0)[lo:hi].contiguous().pin_memory()
+    start = I.start_indices(B_total, N, 2)[lo:hi].to(dev)
+    cube = cube_h.to(dev)
+
+    def step():
+        _, new_xyz = pn2.farthest_point_sample(cube, S, start=start, return_xyz=True)
+        return pn2.query_ball_point(0.1, 32, cube, new_xyz)
+
+    for _ in range(args.warmup):
+        step()
+    lib_mod.time_entry_point("*")
+    step()
+    calls = lib_mod.timed_calls()
+    lib_mod.time_entry_point(None)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = _rank_max(torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64), world).item()
+    # end to end: pinned host coordinates in, ball-query indices (int64, as the reference returns them) back on the host
+    out_h = torch.empty(hi - lo, S, 32, dtype=torch.int64).pin_memory()
+    barrier()
+    e0.record()
+    for _ in range(max(1, args.steps // 4)):
+        cube.copy_(cube_h, non_blocking=True)
+        out_h.copy_(step(), non_blocking=True)
+    e1.record()
+    barrier()
+    e2e = _rank_max(torch.tensor([e0.elapsed_time(e1) / max(1, args.steps // 4)], device=dev, dtype=torch.float64), world).item()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    pk, pk_kind = peaks()
+    by = {n: (a, t) for n, a, t in calls}
+    fps_ms, ball_ms = by["pn2_farthest_point_sample"][1], by["pn2_query_ball_point"][1]
+    b = hi - lo
+    ball_bytes = b * (12 * N + 12 * S + 8 * S * 32)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import c_oracle as C
+        n_cpu = 4
+        t = time.perf_counter()
+        xs = cube_h[:n_cpu].numpy()
+        idx = C.fps(xs, S, start[:n_cpu].cpu().numpy())
+        nx = np.take_along_axis(xs, idx[:, :, None].repeat(3, 2), 1)
+        C.ball_query(0.1, 32, xs, np.ascontiguousarray(nx))
+        sec = time.perf_counter() - t
+        cpu = {"value": n_cpu * N / sec, "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": "C oracle (scalar, one core), the complete workload for %d of the 64 clouds: %.1f s" % (n_cpu, sec)}
+    line = {
+        "metric": "points/sec (FPS 65536->16384 + ball query r=0.1 k=32, 64 clouds)", "value": B_total * N / (ms * 1e-3),
+        "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "kernel microbench: FPS 65536 -> 16384 + ball query r=0.1 nsample=32, 64 unit-cube clouds sharded over the ranks",
+                   "clouds_per_rank": b, "l2": "inputs (50 MB) and outputs (268 MB) per rank exceed nothing on their own; each kernel streams its cloud once"},
+        "e2e": {"value": B_total * N / (e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": b * N * 12, "d2h_bytes_per_step": b * S * 32 * 8,
+                "ms_per_step": e2e},
+        "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "roofline": {"kernel": "ball_query_kernel", "bound": "hbm", "achieved": ball_bytes / (ball_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": ball_bytes / (ball_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": ball_ms,
+                     "note": "the int64 index output dominates the bytes; fp32-ALU view: %.2f Tpair/s brute-force basis. "
+                             "fps_kernel: %.2f ms (%.3f us per iteration, latency chain, %d 8-CTA clusters at a time)"
+                             % (b * S * N / (ball_ms * 1e-3) / 1e12, fps_ms, fps_ms * 1e3 / S, 16)},
+        "cpu_baseline": cpu, "kernel_ms": {"fps": fps_ms, "ball_query": ball_ms},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_facade(args, rank, world, dev, pn2, barrier, sampler):
+    """BASELINE.json configs[3]: sem_seg_testing-style whole-facade inference (num_votes = 1): the block slots of a
+    synthetic ~10 M-point facade (8544 blocks of 4096 points, SURVEY 8(d) "Cfg 4": ~3.5 block slots per point) sharded
+    contiguously over the ranks, labelled batch by batch through the CUDA-graph predictor.  The whole measurement is end
+    to end (host blocks in, host labels out); a step = one batch."""
+    import _inputs as I
+    nb_total, batch = args.blocks, args.batch
+    lo, hi = pn2.shard_range(nb_total, rank, world)
+    torch.manual_seed(1234)
+    net = pn2.get_model(NUM_CLASSES, CHANNELS - 6).to(dev).eval()
+    chunks = [I.facade_batch(min(256, hi - s), NPOINT, CHANNELS, 7000 + s) for s in range(lo, hi, 256)]
+    blocks = torch.cat(chunks).pin_memory()
+    predictor = pn2.SemSegPredictor(net, batch, NPOINT, CHANNELS, dev)
+    for i in range(args.warmup):
+        predictor.predict_host(blocks[:batch])
+    labels = torch.empty(hi - lo, NPOINT, dtype=torch.int64)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n_batches = 0
+    for s in range(0, hi - lo, batch):
+        e = min(hi - lo, s + batch)
+        labels[s:e] = predictor.predict_host(blocks[s:e])
+        n_batches += 1
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = _rank_max(torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64), world).item()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    pts = nb_total * NPOINT
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import pn2_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        ref = O.OracleSemSeg(NUM_CLASSES, CHANNELS - 6).eval()
+        x = blocks[:16].float().transpose(2, 1)
+        with torch.no_grad():
+            ref(x)
+            t = time.perf_counter()
+            ref(x)
+            sec = time.perf_counter() - t
+        cpu = {"value": 16 * NPOINT / sec, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": "oracle port, eval forward of 16 blocks (%.2f s); the reference's own add_vote loop is not included" % sec}
+    value = pts / (ms * 1e-3)
+    line = {
+        "metric": "points/sec (whole-facade sliding-block inference, num_votes=1)", "value": value, "unit": "points/s",
+        "n_gpus": world, "steps": n_batches, "warmup": args.warmup, "ms_per_step": ms / n_batches, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "sem_seg_testing-style inference, %d block slots x %d points x %d ch (synthetic ~10 M-point facade), batch %d, "
+                               "blocks sharded over the ranks, labels per block slot returned to the host" % (nb_total, NPOINT, CHANNELS, batch),
+                   "blocks_per_rank": hi - lo, "launch": "one CUDA graph per batch", "wall_s_rank0": wall},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": batch * NPOINT * CHANNELS * 4,
+                "d2h_bytes_per_step": batch * NPOINT * 8, "ms_per_step": ms / n_batches},
+        "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,7 +408,16 @@ def main():
     ap.add_argument("--ref-sample-clouds", type=int, default=16,
                     help="clouds per step of the CPU reference arm (a bounded sample of the 32-cloud batch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--workload", default="train", choices=["train", "fps_ball", "facade"],
+                    help="train: BASELINE.json configs[1] (the headline; --channels 6 gives configs[4], the --RGB_OFF data-parallel run); "
+                         "fps_ball: configs[2]; facade: configs[3]")
+    ap.add_argument("--channels", type=int, default=9, choices=[6, 9], help="input channels: 9 = xyz+norm-xyz+RGB, 6 = --RGB_OFF")
+    ap.add_argument("--blocks", type=int, default=8544, help="facade workload: block slots of the synthetic facade")
+    ap.add_argument("--batch", type=int, default=128, help="facade workload: blocks per forward")
     args = ap.parse_args()
+    global CHANNELS, WORKLOAD
+    CHANNELS = args.channels
+    WORKLOAD = "sem_seg train step, synthetic facade blocks %dx%dx%dch per GPU, %d classes" % (B_PER_GPU, NPOINT, CHANNELS, NUM_CLASSES)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,13 +438,6 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     pn2.set_precision(args.precision)
 
-    torch.manual_seed(1234)                           # identical initial weights on every rank
-    trainer = pn2.SemSegTrainer(NUM_CLASSES, CHANNELS - 6, device=dev)
-    n_batches = 4
-    host = synthetic_batches(n_batches, 1000 * rank + 11)
-    resident = [(p.to(dev), t.to(dev)) for p, t in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -291,6 +445,25 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if args.workload != "train":
+        if args.workload == "fps_ball":
+            run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler)
+        else:
+            run_facade(args, rank, world, dev, pn2, barrier, sampler)
+        if world > 1:
+            sys.stdout.flush()
+            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            t.start()
+            t.join(20.0)
+            os._exit(0)
+        return
+
+    torch.manual_seed(1234)                           # identical initial weights on every rank
+    trainer = pn2.SemSegTrainer(NUM_CLASSES, CHANNELS - 6, device=dev)
+    n_batches = 4
+    host = synthetic_batches(n_batches, 1000 * rank + 11)
+    resident = [(p.to(dev), t.to(dev)) for p, t in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     # ---- every kernel of the path, event-timed live on its launching stream in an eager pass with the stream
     #      overlap switched off (a graph replay cannot carry events around one node; overlapping kernels would
