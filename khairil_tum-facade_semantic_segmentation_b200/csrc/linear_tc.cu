@@ -20,6 +20,7 @@
 //     stores; the train-mode BatchNorm column sums (sum z, sum z^2 of the STORED values) are
 //     accumulated from the staging tile with lanes walking columns (bank-conflict free) and
 //     kept in registers across tiles; added once per CTA into fp64 accumulators at the end.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -431,14 +432,28 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         a.w_resident = img_bytes <= 64 * 1024 ? 1 : 0;
         const size_t fixed = 1024 + (a.w_resident ? img_bytes : 0) + (size_t)((n_store + 63) / 64) * kTcAStage;
         const size_t slot = kTcAStage + (a.w_resident ? 0 : (size_t)n_pad * 128);
-        const size_t budgets[3] = {(size_t)(227 * 1024 / 3 - 1024 - static_smem), (size_t)(227 * 1024 / 2 - 1024 - static_smem),
-                                   (size_t)(227 * 1024 - static_smem)};
-        int stages = 0, per_sm = 1;
-        for (int b = 0; b < 3 && stages == 0; ++b) {
-            if (budgets[b] < fixed + slot * (b < 2 ? 3 : 2)) continue;
-            stages = (int)((budgets[b] - fixed) / slot);
-            per_sm = 3 - b;
+        // CTAs per SM: these layers stream rows and every tile is a serial chain (TMA -> transform -> MMA -> epilogue ->
+        // store), so co-resident CTAs are what hides the latency.  Take the densest packing (<= max_ctas, tensor memory
+        // allowing: n * columns <= 512) that still leaves a ring of >= 2 slots, except that 1-2 CTAs/SM prefer >= 3 slots.
+        // Measured: the 128 x 128 layers missed a third slot at 2/SM by 160 bytes, ran 1/SM at 0.8 TB/s, tensor pipe 5 % busy.
+        static int max_ctas = 0;
+        if (!max_ctas) {
+            const char *e = getenv("PN2_TC_MAX_CTAS");
+            max_ctas = e ? atoi(e) : 4;
+            if (max_ctas < 1 || max_ctas > 8) max_ctas = 4;
         }
+        uint32_t tmem_cols = 32;
+        while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
+        int stages = 0, per_sm = 1;
+        for (int pass = 0; pass < 2 && stages == 0; ++pass)
+            for (int n = max_ctas; n >= 1 && stages == 0; --n) {
+                if (n * (int)tmem_cols > 512) continue;
+                const size_t budget = (size_t)(233472 / n) - 1024 - (size_t)static_smem;
+                const int min_slots = (pass == 0 && n <= 2) ? 3 : 2;
+                if (budget < fixed + slot * (size_t)min_slots) continue;
+                stages = (int)((budget - fixed) / slot);
+                per_sm = n;
+            }
         if (stages < 2) {
             set_error("linear_tc: layer K=%d N=%d does not fit shared memory", K, nb);
             return PN2_ERR_UNSUPPORTED;
