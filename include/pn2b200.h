@@ -153,6 +153,13 @@ size_t pn2_linear_wgrad_scratch_bytes(int64_t M, int K, int N);
 int pn2_linear_bwd_weight(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx,
                           int x_dtype, const float *in_scale, const float *in_shift, int64_t M,
                           int K, int N, float *dW, void *scratch, void *stream);
+/* dW[N,K] += sum_m dZ[m,n] * act(X)[m,k]  (bf16 rows only): no scratch, no reduce launch -- every CTA adds its fp32
+ * block into dW with L2 reductions (red.global.add), so the caller zeroes dW first (the trainer's flat gradient
+ * buffer is zeroed once per step) and the summation order, hence the last fp32 bit, varies run to run -- like the
+ * reference's own cuDNN weight gradients (pointnet2_utils.py:198 backward); pn2_linear_bwd_weight is the fixed-order one */
+int pn2_linear_bwd_weight_accum(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx,
+                                int x_dtype, const float *in_scale, const float *in_shift, int64_t M,
+                                int K, int N, float *dW, void *stream);
 
 /* ---- BatchNorm (train statistics / eval fold) ---------------------------------
  * Train (:198 with module.training): turns the [PN2_STAT_REPLICAS][2][N] fp64 sums of pn2_linear_fwd
@@ -285,6 +292,17 @@ int pn2_to_rows(const float *src, int64_t sB, int64_t sR, int64_t sC, int B, int
 /* dst fp32 [M,C] contiguous = rows (any dtype) [M, ld] columns c0..c0+C */
 int pn2_rows_to_f32(const void *rows, int ld, int dtype, int64_t M, int c0, int C, float *dst,
                     void *stream);
+
+/* ---- test-time vote accumulation and final arg-max -------------------------
+ * replaces /root/reference/localfunctions.py:336-343 (add_vote, a Python loop over B x N pairs) and :405
+ * (np.argmax(vote_label_pool, 1)).  For every pair i < count with weight[i] != 0 and not inf (weight NULL = all
+ * pairs; fp32, or fp64 when weight_is_f64): votes[point_idx[i], pred_label[i]] += 1.  votes is the [P, NC] int32
+ * pool (the reference keeps float64 counts -- same integers), accumulated across calls; pairs whose index or label is
+ * out of range (an IndexError in the reference) are skipped and counted into *skipped (device, may be NULL). */
+int pn2_add_vote(const int64_t *point_idx, const int64_t *pred_label, const void *weight, int weight_is_f64,
+                 int64_t count, int64_t P, int NC, int32_t *votes, unsigned long long *skipped, void *stream);
+/* labels[p] = first class with the largest count (np.argmax); labels is int64 [P], or uint8 [P] when labels_are_u8 */
+int pn2_vote_argmax(const int32_t *votes, int64_t P, int NC, void *labels, int labels_are_u8, void *stream);
 
 #ifdef __cplusplus
 }

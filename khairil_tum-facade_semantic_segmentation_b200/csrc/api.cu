@@ -113,6 +113,16 @@ extern "C" int pn2_pack_weights(int n, const float *const *W_host, const int *K_
 
 static_assert(sizeof(pn2_bn_finalize) == sizeof(BnFinalize), "pn2_bn_finalize must mirror pn2::BnFinalize");
 
+extern "C" int pn2_linear_bwd_weight_accum(const void *dZ, int lddz, int dz_dtype, const void *X, int ldx, int x_dtype,
+                                           const float *in_scale, const float *in_shift, int64_t M, int K, int N,
+                                           float *dW, void *stream) {
+    PN2_REQUIRE(dZ && X && dW, "linear_bwd_weight_accum: null pointer");
+    PN2_REQUIRE(M >= 1 && K >= 1 && N >= 1 && lddz >= N && ldx >= K, "linear_bwd_weight_accum: bad sizes");
+    PN2_REQUIRE(!in_scale == !in_shift, "linear_bwd_weight_accum: in_scale and in_shift go together");
+    PN2_REQUIRE(tc_eligible(dz_dtype, lddz, x_dtype, ldx, dW), "linear_bwd_weight_accum: bf16 rows with 16-byte row pitch only");
+    return tc_linear_wgrad(dZ, lddz, X, ldx, in_scale, in_shift, M, K, N, dW, nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int pn2_linear_fwd_prepacked(const void *X, int ldx, int x_dtype, const float *in_scale,
                                         const float *in_shift, const float *W, const float *bias, int64_t M, int K, int N,
                                         void *Z, int ldz, int z_dtype, double *stat_accum, const void *wpack,

@@ -11,6 +11,7 @@
 
 namespace pn2 {
 
+
 int linear_num_partials(int64_t M);
 
 // "Last block finalizes": every block has added its partial sums into the fp64 accumulator (L2 atomics); the block
@@ -99,13 +100,68 @@ __global__ void bn_relu_max_kernel(const T *__restrict__ Z, int ldz, const float
     }
 }
 
+// bf16 rows, C % 8 == 0: one thread owns 8 channels of one group and streams its nsample rows with 16-byte loads, U rows
+// in flight (the scalar kernel above issues one 2-byte load per element: 1.9 TB/s on sa1's 134 MB; this one is HBM-bound)
+__global__ void __launch_bounds__(256)
+bn_relu_max_vec8_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                        const float *__restrict__ shift, int64_t G, int nsample, int C, float *__restrict__ out,
+                        int32_t *__restrict__ arg) {
+    const int cpr = C >> 3;
+    const int64_t total = G * cpr;
+    constexpr int U = 8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t g;
+        int c8;
+        fast_divmod(t, cpr, g, c8);
+        const int c0 = c8 << 3;
+        float sc[8], sh[8], best[8];
+        int bk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sc[e] = scale[c0 + e];
+            sh[e] = shift[c0 + e];
+            best[e] = -1.0f;
+            bk[e] = 0;
+        }
+        const __nv_bfloat16 *z = Z + g * nsample * (int64_t)ldz + c0;
+        for (int k0 = 0; k0 < nsample; k0 += U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < nsample) v[u] = *reinterpret_cast<const uint4 *>(z + (int64_t)(k0 + u) * ldz);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u >= nsample) break;
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(&v[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+                    const float a0 = fmaxf(fmaf(f.x, sc[2 * i], sh[2 * i]), 0.0f);
+                    const float a1 = fmaxf(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]), 0.0f);
+                    if (a0 > best[2 * i]) { best[2 * i] = a0; bk[2 * i] = k0 + u; }
+                    if (a1 > best[2 * i + 1]) { best[2 * i + 1] = a1; bk[2 * i + 1] = k0 + u; }
+                }
+            }
+        }
+        float *o = out + g * C + c0;
+        *reinterpret_cast<float4 *>(o) = make_float4(best[0], best[1], best[2], best[3]);
+        *reinterpret_cast<float4 *>(o + 4) = make_float4(best[4], best[5], best[6], best[7]);
+        if (arg) {
+            int32_t *a = arg + g * C + c0;
+            *reinterpret_cast<int4 *>(a) = make_int4(bk[0], bk[1], bk[2], bk[3]);
+            *reinterpret_cast<int4 *>(a + 4) = make_int4(bk[4], bk[5], bk[6], bk[7]);
+        }
+    }
+}
+
 template <typename T>
 __global__ void bn_relu_kernel(const T *__restrict__ Z, int ldz, const float *__restrict__ scale,
                                const float *__restrict__ shift, int64_t M, int C, float *__restrict__ out) {
     const int64_t total = M * C;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(e % C);
-        int64_t m = e / C;
+        int c;
+        int64_t m;
+        fast_divmod(e, C, m, c);
         out[e] = fmaxf(fmaf(ld_act<T>(Z + m * ldz + c), scale[c], shift[c]), 0.0f);
     }
 }
@@ -156,7 +212,7 @@ bn_bwd_reduce_kernel(const TA *__restrict__ dA, int ldda, const int32_t *__restr
 // (256 / (C/8))-th row, four rows in flight per thread, 16 fp32 accumulators in registers.
 // MODE 0: dense bf16 dA, 1: dense fp32 dA, 2: pooled fp32 dOut + arg-max map ("rows" are groups).
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_vec8_kernel(const void *__restrict__ dA_, int ldda, const int32_t *__restrict__ arg,
                           const __nv_bfloat16 *__restrict__ Z, int ldz, const float *__restrict__ scale,
                           const float *__restrict__ shift, const float *__restrict__ save_mean,
@@ -337,13 +393,16 @@ bn_bwd_dz_vec8_kernel(const __nv_bfloat16 *dA, int ldda, const float *__restrict
     const int cpr = C >> 3;
     const int64_t total = M * cpr;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(q % cpr) << 3;
-        const int64_t m = q / cpr;
+        int64_t m;
+        int c8;
+        fast_divmod(q, cpr, m, c8);
+        const int c0 = c8 << 3;
         const uint4 zr = *reinterpret_cast<const uint4 *>(Z + m * ldz + c0);
         float g[8];
         if (POOL) {
-            const int64_t grp = m / nsample;
-            const int k = (int)(m - grp * nsample);
+            int64_t grp;
+            int k;
+            fast_divmod(m, nsample, grp, k);
             const int4 a0 = *reinterpret_cast<const int4 *>(arg + grp * C + c0);
             const int4 a1 = *reinterpret_cast<const int4 *>(arg + grp * C + c0 + 4);
             const float4 d0 = *reinterpret_cast<const float4 *>(dOut + grp * C + c0);
@@ -418,6 +477,13 @@ extern "C" int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float 
     PN2_REQUIRE(valid_dtype(z_dtype) && nsample >= 1 && C >= 1 && ldz >= C, "bn_relu_max: bad arguments");
     int64_t total = G * C;
     if (total == 0) return PN2_OK;
+    if (z_dtype == PN2_BF16 && C % 8 == 0 && ldz % 8 == 0 && ((uintptr_t)Z & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+        (!arg || ((uintptr_t)arg & 15) == 0)) {
+        bn_relu_max_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)Z, ldz, scale, shift, G, nsample, C, out, arg);
+        count_launch();
+        return check_launch("bn_relu_max_vec8");
+    }
     PN2_DISPATCH_DTYPE(z_dtype, T, (bn_relu_max_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T *)Z, ldz, scale, shift, G, nsample, C, out, arg)));
     count_launch();
@@ -447,7 +513,9 @@ static int reduce_dispatch(const void *dA, int ldda, int da_dtype, const int32_t
         const int rstep = 256 / (C / 8);
         const int per_pass = rstep * (POOL ? 2 : 4);
         int64_t want = (R + per_pass - 1) / per_pass;
-        const int grid = (int)(want < 1 ? 1 : (want > 2 * kNumSMs ? 2 * kNumSMs : want));
+        // three co-resident CTAs per SM (register-limited, __launch_bounds__(256, 3)): every loop trip exposes one
+        // full memory latency, so the bytes in flight come from co-resident warps (2/SM measured 2.3 TB/s on sa1)
+        const int grid = (int)(want < 1 ? 1 : (want > 3 * kNumSMs ? 3 * kNumSMs : want));
         if (POOL)
             bn_bwd_reduce_vec8_kernel<2><<<grid, 256, 0, st>>>(dA, ldda, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift,
                                                                save_mean, save_invstd, R, nsample, C, accum, ticket, dgamma, dbeta);
@@ -525,6 +593,76 @@ extern "C" int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *d
     return check_launch("bn_bwd_finalize");
 }
 
+// Pooled variant of bn_bwd_dz_vec8_kernel with the group's gradient and arg-max map loaded ONCE per thread for KU samples:
+// the per-sample form re-reads 64 bytes of (dOut, arg) from L2 for every 16 bytes of Z, which made it L2-bound (1.8 TB/s of
+// HBM traffic on sa1); here the ratio is 64 : 16*KU and the KU row loads are in flight together.
+template <int KU>
+__global__ void __launch_bounds__(256)
+pool_bwd_dz_vec8_kernel(const float *__restrict__ dOut, const int32_t *__restrict__ arg, const __nv_bfloat16 *__restrict__ Z,
+                        int ldz, const float *__restrict__ scale, const float *__restrict__ shift,
+                        const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                        const float *__restrict__ dgamma, const float *__restrict__ dbeta, int64_t G, int nsample, int C,
+                        float inv_m, __nv_bfloat16 *__restrict__ dZ, int lddz) {
+    extern __shared__ float coef[];   // [4][C]: sc, sh, a, b
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = scale[c];
+        float a = 0.0f, b = 0.0f;
+        if (save_mean) {
+            a = -sc * dgamma[c] * save_invstd[c] * inv_m;
+            b = -sc * dbeta[c] * inv_m - a * save_mean[c];
+        }
+        coef[c] = sc;
+        coef[C + c] = shift[c];
+        coef[2 * C + c] = a;
+        coef[3 * C + c] = b;
+    }
+    __syncthreads();
+    const int cpr = C >> 3, kchunks = (nsample + KU - 1) / KU;
+    const int64_t total = G * kchunks * cpr;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        int64_t t, grp;
+        int c8, kc;
+        fast_divmod(q, cpr, t, c8);
+        fast_divmod(t, kchunks, grp, kc);
+        const int c0 = c8 << 3, k0 = kc * KU;
+        const int4 a0 = *reinterpret_cast<const int4 *>(arg + grp * C + c0);
+        const int4 a1 = *reinterpret_cast<const int4 *>(arg + grp * C + c0 + 4);
+        const float4 d0 = *reinterpret_cast<const float4 *>(dOut + grp * C + c0);
+        const float4 d1 = *reinterpret_cast<const float4 *>(dOut + grp * C + c0 + 4);
+        const int ai[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float di[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const int64_t m0 = grp * nsample + k0;
+        uint4 zr[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u)
+            if (k0 + u < nsample) zr[u] = *reinterpret_cast<const uint4 *>(Z + (m0 + u) * ldz + c0);
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            if (k0 + u >= nsample) break;
+            const uint32_t *zw = reinterpret_cast<const uint32_t *>(&zr[u]);
+            uint4 out;
+            uint32_t *ow = reinterpret_cast<uint32_t *>(&out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&zw[i]));
+                float d[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int e = 2 * i + j, c = c0 + e;
+                    const float zz = j ? z.y : z.x;
+                    const float sc = coef[c];
+                    const float g = ai[e] == k0 + u ? di[e] : 0.0f;
+                    const float gg = (fmaf(zz, sc, coef[C + c]) > 0.0f) ? g : 0.0f;
+                    d[j] = fmaf(sc, gg, fmaf(coef[2 * C + c], zz, coef[3 * C + c]));
+                }
+                __nv_bfloat162 o = __floats2bfloat162_rn(d[0], d[1]);
+                ow[i] = *reinterpret_cast<uint32_t *>(&o);
+            }
+            *reinterpret_cast<uint4 *>(dZ + (m0 + u) * lddz + c0) = out;
+        }
+    }
+}
+
 template <bool POOL>
 static int dz_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *arg, const void *Z, int ldz,
                        int z_dtype, const float *scale, const float *shift, const float *save_mean,
@@ -533,6 +671,16 @@ static int dz_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *ar
     const float inv_m = 1.0f / (float)M;
     if (z_dtype == PN2_BF16 && dz_dtype == PN2_BF16 && (POOL || da_dtype == PN2_BF16) && C % 8 == 0 && ldz % 8 == 0 &&
         lddz % 8 == 0 && (POOL || ldda % 8 == 0) && C <= 2048) {
+        if (POOL && M % nsample == 0) {
+            constexpr int KU = 8;
+            const int64_t G = M / nsample;
+            const int pgrid = grid_for(G * ((nsample + KU - 1) / KU) * (C / 8), 256, kNumSMs * 4);
+            pool_bwd_dz_vec8_kernel<KU><<<pgrid, 256, sizeof(float) * 4 * C, st>>>(
+                (const float *)dA, arg, (const __nv_bfloat16 *)Z, ldz, scale, shift, save_mean, save_invstd, dgamma, dbeta, G,
+                nsample, C, inv_m, (__nv_bfloat16 *)dZ, lddz);
+            count_launch();
+            return check_launch("pool_bwd_dz_vec8");
+        }
         const int vgrid = grid_for(M * (C / 8), 256, kNumSMs * 8);
         bn_bwd_dz_vec8_kernel<POOL><<<vgrid, 256, sizeof(float) * 4 * C, st>>>(
             POOL ? nullptr : (const __nv_bfloat16 *)dA, ldda, POOL ? (const float *)dA : nullptr, arg,

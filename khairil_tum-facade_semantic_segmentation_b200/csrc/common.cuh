@@ -40,6 +40,24 @@ __device__ __forceinline__ float expanded_sqdist(float ax, float ay, float az, f
     return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, mm), an), bn);
 }
 
+// q = quo * d + rem for a small positive divisor: a shift when d is a power of two (channel chunks per row and nsample
+// almost always are), 32-bit division when q fits, 64-bit division (~100 instructions) only as the last resort --
+// the streaming kernels below do 2-3 of these per 16-byte element
+__device__ __forceinline__ void fast_divmod(int64_t q, int d, int64_t &quo, int &rem) {
+    if ((d & (d - 1)) == 0) {
+        const int sh = 31 - __clz(d);
+        quo = q >> sh;
+        rem = (int)(q & (d - 1));
+    } else if (q <= 0xffffffffLL) {
+        const uint32_t u = (uint32_t)q, v = u / (uint32_t)d;
+        quo = v;
+        rem = (int)(u - v * (uint32_t)d);
+    } else {
+        quo = q / d;
+        rem = (int)(q - quo * d);
+    }
+}
+
 // ---- row element access for fp32 / bf16 activations -----------------------------
 template <typename T> __device__ __forceinline__ float ld_act(const T *p);
 template <> __device__ __forceinline__ float ld_act<float>(const float *p) { return *p; }

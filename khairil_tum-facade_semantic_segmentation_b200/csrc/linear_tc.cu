@@ -335,6 +335,250 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Version 2 of the layer kernel: the same tile arithmetic, software-pipelined across tiles inside ONE persistent CTA.
+//   warps 0-3  epilogue group : TMEM -> (+bias) -> bf16 -> staging -> TMA store (+ column statistics)
+//   warps 4-7  transform group: previous layer's BatchNorm+ReLU in place on the landed A chunk; thread 128 issues the MMAs
+//   warp  8    producer       : TMA loads of the A chunks (and W chunks when streamed) into a deep ring
+// The accumulator is double buffered in tensor memory (2 x n_pad columns), so the MMAs of tile t+1 (and the loads of
+// tiles t+2...) run while the epilogue group drains tile t: the ring, not the number of co-resident CTAs, hides the HBM
+// latency (v1 measured 0.8-2.1 TB/s on the 128 x 128 layers with the tensor pipe 5 % busy).
+// -------------------------------------------------------------------------------------------------
+constexpr int kLinTc2Threads = 288;
+constexpr int kTc2MaxStages = 12;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid_constant__ TcLinearArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kTc2MaxStages], bar_empty[kTc2MaxStages], bar_w, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
+    const int z_slabs = (a.n_store + 63) >> 6;
+    uint8_t *const w_res = smem;
+    uint8_t *const staging = smem + (a.w_resident ? (size_t)a.KC * b_bytes : 0);
+    uint8_t *const ring = staging + (size_t)z_slabs * kTcAStage;
+    const uint32_t slot_bytes = kTcAStage + (a.w_resident ? 0u : b_bytes);
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * a.n_pad) tmem_cols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+        }
+        mbar_init(&bar_w, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 1);
+        }
+        mbar_init_fence();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const int64_t m_tiles = (a.M + kTcBM - 1) / kTcBM;
+
+    if (warp == 8) {
+        // ---- producer ----
+        if (lane == 0) {
+            tma_prefetch_desc(&a.tm_x);
+            if (a.w_resident) {
+                mbar_expect_tx(&bar_w, (uint32_t)a.KC * b_bytes);
+                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
+            }
+            uint32_t n = 0;
+            for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x)
+                for (int kc = 0; kc < a.KC; ++kc, ++n) {
+                    const uint32_t s = n % (uint32_t)a.stages, use = n / (uint32_t)a.stages;
+                    if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1u);
+                    uint8_t *slot = ring + (size_t)s * slot_bytes;
+                    mbar_expect_tx(&bar_full[s], slot_bytes);
+                    tma_load_2d(slot, &a.tm_x, kc * kTcBK, (int)(tile * kTcBM), &bar_full[s]);
+                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
+                }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ---- transform group + MMA issue (thread 128) ----
+        const int ttid = tid - 128;
+        const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
+        const int t_cc = (ttid & 7) ^ ((ttid >> 3) & 7);
+        if (a.w_resident && ttid == 0) mbar_wait(&bar_w, 0);
+        uint32_t n = 0, t = 0;
+        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+            const uint32_t buf = t & 1u, buse = t >> 1;
+            for (int kc = 0; kc < a.KC; ++kc, ++n) {
+                const uint32_t s = n % (uint32_t)a.stages, par = (n / (uint32_t)a.stages) & 1u;
+                uint8_t *slot = ring + (size_t)s * slot_bytes;
+                if (a.in_scale) {
+                    const int k = kc * kTcBK + t_cc * 8;
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const bool ok = k + e < a.K;
+                        sc[e] = ok ? a.in_scale[k + e] : 0.0f;
+                        sh[e] = ok ? a.in_shift[k + e] : 0.0f;
+                    }
+                    mbar_wait(&bar_full[s], par);
+                    if (k < a.K) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint4 *ptr = reinterpret_cast<uint4 *>(slot + (size_t)(ttid + 128 * i) * 16);
+                            uint4 v = *ptr;
+                            uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float2 f = unpack_bf16x2(w[e2]);
+                                f.x = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.0f);
+                                f.y = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f);
+                                w[e2] = pack_bf16x2(f.x, f.y);
+                            }
+                            *ptr = v;
+                        }
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(2, 128);
+                } else if (ttid == 0) {
+                    mbar_wait(&bar_full[s], par);
+                }
+                if (ttid == 0) {
+                    if (kc == 0 && buse > 0) mbar_wait(&acc_empty[buf], (buse - 1) & 1u);   // the epilogue drained this buffer
+                    fence_after_sync();
+                    const int k_left = a.K - kc * kTcBK;
+                    const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
+                    const uint32_t a_base = smem_addr(slot);
+                    const uint32_t b_base = smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage);
+                    for (int j = 0; j < nk; ++j)
+                        umma_bf16(tmem + buf * (uint32_t)a.n_pad, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024),
+                                  idesc, (uint32_t)((kc | j) != 0));
+                    umma_commit(&bar_empty[s]);
+                    if (kc == a.KC - 1) umma_commit(&acc_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ---- epilogue group ----
+        float sum1[8], sum2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum1[i] = sum2[i] = 0.0f;
+        uint32_t t = 0;
+        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+            const int64_t m0 = tile * kTcBM;
+            const uint32_t buf = t & 1u;
+            mbar_wait(&acc_full[buf], (t >> 1) & 1u);
+            fence_after_sync();
+            const uint32_t taddr = tmem + buf * (uint32_t)a.n_pad + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < a.n_store; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (a.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.N) v[i] += a.bias[c0 + i];
+                }
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
+                lo.z = pack_bf16x2(v[4], v[5]);   lo.w = pack_bf16x2(v[6], v[7]);
+                hi.x = pack_bf16x2(v[8], v[9]);   hi.y = pack_bf16x2(v[10], v[11]);
+                hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+                uint8_t *slab = staging + (size_t)(c0 >> 6) * kTcAStage;
+                const int ch = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch)) = lo;
+                if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
+            }
+            fence_before_sync();     // this thread's TMEM reads are complete
+            fence_proxy_async();     // staging writes -> visible to the TMA store
+            named_bar_sync(1, 128);
+            if (tid == 0) {
+                mbar_arrive(&acc_empty[buf]);    // the MMAs of tile t+2 may overwrite this accumulator buffer
+                for (int j = 0; j < z_slabs; ++j) tma_store_2d(&a.tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
+            }
+            if (STATS) {
+                const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int p = lane + 32 * j;
+                    if (2 * p < a.N) {
+                        const uint8_t *slab = staging + (size_t)(p >> 5) * kTcAStage;
+                        const int ch = (p & 31) >> 2, inb = (p & 3) * 4;
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                        for (int r = 0; r < rows; ++r) {
+                            const float2 f = unpack_bf16x2(
+                                *reinterpret_cast<const uint32_t *>(slab + sw128_offset(warp * 32 + r, ch) + inb));
+                            s1a += f.x; s1b += f.y;
+                            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+                        }
+                        sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
+                        sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
+                    }
+                }
+            }
+            if (tid == 0) tma_store_wait_read();
+            named_bar_sync(1, 128);   // staging free again
+        }
+        if (tid == 0) tma_store_wait_all();
+
+        if (STATS) {
+            float(*s_part)[2][256] = reinterpret_cast<float(*)[2][256]>(staging);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p = lane + 32 * j;
+                s_part[warp][0][2 * p] = sum1[2 * j];     s_part[warp][0][2 * p + 1] = sum1[2 * j + 1];
+                s_part[warp][1][2 * p] = sum2[2 * j];     s_part[warp][1][2 * p + 1] = sum2[2 * j + 1];
+            }
+            named_bar_sync(1, 128);
+            for (int c = tid; c < a.N; c += 128) {
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
+                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
+                atomicAdd(acc + c, (double)t1);
+                atomicAdd(acc + a.stat_ld + c, (double)t2);
+            }
+            if (a.fin.ticket) {
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (tid == 0) s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+                named_bar_sync(1, 128);
+                if (s_last) {
+                    __threadfence();
+                    for (int c = tid; c < a.N; c += 128) {
+                        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                        for (int r = 0; r < kStatReplicas; ++r) {
+                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + a.stat_off;
+                            s1 += __ldcg(acc + c);
+                            s2 += __ldcg(acc + a.stat_ld + c);
+                            acc[c] = 0.0;
+                            acc[a.stat_ld + c] = 0.0;
+                        }
+                        bn_finalize_channel(s1, s2, a.M, a.stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
+                                            a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
+                                            a.fin.save_mean, a.fin.save_invstd);
+                    }
+                    if (tid == 0) {
+                        *a.fin.ticket = 0u;
+                        if (a.fin.num_batches_tracked && a.stat_off == 0) *a.fin.num_batches_tracked += 1;
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 int tc_pack_weights(int n, const float *const *W, const int *K, const int *N, const int *transposed, void *const *wpack,
@@ -378,7 +622,16 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
                  int64_t w_sk, const float *bias, int64_t M, int K, int N, void *Z, int ldz, double *stat_accum,
                  void *wpack, cudaStream_t st, bool packed, const BnFinalize *fin) {
     static bool attr_done = false;
-    static int static_smem = 0;
+    static int static_smem = 0, static_smem2 = 0;
+    // PN2_TC2: 0 = v1 kernel (co-resident CTAs), 1 = v2 pipelined kernel with one CTA per SM, 2 = v2 with up to two,
+    // 3 (default) = per layer: v1 when K is one 64-wide chunk (the sa1/sa2 layers: a tile is one load + <= 4 MMAs, the
+    // co-resident CTAs win by 5-15 %), v2 (<= 2 CTAs) when K spans several chunks (fp1 128 x 128: 46 -> 34 us, sa3.3 38 -> 32 us)
+    static int tc2_mode = -1;
+    if (tc2_mode < 0) {
+        const char *e = getenv("PN2_TC2");
+        tc2_mode = e ? atoi(e) : 3;
+        if (tc2_mode < 0 || tc2_mode > 3) tc2_mode = 3;
+    }
     if (!attr_done) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, linear_tc_kernel<true>);
@@ -389,6 +642,14 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, linear_tc_kernel<false>);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, linear_tc2_kernel<true>);
+        static_smem2 = (int)fa.sharedSizeBytes;
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(linear_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024 - (int)fa.sharedSizeBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(linear_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024 - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) {
             set_error("linear_tc: shared-memory opt-in failed: %s", cudaGetErrorString(e));
@@ -441,6 +702,37 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
             const char *e = getenv("PN2_TC_MAX_CTAS");
             max_ctas = e ? atoi(e) : 4;
             if (max_ctas < 1 || max_ctas > 8) max_ctas = 4;
+        }
+        const int v2_ctas = tc2_mode == 3 ? (KC >= 2 ? 2 : 0) : tc2_mode;
+        if (v2_ctas > 0) {
+            // v2: the ring hides the latency -- one CTA per SM with every byte of shared memory that is left as ring slots
+            // (or two CTAs when each still gets >= 4 slots and 2 x 2 accumulator buffers fit tensor memory)
+            uint32_t cols2 = 32;
+            while ((int)cols2 < 2 * n_pad) cols2 <<= 1;
+            int stages2 = 0, per_sm2 = 1;
+            for (int n = v2_ctas; n >= 1 && stages2 == 0; --n) {
+                if (n * (int)cols2 > 512) continue;
+                const size_t budget = (size_t)(233472 / n) - 1024 - (size_t)static_smem2;
+                if (budget < fixed + slot * (size_t)(n > 1 ? 4 : 2)) continue;
+                stages2 = (int)((budget - fixed) / slot);
+                per_sm2 = n;
+            }
+            if (stages2 >= 2) {
+                if (stages2 > kTc2MaxStages) stages2 = kTc2MaxStages;
+                a.stages = stages2;
+                const size_t dyn2 = fixed + slot * stages2;
+                int64_t grid2 = (int64_t)per_sm2 * kNumSMs;
+                if (grid2 > m_tiles) grid2 = m_tiles;
+                if (stat_accum)
+                    linear_tc2_kernel<true><<<(unsigned)grid2, kLinTc2Threads, dyn2, st>>>(a);
+                else
+                    linear_tc2_kernel<false><<<(unsigned)grid2, kLinTc2Threads, dyn2, st>>>(a);
+                count_launch();
+                int rc2 = check_launch("linear_tc2");
+                if (rc2 != PN2_OK) return rc2;
+                img += img_bytes;
+                continue;
+            }
         }
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
@@ -499,7 +791,16 @@ struct TcWgradArgs {
     int nblk_k;        // blockIdx.y = (dW row block of 128) * nblk_k + (dW column block of 256)
     int a_slabs, b_slabs, R;   // ring-slot geometry of the largest block
     float *scratch;    // [splits][N][K_ld]
+    float *dW_accum;   // non-null: no partials -- every CTA adds its block straight into dW[N][K] (red.global.add.f32)
+    int accum_vec4;    // dW is 16-byte aligned and K % 4 == 0: red.global.add.v4.f32
 };
+
+__device__ __forceinline__ void red_add_f32(float *p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 constexpr int kWgStages = 4;           // ring slots
 constexpr int kWgThreads = 160;        // warps 0-3: activation transform + epilogue (thread 0 issues the MMAs); warp 4: TMA producer
@@ -616,6 +917,26 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
         const int n = n0 + tid;
         float *out = a.scratch + ((size_t)blockIdx.x * a.N + n) * a.K_ld + k0;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        if (a.dW_accum) {
+            // accumulate mode: dW was zeroed by its owner (the gradient sink, once per step); fp32 reductions at L2
+            float *acc = a.dW_accum + (size_t)n * a.K + k0;
+            if (n_it > 0)
+                for (int c0 = 0; c0 < kb_pad; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    if (tid < nb) {
+                        if (a.accum_vec4) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                if (c0 + i < kb) red_add_v4_f32(acc + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < kb) red_add_f32(acc + c0 + i, v[i]);
+                        }
+                    }
+                }
+        } else
         for (int c0 = 0; c0 < kb_pad; c0 += 16) {
             float v[16];
             if (n_it > 0) tmem_ld16(taddr + c0, v);
@@ -663,7 +984,7 @@ struct WgradPlan {
     size_t dyn_smem;
 };
 
-static WgradPlan tc_wgrad_plan(int64_t M, int K, int N) {
+static WgradPlan tc_wgrad_plan(int64_t M, int K, int N, bool accumulate = false) {
     WgradPlan p;
     p.nblk_n = (N + 127) / 128;
     p.nblk_k = (K + 255) / 256;
@@ -681,7 +1002,9 @@ static WgradPlan tc_wgrad_plan(int64_t M, int K, int N) {
     const int blocks = p.nblk_n * p.nblk_k;
     int64_t s = (2 * kNumSMs + blocks - 1) / blocks;
     const int64_t max_rows = (M + 2 * R - 1) / (2 * R);
-    const double chain = (double)M / R * 1e-6, part = 2.0 * N * p.K_ld * 4.0 / 3.0e12;
+    // partial cost per split: write + re-read of an fp32 block (reduce kernel), or -- accumulate mode -- one pass of
+    // L2 reductions, which also lets the small layers use every SM
+    const double chain = (double)M / R * 1e-6, part = (accumulate ? 0.5 : 2.0) * N * p.K_ld * 4.0 / 3.0e12;
     int64_t s_bal = (int64_t)(sqrt(chain / part) + 0.5);
     if (s > max_rows) s = max_rows;
     if (s > s_bal) s = s_bal;
@@ -696,8 +1019,10 @@ size_t tc_wgrad_scratch_bytes(int64_t M, int K, int N) {
     return sizeof(float) * (size_t)p.splits * (size_t)N * (size_t)p.K_ld + 16;
 }
 
+// scratch == nullptr: accumulate mode, dW += dZ^T act(X) (dW zeroed by the caller); else dW = ... through fp32 partials
 int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const float *in_scale, const float *in_shift,
                     int64_t M, int K, int N, float *dW, void *scratch, cudaStream_t st) {
+    const bool accumulate = scratch == nullptr;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncAttributes fa;
@@ -712,7 +1037,7 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
         }
         attr_done = true;
     }
-    const WgradPlan p = tc_wgrad_plan(M, K, N);
+    const WgradPlan p = tc_wgrad_plan(M, K, N, accumulate);
     TcWgradArgs a;
     if (!make_rows_tensor_map(&a.tm_dz, dZ, M, lddz, lddz, p.R) || !make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, p.R)) {
         set_error("wgrad_tc: cuTensorMapEncodeTiled failed (M=%lld lddz=%d ldx=%d R=%d)", (long long)M, lddz, ldx, p.R);
@@ -723,10 +1048,12 @@ int tc_linear_wgrad(const void *dZ, int lddz, const void *X, int ldx, const floa
     a.M = M; a.rows_per_split = p.rows_per_split; a.K = K; a.N = N; a.K_ld = p.K_ld;
     a.nblk_k = p.nblk_k; a.a_slabs = p.a_slabs; a.b_slabs = p.b_slabs; a.R = p.R;
     a.scratch = (float *)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+    a.dW_accum = accumulate ? dW : nullptr;
+    a.accum_vec4 = (accumulate && ((uintptr_t)dW & 15) == 0 && K % 4 == 0) ? 1 : 0;
     wgrad_tc_kernel<<<dim3((unsigned)p.splits, (unsigned)(p.nblk_n * p.nblk_k)), kWgThreads, p.dyn_smem, st>>>(a);
     count_launch();
     int rc = check_launch("wgrad_tc");
-    if (rc != PN2_OK) return rc;
+    if (rc != PN2_OK || accumulate) return rc;
     const int64_t NK = (int64_t)N * K;
     wgrad_reduce_kernel2<<<(unsigned)((NK + 31) / 32), dim3(32, 8), 0, st>>>(a.scratch, p.splits, N, K, p.K_ld, dW);
     count_launch();

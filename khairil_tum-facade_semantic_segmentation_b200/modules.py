@@ -12,6 +12,7 @@ One autograd.Function per module: forward = FPS -> ball query -> gather -> MLP
 (-> max over nsample); backward is hand written on the same kernels.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -42,33 +43,39 @@ _ACCUM_COLS = 4096
 _ACCUM_REPLICAS = 8          # PN2_STAT_REPLICAS of include/pn2b200.h
 
 
-def _stat_accum(dev):
-    """[PN2_STAT_REPLICAS][2][C <= 4096] fp64 accumulator of the column-sum epilogues, one per (device, stream).  It is
-    zero whenever no producer/finalize pair is in flight on that stream: allocated zeroed, and every
-    *_finalize entry point zeroes what it consumed (so a step needs no extra memset launches)."""
+def _scratch(table, dev, make):
+    """One zero-initialised scratch tensor per (device, stream) for eager launches, plus ONE per device shared by every
+    CUDA-graph capture (allocated eagerly -- outside any graph pool -- the first time an eager launch needs scratch, which
+    the warm-up passes before a capture always do).  The kernels leave these buffers zeroed, so neither eager steps nor
+    graph replays need memset launches; captured graphs that use them must not be replayed concurrently with each other."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        buf = table.get((dev.index, "capture"))
+        # no eager launch preceded this capture: a buffer created now lives in the graph's pool, zeroed by a memset node
+        return buf if buf is not None else make()
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    buf = _ACCUM.get(key)
-    if buf is None or torch.cuda.is_current_stream_capturing():
-        # a buffer created while capturing lives in the graph's pool and is zeroed by a memset node
-        buf = torch.zeros(_ACCUM_REPLICAS * 2 * _ACCUM_COLS, device=dev, dtype=torch.float64)
-        if not torch.cuda.is_current_stream_capturing():
-            _ACCUM[key] = buf
+    buf = table.get(key)
+    if buf is None:
+        buf = table[key] = make()
+        if (dev.index, "capture") not in table:
+            table[(dev.index, "capture")] = make()
     return buf
+
+
+def _stat_accum(dev):
+    """[PN2_STAT_REPLICAS][2][C <= 4096] fp64 accumulator of the column-sum epilogues.  It is zero whenever no
+    producer/finalize pair is in flight on its stream: allocated zeroed, and every *_finalize entry point zeroes what it
+    consumed (so a step needs no extra memset launches)."""
+    return _scratch(_ACCUM, dev, lambda: torch.zeros(_ACCUM_REPLICAS * 2 * _ACCUM_COLS, device=dev, dtype=torch.float64))
 
 
 _TICKET = {}
 
 
 def _ticket(dev):
-    """Zero-initialised uint32 the "last block finalizes" kernels count on; they leave it zero, so one per
-    (device, stream) serves every layer (same life cycle as _stat_accum)."""
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    buf = _TICKET.get(key)
-    if buf is None or torch.cuda.is_current_stream_capturing():
-        buf = torch.zeros(4, device=dev, dtype=torch.int32)
-        if not torch.cuda.is_current_stream_capturing():
-            _TICKET[key] = buf
-    return buf
+    """Zero-initialised uint32 the "last block finalizes" kernels count on; they leave it zero, so one serves every layer
+    (same life cycle as _stat_accum)."""
+    return _scratch(_TICKET, dev, lambda: torch.zeros(4, device=dev, dtype=torch.int32))
 
 
 def _pack_weights(Ws, Ks, Ns, transposed, dev):
@@ -167,6 +174,30 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     return layers
 
 
+WGRAD_ACCUMULATE = os.environ.get("PN2_WGRAD_DETERMINISTIC", "0") != "1" and os.environ.get("PN2_DISABLE_TC", "0") != "1"
+# bf16 rows: weight gradients are added straight into the (zeroed) gradient buffer with L2 reductions -- no fp32 partials,
+# no reduce launch; PN2_WGRAD_DETERMINISTIC=1 keeps the fixed-order partial + reduce path (pn2_linear_bwd_weight)
+
+
+def _weight_grad(dZ, xin, ldx, sc, sh, M, K, N, param, dev, cuda_stream, keep):
+    """dW [N, K] of one layer on `cuda_stream`: into the parameter's gradient-sink view when there is one."""
+    lib = load()
+    dW = _sink(param, (N, K))
+    if WGRAD_ACCUMULATE and dZ.dtype == torch.bfloat16 and xin.dtype == torch.bfloat16 and dZ.shape[1] % 8 == 0 and ldx % 8 == 0:
+        if dW is None:
+            dW = torch.zeros(N, K, device=dev, dtype=torch.float32)      # a sink is zeroed once per step by its owner
+        call("pn2_linear_bwd_weight_accum", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M, K, N,
+             ptr(dW), cuda_stream)
+        return dW
+    if dW is None:
+        dW = torch.empty(N, K, device=dev, dtype=torch.float32)
+    scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, K, N), device=dev, dtype=torch.uint8)
+    call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M, K, N, ptr(dW),
+         ptr(scratch), cuda_stream)
+    keep.append(scratch)
+    return dW
+
+
 OVERLAP_WGRAD = True      # weight gradients on a side stream, concurrently with the data-gradient / BatchNorm chain
 _SIDE = {}
 _GRAD_SINK = {}           # id(parameter) -> flat fp32 view the parameter's gradient is written into (trainer.FlatGradients)
@@ -251,18 +282,13 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
             prev = layers[l - 1]
             xin, ldx, sc, sh = prev.Z, prev.Z.shape[1], prev.scale, prev.shift
         conv = convs[l] if convs is not None else None
-        dW = _sink(getattr(conv, "weight", None), (st.N, st.K))
-        if dW is None:
-            dW = torch.empty(st.N, st.K, device=dev, dtype=torch.float32)
-        scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, st.K, st.N), device=dev, dtype=torch.uint8)
         if side is not None:          # dZ is complete on the main stream here; the side stream picks it up
             side.wait_stream(main)
-            call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M,
-                 st.K, st.N, ptr(dW), ptr(scratch), side.cuda_stream)
-            keep += [dZ, xin, sc, sh, scratch]
+            with torch.cuda.stream(side):     # (allocations of this call belong to the side stream)
+                dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, side.cuda_stream, keep)
+            keep += [dZ, xin, sc, sh]
         else:
-            call("pn2_linear_bwd_weight", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M,
-                 st.K, st.N, ptr(dW), ptr(scratch), stream())
+            dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, stream(), keep)
         if not st.has_bias:
             dbias = None
         elif st.train:      # batch-norm's mean subtraction cancels the conv bias exactly
@@ -537,12 +563,7 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
             db2 = torch.empty(NC, device=dev, dtype=torch.float32)
         call("pn2_head_tail_bwd", ptr(dlogp), ptr(logp), ptr(W2), M, C, NC, drop_p, ptr(seed), ptr(dA), dA.shape[1],
              ptr(dl_rows), lddl, ptr(_stat_accum(dev)), ptr(db2), stream())
-        dW2 = _sink(conv2.weight, (NC, C))
-        if dW2 is None:
-            dW2 = torch.empty(NC, C, device=dev, dtype=torch.float32)
-        scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, C, NC), device=dev, dtype=torch.uint8)
-        call("pn2_linear_bwd_weight", ptr(dl_rows), lddl, dt(dl_rows), ptr(act), act.shape[1], dt(act), None, None, M, C, NC,
-             ptr(dW2), ptr(scratch), stream())
+        dW2 = _weight_grad(dl_rows, act, act.shape[1], None, None, M, C, NC, conv2.weight, dev, stream(), [])
         grads, dx0 = mlp_backward(layers, x0, K0, M, dA, None, 1, need1 or need2, convs, bns)
         dp1 = dp2 = None
         if need1:

@@ -84,21 +84,32 @@ def index_points(points, idx):
 
 
 class StartIndexStaging:
-    """Pinned host + device buffers for the FPS start indices of one call site, so that the
-    host->device copy of the torch.randint draw (:75) is a CUDA-graph-capturable memcpy node whose
-    source can be refreshed before every replay (see trainer.SemSegTrainer.enable_cuda_graph)."""
+    """Host ring + ONE static device buffer for the FPS start indices of one call site.  A captured CUDA graph reads the
+    device buffer; before every replay draw() makes the reference's torch.randint draw (:75) into the next pinned ring
+    slot and enqueues its host->device copy on the current stream -- ordinary stream work ahead of the replay, so the
+    host may run several replays ahead without ever rewriting indices a queued replay has not consumed yet (a ring slot
+    is only reused after its own copy has completed).  See trainer.SemSegTrainer.enable_cuda_graph."""
+    SLOTS = 8
 
     def __init__(self, B, N, device):
         self.B, self.N = B, N
-        self.host = torch.empty(B, dtype=torch.int64).pin_memory()
+        self.host = torch.empty(self.SLOTS, B, dtype=torch.int64).pin_memory()
         self.dev = torch.empty(B, dtype=torch.int64, device=device)
+        self._events = [None] * self.SLOTS
+        self._slot = 0
 
     def draw(self):
-        """One CPU-generator draw, exactly the reference's torch.randint(0, N, (B,), dtype=torch.long)."""
-        self.host.copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
+        """One CPU-generator draw, exactly the reference's torch.randint(0, N, (B,), dtype=torch.long), sent to the device."""
+        j = self._slot
+        self._slot = (j + 1) % self.SLOTS
+        if self._events[j] is not None:
+            self._events[j].synchronize()
+        self.host[j].copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
+        self.dev.copy_(self.host[j], non_blocking=True)
+        ev = self._events[j] = self._events[j] or torch.cuda.Event()
+        ev.record()
 
     def upload(self):
-        self.dev.copy_(self.host, non_blocking=True)
         return self.dev
 
 
@@ -211,3 +222,46 @@ def sample_and_group_all(xyz, points):
     if points is not None:
         grouped = torch.cat([grouped, points.reshape(B, 1, N, -1)], dim=-1)
     return new_xyz, grouped
+
+
+def new_vote_pool(num_points, num_classes, device="cuda"):
+    """The [P, NC] vote pool of /root/reference/localfunctions.py:385 (np.zeros((P, NUM_CLASSES))), as int32 counts in HBM."""
+    return torch.zeros(int(num_points), int(num_classes), dtype=torch.int32, device=device)
+
+
+def add_vote(vote_label_pool, point_idx, pred_label, weight=None):
+    """localfunctions.py:336-343 -- vote_label_pool[point_idx[b,n], pred_label[b,n]] += 1 for every (b, n) whose weight is
+    neither 0 nor inf; the reference's Python double loop as one kernel.  `vote_label_pool` is a CUDA int32 [P, NC] tensor
+    (new_vote_pool) updated in place and returned; `point_idx` / `pred_label` are [B, N] integer (or integral float, as the
+    reference's np.zeros-backed batch arrays are) tensors, `weight` [B, N] float32/float64 or None."""
+    require_cuda(vote_label_pool, "vote_label_pool", dtype=None)
+    if vote_label_pool.dtype != torch.int32 or vote_label_pool.dim() != 2 or not vote_label_pool.is_contiguous():
+        raise TypeError("vote_label_pool must be a contiguous int32 [P, NC] tensor (ops.new_vote_pool)")
+    dev = vote_label_pool.device
+    if tuple(point_idx.shape) != tuple(pred_label.shape) or (weight is not None and tuple(weight.shape) != tuple(pred_label.shape)):
+        raise ValueError("point_idx, pred_label and weight must have the same shape")
+    pi = point_idx.to(dev, non_blocking=True).long().contiguous()
+    pl = pred_label.to(dev, non_blocking=True).long().contiguous()
+    w = None
+    if weight is not None:
+        w = weight.to(dev, non_blocking=True)
+        if w.dtype not in (torch.float32, torch.float64):
+            w = w.float()
+        w = w.contiguous()
+    P, NC = vote_label_pool.shape
+    call("pn2_add_vote", ptr(pi), ptr(pl), ptr(w), int(w is not None and w.dtype == torch.float64), pi.numel(), P, NC,
+         ptr(vote_label_pool), None, stream())
+    return vote_label_pool
+
+
+def vote_argmax(vote_label_pool, dtype=torch.int64):
+    """localfunctions.py:405 -- np.argmax(vote_label_pool, 1): the first class with the most votes, per point."""
+    require_cuda(vote_label_pool, "vote_label_pool", dtype=None)
+    if vote_label_pool.dtype != torch.int32 or vote_label_pool.dim() != 2 or not vote_label_pool.is_contiguous():
+        raise TypeError("vote_label_pool must be a contiguous int32 [P, NC] tensor (ops.new_vote_pool)")
+    if dtype not in (torch.int64, torch.uint8):
+        raise TypeError("labels come back as int64 or uint8")
+    P, NC = vote_label_pool.shape
+    labels = torch.empty(P, dtype=dtype, device=vote_label_pool.device)
+    call("pn2_vote_argmax", ptr(vote_label_pool), P, NC, ptr(labels), int(dtype == torch.uint8), stream())
+    return labels

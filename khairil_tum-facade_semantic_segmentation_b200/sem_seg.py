@@ -30,6 +30,12 @@ def _geometry_stream(dev):
     return s
 
 
+class _NoWait:
+    @staticmethod
+    def wait_event(_):
+        pass
+
+
 class get_model(nn.Module):
     def __init__(self, num_classes, num_extra_features, sa_cls=PointNetSetAbstraction,
                  fp_cls=PointNetFeaturePropagation):
@@ -67,15 +73,41 @@ class get_model(nn.Module):
                 events.append(side.record_event())
         return geo, nn3, events, main
 
-    def forward(self, xyz):
+    def geometry_all(self, xyz0):
+        """The whole coordinate-only index pipeline of one batch on the CURRENT stream: (geo, nn3) as forward() takes
+        them through `geometry=`.  A pipelined caller (trainer.SemSegTrainer / SemSegPredictor with pipeline=True)
+        runs it for batch i+1 while the feature path of batch i is still busy -- the 1 360-iteration FPS chain keeps
+        only B of the 148 SMs busy, so it hides completely behind the MLPs of the previous batch."""
+        geo, nn3 = [], []
+        coords = [xyz0]
+        for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+            g = sa.geometry(coords[-1])
+            geo.append(g)
+            coords.append(g[0].permute(0, 2, 1))
+        for fine, coarse in ((3, 4), (2, 3), (1, 2), (0, 1)):
+            nn3.append(PointNetFeaturePropagation.neighbours(coords[fine], coords[coarse]))
+        return geo, nn3
+
+    @staticmethod
+    def geometry_tensors(geometry):
+        """Flat list of the tensors inside a geometry_all() result (fixed order)."""
+        geo, nn3 = geometry
+        return [t for g in geo for t in g] + [t for n in nn3 for t in n]
+
+    def forward(self, xyz, geometry=None):
         feats = [xyz]
         coords = [xyz[:, :3, :]]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         fps = (self.fp4, self.fp3, self.fp2, self.fp1)
-        ahead = xyz.is_cuda and self.overlap_geometry and all(
+        ahead = xyz.is_cuda and (self.overlap_geometry or geometry is not None) and all(
             type(m) is PointNetSetAbstraction and not m.group_all for m in sas) and all(
             type(m) is PointNetFeaturePropagation for m in fps)
-        if ahead:
+        if geometry is not None:
+            if not ahead:
+                raise ValueError("geometry= needs the stock set-abstraction / feature-propagation modules on CUDA")
+            geo, nn3 = geometry          # computed earlier by geometry_all(); the caller ordered the streams
+            main, events = _NoWait, [None] * 8
+        elif ahead:
             geo, nn3, events, main = self._geometry_ahead(coords[0])
         for i, sa in enumerate(sas):
             if ahead:

@@ -31,12 +31,14 @@ class FlatGradients:
     def __init__(self, params):
         from . import modules
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
-        self.views, off = [], 0
+        # every parameter's slice starts on a 16-byte boundary (the weight-gradient kernels add into it with
+        # red.global.add.v4.f32); the few padding elements stay zero
+        offsets, total = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
+        self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, offsets)]
         if self.flat.is_cuda:
             modules.set_grad_sink({id(p): v for p, v in zip(self.params, self.views)})
 
@@ -76,9 +78,12 @@ class SemSegTrainer:
         self.class_weights = (torch.ones(num_classes) if class_weights is None else class_weights).to(self.device)
         self._graph = None
 
-    def _step_impl(self, points, target):
+    def _step_impl(self, points, target, geometry=None):
         self.grads.zero()
-        pred, feat = self.model(points.transpose(2, 1))
+        if geometry is None:
+            pred, feat = self.model(points.transpose(2, 1))
+        else:
+            pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
         loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
         loss.backward()
         self.grads.adopt()
@@ -86,14 +91,23 @@ class SemSegTrainer:
         self.optimizer.step()
         return loss.detach()
 
-    def enable_cuda_graph(self, batch_clouds, npoint, channels, warmup=3):
+    def enable_cuda_graph(self, batch_clouds, npoint, channels, warmup=3, pipeline=False):
         """Capture the whole training step (forward, loss, backward, gradient all-reduce, Adam) into ONE
         CUDA graph replayed per step: the ~420 kernel launches of a step cost no host time any more.
         Inputs are copied into static buffers; the FPS start indices stay a fresh CPU-generator draw per
         step (drawn on the host before each replay into pinned buffers the graph's memcpy nodes read).
-        Re-capture after changing BatchNorm momentum or the learning-rate schedule's Python state."""
+        Re-capture after changing BatchNorm momentum or the learning-rate schedule's Python state.
+
+        pipeline=True software-pipelines consecutive batches inside that one graph: a forked branch runs the
+        coordinate-only index pipeline (FPS, ball query, 3-NN: get_model.geometry_all) of the batch just SUBMITTED
+        while the main branch runs forward/backward/Adam of the batch submitted one call earlier with the indices
+        computed for it during the previous replay; after the join the new indices and inputs are shifted into the
+        "current" slot.  The FPS dependency chain (0.5 ms on 32 of 148 SMs) thereby leaves the critical path.
+        step()/step_device() then return the loss of the PREVIOUS batch (None on the first call); flush() finishes
+        the batch in flight.  Same arithmetic per batch as pipeline=False."""
         from .modules import PointNetSetAbstraction
         dev = self.device
+        rng_state = torch.get_rng_state()     # warm-up / capture must not advance the CPU generator the FPS start draws use
         self.model.train()
         self._sa = [m for m in self.model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
         for m in self._sa:
@@ -101,13 +115,19 @@ class SemSegTrainer:
         self._g_points = torch.zeros(batch_clouds, npoint, channels, device=dev)
         self._g_target = torch.zeros(batch_clouds * npoint, dtype=torch.int64, device=dev)
         self._g_points.uniform_(-0.5, 0.5)
+        self._pipeline, self._primed, self._geo = bool(pipeline), False, None
         side = torch.cuda.Stream(device=dev)
+        if pipeline:
+            self._n_points = self._g_points.clone()
+            self._n_target = self._g_target.clone()
+            self._geo_stream = torch.cuda.Stream(device=dev)
+            with torch.no_grad():       # persistent "current batch" index tensors (outside any graph pool)
+                self._geo = self.model.geometry_all(self._g_points.transpose(2, 1)[:, :3, :])
         side.wait_stream(torch.cuda.current_stream(dev))
         saved = [(p.detach().clone()) for p in self.model.state_dict().values()]
-        opt_state = None
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._step_impl(self._g_points, self._g_target)
+                self._step_impl(self._g_points, self._g_target, self._geo)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # the warm-up steps must not count as training: restore parameters/buffers and optimizer moments
@@ -120,18 +140,60 @@ class SemSegTrainer:
                         v.zero_()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self._g_loss = self._step_impl(self._g_points, self._g_target)
+            if pipeline:
+                main = torch.cuda.current_stream(dev)
+                self._geo_stream.wait_stream(main)
+                with torch.cuda.stream(self._geo_stream), torch.no_grad():
+                    nxt = self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :])
+                self._g_loss = self._step_impl(self._g_points, self._g_target, self._geo)
+                main.wait_stream(self._geo_stream)
+                self._shift(nxt)
+                del nxt
+            else:
+                self._g_loss = self._step_impl(self._g_points, self._g_target)
         with torch.no_grad():                         # capture does not execute, but keep the state pristine anyway
             for t, s in zip(self.model.state_dict().values(), saved):
                 t.copy_(s)
         self._graph = graph
+        torch.set_rng_state(rng_state)
         return self
+
+    def _shift(self, nxt):
+        """next-batch indices and inputs -> the "current" slot the feature path reads (a few multi-tensor copies)."""
+        cur, new = get_model.geometry_tensors(self._geo), get_model.geometry_tensors(nxt)
+        for dt in (torch.int64, torch.float32):
+            torch._foreach_copy_([c for c in cur if c.dtype == dt], [n for n in new if n.dtype == dt])
+        self._g_points.copy_(self._n_points)
+        self._g_target.copy_(self._n_target)
+
+    def _submit(self, points, target):
+        """pipeline mode: stage the new batch, run its index pipeline next to the previous batch's feature path."""
+        self._n_points.copy_(points, non_blocking=True)
+        self._n_target.copy_(target.view(-1), non_blocking=True)
+        if not self._primed:                          # first batch: only its index pipeline, eagerly
+            with torch.no_grad():
+                self._shift(self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :]))
+            self._primed = True
+            return None
+        for m in self._sa:
+            m.start_staging.draw()
+        self._graph.replay()
+        return self._g_loss
+
+    def flush(self):
+        """pipeline mode: run the feature path of the batch still in flight (eagerly); returns its loss or None."""
+        if not getattr(self, "_pipeline", False) or not self._primed:
+            return None
+        self._primed = False
+        return self._step_impl(self._g_points, self._g_target, self._geo)
 
     def step_device(self, points, target):
         """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
         self.model.train()
         if self._graph is None:
             return self._step_impl(points, target)
+        if self._pipeline:
+            return self._submit(points, target)
         self._g_points.copy_(points, non_blocking=True)
         self._g_target.copy_(target.view(-1), non_blocking=True)
         for m in self._sa:                            # the reference's per-forward randint draws, in module order
@@ -142,6 +204,10 @@ class SemSegTrainer:
     def step(self, points_host, target_host):
         """One training step from HOST buffers (pinned memory recommended); returns the loss as a float
         (a device->host read, like the reference's per-batch `seg_pred.cpu()`)."""
+        if self._graph is not None and self._pipeline:
+            self.model.train()
+            loss = self._submit(points_host, target_host)
+            return None if loss is None else float(loss)
         if self._graph is not None:                  # host -> static device buffers directly
             self.model.train()
             self._g_points.copy_(points_host, non_blocking=True)
@@ -160,54 +226,124 @@ class SemSegPredictor:
     (the ~100 kernel launches of a forward cost no host time per batch).  The body is the
     reference's test-time batch step (/root/reference/localfunctions.py:396-400: host->device copy,
     transpose, `classifier(torch_data)`, arg-max of the log-probabilities); the FPS start indices stay a
-    fresh CPU-generator draw per forward (pointnet2_utils.py:75), staged through pinned buffers."""
+    fresh CPU-generator draw per forward (pointnet2_utils.py:75), staged through pinned buffers.
 
-    def __init__(self, model, batch_clouds, npoint, channels, device="cuda", warmup=2):
+    pipeline=True: the graph additionally runs, on a forked branch, the coordinate-only index pipeline
+    (get_model.geometry_all) of the batch just submitted while the main branch runs the feature path of the
+    batch submitted one call earlier (see SemSegTrainer.enable_cuda_graph); use submit()/flush(), which hand
+    back the labels of the PREVIOUS batch."""
+
+    def __init__(self, model, batch_clouds, npoint, channels, device="cuda", warmup=2, pipeline=False):
         from .modules import PointNetSetAbstraction
         self.model = model.eval()
         self.device = dev = torch.device(device)
         self.batch = batch_clouds
+        self.pipeline = bool(pipeline)
+        rng_state = torch.get_rng_state()     # construction must not advance the CPU generator the FPS start draws use
         self._sa = [m for m in model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
         for m in self._sa:
             m.use_static_start_buffers(True)
         self.points = torch.zeros(batch_clouds, npoint, channels, device=dev)
         self.points.uniform_(-0.5, 0.5)
+        self._geo, self._pending = None, None
         side = torch.cuda.Stream(device=dev)
+        if self.pipeline:
+            self.next_points = self.points.clone()
+            self._geo_stream = torch.cuda.Stream(device=dev)
+            with torch.no_grad():
+                self._geo = self.model.geometry_all(self.points.transpose(2, 1)[:, :3, :])
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):
-                self.model(self.points.transpose(2, 1))
+                self._forward(self.points)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.log_probs, _ = self.model(self.points.transpose(2, 1))       # [B, npoint, classes]
+            if self.pipeline:
+                main = torch.cuda.current_stream(dev)
+                self._geo_stream.wait_stream(main)
+                with torch.cuda.stream(self._geo_stream):
+                    nxt = self.model.geometry_all(self.next_points.transpose(2, 1)[:, :3, :])
+            self.log_probs, _ = self._forward(self.points)                     # [B, npoint, classes]
             self.labels = self.log_probs.argmax(dim=2)
+            if self.pipeline:
+                main.wait_stream(self._geo_stream)
+                self._shift(nxt)
+                del nxt
         self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
+        torch.set_rng_state(rng_state)
 
-    def forward_device(self, points):
-        """points [b <= batch, npoint, C] on the device -> (log_probs, labels) views of the static outputs."""
-        b = points.shape[0]
-        self.points[:b].copy_(points, non_blocking=True)
+    def _forward(self, points):
+        if self._geo is None:
+            return self.model(points.transpose(2, 1))
+        return self.model(points.transpose(2, 1), geometry=self._geo)
+
+    def _shift(self, nxt):
+        cur, new = get_model.geometry_tensors(self._geo), get_model.geometry_tensors(nxt)
+        for dt in (torch.int64, torch.float32):
+            torch._foreach_copy_([c for c in cur if c.dtype == dt], [n for n in new if n.dtype == dt])
+        self.points.copy_(self.next_points)
+
+    def _replay(self):
         for m in self._sa:
             m.start_staging.draw()
         self.graph.replay()
+
+    def forward_device(self, points):
+        """points [b <= batch, npoint, C] on the device -> (log_probs, labels) views of the static outputs."""
+        if self.pipeline:
+            raise RuntimeError("pipelined predictor: use submit() / flush()")
+        b = points.shape[0]
+        self.points[:b].copy_(points, non_blocking=True)
+        self._replay()
         return self.log_probs[:b], self.labels[:b]
 
     def predict_host(self, points_host):
         """points [b <= batch, npoint, C] on the host (pinned recommended) -> labels [b, npoint] on the host."""
+        if self.pipeline:
+            raise RuntimeError("pipelined predictor: use submit() / flush()")
         b = points_host.shape[0]
         self.points[:b].copy_(points_host, non_blocking=True)
-        for m in self._sa:
-            m.start_staging.draw()
-        self.graph.replay()
+        self._replay()
+        self._host_labels.copy_(self.labels, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_labels[:b]
+
+    def submit(self, points, to_host=True):
+        """pipeline mode.  Stage batch `points` [b <= batch, npoint, C] (host or device), run its index pipeline next
+        to the feature path of the batch submitted one call earlier, and return that EARLIER batch's labels
+        ([b', npoint]; on the host when to_host, else a view of the static device output) -- None on the first call."""
+        if not self.pipeline:
+            raise RuntimeError("submit() needs pipeline=True")
+        b = points.shape[0]
+        self.next_points[:b].copy_(points, non_blocking=True)
+        prev, self._pending = self._pending, b
+        if prev is None:                           # first batch: only its index pipeline, eagerly
+            with torch.no_grad():
+                self._shift(self.model.geometry_all(self.next_points.transpose(2, 1)[:, :3, :]))
+            return None
+        self._replay()
+        return self._read(prev, to_host)
+
+    def flush(self, to_host=True):
+        """pipeline mode: finish the batch in flight and return its labels (None if there is none)."""
+        prev, self._pending = self._pending, None
+        if prev is None:
+            return None
+        self._replay()                             # the index branch re-runs on the stale "next" slot: harmless
+        return self._read(prev, to_host)
+
+    def _read(self, b, to_host):
+        if not to_host:
+            return self.labels[:b]
         self._host_labels.copy_(self.labels, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._host_labels[:b]
 
 
 @torch.no_grad()
-def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="cuda", use_graph=True):
+def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="cuda", use_graph=True, pipeline=True):
     """sem_seg_testing-style inference (num_votes=1) over [nb, 4096, C] blocks held on the host:
     this rank labels its contiguous shard of blocks; no collective is needed (eval-mode BatchNorm
     uses running statistics, so blocks are independent).  Returns (lo, hi, labels [hi-lo, 4096] on host)."""
@@ -216,7 +352,19 @@ def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="c
     out = torch.empty(hi - lo, blocks_host.shape[1], dtype=torch.int64)
     predictor = None
     if use_graph and hi - lo >= batch_size:
-        predictor = SemSegPredictor(model, batch_size, blocks_host.shape[1], blocks_host.shape[2], device)
+        predictor = SemSegPredictor(model, batch_size, blocks_host.shape[1], blocks_host.shape[2], device,
+                                    pipeline=pipeline and hi - lo >= 2 * batch_size)
+    if predictor is not None and predictor.pipeline:
+        # consecutive batches overlap inside the graph: labels come back one call late
+        done = lo
+        for s in range(lo, hi, batch_size):
+            prev = predictor.submit(blocks_host[s:min(hi, s + batch_size)].float())
+            if prev is not None:
+                out[done - lo:done - lo + prev.shape[0]] = prev
+                done += prev.shape[0]
+        last = predictor.flush()
+        out[done - lo:done - lo + last.shape[0]] = last
+        return lo, hi, out
     for s in range(lo, hi, batch_size):
         e = min(hi, s + batch_size)
         if predictor is not None:         # a short tail batch rides in the same fixed-shape graph
@@ -226,3 +374,55 @@ def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="c
             pred, _ = model(x)
             out[s - lo:e - lo] = pred.argmax(dim=2).cpu()
     return lo, hi, out
+
+
+@torch.no_grad()
+def predict_scene(model, blocks_host, point_idx_host, weight_host, num_points, num_classes, batch_size=32, rank=0, world=1,
+                  device="cuda", pipeline=True, vote_pool=None, merge=True, predictor=None):
+    """Whole-scene inference with one vote per block slot -- the body of the reference's per-scene test loop
+    (/root/reference/localfunctions.py:385-405): batches of `blocks_host` [nb, npoint, C] go through the network, the
+    arg-max labels vote into a [num_points, num_classes] pool through `point_idx_host` [nb, npoint] with the sample
+    weights `weight_host` [nb, npoint] (pairs with weight 0 or inf do not vote, :341), and the scene labels are the
+    arg-max of the pool.  Differences from the reference are where the work happens, not what it computes: the labels
+    never leave the device between the network and the pool (ops.add_vote replaces the Python double loop), this rank
+    only handles its contiguous shard of the blocks, and with merge=True the ranks' pools are summed with ONE
+    all-reduce (torch.distributed initialised, world > 1) before the arg-max.  Returns (labels [num_points] int64 on the
+    host, the int32 device pool).  Pass `vote_pool` to keep accumulating over several votes (num_votes > 1), and a
+    ready `predictor` (SemSegPredictor of the same batch shape) to reuse its captured graph across scenes."""
+    from . import ops
+    model.eval()
+    dev = torch.device(device)
+    lo, hi = shard_range(blocks_host.shape[0], rank, world)
+    pool = vote_pool if vote_pool is not None else ops.new_vote_pool(num_points, num_classes, dev)
+    npoint = blocks_host.shape[1]
+
+    def vote(s, e, labels):
+        ops.add_vote(pool, point_idx_host[s:e], labels, None if weight_host is None else weight_host[s:e])
+
+    if predictor is not None:
+        batch_size = predictor.batch
+    elif hi - lo >= batch_size:
+        predictor = SemSegPredictor(model, batch_size, npoint, blocks_host.shape[2], dev,
+                                    pipeline=pipeline and hi - lo >= 2 * batch_size)
+    if predictor is not None and predictor.pipeline:
+        done = lo
+        for s in range(lo, hi, batch_size):
+            prev = predictor.submit(blocks_host[s:min(hi, s + batch_size)], to_host=False)
+            if prev is not None:          # device labels of the batch before; voted before the next replay rewrites them
+                vote(done, done + prev.shape[0], prev)
+                done += prev.shape[0]
+        last = predictor.flush(to_host=False)
+        vote(done, done + last.shape[0], last)
+    else:
+        for s in range(lo, hi, batch_size):
+            e = min(hi, s + batch_size)
+            if predictor is not None:
+                predictor.points[:e - s].copy_(blocks_host[s:e], non_blocking=True)
+                predictor._replay()
+                vote(s, e, predictor.labels[:e - s])
+            else:
+                pred, _ = model(blocks_host[s:e].to(dev, non_blocking=True).float().transpose(2, 1))
+                vote(s, e, pred.argmax(dim=2))
+    if merge and world > 1 and dist.is_available() and dist.is_initialized():
+        dist.all_reduce(pool, op=dist.ReduceOp.SUM)
+    return ops.vote_argmax(pool).cpu(), pool

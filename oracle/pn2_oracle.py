@@ -17,6 +17,8 @@ unless another file is named):
   OracleFP             PointNetFeaturePropagation :265-315
   OracleSemSeg         get_model   (models/pointnet2_sem_seg.py:6-40)
   nll                  get_loss    (models/pointnet2_sem_seg.py:44-50)
+  add_vote             add_vote    (localfunctions.py:336-343)
+  vote_argmax          np.argmax(vote_label_pool, 1)   (localfunctions.py:405)
 
 The arithmetic itself lives in PyTorch (third party, un-pinned by the reference;
 effective pin torch 2.11.0+cu128 of this image), so this port issues the same
@@ -245,3 +247,22 @@ class OracleSemSeg(nn.Module):
 def nll(pred, target, weight=None):
     # models/pointnet2_sem_seg.py:47-48
     return F.nll_loss(pred, target, weight=weight)
+
+
+def add_vote(vote_label_pool, point_idx, pred_label, weight):
+    """localfunctions.py:336-343 -- for every (b, n) with weight != 0 and not inf: pool[int(idx), int(label)] += 1.
+    numpy restatement of the Python double loop (np.add.at handles repeated indices like the loop does); the pool is
+    the reference's float64 [P, NC] array, updated in place and returned."""
+    import numpy as np
+    w = np.asarray(weight)
+    keep = (w != 0) & ~np.isinf(w)
+    idx = np.asarray(point_idx)[keep].astype(np.int64)
+    lab = np.asarray(pred_label)[keep].astype(np.int64)
+    np.add.at(vote_label_pool, (idx, lab), 1)
+    return vote_label_pool
+
+
+def vote_argmax(vote_label_pool):
+    """localfunctions.py:405"""
+    import numpy as np
+    return np.argmax(vote_label_pool, 1)

@@ -228,8 +228,57 @@ def model():
     save("model.npz", out)
 
 
+def _reference_localfunctions():
+    """Import the UNMODIFIED /root/reference/localfunctions.py.  Its module-level imports pull in IO / plotting packages
+    that this image does not have and add_vote does not use (laspy, open3d, h5py, matplotlib, pytz): empty stand-in
+    modules satisfy the import statements, nothing of them is ever called."""
+    import types
+    for name in ("laspy", "open3d", "h5py", "matplotlib", "matplotlib.pyplot", "pytz"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if isinstance(sys.modules.get("matplotlib"), types.ModuleType) and not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if not hasattr(sys.modules["pytz"], "timezone"):          # localfunctions.py:102 builds a module-level timestamp with it
+        import datetime
+        sys.modules["pytz"].timezone = lambda name: datetime.timezone.utc
+    import localfunctions as LF
+    assert LF.__file__.startswith(REF), LF.__file__
+    return LF
+
+
+def votes():
+    """localfunctions.py:336-343 add_vote (the reference's own Python loop) + :405 arg-max on seeded block batches:
+    overlapping point indices, repeated (point, label) pairs, zero / inf / nan / negative sample weights."""
+    LF = _reference_localfunctions()
+    out = {}
+    for tag, (P, NC, B, N, seed) in {"small": (300, 18, 3, 128, 0), "wide": (1000, 5, 4, 256, 1), "dense": (64, 18, 6, 512, 2)}.items():
+        g = np.random.RandomState(seed)
+        pool = np.zeros((P, NC))
+        batches = []
+        for it in range(3):
+            idx = g.randint(0, P, size=(B, N)).astype(np.float64)          # the reference's batch arrays are np.zeros -> float64
+            lab = g.randint(0, NC, size=(B, N)).astype(np.int64)
+            w = g.rand(B, N)
+            w[g.rand(B, N) < 0.2] = 0.0
+            w[g.rand(B, N) < 0.05] = np.inf
+            w[g.rand(B, N) < 0.05] = np.nan
+            w[g.rand(B, N) < 0.05] *= -1.0
+            pool = LF.add_vote(pool, idx, lab, w)
+            batches.append((idx, lab, w))
+        out[tag + "_idx"] = np.stack([b[0] for b in batches]).astype(np.int32)
+        out[tag + "_lab"] = np.stack([b[1] for b in batches]).astype(np.uint8)
+        out[tag + "_w"] = np.stack([b[2] for b in batches])
+        out[tag + "_pool"] = pool.astype(np.int32)
+        assert np.array_equal(pool, pool.astype(np.int32))
+        out[tag + "_labels"] = np.argmax(pool, 1).astype(np.uint8)             # :405
+    save("votes.npz", out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model"]
+    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes"]
     for w in which:
         t = time.time()
         globals()[w]()

@@ -120,14 +120,69 @@ def test_linear_backward_weight(lib, M, K, N, dtype):
     assert err <= tol, err
 
 
+@pytest.mark.parametrize("G,ns,C", [(512, 32, 64), (100, 32, 128), (33, 16, 256), (7, 5, 24), (64, 32, 12), (3, 1, 512)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_bn_relu_max_tail(lib, G, ns, C, dtype):
+    """max over nsample of relu(scale*z + shift) (pointnet2_utils.py:198-200) with the arg-max sample (first on ties) for the
+    backward pass: vectorised bf16 kernel (C % 8 == 0) and the scalar kernel against torch on the same stored values."""
+    g = torch.Generator().manual_seed(G + C)
+    ld = _ld(C) if dtype == torch.bfloat16 else C
+    Z = torch.zeros(G * ns, ld)
+    Z[:, :C] = torch.randn(G * ns, C, generator=g)
+    if ns > 3:
+        Z.view(G, ns, ld)[:, 3] = Z.view(G, ns, ld)[:, 1]                   # exact ties: sample 3 repeats sample 1
+    Z = Z.to(DEV).to(dtype)
+    scale = (torch.rand(C, generator=g) - 0.3).to(DEV)                     # some negative gammas
+    shift = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    out = torch.full((G, C), float("nan"), device=DEV)
+    arg = torch.full((G, C), -1, device=DEV, dtype=torch.int32)
+    lib.call("pn2_bn_relu_max", lib.ptr(Z), ld, lib.dt(Z), lib.ptr(scale), lib.ptr(shift), G, ns, C, lib.ptr(out), lib.ptr(arg),
+             lib.stream())
+    act = torch.relu(Z[:, :C].double() * scale.double() + shift.double()).view(G, ns, C)
+    want, _ = act.max(dim=1)
+    assert float((out.double() - want).abs().max()) <= 1e-5
+    assert int(arg.min()) >= 0 and int(arg.max()) < ns
+    picked = act.gather(1, arg.long().unsqueeze(1)).squeeze(1)
+    assert float((picked - want).abs().max()) <= 1e-5                       # the recorded sample attains the maximum
+    if ns > 3:
+        assert not bool((arg == 3).any())                                   # the first of two equal samples wins
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+@pytest.mark.parametrize("misalign", [0, 1])
+def test_linear_backward_weight_accumulate(lib, M, K, N, misalign):
+    """pn2_linear_bwd_weight_accum: dW += dZ^T act(X) with L2 reductions (vector form when dW is 16-byte aligned and
+    K % 4 == 0, scalar otherwise); same tolerance as the fixed-order entry, on top of a non-zero starting value."""
+    g = torch.Generator().manual_seed(M + 7 * K + N)
+    x, dz = _rows(M, K, torch.bfloat16, 3), _rows(M, N, torch.bfloat16, 4)
+    scale = (0.5 + torch.rand(K, generator=g)).to(DEV)
+    shift = (torch.randn(K, generator=g) * 0.3).to(DEV)
+    buf = torch.zeros(N * K + 4, device=DEV)
+    dW = buf[misalign:misalign + N * K].view(N, K)
+    start = torch.randn(N, K, generator=g).to(DEV)
+    dW.copy_(start)
+    for use_act in (True, False):
+        lib.call("pn2_linear_bwd_weight_accum", lib.ptr(dz), dz.shape[1], lib.dt(dz), lib.ptr(x), x.shape[1], lib.dt(x),
+                 lib.ptr(scale) if use_act else None, lib.ptr(shift) if use_act else None, M, K, N, lib.ptr(dW), lib.stream())
+    a = torch.relu(x[:, :K].float() * scale + shift)
+    want = dz[:, :N].double().t() @ a.double() + dz[:, :N].double().t() @ x[:, :K].double()
+    err = ((dW.double() - start.double() - want).abs().max() / (want.abs().max() + 1e-9)).item()
+    assert err <= 2e-2, err
+    assert float(buf[:misalign].abs().sum()) == 0.0 and float(buf[misalign + N * K:].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("M,C", [(1000, 32), (4096, 64), (333, 128), (5000, 256), (640, 24), (8, 512)])
 @pytest.mark.parametrize("mode", ["bf16", "f32dA", "pool", "fp32rows"])
 @pytest.mark.parametrize("train", [True, False])
-def test_bn_relu_backward_kernels(lib, M, C, mode, train):
+@pytest.mark.parametrize("ns", [8, 32, 5])
+def test_bn_relu_backward_kernels(lib, M, C, mode, train, ns):
     """dgamma/dbeta reduction (fp64 accumulators) and dz of BN(train or frozen)+ReLU against the formulas of
     include/pn2b200.h, dense and pooled (arg-max routed) variants, vectorised bf16 and scalar paths."""
+    if mode != "pool" and ns != 8:
+        pytest.skip("nsample only matters for the pooled variants")
+    if M < ns:
+        M = 2 * ns
     g = torch.Generator().manual_seed(M + C)
-    ns = 8
     zt = torch.float32 if mode == "fp32rows" else torch.bfloat16
     ldz = C if zt == torch.float32 else _ld(C)
     Z = torch.zeros(M, ldz, dtype=zt, device=DEV)

@@ -1,0 +1,106 @@
+"""Software-pipelined drivers (trainer.SemSegTrainer / SemSegPredictor with pipeline=True): the index pipeline of
+batch i+1 runs beside the feature path of batch i inside one CUDA graph.  Per batch the arithmetic is the same as in
+the un-pipelined graph, so with the same seeds the two must agree: labels exactly (the inference kernels have no
+atomics), training losses to 1e-3 relative over several optimizer steps (fp32 scatter-add order differs run to run).
+The body mirrors /root/reference/localfunctions.py:202-218 (train batch) and :396-400 (test batch)."""
+import pytest
+import torch
+
+import _inputs as I
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, N, C, NC = 4, 1024, 9, 18
+
+
+def _batches(n, seed):
+    return [(I.facade_batch(B, N, C, seed + i).to(DEV), I.labels(B, N, NC, seed + 50 + i).to(DEV)) for i in range(n)]
+
+
+def _trainer(pn2, pipeline):
+    pn2.set_precision("bf16")
+    torch.manual_seed(7)
+    # lr 1e-5: Adam's first updates are lr * sign(g), so the run-to-run order of the fp32 scatter-adds (near-zero gradients
+    # flipping sign) would otherwise send two runs of the SAME code on visibly different trajectories within 3 steps
+    t = pn2.SemSegTrainer(NC, C - 6, lr=1e-5, device=DEV)
+    t.model.drop1.p = 0.0                       # the dropout mask comes from the CUDA generator: keep the two runs comparable
+    t.enable_cuda_graph(B, N, C, pipeline=pipeline)
+    return t
+
+
+def test_pipelined_train_steps_match_unpipelined(pn2):
+    data = _batches(5, 300)
+    plain = _trainer(pn2, False)
+    torch.manual_seed(99)                       # FPS start draws: 4 per batch, in batch order, in both modes
+    want = [float(plain.step_device(p, t)) for p, t in data]
+    piped = _trainer(pn2, True)
+    torch.manual_seed(99)
+    got = []
+    for p, t in data:
+        loss = piped.step_device(p, t)
+        if loss is not None:
+            got.append(float(loss))
+    assert len(got) == len(data) - 1            # one batch is still in flight
+    got.append(float(piped.flush()))
+    assert piped.flush() is None
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-3 * abs(b), (got, want)
+    assert got[0] == want[0]                    # nothing has been updated yet: same batch, same indices, same kernels
+    # running statistics after the same five batches: equal up to the bf16 noise the (1e-5-sized, order-dependent) weight
+    # updates put on the deep activations (measured 1e-3 absolute on sa4) -- a skipped or repeated batch would be far off
+    for (k, a), b in zip(piped.model.state_dict().items(), plain.model.state_dict().values()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=5e-2, atol=1e-2), k
+        else:
+            assert torch.equal(a, b), k          # num_batches_tracked
+    pn2.set_precision("fp32")
+
+
+def test_pipelined_step_from_host_returns_previous_loss(pn2):
+    piped = _trainer(pn2, True)
+    p, t = I.facade_batch(B, N, C, 1).pin_memory(), I.labels(B, N, NC, 2).pin_memory()
+    assert piped.step(p, t) is None
+    loss = piped.step(p, t)
+    assert isinstance(loss, float) and 0.0 < loss < 10.0
+    pn2.set_precision("fp32")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_pipelined_predictor_matches_unpipelined(pn2, precision):
+    pn2.set_precision(precision)
+    torch.manual_seed(3)
+    net = I.randomize_module_(pn2.get_model(NC, C - 6), 17).to(DEV).eval()
+    data = [I.facade_batch(B, N, C, 500 + i) for i in range(4)]
+    data.append(I.facade_batch(B - 1, N, C, 600))                  # a short tail batch
+    plain = pn2.SemSegPredictor(net, B, N, C, DEV)
+    torch.manual_seed(5)
+    want = [plain.predict_host(x).clone() for x in data]
+    piped = pn2.SemSegPredictor(net, B, N, C, DEV, pipeline=True)
+    torch.manual_seed(5)
+    got = []
+    for x in data:
+        out = piped.submit(x)
+        if out is not None:
+            got.append(out.clone())
+    got.append(piped.flush().clone())
+    assert piped.flush() is None
+    assert [g.shape for g in got] == [w.shape for w in want]
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    with pytest.raises(RuntimeError):
+        piped.predict_host(data[0])
+    pn2.set_precision("fp32")
+
+
+def test_predict_blocks_pipelined_equals_plain(pn2):
+    pn2.set_precision("bf16")
+    torch.manual_seed(3)
+    net = I.randomize_module_(pn2.get_model(NC, C - 6), 19).to(DEV).eval()
+    blocks = torch.cat([I.facade_batch(B, N, C, 700 + i) for i in range(3)])[:11]
+    torch.manual_seed(8)
+    lo, hi, want = pn2.predict_blocks(net, blocks, batch_size=B, device=DEV, pipeline=False)
+    torch.manual_seed(8)
+    lo2, hi2, got = pn2.predict_blocks(net, blocks, batch_size=B, device=DEV, pipeline=True)
+    assert (lo, hi) == (lo2, hi2) == (0, 11)
+    assert torch.equal(got, want)
+    pn2.set_precision("fp32")

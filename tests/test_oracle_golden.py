@@ -147,3 +147,14 @@ def test_torch_port_model(golden):
     pred, _ = net(x)
     loss = O.nll(pred.contiguous().view(-1, 18), I.labels(2, 2048, 18, 7), torch.linspace(0.5, 1.5, 18))
     assert abs(loss.item() - float(g["train_loss"])) < 1e-5
+
+
+@pytest.mark.parametrize("tag,NC", [("small", 18), ("wide", 5), ("dense", 18)])
+def test_vote_oracle_matches_reference_loop(golden, tag, NC):
+    """oracle add_vote / vote_argmax (numpy) == the reference's Python double loop (localfunctions.py:336-343, :405)."""
+    v = golden("votes")
+    pool = np.zeros((v[tag + "_pool"].shape[0], NC))
+    for it in range(v[tag + "_idx"].shape[0]):
+        pool = O.add_vote(pool, v[tag + "_idx"][it].astype(np.float64), v[tag + "_lab"][it], v[tag + "_w"][it])
+    assert np.array_equal(pool, v[tag + "_pool"].astype(np.float64))
+    assert np.array_equal(O.vote_argmax(pool), v[tag + "_labels"].astype(np.int64))
