@@ -873,24 +873,34 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
             uint8_t *stA = smem + (size_t)s * stage_bytes;
             uint8_t *stB = stA + (size_t)a.a_slabs * slab_bytes;
             if (a.in_scale) {
-                // act(X) = relu(bn(.)) of the previous layer, in place; threads walk PHYSICAL 16-byte units
-                // (conflict-free), the logical column chunk of unit pc in row r is pc ^ (r & 7)
+                // act(X) = relu(bn(.)) of the previous layer, in place; threads walk PHYSICAL 16-byte units (conflict-free).
+                // Unit q = tid + 128 i sits in row r = q >> 3 at logical column chunk cc = (q & 7) ^ (r & 7); both q & 7 and
+                // r & 7 depend on tid only, so a thread transforms the SAME 8 columns of every row it touches: their
+                // scale/shift live in registers per slab (columns past kb get scale = shift = 0 -> stay 0), two units in flight
                 mbar_wait(&bar_full[s], par);
+                const int cc = (tid & 7) ^ ((tid >> 3) & 7);
+                const int n_units = rows16 * 8;
                 for (int j = 0; j < b_sl; ++j) {
+                    const int i0 = j * 64 + cc * 8;
+                    if (i0 >= kb) continue;
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const bool ok = i0 + e < kb;
+                        sc[e] = ok ? s_scale[i0 + e] : 0.0f;
+                        sh[e] = ok ? s_shift[i0 + e] : 0.0f;
+                    }
                     uint8_t *slab = stB + (size_t)j * slab_bytes;
-                    for (int q = tid; q < rows16 * 8; q += 128) {
-                        const int r = q >> 3, cc = (q & 7) ^ (r & 7);
-                        const int i0 = j * 64 + cc * 8;
-                        if (i0 >= kb) continue;
+#pragma unroll 2
+                    for (int q = tid; q < n_units; q += 128) {
                         uint4 *ptr = reinterpret_cast<uint4 *>(slab + (size_t)q * 16);
                         uint4 v = *ptr;
                         uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
                         for (int e2 = 0; e2 < 4; ++e2) {
                             float2 f = unpack_bf16x2(w[e2]);
-                            const int i = i0 + 2 * e2;
-                            f.x = i < kb ? fmaxf(fmaf(f.x, s_scale[i], s_shift[i]), 0.0f) : 0.0f;
-                            f.y = i + 1 < kb ? fmaxf(fmaf(f.y, s_scale[i + 1], s_shift[i + 1]), 0.0f) : 0.0f;
+                            f.x = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.0f);
+                            f.y = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f);
                             w[e2] = pack_bf16x2(f.x, f.y);
                         }
                         *ptr = v;

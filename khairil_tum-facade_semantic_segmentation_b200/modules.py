@@ -183,7 +183,10 @@ def _weight_grad(dZ, xin, ldx, sc, sh, M, K, N, param, dev, cuda_stream, keep):
     """dW [N, K] of one layer on `cuda_stream`: into the parameter's gradient-sink view when there is one."""
     lib = load()
     dW = _sink(param, (N, K))
-    if WGRAD_ACCUMULATE and dZ.dtype == torch.bfloat16 and xin.dtype == torch.bfloat16 and dZ.shape[1] % 8 == 0 and ldx % 8 == 0:
+    # K % 4 != 0 (the 3 + D wide first layers: 67, 131, 259): rows of dW are not 16-byte aligned, the reductions would be
+    # scalar -- 4x the L2 operations on the same addresses (measured 107 us vs 27 us for sa3.1) -- so those keep the partials
+    if (WGRAD_ACCUMULATE and K % 4 == 0 and dZ.dtype == torch.bfloat16 and xin.dtype == torch.bfloat16
+            and dZ.shape[1] % 8 == 0 and ldx % 8 == 0):
         if dW is None:
             dW = torch.zeros(N, K, device=dev, dtype=torch.float32)      # a sink is zeroed once per step by its owner
         call("pn2_linear_bwd_weight_accum", ptr(dZ), dZ.shape[1], dt(dZ), ptr(xin), ldx, dt(xin), ptr(sc), ptr(sh), M, K, N,

@@ -21,6 +21,47 @@ def shard_range(n_items, rank, world):
     return lo, min(n_items, lo + per)
 
 
+class _HostStager:
+    """Two device staging slots fed from (pinned) host memory over a dedicated copy stream, so the host->device copy of the
+    batch handed in by call i runs while the GPU is still busy with the replay launched by call i-1.  put() enqueues the
+    copies of this call's batch and returns its slot; the slot filled by the previous call is then consumed on the
+    compute stream (take -> use -> release).  One more stage of software pipelining: results come back one call later."""
+
+    def __init__(self, templates, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [[torch.empty_like(t) for t in templates] for _ in range(2)]
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [None, None]
+        self.rows = [None, None]          # leading-dimension sizes of the tensors staged in each slot, None = empty
+        self.k = 0
+
+    def put(self, *host_tensors):
+        k, self.k = self.k, self.k ^ 1
+        with torch.cuda.stream(self.stream):
+            if self.consumed[k] is not None:                 # the compute stream has finished reading this slot
+                self.stream.wait_event(self.consumed[k])
+            for dst, src in zip(self.slots[k], host_tensors):
+                dst[:src.shape[0]].copy_(src, non_blocking=True)
+            self.copied[k].record(self.stream)
+        self.rows[k] = [t.shape[0] for t in host_tensors]
+        return k
+
+    def take(self, k):
+        """the staged tensors of slot k, readable on the current stream"""
+        torch.cuda.current_stream(self.slots[k][0].device).wait_event(self.copied[k])
+        return [t[:n] for t, n in zip(self.slots[k], self.rows[k])]
+
+    def release(self, k):
+        ev = self.consumed[k] = self.consumed[k] or torch.cuda.Event()
+        ev.record()
+        self.rows[k] = None
+
+    def pending(self):
+        """slots that hold a staged, not yet consumed batch, oldest first"""
+        order = [self.k, self.k ^ 1]      # self.k is the slot the NEXT put() will use, i.e. the older one
+        return [k for k in order if self.rows[k] is not None]
+
+
 class FlatGradients:
     """One flat fp32 buffer holding every parameter gradient, so data-parallel training needs a single
     all-reduce per step (no bucketing: the buffer is latency-, not bandwidth-bound).  The buffer is also the
@@ -103,8 +144,12 @@ class SemSegTrainer:
         while the main branch runs forward/backward/Adam of the batch submitted one call earlier with the indices
         computed for it during the previous replay; after the join the new indices and inputs are shifted into the
         "current" slot.  The FPS dependency chain (0.5 ms on 32 of 148 SMs) thereby leaves the critical path.
-        step()/step_device() then return the loss of the PREVIOUS batch (None on the first call); flush() finishes
-        the batch in flight.  Same arithmetic per batch as pipeline=False."""
+        step_device() then returns the loss of the PREVIOUS batch (None on the first call).  step() -- host buffers --
+        adds two more stages: the host->device copy of the batch handed in runs on a copy stream beside the replay that
+        works on the two batches before it, and the loss of a replay is read back by the NEXT call (the host never waits on
+        the replay it has just launched), so it returns the loss of the batch handed in THREE calls earlier (None 3 times).
+        flush() finishes what is in flight and returns the remaining losses in batch order.  Same arithmetic per batch
+        as pipeline=False."""
         from .modules import PointNetSetAbstraction
         dev = self.device
         rng_state = torch.get_rng_state()     # warm-up / capture must not advance the CPU generator the FPS start draws use
@@ -121,6 +166,10 @@ class SemSegTrainer:
             self._n_points = self._g_points.clone()
             self._n_target = self._g_target.clone()
             self._geo_stream = torch.cuda.Stream(device=dev)
+            self._stager = _HostStager([self._g_points, self._g_target], dev)
+            self._loss_host = torch.zeros(2).pin_memory()            # step(): losses come back through a pinned ring,
+            self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]  # read one call after their replay was launched
+            self._loss_valid, self._loss_slot = [False, False], 0
             with torch.no_grad():       # persistent "current batch" index tensors (outside any graph pool)
                 self._geo = self.model.geometry_all(self._g_points.transpose(2, 1)[:, :3, :])
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -180,12 +229,33 @@ class SemSegTrainer:
         self._graph.replay()
         return self._g_loss
 
-    def flush(self):
-        """pipeline mode: run the feature path of the batch still in flight (eagerly); returns its loss or None."""
-        if not getattr(self, "_pipeline", False) or not self._primed:
+    def _take_loss(self, j):
+        if not self._loss_valid[j]:
             return None
-        self._primed = False
-        return self._step_impl(self._g_points, self._g_target, self._geo)
+        self._loss_ev[j].synchronize()
+        self._loss_valid[j] = False
+        return float(self._loss_host[j])
+
+    def flush(self):
+        """pipeline mode: finish every batch still in flight (a loss whose read-back is queued, staged host copies, then the
+        feature path of the last one, eagerly); returns their losses as floats in batch order ([] if nothing was pending)."""
+        out = []
+        if not getattr(self, "_pipeline", False):
+            return out
+        for j in (self._loss_slot, self._loss_slot ^ 1):         # older slot first
+            v = self._take_loss(j)
+            if v is not None:
+                out.append(v)
+        for k in self._stager.pending():
+            pts, tgt = self._stager.take(k)
+            loss = self._submit(pts, tgt)
+            self._stager.release(k)
+            if loss is not None:
+                out.append(float(loss))
+        if self._primed:
+            self._primed = False
+            out.append(float(self._step_impl(self._g_points, self._g_target, self._geo)))
+        return out
 
     def step_device(self, points, target):
         """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
@@ -206,8 +276,23 @@ class SemSegTrainer:
         (a device->host read, like the reference's per-batch `seg_pred.cpu()`)."""
         if self._graph is not None and self._pipeline:
             self.model.train()
-            loss = self._submit(points_host, target_host)
-            return None if loss is None else float(loss)
+            st = self._stager
+            k = st.put(points_host, target_host.view(-1))          # this batch: host -> device on the copy stream
+            ret = None
+            if st.rows[k ^ 1] is not None:                         # the previous call's batch has (long) arrived
+                pts, tgt = st.take(k ^ 1)
+                loss = self._submit(pts, tgt)
+                st.release(k ^ 1)
+                if loss is not None:
+                    # queue the read-back of the loss this replay will produce; hand out the one queued by the call before
+                    # (its replay has finished meanwhile), so the host never waits on the replay it has just launched
+                    j, self._loss_slot = self._loss_slot, self._loss_slot ^ 1
+                    ret = self._take_loss(j ^ 1)
+                    self._loss_host[j].copy_(loss, non_blocking=True)
+                    self._loss_ev[j].record()
+                    self._loss_valid[j] = True
+            st.copied[k].synchronize()                             # the caller may reuse its host buffers
+            return ret
         if self._graph is not None:                  # host -> static device buffers directly
             self.model.train()
             self._g_points.copy_(points_host, non_blocking=True)
@@ -250,6 +335,7 @@ class SemSegPredictor:
         if self.pipeline:
             self.next_points = self.points.clone()
             self._geo_stream = torch.cuda.Stream(device=dev)
+            self._stager = _HostStager([self.points], dev)
             with torch.no_grad():
                 self._geo = self.model.geometry_all(self.points.transpose(2, 1)[:, :3, :])
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -311,11 +397,25 @@ class SemSegPredictor:
         return self._host_labels[:b]
 
     def submit(self, points, to_host=True):
-        """pipeline mode.  Stage batch `points` [b <= batch, npoint, C] (host or device), run its index pipeline next
-        to the feature path of the batch submitted one call earlier, and return that EARLIER batch's labels
-        ([b', npoint]; on the host when to_host, else a view of the static device output) -- None on the first call."""
+        """pipeline mode.  Hand in batch `points` [b <= batch, npoint, C] and get back the labels of an EARLIER batch
+        ([b', npoint]; on the host when to_host, else a view of the static device output that the next call rewrites), or
+        None while the pipeline fills.  Device input: its index pipeline runs next to the feature path of the batch handed
+        in one call earlier, whose labels are returned.  Host input (pinned recommended): additionally its host->device
+        copy runs on a copy stream beside that replay, so the labels returned belong to the batch TWO calls earlier."""
         if not self.pipeline:
             raise RuntimeError("submit() needs pipeline=True")
+        if points.is_cuda:
+            return self._advance(points, to_host)
+        st = self._stager
+        k = st.put(points)
+        out = None
+        if st.rows[k ^ 1] is not None:
+            (staged,) = st.take(k ^ 1)
+            out = self._advance(staged, to_host)
+            st.release(k ^ 1)
+        return out
+
+    def _advance(self, points, to_host):
         b = points.shape[0]
         self.next_points[:b].copy_(points, non_blocking=True)
         prev, self._pending = self._pending, b
@@ -326,13 +426,33 @@ class SemSegPredictor:
         self._replay()
         return self._read(prev, to_host)
 
-    def flush(self, to_host=True):
-        """pipeline mode: finish the batch in flight and return its labels (None if there is none)."""
+    def flush_one(self, to_host=True):
+        """pipeline mode: finish ONE more batch in flight and return its labels (like submit()), None once the pipeline
+        is empty."""
+        while True:
+            pend = self._stager.pending()
+            if not pend:
+                break
+            (staged,) = self._stager.take(pend[0])
+            r = self._advance(staged, to_host)
+            self._stager.release(pend[0])
+            if r is not None:
+                return r
         prev, self._pending = self._pending, None
         if prev is None:
             return None
         self._replay()                             # the index branch re-runs on the stale "next" slot: harmless
         return self._read(prev, to_host)
+
+    def flush(self, to_host=True):
+        """pipeline mode: finish every batch still in flight; returns the list of their label tensors (copies) in batch
+        order, [] if nothing was pending."""
+        out = []
+        while True:
+            r = self.flush_one(to_host)
+            if r is None:
+                return out
+            out.append(r.clone())
 
     def _read(self, b, to_host):
         if not to_host:
@@ -362,8 +482,9 @@ def predict_blocks(model, blocks_host, batch_size=32, rank=0, world=1, device="c
             if prev is not None:
                 out[done - lo:done - lo + prev.shape[0]] = prev
                 done += prev.shape[0]
-        last = predictor.flush()
-        out[done - lo:done - lo + last.shape[0]] = last
+        for last in predictor.flush():
+            out[done - lo:done - lo + last.shape[0]] = last
+            done += last.shape[0]
         return lo, hi, out
     for s in range(lo, hi, batch_size):
         e = min(hi, s + batch_size)
@@ -411,8 +532,12 @@ def predict_scene(model, blocks_host, point_idx_host, weight_host, num_points, n
             if prev is not None:          # device labels of the batch before; voted before the next replay rewrites them
                 vote(done, done + prev.shape[0], prev)
                 done += prev.shape[0]
-        last = predictor.flush(to_host=False)
-        vote(done, done + last.shape[0], last)
+        while True:                       # drain: staged batch (if any), then the one in flight -- vote after each replay
+            rest = predictor.flush_one(to_host=False)
+            if rest is None:
+                break
+            vote(done, done + rest.shape[0], rest)
+            done += rest.shape[0]
     else:
         for s in range(lo, hi, batch_size):
             e = min(hi, s + batch_size)

@@ -41,8 +41,9 @@ def test_pipelined_train_steps_match_unpipelined(pn2):
         if loss is not None:
             got.append(float(loss))
     assert len(got) == len(data) - 1            # one batch is still in flight
-    got.append(float(piped.flush()))
-    assert piped.flush() is None
+    rest = piped.flush()
+    assert len(rest) == 1 and piped.flush() == []
+    got += rest
     for a, b in zip(got, want):
         assert abs(a - b) <= 1e-3 * abs(b), (got, want)
     assert got[0] == want[0]                    # nothing has been updated yet: same batch, same indices, same kernels
@@ -56,12 +57,32 @@ def test_pipelined_train_steps_match_unpipelined(pn2):
     pn2.set_precision("fp32")
 
 
-def test_pipelined_step_from_host_returns_previous_loss(pn2):
-    piped = _trainer(pn2, True)
-    p, t = I.facade_batch(B, N, C, 1).pin_memory(), I.labels(B, N, NC, 2).pin_memory()
-    assert piped.step(p, t) is None
-    loss = piped.step(p, t)
-    assert isinstance(loss, float) and 0.0 < loss < 10.0
+def test_pipelined_steps_from_host_match_device_steps(pn2):
+    """step() stages the host batch over a copy stream and reads losses back one call late (two more pipeline stages: the
+    loss of the batch handed in three calls earlier comes back); the losses are those of step_device() on the same batches."""
+    data = _batches(5, 400)
+    dev_tr = _trainer(pn2, True)
+    torch.manual_seed(77)
+    want = []
+    for p, t in data:
+        loss = dev_tr.step_device(p, t)                  # a static tensor the next replay rewrites: read it now
+        if loss is not None:
+            want.append(float(loss))
+    want += dev_tr.flush()
+    host_tr = _trainer(pn2, True)
+    torch.manual_seed(77)
+    got = []
+    for i, (p, t) in enumerate(data):
+        loss = host_tr.step(p.cpu().pin_memory(), t.cpu().pin_memory())
+        assert (loss is None) == (i < 3)
+        if loss is not None:
+            assert isinstance(loss, float)
+            got.append(loss)
+    got += host_tr.flush()
+    assert len(got) == len(want) == len(data) and host_tr.flush() == []
+    assert got[0] == want[0]
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-3 * abs(b), (got, want)
     pn2.set_precision("fp32")
 
 
@@ -77,16 +98,19 @@ def test_pipelined_predictor_matches_unpipelined(pn2, precision):
     want = [plain.predict_host(x).clone() for x in data]
     piped = pn2.SemSegPredictor(net, B, N, C, DEV, pipeline=True)
     torch.manual_seed(5)
-    got = []
-    for x in data:
-        out = piped.submit(x)
-        if out is not None:
-            got.append(out.clone())
-    got.append(piped.flush().clone())
-    assert piped.flush() is None
-    assert [g.shape for g in got] == [w.shape for w in want]
-    for g, w in zip(got, want):
-        assert torch.equal(g, w)
+    for on_device in (False, True):                                # host input: one more stage (the copy stream)
+        torch.manual_seed(5)
+        got = []
+        for i, x in enumerate(data):
+            out = piped.submit(x.to(DEV) if on_device else x.pin_memory())
+            assert (out is None) == (i < (1 if on_device else 2))
+            if out is not None:
+                got.append(out.clone())
+        got += piped.flush()
+        assert piped.flush() == []
+        assert [g.shape for g in got] == [w.shape for w in want]
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
     with pytest.raises(RuntimeError):
         piped.predict_host(data[0])
     pn2.set_precision("fp32")
