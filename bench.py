@@ -628,9 +628,19 @@ def main():
         top_calls = [(a, ms) for n, a, ms in timed_calls if n == top["entry"]]
         alg = sum(KERNEL_MODEL[top["entry"]](a)[0] for a, _ in top_calls)
         dur = sum(ms for _, ms in top_calls) * 1e-3
+        # DRAM traffic of the same entry point from the committed ncu pass (profiles/make_traffic.py), per call like `achieved`
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+                tj = json.load(f)
+            if top["entry"] in tj:
+                traffic = tj[top["entry"]]["dram_bytes_per_step"] / top["calls_per_step"]
+                traffic_src = "profiles/r01_dram_traffic.json: " + tj.get("_source", "")
+        except Exception:
+            pass
         roof = {"kernel": top["entry"] + " (all %d launches of a step; the largest share of kernel time among the streaming kernels)" % round(top["calls_per_step"]),
                 "bound": "hbm", "achieved": alg / dur / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": alg / dur / 1e9 / pk["hbm_gbs"], "traffic": None,
+                "frac": alg / dur / 1e9 / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": dur * 1e3 / len(top_calls),
                 "bytes_per_launch_avg": alg / len(top_calls), "share_of_step": top["ms_per_step"] / ms_per_step,
                 "note": "achieved = sum of algorithmic bytes / sum of CUDA-event durations over the launches of %d eager steps; "

@@ -304,6 +304,13 @@ int pn2_add_vote(const int64_t *point_idx, const int64_t *pred_label, const void
 /* labels[p] = first class with the largest count (np.argmax); labels is int64 [P], or uint8 [P] when labels_are_u8 */
 int pn2_vote_argmax(const int32_t *votes, int64_t P, int NC, void *labels, int labels_are_u8, void *stream);
 
+/* ---- z-rotation augmentation of the training batch, in place in HBM ------------------------
+ * replaces provider.rotate_point_cloud_z (/root/reference/provider.py:66-84) applied to points[:, :, :3] at
+ * localfunctions.py:205: cloud b is rotated about z by the angle whose (cos, sin) is cos_sin[2b], cos_sin[2b+1]
+ * (float64, device), products and sums in float64 in the reference's np.dot order, result rounded to float32.
+ * points: the xyz channels of a [B, N, C] fp32 batch, element strides (sB, sN, sC). */
+int pn2_rotate_z(float *points, int64_t sB, int64_t sN, int64_t sC, const double *cos_sin, int B, int N, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
     "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
+    "pn2_rotate_z": (_i, [_p, _l, _l, _l, _p, _i, _i, _p]),
     "pn2_add_vote": (_i, [_p, _p, _p, _i, _l, _l, _i, _p, _p, _p]),
     "pn2_vote_argmax": (_i, [_p, _l, _i, _p, _i, _p]),
     "pn2_linear_bwd_weight_accum": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p]),

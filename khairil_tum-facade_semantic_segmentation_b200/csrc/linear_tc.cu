@@ -1002,7 +1002,23 @@ static WgradPlan tc_wgrad_plan(int64_t M, int K, int N, bool accumulate = false)
     p.a_slabs = ((N < 128 ? N : 128) + 63) / 64;
     p.b_slabs = ((K < 256 ? K : 256) + 63) / 64;
     const int per_row = 128 * (p.a_slabs + p.b_slabs);
-    int R = (26 * 1024 / per_row) / 16 * 16;          // <= 26 KB per ring slot: four slots, two CTAs per SM
+    // ring-slot size and CTAs per SM (tuning knobs PN2_WG_SLOT_KB / PN2_WG_CTAS).  Measured on B200 (profiles/microbench_mlp.py):
+    // the 1 M-row sa1 layers want two co-resident CTAs with 26 KB slots (60 us vs 82 us with one CTA of 40 KB slots); every
+    // smaller layer is faster with ONE CTA per SM and 40 KB slots -- half the splits, so half the partial blocks to add into
+    // dW, and longer TMA boxes (fp2.2 45 -> 33 us, sa4.2 35 -> 27 us, fp1.1 34 -> 27 us)
+    static int env_slot_kb = -1, env_ctas = -1;
+    if (env_slot_kb < 0) {
+        const char *e = getenv("PN2_WG_SLOT_KB");
+        env_slot_kb = e ? atoi(e) : 0;
+        if (env_slot_kb < 4 || env_slot_kb > 52) env_slot_kb = 0;
+        e = getenv("PN2_WG_CTAS");
+        env_ctas = e ? atoi(e) : 0;
+        if (env_ctas < 1 || env_ctas > 8) env_ctas = 0;
+    }
+    const bool big = M >= (int64_t)1 << 19;
+    const int slot_kb = env_slot_kb ? env_slot_kb : (big ? 26 : 40);
+    const int ctas = env_ctas ? env_ctas : (big ? 2 : 1);
+    int R = (slot_kb * 1024 / per_row) / 16 * 16;
     if (R > 256) R = 256;
     if (R < 16) R = 16;
     p.R = R;
@@ -1010,7 +1026,7 @@ static WgradPlan tc_wgrad_plan(int64_t M, int K, int N, bool accumulate = false)
     // splits: fill the machine (two CTAs per SM), but keep >= 2 ring iterations per CTA, and balance the
     // per-CTA iteration chain (~1 us each) against writing + re-reading the fp32 partials
     const int blocks = p.nblk_n * p.nblk_k;
-    int64_t s = (2 * kNumSMs + blocks - 1) / blocks;
+    int64_t s = (ctas * kNumSMs + blocks - 1) / blocks;
     const int64_t max_rows = (M + 2 * R - 1) / (2 * R);
     // partial cost per split: write + re-read of an fp32 block (reduce kernel), or -- accumulate mode -- one pass of
     // L2 reductions, which also lets the small layers use every SM

@@ -79,3 +79,38 @@ extern "C" int pn2_vote_argmax(const int32_t *votes, int64_t P, int NC, void *la
     count_launch();
     return check_launch("vote_argmax");
 }
+
+// ---- the training loop's z-rotation augmentation (provider.rotate_point_cloud_z, /root/reference/provider.py:66-84,
+// called on points[:, :, :3] at localfunctions.py:205) on the batch that is already in HBM.  The reference multiplies the
+// float32 coordinates with a float64 rotation matrix (np.dot -> float64) and stores the result into a float32 array:
+//   x' = fp32(x*c + y*(-s) + z*0),  y' = fp32(x*s + y*c + z*0),  z' = fp32(x*0 + y*0 + z*1)
+// evaluated here in fp64 in that order (no FMA contraction), per cloud b with (c, s) = cs[b].
+namespace pn2 {
+__global__ void __launch_bounds__(256)
+rotate_z_kernel(float *__restrict__ points, int64_t sB, int64_t sN, int64_t sC, const double *__restrict__ cs, int B, int N) {
+    const int64_t total = (int64_t)B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b;
+        int n;
+        fast_divmod(i, N, b, n);
+        float *p = points + b * sB + (int64_t)n * sN;
+        const double c = cs[2 * b], s = cs[2 * b + 1];
+        const double x = (double)p[0], y = (double)p[sC], z = (double)p[2 * sC];
+        const double xr = __dadd_rn(__dadd_rn(__dmul_rn(x, c), __dmul_rn(y, -s)), __dmul_rn(z, 0.0));
+        const double yr = __dadd_rn(__dadd_rn(__dmul_rn(x, s), __dmul_rn(y, c)), __dmul_rn(z, 0.0));
+        const double zr = __dadd_rn(__dadd_rn(__dmul_rn(x, 0.0), __dmul_rn(y, 0.0)), z);
+        p[0] = (float)xr;
+        p[sC] = (float)yr;
+        p[2 * sC] = (float)zr;
+    }
+}
+}  // namespace pn2
+
+extern "C" int pn2_rotate_z(float *points, int64_t sB, int64_t sN, int64_t sC, const double *cos_sin, int B, int N, void *stream) {
+    PN2_REQUIRE(B >= 0 && N >= 0, "rotate_z: bad sizes B=%d N=%d", B, N);
+    if (B == 0 || N == 0) return PN2_OK;
+    PN2_REQUIRE(points && cos_sin, "rotate_z: null pointer");
+    rotate_z_kernel<<<grid_for((int64_t)B * N, 256), 256, 0, (cudaStream_t)stream>>>(points, sB, sN, sC, cos_sin, B, N);
+    count_launch();
+    return check_launch("rotate_z");
+}

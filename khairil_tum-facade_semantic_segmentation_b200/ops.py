@@ -265,3 +265,59 @@ def vote_argmax(vote_label_pool, dtype=torch.int64):
     labels = torch.empty(P, dtype=dtype, device=vote_label_pool.device)
     call("pn2_vote_argmax", ptr(vote_label_pool), P, NC, ptr(labels), int(dtype == torch.uint8), stream())
     return labels
+
+
+class RotationStaging:
+    """Host ring + one static device buffer for the per-cloud (cos, sin) of rotate_point_cloud_z_, same life cycle as
+    StartIndexStaging: the host may queue several steps ahead without rewriting angles a queued kernel has not read."""
+    SLOTS = 8
+
+    def __init__(self, B, device):
+        self.B = B
+        self.host = torch.empty(self.SLOTS, B, 2, dtype=torch.float64).pin_memory()
+        self.dev = torch.empty(B, 2, dtype=torch.float64, device=device)
+        self._events = [None] * self.SLOTS
+        self._slot = 0
+
+    def send(self, cos_sin):
+        j = self._slot
+        self._slot = (j + 1) % self.SLOTS
+        if self._events[j] is not None:
+            self._events[j].synchronize()
+        self.host[j].copy_(cos_sin)
+        self.dev.copy_(self.host[j], non_blocking=True)
+        ev = self._events[j] = self._events[j] or torch.cuda.Event()
+        ev.record()
+        return self.dev
+
+
+def draw_rotation_angles(B):
+    """The reference's draws (provider.py:76-77): one np.random.uniform() * 2 * np.pi per cloud, in cloud order, from numpy's
+    global generator.  Returns a float64 [B, 2] tensor of (cos, sin)."""
+    import numpy as np
+    ang = np.array([np.random.uniform() * 2 * np.pi for _ in range(B)])
+    return torch.from_numpy(np.stack([np.cos(ang), np.sin(ang)], axis=1))
+
+
+def rotate_point_cloud_z_(points, cos_sin=None, staging=None):
+    """provider.rotate_point_cloud_z (/root/reference/provider.py:66-84) on the xyz channels of a CUDA fp32 batch
+    `points` [B, N, C >= 3], IN PLACE (the reference's `points[:, :, :3] = provider.rotate_point_cloud_z(points[:, :, :3])`,
+    localfunctions.py:205).  cos_sin: float64 [B, 2] per-cloud (cos, sin); None draws the angles exactly as the reference
+    does (draw_rotation_angles).  Returns `points`."""
+    require_cuda(points, "points")
+    if points.dim() != 3 or points.shape[2] < 3:
+        raise ValueError("points must be [B, N, C >= 3], got %s" % (tuple(points.shape),))
+    B, N, _ = points.shape
+    if cos_sin is None:
+        cos_sin = draw_rotation_angles(B)
+    if tuple(cos_sin.shape) != (B, 2) or cos_sin.dtype != torch.float64:
+        raise ValueError("cos_sin must be float64 [B, 2]")
+    if cos_sin.is_cuda:
+        cs = cos_sin.contiguous()
+    elif staging is not None:
+        cs = staging.send(cos_sin)
+    else:
+        cs = cos_sin.to(points.device, non_blocking=True).contiguous()
+    sB, sN, sC = points.stride()
+    call("pn2_rotate_z", ptr(points), sB, sN, sC, ptr(cs), B, N, stream())
+    return points

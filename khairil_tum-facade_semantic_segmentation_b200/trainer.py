@@ -106,7 +106,11 @@ class FlatGradients:
 
 class SemSegTrainer:
     def __init__(self, num_classes=18, num_extra_features=3, lr=1e-3, weight_decay=1e-4, device="cuda",
-                 class_weights=None, model=None, fused_optimizer=True):
+                 class_weights=None, model=None, fused_optimizer=True, augment_rotate_z=False):
+        """augment_rotate_z: apply the training loop's augmentation (provider.rotate_point_cloud_z on points[:, :, :3],
+        /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
+        self.augment_rotate_z = bool(augment_rotate_z)
+        self._rot_staging = None
         self.device = torch.device(device)
         self.num_classes = num_classes
         self.model = (model if model is not None else get_model(num_classes, num_extra_features)).to(self.device)
@@ -207,6 +211,15 @@ class SemSegTrainer:
         torch.set_rng_state(rng_state)
         return self
 
+    def _augment(self, points):
+        """in-place z rotation of a device batch [B, N, C]; angles drawn like the reference does"""
+        if self.augment_rotate_z:
+            from . import ops
+            if self._rot_staging is None or self._rot_staging.B != points.shape[0]:
+                self._rot_staging = ops.RotationStaging(points.shape[0], self.device)
+            ops.rotate_point_cloud_z_(points, ops.draw_rotation_angles(points.shape[0]), staging=self._rot_staging)
+        return points
+
     def _shift(self, nxt):
         """next-batch indices and inputs -> the "current" slot the feature path reads (a few multi-tensor copies)."""
         cur, new = get_model.geometry_tensors(self._geo), get_model.geometry_tensors(nxt)
@@ -219,6 +232,7 @@ class SemSegTrainer:
         """pipeline mode: stage the new batch, run its index pipeline next to the previous batch's feature path."""
         self._n_points.copy_(points, non_blocking=True)
         self._n_target.copy_(target.view(-1), non_blocking=True)
+        self._augment(self._n_points)
         if not self._primed:                          # first batch: only its index pipeline, eagerly
             with torch.no_grad():
                 self._shift(self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :]))
@@ -261,11 +275,12 @@ class SemSegTrainer:
         """points [B, N, C] (point-major, as the DataLoader yields it) and target [B*N], on the device."""
         self.model.train()
         if self._graph is None:
-            return self._step_impl(points, target)
+            return self._step_impl(self._augment(points.clone()) if self.augment_rotate_z else points, target)
         if self._pipeline:
             return self._submit(points, target)
         self._g_points.copy_(points, non_blocking=True)
         self._g_target.copy_(target.view(-1), non_blocking=True)
+        self._augment(self._g_points)
         for m in self._sa:                            # the reference's per-forward randint draws, in module order
             m.start_staging.draw()
         self._graph.replay()
@@ -297,6 +312,7 @@ class SemSegTrainer:
             self.model.train()
             self._g_points.copy_(points_host, non_blocking=True)
             self._g_target.copy_(target_host.view(-1), non_blocking=True)
+            self._augment(self._g_points)
             for m in self._sa:
                 m.start_staging.draw()
             self._graph.replay()

@@ -19,6 +19,7 @@ unless another file is named):
   nll                  get_loss    (models/pointnet2_sem_seg.py:44-50)
   add_vote             add_vote    (localfunctions.py:336-343)
   vote_argmax          np.argmax(vote_label_pool, 1)   (localfunctions.py:405)
+  rotate_z             rotate_point_cloud_z        (provider.py:66-84)
 
 The arithmetic itself lives in PyTorch (third party, un-pinned by the reference;
 effective pin torch 2.11.0+cu128 of this image), so this port issues the same
@@ -266,3 +267,15 @@ def vote_argmax(vote_label_pool):
     """localfunctions.py:405"""
     import numpy as np
     return np.argmax(vote_label_pool, 1)
+
+
+def rotate_z(batch_xyz, angles):
+    """provider.py:66-84 with the angles given instead of drawn: per cloud, float32 xyz [N,3] times the float64 matrix
+    [[c, s, 0], [-s, c, 0], [0, 0, 1]] (np.dot -> float64), stored into a float32 array."""
+    import numpy as np
+    out = np.zeros(batch_xyz.shape, dtype=np.float32)
+    for k in range(batch_xyz.shape[0]):
+        c, s = np.cos(angles[k]), np.sin(angles[k])
+        m = np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])
+        out[k, ...] = np.dot(batch_xyz[k, ...].reshape((-1, 3)), m)
+    return out

@@ -96,6 +96,8 @@ def main():
                                          p(wp2), st()), 2 * M * (ld(K) + ld(N))),
                 "wgrad": (lambda: L.call("pn2_linear_bwd_weight", p(dz), dz.shape[1], 1, p(x), x.shape[1], 1, p(ins), p(insh),
                                          M, K, N, p(dW), p(scratch), st()), 2 * M * (ld(K) + ld(N))),
+                "wgrad_acc": (lambda: L.call("pn2_linear_bwd_weight_accum", p(dz), dz.shape[1], 1, p(x), x.shape[1], 1, p(ins),
+                                             p(insh), M, K, N, p(dW), st()), 2 * M * (ld(K) + ld(N))),
                 "bnred": (lambda: L.call("pn2_bn_relu_bwd_reduce", p(dz), dz.shape[1], 1, p(z), z.shape[1], 1, p(scn), p(shn),
                                          p(mean), p(invstd), M, N, p(accum), st()), 2 * M * 2 * ld(N)),
                 "bndz": (lambda: L.call("pn2_bn_relu_bwd_dz", p(dz), dz.shape[1], 1, p(z), z.shape[1], 1, p(scn), p(shn),
@@ -105,7 +107,9 @@ def main():
             ops["fwd"][0]()        # z must hold real values for the BN kernels
             torch.cuda.synchronize()
             for op, (fn, nbytes) in ops.items():
-                if args.only and op != args.only:
+                if args.only and op not in args.only.split(","):
+                    continue
+                if op == "wgrad_acc" and K % 4:
                     continue
                 ms = timeit(fn, args.reps, flush)
                 key = "%s.%d %s" % (name, li, op)

@@ -277,8 +277,25 @@ def votes():
     save("votes.npz", out)
 
 
+def rotation():
+    """provider.rotate_point_cloud_z (provider.py:66-84), unmodified, under a seeded numpy generator; the fixture keeps the
+    angles it drew (re-drawn from the same seed) so that the device kernel can be checked without numpy's generator."""
+    import provider as P
+    assert P.__file__.startswith(REF), P.__file__
+    out = {}
+    for tag, (B, N, seed) in {"small": (3, 257, 0), "batch": (8, 1024, 1)}.items():
+        xyz = I.facade_batch(B, N, 9, 40 + seed)[:, :, :3].numpy().copy()
+        np.random.seed(100 + seed)
+        rotated = P.rotate_point_cloud_z(xyz)
+        np.random.seed(100 + seed)
+        angles = np.array([np.random.uniform() * 2 * np.pi for _ in range(B)])
+        out[tag + "_xyz"], out[tag + "_angles"], out[tag + "_rotated"] = xyz, angles, rotated
+        assert rotated.dtype == np.float32
+    save("rotation.npz", out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes"]
+    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes", "rotation"]
     for w in which:
         t = time.time()
         globals()[w]()

@@ -94,3 +94,55 @@ def test_predict_scene_equals_blocks_then_host_votes(pn2):
                                       vote_pool=merged, merge=False)
     assert np.array_equal(merged.cpu().numpy(), want.astype(np.int32))
     pn2.set_precision("fp32")
+
+
+@pytest.mark.parametrize("tag", ["small", "batch"])
+def test_rotate_z_matches_reference_fixture(pn2, golden, tag):
+    """provider.rotate_point_cloud_z (provider.py:66-84) on the device, in place on the xyz channels of a
+    [B, N, 9] batch (point-major and the strided channel-first view), with the angles the reference drew: float64 products
+    and sums in np.dot's order, rounded once to float32 -> bit-exact."""
+    v = golden("rotation")
+    xyz, ang, want = v[tag + "_xyz"], v[tag + "_angles"], v[tag + "_rotated"]
+    B, N, _ = xyz.shape
+    cs = torch.from_numpy(np.stack([np.cos(ang), np.sin(ang)], axis=1))
+    batch = torch.rand(B, N, 9)
+    batch[:, :, :3] = torch.from_numpy(xyz)
+    dev = batch.to(DEV)
+    out = pn2.rotate_point_cloud_z_(dev, cs)
+    assert out is dev
+    assert np.array_equal(dev[:, :, :3].cpu().numpy(), want)
+    assert torch.equal(dev[:, :, 3:].cpu(), batch[:, :, 3:])                  # the other channels are untouched
+    assert np.array_equal(O.rotate_z(xyz, ang), want)
+    # device-resident angles and a non-contiguous batch view
+    dev2 = batch.to(DEV).transpose(1, 2).contiguous().transpose(1, 2)          # [B, N, 9] view of a [B, 9, N] buffer
+    pn2.rotate_point_cloud_z_(dev2, cs.to(DEV))
+    assert np.array_equal(dev2[:, :, :3].cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        pn2.rotate_point_cloud_z_(dev, cs[:1])
+
+
+def test_trainer_rotation_augmentation_uses_reference_draws(pn2):
+    """SemSegTrainer(augment_rotate_z=True): the batch the step trains on is the reference's rotated batch (numpy draws in
+    cloud order), in every launch mode; labels and the other channels unchanged."""
+    B, N, C, NC = 4, 512, 9, 18
+    pts, lab = I.facade_batch(B, N, C, 5).to(DEV), I.labels(B, N, NC, 6).to(DEV)
+    for mode in ("eager", "graph", "pipeline"):
+        pn2.set_precision("bf16")
+        torch.manual_seed(1)
+        tr = pn2.SemSegTrainer(NC, C - 6, device=DEV, augment_rotate_z=True)
+        if mode != "eager":
+            tr.enable_cuda_graph(B, N, C, pipeline=mode == "pipeline")
+        np.random.seed(9)
+        tr.step_device(pts, lab)
+        np.random.seed(9)
+        ang = np.array([np.random.uniform() * 2 * np.pi for _ in range(B)])
+        want = O.rotate_z(pts[:, :, :3].cpu().numpy(), ang)
+        if mode == "eager":
+            continue                                                        # (the rotated clone is not kept)
+        seen = tr._g_points if mode == "graph" else tr._g_points            # pipeline: shifted into the current slot
+        if mode == "pipeline":
+            torch.cuda.synchronize()
+        assert np.array_equal(seen[:, :, :3].cpu().numpy(), want), mode
+        assert torch.equal(seen[:, :, 3:], pts[:, :, 3:])
+        assert torch.equal(pts[:, :, :3].cpu(), I.facade_batch(B, N, C, 5)[:, :, :3])   # the caller's tensor is not modified
+    pn2.set_precision("fp32")

@@ -158,3 +158,10 @@ def test_vote_oracle_matches_reference_loop(golden, tag, NC):
         pool = O.add_vote(pool, v[tag + "_idx"][it].astype(np.float64), v[tag + "_lab"][it], v[tag + "_w"][it])
     assert np.array_equal(pool, v[tag + "_pool"].astype(np.float64))
     assert np.array_equal(O.vote_argmax(pool), v[tag + "_labels"].astype(np.int64))
+
+
+@pytest.mark.parametrize("tag", ["small", "batch"])
+def test_rotation_oracle_matches_reference(golden, tag):
+    """oracle rotate_z == provider.rotate_point_cloud_z (provider.py:66-84) on the angles the reference drew."""
+    v = golden("rotation")
+    assert np.array_equal(O.rotate_z(v[tag + "_xyz"], v[tag + "_angles"]), v[tag + "_rotated"])
