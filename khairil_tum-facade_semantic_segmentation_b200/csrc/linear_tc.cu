@@ -95,41 +95,116 @@ __global__ void pack_weights_multi_kernel(const __grid_constant__ PackJobs a) {
     *reinterpret_cast<uint4 *>(a.img[j] + (size_t)blk * KC * 256 * 128 + (size_t)kc * n_pad * 128 + sw128_offset(n, c)) = o;
 }
 
+constexpr int kTcMaxNBlocks = 4;
 struct TcLinearArgs {
-    CUtensorMap tm_x, tm_z;   // X [M, ldx] (boxes 64 x 128 rows) and this call's Z column block [M, n_store] (row stride ldz)
+    CUtensorMap tm_x, tm_z[kTcMaxNBlocks];   // X [M, ldx] (boxes 64 x 128 rows); Z column block y: [M, n_store(y)] (row stride ldz)
     const float *in_scale, *in_shift;
     const uint8_t *Wimg;
     const float *bias;
     int64_t M;
-    int K, N, n_pad, n_store, KC;
+    int K, N, ldz, KC;       // N: all output columns of this launch (blocks of 256 along blockIdx.y)
     double *stat_accum;     // [replicas][2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
     int stat_ld, stat_off;
     int w_resident, stages;
+    uint32_t wait_hint_ns;  // > 0: the all-thread mbarrier waits suspend up to this long per try instead of spinning
     BnFinalize fin;         // fin.ticket != null: the CTA that draws the last ticket turns the sums into scale/shift
 };
 
 constexpr int kLinTcThreads = 160;   // warps 0-3: A transform, MMA issue (thread 0), epilogue; warp 4: TMA producer
+
+// Column statistics (sum z, sum z^2 over this warp's 32 rows) of the bf16 tile staged in SW128 box layout, the values exactly
+// as they are stored.  Lane <-> column pair p (slab p >> 5, 16-byte chunk (p & 31) >> 2, byte (p & 3) * 4 inside it); row
+// 8g + ri of the warp's 4 KB sits at g * 1024 + ri * 128 + ((chunk ^ ri) << 4): with ri unrolled the eight offsets are
+// registers and g an immediate, so an element pair costs LDS + 2 unpack + 4 FP instructions (the rolled loop with the offset
+// recomputed per row was 35 % of the instructions this kernel issued on the sa1 layers).  N <= 32: only 16 lanes own a
+// column pair, so the two half-warps split the rows (groups 0-1 / 2-3); their sums are added once at the end of the CTA.
+template <int GROUPS>
+__device__ __forceinline__ void tile_pair_stats(const uint8_t *base, int ch, int inb, float &s1a, float &s1b, float &s2a, float &s2b) {
+    uint32_t off[8];
+#pragma unroll
+    for (int ri = 0; ri < 8; ++ri) off[ri] = (uint32_t)(ri * 128 + ((ch ^ ri) << 4) + inb);
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+        for (int ri = 0; ri < 8; ++ri) {
+            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(base + g * 1024 + off[ri]));
+            s1a += f.x; s1b += f.y;
+            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+        }
+}
+
+__device__ __forceinline__ void tile_col_stats(const uint8_t *staging, int warp, int lane, int N, int rows, float *sum1, float *sum2) {
+    if (rows == 32 && N <= 32) {
+        const int p = lane & 15;
+        if (2 * p < N)
+            tile_pair_stats<2>(staging + (size_t)(warp * 4 + 2 * (lane >> 4)) * 1024, p >> 2, (p & 3) * 4, sum1[0], sum1[1], sum2[0], sum2[1]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = lane + 32 * j;
+        if (2 * p < N) {
+            const uint8_t *slab = staging + (size_t)(p >> 5) * kTcAStage;
+            const int ch = (p & 31) >> 2, inb = (p & 3) * 4;
+            if (rows == 32) {
+                tile_pair_stats<4>(slab + (size_t)warp * 4096, ch, inb, sum1[2 * j], sum1[2 * j + 1], sum2[2 * j], sum2[2 * j + 1]);
+            } else {                              // the ragged last tile
+                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                for (int r = 0; r < rows; ++r) {
+                    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(slab + sw128_offset(warp * 32 + r, ch) + inb));
+                    s1a += f.x; s1b += f.y;
+                    s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+                }
+                sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
+                sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
+            }
+        }
+    }
+}
+
+// N <= 32: fold the upper half-warp's partial sums (same column pairs, other rows) into the lower one before they are published
+__device__ __forceinline__ void fold_split_stats(int lane, int N, float *sum1, float *sum2) {
+    if (N <= 32) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float o1 = __shfl_down_sync(0xffffffffu, sum1[i], 16), o2 = __shfl_down_sync(0xffffffffu, sum2[i], 16);
+            sum1[i] = lane < 16 ? sum1[i] + o1 : 0.0f;
+            sum2[i] = lane < 16 ? sum2[i] + o2 : 0.0f;
+        }
+    }
+}
 
 // Shared-memory map (1024-byte aligned): [W image: KC chunks if resident] [staging: ceil(n_store/64) slabs of
 // 128 rows x 128 B] [ring: `stages` slots of {A chunk 16 KB, + W chunk n_pad*128 B when W is streamed}]
 template <bool STATS>
 __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_constant__ TcLinearArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    // this CTA's column block: a call with N > 256 output columns runs its <= kTcMaxNBlocks blocks of 256 as blockIdx.y of ONE
+    // launch (they used to be serial launches: fp4.1's data gradient, 3 blocks of 16 tiles, took 46 us)
+    const int yb = blockIdx.y;
+    const int bN = min(256, a.N - 256 * yb);
+    const int b_n_pad = (bN + 15) & ~15;
+    const int b_n_store = min((bN + 7) & ~7, a.ldz - 256 * yb);
+    const uint8_t *const bWimg = a.Wimg + (size_t)yb * a.KC * 256 * 128;
+    const float *const b_bias = a.bias ? a.bias + 256 * yb : nullptr;
+    const int b_stat_off = a.stat_off + 256 * yb;
+    unsigned *const b_ticket = a.fin.ticket ? a.fin.ticket + yb : nullptr;
+    const CUtensorMap *const b_tm_z = &a.tm_z[yb];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_w, bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned (SW128 atoms)
-    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
-    const int z_slabs = (a.n_store + 63) >> 6;
+    const uint32_t b_bytes = (uint32_t)b_n_pad * 128u;
+    const int z_slabs = (b_n_store + 63) >> 6;
     uint8_t *const w_res = smem;
     uint8_t *const staging = smem + (a.w_resident ? (size_t)a.KC * b_bytes : 0);
     uint8_t *const ring = staging + (size_t)z_slabs * kTcAStage;
     const uint32_t slot_bytes = kTcAStage + (a.w_resident ? 0u : b_bytes);
 
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < a.n_pad) tmem_cols <<= 1;
+    while ((int)tmem_cols < b_n_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -152,7 +227,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
             tma_prefetch_desc(&a.tm_x);
             if (a.w_resident) {
                 mbar_expect_tx(&bar_w, (uint32_t)a.KC * b_bytes);
-                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
+                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, bWimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
             }
             uint32_t n = 0;
             for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x)
@@ -162,12 +237,12 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     uint8_t *slot = ring + (size_t)s * slot_bytes;
                     mbar_expect_tx(&bar_full[s], slot_bytes);
                     tma_load_2d(slot, &a.tm_x, kc * kTcBK, (int)(tile * kTcBM), &bar_full[s]);
-                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
+                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, bWimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
                 }
         }
         __syncwarp();
     } else {
-        const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(kTcBM, b_n_pad, 0, 0);
         float sum1[8], sum2[8];   // STATS: this lane's column pairs p = lane + 32 j  (columns 2p, 2p+1)
 #pragma unroll
         for (int i = 0; i < 8; ++i) sum1[i] = sum2[i] = 0.0f;
@@ -191,7 +266,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                         sc[e] = ok ? a.in_scale[k + e] : 0.0f;
                         sh[e] = ok ? a.in_shift[k + e] : 0.0f;
                     }
-                    mbar_wait(&bar_full[s], par);
+                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
                     if (k < a.K) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -211,7 +286,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     fence_proxy_async();
                     named_bar_sync(1, 128);
                 } else if (tid == 0) {
-                    mbar_wait(&bar_full[s], par);
+                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
                 }
                 if (tid == 0) {
                     fence_after_sync();
@@ -226,19 +301,19 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     if (kc == a.KC - 1) umma_commit(&bar_acc);
                 }
             }
-            mbar_wait(&bar_acc, acc_par);
+            mbar_wait_hint(&bar_acc, acc_par, a.wait_hint_ns);
             acc_par ^= 1u;
             fence_after_sync();
 
             // ---- epilogue 1: TMEM -> registers -> (+bias) -> bf16 -> staging row `tid` (SW128 box layout) ----
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < a.n_store; c0 += 16) {
+            for (int c0 = 0; c0 < b_n_store; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (a.bias) {
+                if (b_bias) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < a.N) v[i] += a.bias[c0 + i];
+                        if (c0 + i < bN) v[i] += b_bias[c0 + i];
                 }
                 uint4 lo, hi;
                 lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
@@ -248,7 +323,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                 uint8_t *slab = staging + (size_t)(c0 >> 6) * kTcAStage;
                 const int ch = (c0 & 63) >> 3;
                 *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch)) = lo;
-                if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
+                if (c0 + 8 < b_n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
             }
             fence_before_sync();     // TMEM reads done before the next tile's MMA (issued after the barrier below)
             fence_proxy_async();     // staging writes -> visible to the TMA store
@@ -256,26 +331,10 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
 
             // ---- epilogue 2: TMA store of the tile (rows >= M and columns >= n_store are clipped) + column statistics ----
             if (tid == 0)
-                for (int j = 0; j < z_slabs; ++j) tma_store_2d(&a.tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
+                for (int j = 0; j < z_slabs; ++j) tma_store_2d(b_tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
             if (STATS) {
-                const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int p = lane + 32 * j;
-                    if (2 * p < a.N) {
-                        const uint8_t *slab = staging + (size_t)(p >> 5) * kTcAStage;
-                        const int ch = (p & 31) >> 2, inb = (p & 3) * 4;
-                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                        for (int r = 0; r < rows; ++r) {
-                            const float2 f = unpack_bf16x2(
-                                *reinterpret_cast<const uint32_t *>(slab + sw128_offset(warp * 32 + r, ch) + inb));
-                            s1a += f.x; s1b += f.y;
-                            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
-                        }
-                        sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
-                        sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
-                    }
-                }
+                const int rows = (int)max((int64_t)0, min((int64_t)32, a.M - (m0 + warp * 32)));
+                tile_col_stats(staging, warp, lane, bN, rows, sum1, sum2);
             }
             if (tid == 0) tma_store_wait_read();
             named_bar_sync(1, 128);   // staging free again (store has read it, statistics have read it)
@@ -283,6 +342,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
         if (tid == 0) tma_store_wait_all();
 
         if (STATS) {
+            fold_split_stats(lane, bN, sum1, sum2);
             float(*s_part)[2][256] = reinterpret_cast<float(*)[2][256]>(staging);   // 8 KB of the (now idle) staging tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -291,40 +351,40 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                 s_part[warp][1][2 * p] = sum2[2 * j];     s_part[warp][1][2 * p + 1] = sum2[2 * j + 1];
             }
             named_bar_sync(1, 128);
-            for (int c = tid; c < a.N; c += 128) {
+            for (int c = tid; c < bN; c += 128) {
                 float t1 = 0.f, t2 = 0.f;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
-                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
+                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + b_stat_off;
                 atomicAdd(acc + c, (double)t1);
                 atomicAdd(acc + a.stat_ld + c, (double)t2);
             }
-            if (a.fin.ticket) {
+            if (b_ticket) {
                 // ---- "last CTA finalizes": mean / variance -> scale, shift, running statistics; accumulator and ticket
                 //      are left zeroed for the next layer (saves the finalize launch between two layers) ----
                 __threadfence();
                 named_bar_sync(1, 128);
-                if (tid == 0) s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+                if (tid == 0) s_last = atomicAdd(b_ticket, 1u) == gridDim.x - 1 ? 1 : 0;
                 named_bar_sync(1, 128);
                 if (s_last) {
                     __threadfence();
-                    for (int c = tid; c < a.N; c += 128) {
+                    for (int c = tid; c < bN; c += 128) {
                         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                         for (int r = 0; r < kStatReplicas; ++r) {   // fixed order
-                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + a.stat_off;
+                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + b_stat_off;
                             s1 += __ldcg(acc + c);
                             s2 += __ldcg(acc + a.stat_ld + c);
                             acc[c] = 0.0;
                             acc[a.stat_ld + c] = 0.0;
                         }
-                        bn_finalize_channel(s1, s2, a.M, a.stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
+                        bn_finalize_channel(s1, s2, a.M, b_stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
                                             a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
                                             a.fin.save_mean, a.fin.save_invstd);
                     }
                     if (tid == 0) {
-                        *a.fin.ticket = 0u;
-                        if (a.fin.num_batches_tracked && a.stat_off == 0) *a.fin.num_batches_tracked += 1;
+                        *b_ticket = 0u;
+                        if (a.fin.num_batches_tracked && b_stat_off == 0) *a.fin.num_batches_tracked += 1;
                     }
                 }
             }
@@ -354,21 +414,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 template <bool STATS>
 __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid_constant__ TcLinearArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    // this CTA's column block: a call with N > 256 output columns runs its <= kTcMaxNBlocks blocks of 256 as blockIdx.y of ONE
+    // launch (they used to be serial launches: fp4.1's data gradient, 3 blocks of 16 tiles, took 46 us)
+    const int yb = blockIdx.y;
+    const int bN = min(256, a.N - 256 * yb);
+    const int b_n_pad = (bN + 15) & ~15;
+    const int b_n_store = min((bN + 7) & ~7, a.ldz - 256 * yb);
+    const uint8_t *const bWimg = a.Wimg + (size_t)yb * a.KC * 256 * 128;
+    const float *const b_bias = a.bias ? a.bias + 256 * yb : nullptr;
+    const int b_stat_off = a.stat_off + 256 * yb;
+    unsigned *const b_ticket = a.fin.ticket ? a.fin.ticket + yb : nullptr;
+    const CUtensorMap *const b_tm_z = &a.tm_z[yb];
     __shared__ __align__(8) uint64_t bar_full[kTc2MaxStages], bar_empty[kTc2MaxStages], bar_w, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
-    const int z_slabs = (a.n_store + 63) >> 6;
+    const uint32_t b_bytes = (uint32_t)b_n_pad * 128u;
+    const int z_slabs = (b_n_store + 63) >> 6;
     uint8_t *const w_res = smem;
     uint8_t *const staging = smem + (a.w_resident ? (size_t)a.KC * b_bytes : 0);
     uint8_t *const ring = staging + (size_t)z_slabs * kTcAStage;
     const uint32_t slot_bytes = kTcAStage + (a.w_resident ? 0u : b_bytes);
 
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < 2 * a.n_pad) tmem_cols <<= 1;
+    while ((int)tmem_cols < 2 * b_n_pad) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -394,7 +465,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
             tma_prefetch_desc(&a.tm_x);
             if (a.w_resident) {
                 mbar_expect_tx(&bar_w, (uint32_t)a.KC * b_bytes);
-                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
+                for (int kc = 0; kc < a.KC; ++kc) bulk_g2s(w_res + (size_t)kc * b_bytes, bWimg + (size_t)kc * b_bytes, b_bytes, &bar_w);
             }
             uint32_t n = 0;
             for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x)
@@ -404,14 +475,14 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                     uint8_t *slot = ring + (size_t)s * slot_bytes;
                     mbar_expect_tx(&bar_full[s], slot_bytes);
                     tma_load_2d(slot, &a.tm_x, kc * kTcBK, (int)(tile * kTcBM), &bar_full[s]);
-                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, a.Wimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
+                    if (!a.w_resident) bulk_g2s(slot + kTcAStage, bWimg + (size_t)kc * b_bytes, b_bytes, &bar_full[s]);
                 }
         }
         __syncwarp();
     } else if (warp >= 4) {
         // ---- transform group + MMA issue (thread 128) ----
         const int ttid = tid - 128;
-        const uint32_t idesc = make_idesc_bf16(kTcBM, a.n_pad, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(kTcBM, b_n_pad, 0, 0);
         const int t_cc = (ttid & 7) ^ ((ttid >> 3) & 7);
         if (a.w_resident && ttid == 0) mbar_wait(&bar_w, 0);
         uint32_t n = 0, t = 0;
@@ -429,7 +500,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                         sc[e] = ok ? a.in_scale[k + e] : 0.0f;
                         sh[e] = ok ? a.in_shift[k + e] : 0.0f;
                     }
-                    mbar_wait(&bar_full[s], par);
+                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
                     if (k < a.K) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -449,7 +520,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                     fence_proxy_async();
                     named_bar_sync(2, 128);
                 } else if (ttid == 0) {
-                    mbar_wait(&bar_full[s], par);
+                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
                 }
                 if (ttid == 0) {
                     if (kc == 0 && buse > 0) mbar_wait(&acc_empty[buf], (buse - 1) & 1u);   // the epilogue drained this buffer
@@ -459,7 +530,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                     const uint32_t a_base = smem_addr(slot);
                     const uint32_t b_base = smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage);
                     for (int j = 0; j < nk; ++j)
-                        umma_bf16(tmem + buf * (uint32_t)a.n_pad, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024),
+                        umma_bf16(tmem + buf * (uint32_t)b_n_pad, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024),
                                   idesc, (uint32_t)((kc | j) != 0));
                     umma_commit(&bar_empty[s]);
                     if (kc == a.KC - 1) umma_commit(&acc_full[buf]);
@@ -475,16 +546,16 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
         for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
             const int64_t m0 = tile * kTcBM;
             const uint32_t buf = t & 1u;
-            mbar_wait(&acc_full[buf], (t >> 1) & 1u);
+            mbar_wait_hint(&acc_full[buf], (t >> 1) & 1u, a.wait_hint_ns);
             fence_after_sync();
-            const uint32_t taddr = tmem + buf * (uint32_t)a.n_pad + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < a.n_store; c0 += 16) {
+            const uint32_t taddr = tmem + buf * (uint32_t)b_n_pad + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < b_n_store; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (a.bias) {
+                if (b_bias) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < a.N) v[i] += a.bias[c0 + i];
+                        if (c0 + i < bN) v[i] += b_bias[c0 + i];
                 }
                 uint4 lo, hi;
                 lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
@@ -494,34 +565,18 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                 uint8_t *slab = staging + (size_t)(c0 >> 6) * kTcAStage;
                 const int ch = (c0 & 63) >> 3;
                 *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch)) = lo;
-                if (c0 + 8 < a.n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
+                if (c0 + 8 < b_n_store) *reinterpret_cast<uint4 *>(slab + sw128_offset(tid, ch + 1)) = hi;
             }
             fence_before_sync();     // this thread's TMEM reads are complete
             fence_proxy_async();     // staging writes -> visible to the TMA store
             named_bar_sync(1, 128);
             if (tid == 0) {
                 mbar_arrive(&acc_empty[buf]);    // the MMAs of tile t+2 may overwrite this accumulator buffer
-                for (int j = 0; j < z_slabs; ++j) tma_store_2d(&a.tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
+                for (int j = 0; j < z_slabs; ++j) tma_store_2d(b_tm_z, 64 * j, (int)m0, staging + (size_t)j * kTcAStage);
             }
             if (STATS) {
-                const int rows = (int)min((int64_t)32, a.M - (m0 + warp * 32));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int p = lane + 32 * j;
-                    if (2 * p < a.N) {
-                        const uint8_t *slab = staging + (size_t)(p >> 5) * kTcAStage;
-                        const int ch = (p & 31) >> 2, inb = (p & 3) * 4;
-                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                        for (int r = 0; r < rows; ++r) {
-                            const float2 f = unpack_bf16x2(
-                                *reinterpret_cast<const uint32_t *>(slab + sw128_offset(warp * 32 + r, ch) + inb));
-                            s1a += f.x; s1b += f.y;
-                            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
-                        }
-                        sum1[2 * j] += s1a; sum1[2 * j + 1] += s1b;
-                        sum2[2 * j] += s2a; sum2[2 * j + 1] += s2b;
-                    }
-                }
+                const int rows = (int)max((int64_t)0, min((int64_t)32, a.M - (m0 + warp * 32)));
+                tile_col_stats(staging, warp, lane, bN, rows, sum1, sum2);
             }
             if (tid == 0) tma_store_wait_read();
             named_bar_sync(1, 128);   // staging free again
@@ -529,6 +584,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
         if (tid == 0) tma_store_wait_all();
 
         if (STATS) {
+            fold_split_stats(lane, bN, sum1, sum2);
             float(*s_part)[2][256] = reinterpret_cast<float(*)[2][256]>(staging);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -537,38 +593,38 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                 s_part[warp][1][2 * p] = sum2[2 * j];     s_part[warp][1][2 * p + 1] = sum2[2 * j + 1];
             }
             named_bar_sync(1, 128);
-            for (int c = tid; c < a.N; c += 128) {
+            for (int c = tid; c < bN; c += 128) {
                 float t1 = 0.f, t2 = 0.f;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) { t1 += s_part[w][0][c]; t2 += s_part[w][1][c]; }
-                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + a.stat_off;
+                double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.stat_ld + b_stat_off;
                 atomicAdd(acc + c, (double)t1);
                 atomicAdd(acc + a.stat_ld + c, (double)t2);
             }
-            if (a.fin.ticket) {
+            if (b_ticket) {
                 __threadfence();
                 named_bar_sync(1, 128);
-                if (tid == 0) s_last = atomicAdd(a.fin.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+                if (tid == 0) s_last = atomicAdd(b_ticket, 1u) == gridDim.x - 1 ? 1 : 0;
                 named_bar_sync(1, 128);
                 if (s_last) {
                     __threadfence();
-                    for (int c = tid; c < a.N; c += 128) {
+                    for (int c = tid; c < bN; c += 128) {
                         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                         for (int r = 0; r < kStatReplicas; ++r) {
-                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + a.stat_off;
+                            double *acc = a.stat_accum + (size_t)r * 2 * a.stat_ld + b_stat_off;
                             s1 += __ldcg(acc + c);
                             s2 += __ldcg(acc + a.stat_ld + c);
                             acc[c] = 0.0;
                             acc[a.stat_ld + c] = 0.0;
                         }
-                        bn_finalize_channel(s1, s2, a.M, a.stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
+                        bn_finalize_channel(s1, s2, a.M, b_stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
                                             a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
                                             a.fin.save_mean, a.fin.save_invstd);
                     }
                     if (tid == 0) {
-                        *a.fin.ticket = 0u;
-                        if (a.fin.num_batches_tracked && a.stat_off == 0) *a.fin.num_batches_tracked += 1;
+                        *b_ticket = 0u;
+                        if (a.fin.num_batches_tracked && b_stat_off == 0) *a.fin.num_batches_tracked += 1;
                     }
                 }
             }
@@ -661,33 +717,59 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
     const int KC = (K + kTcBK - 1) / kTcBK;
     uint8_t *img = (uint8_t *)wpack;
     const int64_t m_tiles = (M + kTcBM - 1) / kTcBM;
-    for (int n0 = 0; n0 < N; n0 += 256) {
-        const int nb = N - n0 < 256 ? N - n0 : 256;
-        const int n_pad = round_up(nb, 16);
-        int n_store = round_up(nb, 8);
-        if (n0 + n_store > ldz) n_store = ldz - n0;      // ldz is a multiple of 8 on this path
-        const size_t img_bytes = (size_t)KC * n_pad * 128;
-        const int total = KC * n_pad * 8;
-        if (!packed) {
-            pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad, KC, 0, img);
-            count_launch();
-        }
+    static int hint_ns = -1, max_ctas = 0;
+    if (hint_ns < 0) {
+        const char *e = getenv("PN2_MBAR_HINT_NS");      // measured: no effect on B200 (0 = plain try_wait loop)
+        hint_ns = e ? atoi(e) : 0;
+        if (hint_ns < 0 || hint_ns > 100000) hint_ns = 0;
+        e = getenv("PN2_TC_MAX_CTAS");
+        max_ctas = e ? atoi(e) : 4;
+        if (max_ctas < 1 || max_ctas > 8) max_ctas = 4;
+    }
+    // output columns in blocks of 256 (one accumulator tile); up to kTcMaxNBlocks blocks share ONE launch as blockIdx.y
+    for (int g0 = 0; g0 < N; g0 += 256 * kTcMaxNBlocks) {
+        const int gN = N - g0 < 256 * kTcMaxNBlocks ? N - g0 : 256 * kTcMaxNBlocks;
+        const int ng = (gN + 255) / 256;
         TcLinearArgs a;
         memset(&a.fin, 0, sizeof(a.fin));
         if (fin && stat_accum) a.fin = *fin;
-        if (!make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, kTcBM) ||
-            !make_rows_tensor_map(&a.tm_z, (const __nv_bfloat16 *)Z + n0, M, n_store, ldz, kTcBM)) {
+        bool maps_ok = make_rows_tensor_map(&a.tm_x, X, M, ldx, ldx, kTcBM);
+        size_t group_img_bytes = 0;
+        for (int y = 0; y < ng; ++y) {
+            const int n0 = g0 + 256 * y;
+            const int nb = N - n0 < 256 ? N - n0 : 256;
+            const int n_pad_y = round_up(nb, 16);
+            int n_store_y = round_up(nb, 8);
+            if (n0 + n_store_y > ldz) n_store_y = ldz - n0;      // ldz is a multiple of 8 on this path
+            if (!packed) {
+                const int total = KC * n_pad_y * 8;
+                pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W + (int64_t)n0 * w_sn, w_sn, w_sk, nb, K, n_pad_y, KC, 0,
+                                                                        img + group_img_bytes);
+                count_launch();
+            }
+            group_img_bytes += (size_t)KC * n_pad_y * 128;
+            maps_ok = maps_ok && make_rows_tensor_map(&a.tm_z[y], (const __nv_bfloat16 *)Z + n0, M, n_store_y, ldz, kTcBM);
+        }
+        for (int y = ng; y < kTcMaxNBlocks; ++y) a.tm_z[y] = a.tm_z[0];
+        if (!maps_ok) {
             set_error("linear_tc: cuTensorMapEncodeTiled failed (M=%lld ldx=%d ldz=%d)", (long long)M, ldx, ldz);
             return PN2_ERR_CUDA;
         }
+        // the plan below is made for the group's first (widest) block; narrower last blocks use less of the same carve-up
+        const int nb = gN < 256 ? gN : 256;
+        const int n_pad = round_up(nb, 16);
+        int n_store = round_up(nb, 8);
+        if (g0 + n_store > ldz) n_store = ldz - g0;
+        const size_t img_bytes = (size_t)KC * n_pad * 128;
         a.in_scale = in_scale;
         a.in_shift = in_shift;
         a.Wimg = img;
-        a.bias = bias ? bias + n0 : nullptr;
-        a.M = M; a.K = K; a.N = nb; a.n_pad = n_pad; a.n_store = n_store; a.KC = KC;
+        a.bias = bias ? bias + g0 : nullptr;
+        a.M = M; a.K = K; a.N = gN; a.ldz = ldz - g0; a.KC = KC;
+        a.wait_hint_ns = (uint32_t)hint_ns;
         a.stat_accum = stat_accum;
         a.stat_ld = N;
-        a.stat_off = n0;
+        a.stat_off = g0;
         // shared-memory plan: resident W when its image is <= 64 KB; as many ring slots as fit the per-CTA budget
         // of 3, 2 or 1 CTAs per SM (whichever is the densest that still leaves >= 3 slots, at most 8)
         a.w_resident = img_bytes <= 64 * 1024 ? 1 : 0;
@@ -697,13 +779,8 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         // store), so co-resident CTAs are what hides the latency.  Take the densest packing (<= max_ctas, tensor memory
         // allowing: n * columns <= 512) that still leaves a ring of >= 2 slots, except that 1-2 CTAs/SM prefer >= 3 slots.
         // Measured: the 128 x 128 layers missed a third slot at 2/SM by 160 bytes, ran 1/SM at 0.8 TB/s, tensor pipe 5 % busy.
-        static int max_ctas = 0;
-        if (!max_ctas) {
-            const char *e = getenv("PN2_TC_MAX_CTAS");
-            max_ctas = e ? atoi(e) : 4;
-            if (max_ctas < 1 || max_ctas > 8) max_ctas = 4;
-        }
         const int v2_ctas = tc2_mode == 3 ? (KC >= 2 ? 2 : 0) : tc2_mode;
+        bool launched = false;
         if (v2_ctas > 0) {
             // v2: the ring hides the latency -- one CTA per SM with every byte of shared memory that is left as ring slots
             // (or two CTAs when each still gets >= 4 slots and 2 x 2 accumulator buffers fit tensor memory)
@@ -721,48 +798,51 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
                 if (stages2 > kTc2MaxStages) stages2 = kTc2MaxStages;
                 a.stages = stages2;
                 const size_t dyn2 = fixed + slot * stages2;
-                int64_t grid2 = (int64_t)per_sm2 * kNumSMs;
+                int64_t grid2 = ((int64_t)per_sm2 * kNumSMs + ng - 1) / ng;
                 if (grid2 > m_tiles) grid2 = m_tiles;
+                const dim3 grid((unsigned)grid2, (unsigned)ng);
                 if (stat_accum)
-                    linear_tc2_kernel<true><<<(unsigned)grid2, kLinTc2Threads, dyn2, st>>>(a);
+                    linear_tc2_kernel<true><<<grid, kLinTc2Threads, dyn2, st>>>(a);
                 else
-                    linear_tc2_kernel<false><<<(unsigned)grid2, kLinTc2Threads, dyn2, st>>>(a);
+                    linear_tc2_kernel<false><<<grid, kLinTc2Threads, dyn2, st>>>(a);
                 count_launch();
                 int rc2 = check_launch("linear_tc2");
                 if (rc2 != PN2_OK) return rc2;
-                img += img_bytes;
-                continue;
+                launched = true;
             }
         }
-        uint32_t tmem_cols = 32;
-        while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
-        int stages = 0, per_sm = 1;
-        for (int pass = 0; pass < 2 && stages == 0; ++pass)
-            for (int n = max_ctas; n >= 1 && stages == 0; --n) {
-                if (n * (int)tmem_cols > 512) continue;
-                const size_t budget = (size_t)(233472 / n) - 1024 - (size_t)static_smem;
-                const int min_slots = (pass == 0 && n <= 2) ? 3 : 2;
-                if (budget < fixed + slot * (size_t)min_slots) continue;
-                stages = (int)((budget - fixed) / slot);
-                per_sm = n;
+        if (!launched) {
+            uint32_t tmem_cols = 32;
+            while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
+            int stages = 0, per_sm = 1;
+            for (int pass = 0; pass < 2 && stages == 0; ++pass)
+                for (int n = max_ctas; n >= 1 && stages == 0; --n) {
+                    if (n * (int)tmem_cols > 512) continue;
+                    const size_t budget = (size_t)(233472 / n) - 1024 - (size_t)static_smem;
+                    const int min_slots = (pass == 0 && n <= 2) ? 3 : 2;
+                    if (budget < fixed + slot * (size_t)min_slots) continue;
+                    stages = (int)((budget - fixed) / slot);
+                    per_sm = n;
+                }
+            if (stages < 2) {
+                set_error("linear_tc: layer K=%d N=%d does not fit shared memory", K, nb);
+                return PN2_ERR_UNSUPPORTED;
             }
-        if (stages < 2) {
-            set_error("linear_tc: layer K=%d N=%d does not fit shared memory", K, nb);
-            return PN2_ERR_UNSUPPORTED;
+            if (stages > 8) stages = 8;
+            a.stages = stages;
+            const size_t dyn = fixed + slot * stages;
+            int64_t gx = ((int64_t)per_sm * kNumSMs + ng - 1) / ng;
+            if (gx > m_tiles) gx = m_tiles;
+            const dim3 grid((unsigned)gx, (unsigned)ng);
+            if (stat_accum)
+                linear_tc_kernel<true><<<grid, kLinTcThreads, dyn, st>>>(a);
+            else
+                linear_tc_kernel<false><<<grid, kLinTcThreads, dyn, st>>>(a);
+            count_launch();
+            int rc = check_launch("linear_tc");
+            if (rc != PN2_OK) return rc;
         }
-        if (stages > 8) stages = 8;
-        a.stages = stages;
-        const size_t dyn = fixed + slot * stages;
-        int64_t grid = (int64_t)per_sm * kNumSMs;
-        if (grid > m_tiles) grid = m_tiles;
-        if (stat_accum)
-            linear_tc_kernel<true><<<(unsigned)grid, kLinTcThreads, dyn, st>>>(a);
-        else
-            linear_tc_kernel<false><<<(unsigned)grid, kLinTcThreads, dyn, st>>>(a);
-        count_launch();
-        int rc = check_launch("linear_tc");
-        if (rc != PN2_OK) return rc;
-        img += img_bytes;
+        img += group_img_bytes;
     }
     return PN2_OK;
 }

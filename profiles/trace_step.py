@@ -8,8 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _inputs as I
 pn2 = importlib.import_module("khairil_tum-facade_semantic_segmentation_b200")
-mode = sys.argv[1] if len(sys.argv) > 1 else "train"
-out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/trace_%s.csv" % mode
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+mode = args[0] if len(args) > 0 else "train"
+out = args[1] if len(args) > 1 else "gpurun_out/trace_%s.csv" % mode
 pn2.set_precision("bf16")
 torch.manual_seed(1234)
 B, N, C = 32, 4096, 9
@@ -17,13 +18,14 @@ pts = I.facade_batch(B, N, C, 11).cuda()
 lab = I.labels(B, N, 18, 111).cuda()
 if mode == "train":
     trainer = pn2.SemSegTrainer(18, 3, device="cuda")
-    trainer.enable_cuda_graph(B, N, C)
+    trainer.enable_cuda_graph(B, N, C, pipeline="--no-pipeline" not in sys.argv)
     run = lambda: trainer.step_device(pts, lab)
 else:
     net = pn2.get_model(18, 3).cuda().eval()
-    pred = pn2.SemSegPredictor(net, B, N, C, "cuda")
-    run = lambda: pred.forward_device(pts)
-for _ in range(3):
+    pipe = "--no-pipeline" not in sys.argv
+    pred = pn2.SemSegPredictor(net, B, N, C, "cuda", pipeline=pipe)
+    run = (lambda: pred.submit(pts, to_host=False)) if pipe else (lambda: pred.forward_device(pts))
+for _ in range(4):
     run()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
