@@ -272,7 +272,7 @@ def run_reference(args, rank):
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "oracle port of the reference modules (torch CPU ops in the reference's order), "
-                   "fp32, each step a %d-cloud sample of the 32-cloud batch; median step; at most 150 s of timed steps" % sample_clouds},
+                   "fp32, %d of the batch's 32 clouds per step; median step; at most 150 s of timed steps" % sample_clouds},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d x %d-point clouds per step (train step: fwd+bwd+Adam)" % (sample_clouds, NPOINT)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -461,8 +461,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-sample-clouds", type=int, default=16,
-                    help="clouds per step of the CPU reference arm (a bounded sample of the 32-cloud batch)")
+    ap.add_argument("--ref-sample-clouds", type=int, default=32,
+                    help="clouds per step of the CPU reference arm (32 = the whole batch of the configuration; fewer = a bounded sample)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="do not overlap the index pipeline (FPS, ball query, 3-NN) of batch i+1 with the feature path of batch i")
@@ -649,9 +649,10 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        rate, sec, done = cpu_train_step_rate(16, 2, 1, threads)
+        rate, sec, done = cpu_train_step_rate(B_PER_GPU, 5, 1, threads, budget_s=25.0)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d timed train steps on 16 x %d-point clouds (oracle port of the reference, fp32), %.1f s/step" % (done, NPOINT, sec)}
+               "sample": "%d timed train steps on the whole %d x %d-point batch (oracle port of the reference, fp32, fwd+bwd+Adam), "
+                         "%.1f s/step, median" % (done, B_PER_GPU, NPOINT, sec)}
 
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
     line = {
