@@ -313,6 +313,30 @@ int pn2_vote_argmax(const int32_t *votes, int64_t P, int NC, void *labels, int l
  * points: the xyz channels of a [B, N, C] fp32 batch, element strides (sB, sN, sC). */
 int pn2_rotate_z(float *points, int64_t sB, int64_t sN, int64_t sC, const double *cos_sin, int B, int N, void *stream);
 
+/* ---- sliding-block slicer of the test-time dataset -----------------------------------------
+ * replaces TestCustomDataset.__getitem__ (/root/reference/sem_seg_testing.py:182-254).  The grid of cells (index_y outer,
+ * index_x inner, :193-194) is described per column / row by lo = s - padding, hi = e + padding (the reference's s_x/e_x
+ * expressions, :196-201, evaluated on the host in float64); cell = iy * gx + ix.
+ * pn2_slice_cells: for every point p (float64 xyz, element strides sP / sC) and every cell with lo_x <= x <= hi_x and
+ *   lo_y <= y <= hi_y (:202): k = counts[cell]++ and, in the fill pass (cell_offset / slot_point / slot_cell non-NULL),
+ *   slot_point[cell_offset[cell] + k] = p.  Count pass first, then zero `counts` and run the fill pass.
+ * pn2_slice_pad: padding slot i (pad_cell[i], rank pad_rank[i] among the cell's padding slots) takes the pad_rank-th
+ *   member when the cell needs no more padding than it has members (np.random.choice(..., replace=False), :207-208; the
+ *   caller has randomly permuted the members), else member rnd[i] % n (replace=True).
+ * pn2_slice_rows: rows[s] = [x - cx, y - cy, z, x/max_x, y/max_y, z/max_z, extra_e / extra_div_e ...] of slot s's point in
+ *   float64, rounded once to float32 (:216-241, localfunctions.py:394); label and labelweights[label] (:223-224). */
+int pn2_slice_cells(const double *points, int64_t sP, int64_t sC, int64_t P, const double *lo_x, const double *hi_x,
+                    int gx, const double *lo_y, const double *hi_y, int gy, double min_x, double min_y, double stride,
+                    double block_size, double padding, int32_t *counts, const int64_t *cell_offset,
+                    int64_t *slot_point, int32_t *slot_cell, void *stream);
+int pn2_slice_pad(const int32_t *counts, const int64_t *cell_offset, const int32_t *pad_cell, const int64_t *pad_rank,
+                  const int64_t *rnd, int64_t n_pad, int block_points, int64_t *slot_point, int32_t *slot_cell,
+                  void *stream);
+int pn2_slice_rows(const double *points, int64_t sP, int64_t sC, const int64_t *labels, const double *extra, int64_t eE,
+                   int64_t eP, const double *extra_div, int E, const float *labelweights, const int64_t *slot_point,
+                   const int32_t *slot_cell, const double *cx, const double *cy, int gx, double max_x, double max_y,
+                   double max_z, int64_t S, float *rows, int64_t *out_label, float *out_weight, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ class Pn2Error(RuntimeError):
     """A libpn2b200 call returned a negative status."""
 
 
-_i, _l, _f, _p, _z = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+_i, _l, _f, _p, _z, _d = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/pn2b200.h one to one
 _SIGNATURES = {
@@ -43,6 +43,9 @@ _SIGNATURES = {
     "pn2_linear_bwd_data": (_i, [_p, _i, _i, _p, _l, _i, _i, _p, _i, _i, _p, _p]),
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
     "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
+    "pn2_slice_cells": (_i, [_p, _l, _l, _l, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _p, _p, _p, _p, _p]),
+    "pn2_slice_pad": (_i, [_p, _p, _p, _p, _p, _l, _i, _p, _p, _p]),
+    "pn2_slice_rows": (_i, [_p, _l, _l, _p, _p, _l, _l, _p, _i, _p, _p, _p, _p, _p, _i, _d, _d, _d, _l, _p, _p, _p, _p]),
     "pn2_rotate_z": (_i, [_p, _l, _l, _l, _p, _i, _i, _p]),
     "pn2_add_vote": (_i, [_p, _p, _p, _i, _l, _l, _i, _p, _p, _p]),
     "pn2_vote_argmax": (_i, [_p, _l, _i, _p, _i, _p]),

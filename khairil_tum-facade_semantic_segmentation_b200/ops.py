@@ -321,3 +321,114 @@ def rotate_point_cloud_z_(points, cos_sin=None, staging=None):
     sB, sN, sC = points.stride()
     call("pn2_rotate_z", ptr(points), sB, sN, sC, ptr(cs), B, N, stream())
     return points
+
+
+def slice_scene(points, labels=None, extra=None, extra_names=(), labelweights=None, block_size=1.0, stride=0.5,
+                padding=0.001, block_points=4096, generator=None):
+    """TestCustomDataset.__getitem__ (/root/reference/sem_seg_testing.py:182-254) for one scene, on the device.
+
+    points [P, 3] float64 CUDA (scene coordinates as laspy yields them), labels [P] int64 or None, extra [E, P] float64 or
+    None with `extra_names` (features named red / green / blue are divided by 255, :236-237), labelweights [NC] float32.
+    Returns (data_room [nb, block_points, 6 + E] float32, label_room [nb, block_points] int64, sample_weight
+    [nb, block_points] float32, index_room [nb, block_points] int64), all on the device: the reference's four arrays, the
+    rows already rounded to float32 as `torch.Tensor(batch_data)` does before the forward (localfunctions.py:394).
+
+    Same cells in the same (index_y, index_x) order, same member points per cell (the reference's float64 comparisons),
+    same number of blocks per cell, bit-identical rows per (cell, point); WHICH members pad a cell and the order inside a
+    cell are random in the reference as well (numpy's global generator) -- here they come from `generator` (a CUDA
+    torch.Generator, default: the device's)."""
+    import numpy as np
+    require_cuda(points, "points", dtype=torch.float64)
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise ValueError("points must be [P, 3] float64, got %s" % (tuple(points.shape),))
+    dev, P = points.device, points.shape[0]
+    E = 0 if extra is None else extra.shape[0]
+    if E != len(extra_names):
+        raise ValueError("extra has %d rows but %d names were given" % (E, len(extra_names)))
+    C = 6 + E
+    bp = int(block_points)
+
+    def empty():
+        return (torch.empty(0, bp, C, device=dev), torch.empty(0, bp, dtype=torch.int64, device=dev),
+                torch.empty(0, bp, device=dev), torch.empty(0, bp, dtype=torch.int64, device=dev))
+
+    if P == 0:
+        return empty()
+    cmin = points.amin(dim=0).cpu().numpy()            # np.amin / np.amax of :186 (exact)
+    cmax = points.amax(dim=0).cpu().numpy()
+    block_size, stride, padding = float(block_size), float(stride), float(padding)
+    gx = int(np.ceil(float(cmax[0] - cmin[0] - block_size) / stride) + 1)     # :187-188
+    gy = int(np.ceil(float(cmax[1] - cmin[1] - block_size) / stride) + 1)
+    if gx <= 0 or gy <= 0:
+        return empty()
+
+    def axis(lo, hi, g):                               # :196-201 per column / row, the reference's own expressions
+        los, his, ctr = np.empty(g), np.empty(g), np.empty(g)
+        for i in range(g):
+            s = lo + i * stride
+            e = min(s + block_size, hi)
+            s = e - block_size
+            los[i], his[i], ctr[i] = s - padding, e + padding, s + block_size / 2.0
+        return los, his, ctr
+
+    lo_x, hi_x, cx = axis(cmin[0], cmax[0], gx)
+    lo_y, hi_y, cy = axis(cmin[1], cmax[1], gy)
+    bounds = torch.from_numpy(np.concatenate([lo_x, hi_x, cx, lo_y, hi_y, cy])).to(dev)
+    d_lo_x, d_hi_x, d_cx = bounds[0:gx], bounds[gx:2 * gx], bounds[2 * gx:3 * gx]
+    d_lo_y, d_hi_y, d_cy = bounds[3 * gx:3 * gx + gy], bounds[3 * gx + gy:3 * gx + 2 * gy], bounds[3 * gx + 2 * gy:]
+    sP, sC = points.stride()
+    cells = gx * gy
+    counts = torch.zeros(cells, dtype=torch.int32, device=dev)
+
+    def walk(cell_offset, slot_point, slot_cell):
+        call("pn2_slice_cells", ptr(points), sP, sC, P, ptr(d_lo_x), ptr(d_hi_x), gx, ptr(d_lo_y), ptr(d_hi_y), gy,
+             float(cmin[0]), float(cmin[1]), stride, block_size, padding, ptr(counts), ptr(cell_offset), ptr(slot_point),
+             ptr(slot_cell), stream())
+
+    walk(None, None, None)                             # pass 1: members per cell
+    n = counts.long()
+    padded = (n + bp - 1) // bp * bp                    # :204-205 (empty cells are skipped, :202)
+    cell_offset = torch.cumsum(padded, 0) - padded
+    S = int(padded.sum())
+    if S == 0:
+        return empty()
+    slot_point = torch.empty(S, dtype=torch.int64, device=dev)
+    slot_cell = torch.empty(S, dtype=torch.int32, device=dev)
+    counts.zero_()
+    walk(cell_offset, slot_point, slot_cell)           # pass 2: member lists (counts is the per-cell cursor)
+    cell_of_slot = torch.repeat_interleave(torch.arange(cells, device=dev), padded, output_size=S)
+    rank = torch.arange(S, device=dev) - cell_offset[cell_of_slot]
+    is_pad = rank >= n[cell_of_slot]
+
+    def rand(k):
+        return torch.randint(0, 2 ** 31, (k,), device=dev, dtype=torch.int64, generator=generator)
+
+    # a random permutation of every cell's members (padding slots stay behind them)
+    order = torch.argsort((cell_of_slot << 33) | (is_pad.long() << 32) | rand(S))
+    slot_point = slot_point[order]
+    pad_slots = torch.nonzero(is_pad).squeeze(1)
+    if pad_slots.numel():
+        pad_cell = cell_of_slot[pad_slots].int()
+        pad_rank = (rank[pad_slots] - n[cell_of_slot[pad_slots]]).contiguous()
+        call("pn2_slice_pad", ptr(counts), ptr(cell_offset), ptr(pad_cell), ptr(pad_rank), ptr(rand(pad_slots.numel())),
+             pad_slots.numel(), bp, ptr(slot_point), ptr(slot_cell), stream())
+    slot_cell = cell_of_slot.int()
+    # np.random.shuffle of the padded list (:209)
+    order = torch.argsort((cell_of_slot << 32) | rand(S))
+    slot_point = slot_point[order].contiguous()
+    rows = torch.empty(S, C, device=dev, dtype=torch.float32)
+    out_label = torch.empty(S, dtype=torch.int64, device=dev)
+    out_weight = torch.empty(S, dtype=torch.float32, device=dev)
+    div = None
+    eE = eP = 0
+    if E:
+        require_cuda(extra, "extra", dtype=torch.float64)
+        div = torch.tensor([255.0 if nm in ("red", "green", "blue") else 1.0 for nm in extra_names], dtype=torch.float64, device=dev)
+        eE, eP = extra.stride()
+    lw = None if labelweights is None else labelweights.to(dev, torch.float32).contiguous()
+    lab = None if labels is None else require_cuda(labels, "labels", dtype=torch.int64).contiguous()
+    call("pn2_slice_rows", ptr(points), sP, sC, ptr(lab), ptr(extra), eE, eP, ptr(div), E, ptr(lw), ptr(slot_point),
+         ptr(slot_cell), ptr(d_cx), ptr(d_cy), gx, float(cmax[0]), float(cmax[1]), float(cmax[2]), S, ptr(rows), ptr(out_label),
+         ptr(out_weight), stream())
+    nb = S // bp
+    return rows.view(nb, bp, C), out_label.view(nb, bp), out_weight.view(nb, bp), slot_point.view(nb, bp)

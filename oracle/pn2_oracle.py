@@ -20,6 +20,7 @@ unless another file is named):
   add_vote             add_vote    (localfunctions.py:336-343)
   vote_argmax          np.argmax(vote_label_pool, 1)   (localfunctions.py:405)
   rotate_z             rotate_point_cloud_z        (provider.py:66-84)
+  slice_scene          TestCustomDataset.__getitem__  (sem_seg_testing.py:182-254)
 
 The arithmetic itself lives in PyTorch (third party, un-pinned by the reference;
 effective pin torch 2.11.0+cu128 of this image), so this port issues the same
@@ -279,3 +280,64 @@ def rotate_z(batch_xyz, angles):
         m = np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])
         out[k, ...] = np.dot(batch_xyz[k, ...].reshape((-1, 3)), m)
     return out
+
+
+def slice_scene(points, labels, extra, extra_names, labelweights, block_size=1.0, stride=0.5, padding=0.001, block_points=4096):
+    """sem_seg_testing.py:182-254 for one scene: numpy restatement of TestCustomDataset.__getitem__ that makes the SAME
+    calls to numpy's global generator in the same order (np.random.choice, np.random.shuffle per non-empty cell), so under
+    the same seed it reproduces the reference's four arrays exactly.  Also returns the per-cell structure
+    [(cell index iy * grid_x + ix, member point indices, number of blocks)] that the random parts do not change.
+    points [P,3] float64, labels [P] int, extra: list of E arrays [P], labelweights [NC]."""
+    import numpy as np
+    pts = points[:, :3]
+    coord_min, coord_max = np.amin(pts, axis=0)[:3], np.amax(pts, axis=0)[:3]
+    grid_x = int(np.ceil(float(coord_max[0] - coord_min[0] - block_size) / stride) + 1)
+    grid_y = int(np.ceil(float(coord_max[1] - coord_min[1] - block_size) / stride) + 1)
+    data_room, label_room, sample_weight, index_room = np.array([]), np.array([]), np.array([]), np.array([])
+    cells = []
+    for index_y in range(grid_y):
+        for index_x in range(grid_x):
+            s_x = coord_min[0] + index_x * stride
+            e_x = min(s_x + block_size, coord_max[0])
+            s_x = e_x - block_size
+            s_y = coord_min[1] + index_y * stride
+            e_y = min(s_y + block_size, coord_max[1])
+            s_y = e_y - block_size
+            idxs = np.where((pts[:, 0] >= s_x - padding) & (pts[:, 0] <= e_x + padding) &
+                            (pts[:, 1] >= s_y - padding) & (pts[:, 1] <= e_y + padding))[0]
+            if idxs.size == 0:
+                continue
+            num_batch = int(np.ceil(idxs.size / block_points))
+            point_size = int(num_batch * block_points)
+            cells.append((index_y * grid_x + index_x, idxs.copy(), num_batch))
+            replace = False if (point_size - idxs.size <= idxs.size) else True
+            rep = np.random.choice(idxs, point_size - idxs.size, replace=replace)
+            idxs = np.concatenate((idxs, rep))
+            np.random.shuffle(idxs)
+            batch = pts[idxs, :]
+            norm = np.zeros((point_size, 3))
+            norm[:, 0] = batch[:, 0] / coord_max[0]
+            norm[:, 1] = batch[:, 1] / coord_max[1]
+            norm[:, 2] = batch[:, 2] / coord_max[2]
+            batch[:, 0] = batch[:, 0] - (s_x + block_size / 2.0)
+            batch[:, 1] = batch[:, 1] - (s_y + block_size / 2.0)
+            batch = np.concatenate((batch, norm), axis=1)
+            lab = labels[idxs].astype(int)
+            w = labelweights[lab]
+            if len(extra_names) > 0:
+                feats = np.zeros((point_size, len(extra_names)))
+                for ix, name in enumerate(extra_names):
+                    sel = extra[ix][idxs]
+                    if name in ("red", "blue", "green"):
+                        sel = sel / 255
+                    feats[:, ix] = np.array(sel)
+                batch = np.concatenate((batch, feats), axis=1)
+            data_room = np.vstack([data_room, batch]) if data_room.size else batch
+            label_room = np.hstack([label_room, lab]) if label_room.size else lab
+            sample_weight = np.hstack([sample_weight, w]) if label_room.size else w
+            index_room = np.hstack([index_room, idxs]) if index_room.size else idxs
+    if not cells:
+        return None, None, None, None, cells
+    data_room = data_room.reshape((-1, block_points, data_room.shape[1]))
+    return (data_room, label_room.reshape((-1, block_points)), sample_weight.reshape((-1, block_points)),
+            index_room.reshape((-1, block_points)), cells)

@@ -294,8 +294,56 @@ def rotation():
     save("rotation.npz", out)
 
 
+def synthetic_scene(P, seed, extent=(6.3, 2.2, 3.0)):
+    """A small facade-like scene: float64 coordinates with an offset origin (as LAS files have), duplicated points, points
+    exactly on cell borders, labels, and red / green / blue + one non-colour extra feature."""
+    g = np.random.RandomState(seed)
+    pts = np.stack([g.uniform(0, extent[0], P), np.clip(g.normal(extent[1] / 2, extent[1] / 5, P), 0, extent[1]),
+                    g.uniform(0, extent[2], P)], axis=1) + np.array([690000.25, 5335000.5, 512.0])
+    pts[: P // 20] = pts[P // 20: 2 * (P // 20)]                       # duplicates
+    pts[-8:, 0] = pts[:, 0].min() + 0.5 * np.arange(8)                  # on the cell borders (stride 0.5)
+    labels = g.randint(0, 18, P).astype(np.int32)
+    extra = [g.randint(0, 256, P).astype(np.float64) for _ in range(3)] + [g.normal(size=P)]
+    return pts, labels, extra, ["red", "blue", "green", "planarity"]
+
+
+def slicer():
+    """TestCustomDataset.__getitem__ (sem_seg_testing.py:182-254), unmodified, on synthetic scenes: a dataset object built
+    through the reference's own `las_file_list=None` constructor path and filled by hand (no LAS IO)."""
+    _reference_localfunctions()
+    import types
+    if "geofunction" not in sys.modules:
+        try:
+            import geofunction                                          # noqa: F401
+        except Exception:
+            sys.modules["geofunction"] = types.ModuleType("geofunction")
+            sys.modules["geofunction"].cal_geofeature = None
+    import sem_seg_testing as T
+    assert T.__file__.startswith(REF), T.__file__
+    out = {}
+    for tag, (P, seed, bp, extent) in {"wall": (6000, 0, 256, (6.3, 2.2, 3.0)), "sparse": (900, 1, 128, (3.1, 1.6, 2.0))}.items():
+        pts, labels, extra, names = synthetic_scene(P, seed, extent)
+        ds = T.TestCustomDataset(None, las_file_list=None, num_classes=18, block_points=bp)
+        ds.scene_points_list, ds.semantic_labels_list = [pts.copy()], [labels.copy()]
+        ds.num_extra_features, ds.feature_name, ds.extra_features_data = len(names), list(names), [extra]
+        lw = np.histogram(labels, range(19))[0].astype(np.float32)
+        lw = lw / np.sum(lw)
+        ds.labelweights = np.power(np.amax(lw) / lw, 1 / 3.0)            # :178-180
+        np.random.seed(50 + seed)
+        data_room, label_room, sample_weight, index_room = ds[0]
+        out[tag + "_points"], out[tag + "_labels"] = pts, labels
+        out[tag + "_extra"] = np.stack(extra)
+        out[tag + "_labelweights"] = ds.labelweights
+        out[tag + "_bp"] = np.array([bp, 50 + seed])
+        out[tag + "_data32"] = torch.Tensor(data_room).numpy()           # what the test loop feeds the network (localfunctions.py:394)
+        out[tag + "_label"] = label_room.astype(np.int32)
+        out[tag + "_weight"] = sample_weight.astype(np.float32)
+        out[tag + "_index"] = index_room.astype(np.int32)
+    save("slicer.npz", out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes", "rotation"]
+    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes", "rotation", "slicer"]
     for w in which:
         t = time.time()
         globals()[w]()

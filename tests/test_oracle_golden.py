@@ -165,3 +165,18 @@ def test_rotation_oracle_matches_reference(golden, tag):
     """oracle rotate_z == provider.rotate_point_cloud_z (provider.py:66-84) on the angles the reference drew."""
     v = golden("rotation")
     assert np.array_equal(O.rotate_z(v[tag + "_xyz"], v[tag + "_angles"]), v[tag + "_rotated"])
+
+
+@pytest.mark.parametrize("tag", ["wall", "sparse"])
+def test_slicer_oracle_reproduces_reference(golden, tag):
+    """oracle slice_scene == TestCustomDataset.__getitem__ (sem_seg_testing.py:182-254) under the same numpy seed: the four
+    arrays exactly (rows after the float32 conversion the test loop applies)."""
+    v = golden("slicer")
+    bp, seed = int(v[tag + "_bp"][0]), int(v[tag + "_bp"][1])
+    np.random.seed(seed)
+    data, lab, w, idx, cells = O.slice_scene(v[tag + "_points"].copy(), v[tag + "_labels"], list(v[tag + "_extra"]),
+                                             ["red", "blue", "green", "planarity"], v[tag + "_labelweights"], block_points=bp)
+    assert np.array_equal(torch.Tensor(data).numpy(), v[tag + "_data32"])
+    assert np.array_equal(lab, v[tag + "_label"]) and np.array_equal(idx, v[tag + "_index"])
+    assert np.array_equal(w.astype(np.float32), v[tag + "_weight"])
+    assert sum(c[2] for c in cells) == data.shape[0] and len(cells) > 4
