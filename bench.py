@@ -370,6 +370,104 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
     print(json.dumps(line), flush=True)
 
 
+def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
+    """BASELINE.json configs[3] from the RAW scene: one synthetic facade (SURVEY 8(d) "Cfg 4": x ~ U(0,60), y ~ N(0,0.15),
+    z ~ U(0,25) float64, labels U{0..17}, rgb U{0..255}, np.random.seed(0)) goes host -> device once, is sliced into
+    4096-point blocks on the device (pn2.slice_scene: sem_seg_testing.py:182-254), this rank's shard of the blocks runs
+    through the pipelined predictor with device votes (pn2.predict_scene), the ranks' pools are summed and the scene labels
+    read back.  Every rank slices the whole scene with the same generator seed (identical blocks), then takes its shard."""
+    import numpy as np
+    P, batch = args.scene_points, args.batch
+    np.random.seed(0)
+    scene = np.stack([np.random.uniform(0, 60, P), np.random.normal(0, 0.15, P), np.random.uniform(0, 25, P)], axis=1)
+    labels = np.random.randint(0, NUM_CLASSES, P).astype(np.int64)
+    rgb = np.random.randint(0, 256, (3, P)).astype(np.float64)
+    hist = np.histogram(labels, range(NUM_CLASSES + 1))[0].astype(np.float32)      # sem_seg_testing.py:172-180
+    hist = hist / np.sum(hist)
+    lw = torch.from_numpy(np.power(np.amax(hist) / hist, 1 / 3.0))
+    h_scene, h_labels, h_rgb = torch.from_numpy(scene).pin_memory(), torch.from_numpy(labels).pin_memory(), torch.from_numpy(rgb).pin_memory()
+    names = ["red", "blue", "green"][:CHANNELS - 6]
+    torch.manual_seed(1234)
+    net = pn2.get_model(NUM_CLASSES, CHANNELS - 6).to(dev).eval()
+    pipeline = not args.no_pipeline
+    predictor = pn2.SemSegPredictor(net, batch, NPOINT, CHANNELS, dev, pipeline=pipeline)
+
+    def run(n_points):
+        gen = torch.Generator(device=dev).manual_seed(5)
+        t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0[0].record()
+        d_scene = h_scene[:n_points].to(dev, non_blocking=True)
+        d_labels = h_labels[:n_points].to(dev, non_blocking=True)
+        d_rgb = h_rgb[:len(names), :n_points].to(dev, non_blocking=True) if names else None
+        data, lab, w, idx = pn2.slice_scene(d_scene, d_labels, d_rgb, names, lw, generator=gen)
+        t0[1].record()
+        lo, hi = pn2.shard_range(data.shape[0], rank, world)
+        pool = pn2.new_vote_pool(n_points, NUM_CLASSES, dev)
+        if hi > lo:
+            pn2.predict_scene(net, data[lo:hi], idx[lo:hi], w[lo:hi], n_points, NUM_CLASSES, predictor=predictor, device=dev,
+                              vote_pool=pool, merge=False)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(pool, op=dist.ReduceOp.SUM)
+        out = pn2.vote_argmax(pool, torch.uint8).cpu()
+        t0[2].record()
+        torch.cuda.synchronize()
+        return data.shape[0], t0[0].elapsed_time(t0[1]), t0[0].elapsed_time(t0[2]), int(pool.sum().item()), out
+
+    for _ in range(max(1, args.warmup - 2)):
+        run(min(P, 400_000))
+    barrier()
+    wall0 = time.perf_counter()
+    nb, slice_ms, total_ms, votes_total, out = run(P)
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms = _rank_max(torch.tensor([total_ms], device=dev, dtype=torch.float64), world).item()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    assert votes_total == nb * NPOINT, (votes_total, nb * NPOINT)
+    lo, hi = pn2.shard_range(nb, 0, world)
+    n_batches = (hi - lo + batch - 1) // batch
+    value = nb * NPOINT / (ms * 1e-3)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import pn2_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sub = min(P, 500_000)                      # the reference scans the WHOLE scene once per grid cell: cost ~ cells x points
+        t = time.perf_counter()
+        np.random.seed(1)
+        d, l, w_, i_, cells = O.slice_scene(scene[:sub].copy(), labels[:sub], [rgb[k][:sub] for k in range(len(names))], names,
+                                            lw.numpy(), block_points=NPOINT)
+        t_slice = time.perf_counter() - t
+        ref = O.OracleSemSeg(NUM_CLASSES, CHANNELS - 6).eval()
+        x = torch.Tensor(d[:16]).transpose(2, 1)
+        with torch.no_grad():
+            ref(x)
+            t = time.perf_counter()
+            pred, _ = ref(x)
+            O.add_vote(np.zeros((sub, NUM_CLASSES)), i_[:16], pred.argmax(2).numpy(), w_[:16])
+            t_fwd = time.perf_counter() - t
+        est = t_slice * (P / sub) + t_fwd * (nb / 16.0)
+        cpu = {"value": nb * NPOINT / est, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": "oracle slicer on the first %d scene points (%.1f s, scaled x%.0f: the per-cell np.where scans are linear in the "
+                         "scene size) + oracle eval forward and numpy votes of 16 blocks (%.2f s, scaled to %d blocks)" % (
+                             sub, t_slice, P / sub, t_fwd, nb)}
+    line = {
+        "metric": "points/sec (whole-facade sliding-block inference, num_votes=1)", "value": value, "unit": "points/s",
+        "n_gpus": world, "steps": n_batches, "warmup": args.warmup, "ms_per_step": ms / n_batches, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "raw synthetic facade of %d points (float64 xyz, labels, rgb) -> device slicer (block 1.0, stride 0.5) -> %d block "
+                               "slots x %d points x %d ch -> network (batch %d, pipelined graph) -> device votes -> scene labels on the host; "
+                               "points/s counts block-slot points" % (P, nb, NPOINT, CHANNELS, batch),
+                   "slice_ms": slice_ms, "total_ms": ms, "blocks": nb, "blocks_per_rank": hi - lo, "wall_s_rank0": wall},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": int(P * (24 + 8 + 8 * len(names)) / n_batches),
+                "d2h_bytes_per_step": int(P / n_batches), "ms_per_step": ms / n_batches},
+        "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_facade(args, rank, world, dev, pn2, barrier, sampler):
     """BASELINE.json configs[3]: sem_seg_testing-style whole-facade inference (num_votes = 1): the block slots of a
     synthetic ~10 M-point facade (8544 blocks of 4096 points, SURVEY 8(d) "Cfg 4": ~3.5 block slots per point) sharded
@@ -471,6 +569,10 @@ def main():
                          "fps_ball: configs[2]; facade: configs[3]")
     ap.add_argument("--channels", type=int, default=9, choices=[6, 9], help="input channels: 9 = xyz+norm-xyz+RGB, 6 = --RGB_OFF")
     ap.add_argument("--blocks", type=int, default=8544, help="facade workload: block slots of the synthetic facade")
+    ap.add_argument("--from-scene", action="store_true",
+                    help="facade workload: start from a raw synthetic 10 M-point scene (SURVEY 8(d) Cfg 4) and slice it into blocks on "
+                         "the device (pn2.slice_scene) inside the timed region, instead of starting from ready host blocks")
+    ap.add_argument("--scene-points", type=int, default=10_000_000, help="facade --from-scene: points of the synthetic scene")
     ap.add_argument("--batch", type=int, default=128, help="facade workload: blocks per forward")
     args = ap.parse_args()
     global CHANNELS, WORKLOAD
@@ -506,6 +608,8 @@ def main():
     if args.workload != "train":
         if args.workload == "fps_ball":
             run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler)
+        elif args.from_scene:
+            run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler)
         else:
             run_facade(args, rank, world, dev, pn2, barrier, sampler)
         if world > 1:
