@@ -106,7 +106,6 @@ struct TcLinearArgs {
     double *stat_accum;     // [replicas][2][stat_ld] fp64 accumulators, this call adds into columns stat_off .. stat_off+N
     int stat_ld, stat_off;
     int w_resident, stages;
-    uint32_t wait_hint_ns;  // > 0: the all-thread mbarrier waits suspend up to this long per try instead of spinning
     BnFinalize fin;         // fin.ticket != null: the CTA that draws the last ticket turns the sums into scale/shift
 };
 
@@ -266,7 +265,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                         sc[e] = ok ? a.in_scale[k + e] : 0.0f;
                         sh[e] = ok ? a.in_shift[k + e] : 0.0f;
                     }
-                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
+                    mbar_wait(&bar_full[s], par);
                     if (k < a.K) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     fence_proxy_async();
                     named_bar_sync(1, 128);
                 } else if (tid == 0) {
-                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
+                    mbar_wait(&bar_full[s], par);
                 }
                 if (tid == 0) {
                     fence_after_sync();
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     if (kc == a.KC - 1) umma_commit(&bar_acc);
                 }
             }
-            mbar_wait_hint(&bar_acc, acc_par, a.wait_hint_ns);
+            mbar_wait(&bar_acc, acc_par);
             acc_par ^= 1u;
             fence_after_sync();
 
@@ -500,7 +499,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                         sc[e] = ok ? a.in_scale[k + e] : 0.0f;
                         sh[e] = ok ? a.in_shift[k + e] : 0.0f;
                     }
-                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
+                    mbar_wait(&bar_full[s], par);
                     if (k < a.K) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -520,7 +519,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                     fence_proxy_async();
                     named_bar_sync(2, 128);
                 } else if (ttid == 0) {
-                    mbar_wait_hint(&bar_full[s], par, a.wait_hint_ns);
+                    mbar_wait(&bar_full[s], par);
                 }
                 if (ttid == 0) {
                     if (kc == 0 && buse > 0) mbar_wait(&acc_empty[buf], (buse - 1) & 1u);   // the epilogue drained this buffer
@@ -546,7 +545,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
         for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
             const int64_t m0 = tile * kTcBM;
             const uint32_t buf = t & 1u;
-            mbar_wait_hint(&acc_full[buf], (t >> 1) & 1u, a.wait_hint_ns);
+            mbar_wait(&acc_full[buf], (t >> 1) & 1u);
             fence_after_sync();
             const uint32_t taddr = tmem + buf * (uint32_t)b_n_pad + ((uint32_t)(warp * 32) << 16);
             for (int c0 = 0; c0 < b_n_store; c0 += 16) {
@@ -717,12 +716,9 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
     const int KC = (K + kTcBK - 1) / kTcBK;
     uint8_t *img = (uint8_t *)wpack;
     const int64_t m_tiles = (M + kTcBM - 1) / kTcBM;
-    static int hint_ns = -1, max_ctas = 0;
-    if (hint_ns < 0) {
-        const char *e = getenv("PN2_MBAR_HINT_NS");      // measured: no effect on B200 (0 = plain try_wait loop)
-        hint_ns = e ? atoi(e) : 0;
-        if (hint_ns < 0 || hint_ns > 100000) hint_ns = 0;
-        e = getenv("PN2_TC_MAX_CTAS");
+    static int max_ctas = 0;
+    if (!max_ctas) {
+        const char *e = getenv("PN2_TC_MAX_CTAS");
         max_ctas = e ? atoi(e) : 4;
         if (max_ctas < 1 || max_ctas > 8) max_ctas = 4;
     }
@@ -766,7 +762,6 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
         a.Wimg = img;
         a.bias = bias ? bias + g0 : nullptr;
         a.M = M; a.K = K; a.N = gN; a.ldz = ldz - g0; a.KC = KC;
-        a.wait_hint_ns = (uint32_t)hint_ns;
         a.stat_accum = stat_accum;
         a.stat_ld = N;
         a.stat_off = g0;

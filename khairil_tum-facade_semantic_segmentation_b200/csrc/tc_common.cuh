@@ -39,25 +39,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
-// the same wait with a suspend-time hint: the warp may sleep up to `ns` per try instead of re-issuing the test (spinning
-// warps take issue slots from the co-resident CTAs that have work); ns == 0 -> the plain loop
-__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
-    if (ns == 0) {
-        mbar_wait(bar, parity);
-        return;
-    }
-    uint32_t done = 0;
-    const uint32_t a = smem_addr(bar);
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity), "r"(ns)
-            : "memory");
-    }
-}
+// (a suspend-time hint on try_wait was measured on B200: no effect on any layer shape, so the plain loop stays)
 
 // ---- bulk asynchronous copy global -> shared (TMA, non-tensor form), completes on an mbarrier --
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
