@@ -346,6 +346,11 @@ extern "C" int pn2_farthest_point_sample(const float *xyz, int64_t sB, int64_t s
         P = 32; T = 256;      // 65536 x 18 clouds, 8-CTA clusters: P=32 1.63 us/iteration, P=16 1.75, P=8 2.10
         CL = 2;
         while (CL <= 16 && (N + CL - 1) / CL > 8192) CL *= 2;
+        {   // tuning knob: PN2_FPS_CL = 2|4|8|16 forces a (larger) cluster, i.e. fewer points per CTA
+            const char *e = getenv("PN2_FPS_CL");
+            const int want = e ? atoi(e) : 0;
+            if ((want == 2 || want == 4 || want == 8 || want == 16) && want >= CL) CL = want;
+        }
         if (CL > 16) {
             set_error("fps: N=%d exceeds the register-resident capacity of a 16-CTA cluster (131072)", N);
             return PN2_ERR_UNSUPPORTED;

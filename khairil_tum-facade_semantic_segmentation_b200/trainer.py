@@ -374,6 +374,10 @@ class SemSegPredictor:
                 self._shift(nxt)
                 del nxt
         self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
+        if self.pipeline:     # host results travel through a two-slot pinned ring and are handed out one call after their replay
+            self._rb_host = [self._host_labels, torch.empty_like(self._host_labels).pin_memory()]
+            self._rb_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._rb_rows, self._rb_slot = [None, None], 0
         torch.set_rng_state(rng_state)
 
     def _forward(self, points):
@@ -416,8 +420,9 @@ class SemSegPredictor:
         """pipeline mode.  Hand in batch `points` [b <= batch, npoint, C] and get back the labels of an EARLIER batch
         ([b', npoint]; on the host when to_host, else a view of the static device output that the next call rewrites), or
         None while the pipeline fills.  Device input: its index pipeline runs next to the feature path of the batch handed
-        in one call earlier, whose labels are returned.  Host input (pinned recommended): additionally its host->device
-        copy runs on a copy stream beside that replay, so the labels returned belong to the batch TWO calls earlier."""
+        in one call earlier (whose labels come back when to_host is False).  Host input (pinned recommended): additionally
+        its host->device copy runs on a copy stream beside that replay -- one more stage.  to_host=True: the labels of a
+        replay are read back by the NEXT call -- one more stage (device in / host out: 2 calls late; host in / host out: 3)."""
         if not self.pipeline:
             raise RuntimeError("submit() needs pipeline=True")
         if points.is_cuda:
@@ -447,18 +452,22 @@ class SemSegPredictor:
         is empty."""
         while True:
             pend = self._stager.pending()
-            if not pend:
-                break
-            (staged,) = self._stager.take(pend[0])
-            r = self._advance(staged, to_host)
-            self._stager.release(pend[0])
+            if pend:
+                (staged,) = self._stager.take(pend[0])
+                r = self._advance(staged, to_host)
+                self._stager.release(pend[0])
+            elif self._pending is not None:
+                prev, self._pending = self._pending, None
+                self._replay()                     # the index branch re-runs on the stale "next" slot: harmless
+                r = self._read(prev, to_host)
+            else:
+                for j in (self._rb_slot, self._rb_slot ^ 1):          # queued read-backs, older first
+                    r = self._take_readback(j)
+                    if r is not None:
+                        return r
+                return None
             if r is not None:
                 return r
-        prev, self._pending = self._pending, None
-        if prev is None:
-            return None
-        self._replay()                             # the index branch re-runs on the stale "next" slot: harmless
-        return self._read(prev, to_host)
 
     def flush(self, to_host=True):
         """pipeline mode: finish every batch still in flight; returns the list of their label tensors (copies) in batch
@@ -470,12 +479,29 @@ class SemSegPredictor:
                 return out
             out.append(r.clone())
 
+    def _take_readback(self, j):
+        if self._rb_rows[j] is None:
+            return None
+        self._rb_ev[j].synchronize()
+        b, self._rb_rows[j] = self._rb_rows[j], None
+        return self._rb_host[j][:b]
+
     def _read(self, b, to_host):
         if not to_host:
             return self.labels[:b]
-        self._host_labels.copy_(self.labels, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._host_labels[:b]
+        if not self.pipeline:
+            self._host_labels.copy_(self.labels, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._host_labels[:b]
+        # pipelined: queue the read-back of the labels the replay just launched will produce and hand out the one queued by
+        # the call before (long finished), so the host never waits on the replay it has just launched.  The returned view
+        # stays valid until the call after next.  (Use one of to_host=True / False consistently on a predictor.)
+        j, self._rb_slot = self._rb_slot, self._rb_slot ^ 1
+        out = self._take_readback(j ^ 1)
+        self._rb_host[j].copy_(self.labels, non_blocking=True)
+        self._rb_ev[j].record()
+        self._rb_rows[j] = b
+        return out
 
 
 @torch.no_grad()

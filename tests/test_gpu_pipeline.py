@@ -121,7 +121,7 @@ def test_pipelined_predictor_matches_unpipelined(pn2, precision):
         got = []
         for i, x in enumerate(data):
             out = piped.submit(x.to(DEV) if on_device else x.pin_memory())
-            assert (out is None) == (i < (1 if on_device else 2))
+            assert (out is None) == (i < (2 if on_device else 3))
             if out is not None:
                 got.append(out.clone())
         got += piped.flush()
