@@ -324,7 +324,8 @@ int pn2_rotate_z(float *points, int64_t sB, int64_t sN, int64_t sC, const double
  *   member when the cell needs no more padding than it has members (np.random.choice(..., replace=False), :207-208; the
  *   caller has randomly permuted the members), else member rnd[i] % n (replace=True).
  * pn2_slice_rows: rows[s] = [x - cx, y - cy, z, x/max_x, y/max_y, z/max_z, extra_e / extra_div_e ...] of slot s's point in
- *   float64, rounded once to float32 (:216-241, localfunctions.py:394); label and labelweights[label] (:223-224). */
+ *   float64, rounded once to float32 (:216-241, localfunctions.py:394); label and labelweights[label] (:223-224).
+ *   gx > 0: slot_cell is a grid cell, centre (cx[cell % gx], cy[cell / gx]); gx == 0: one centre per cell, (cx[cell], cy[cell]). */
 int pn2_slice_cells(const double *points, int64_t sP, int64_t sC, int64_t P, const double *lo_x, const double *hi_x,
                     int gx, const double *lo_y, const double *hi_y, int gy, double min_x, double min_y, double stride,
                     double block_size, double padding, int32_t *counts, const int64_t *cell_offset,
@@ -336,6 +337,17 @@ int pn2_slice_rows(const double *points, int64_t sP, int64_t sC, const int64_t *
                    int64_t eP, const double *extra_div, int E, const float *labelweights, const int64_t *slot_point,
                    const int32_t *slot_cell, const double *cx, const double *cy, int gx, double max_x, double max_y,
                    double max_z, int64_t S, float *rows, int64_t *out_label, float *out_weight, void *stream);
+
+/* ---- SURVEY 8(f) n3, training half: the random crops of TrainCustomDataset.__getitem__ ---------------------
+ * (/root/reference/sem_seg_training.py:200-259).  boxes_host: HOST array [K][4] of float64 {lo_x, hi_x, lo_y, hi_y} =
+ * centre -+ block_size / 2 (:208-209), K <= 64; every point with lo_x <= x <= hi_x and lo_y <= y <= hi_y (:210-213) is
+ * a member of box k.  Count pass (crop_offset / slot_* NULL): counts[k] += members; fill pass (counts zeroed again):
+ * slot_point[crop_offset[k] + i] = point, slot_crop[...] = crop_id0 + k (counts / crop_offset point at box 0 of this call).
+ * Rows of the selected points: pn2_slice_rows with gx = 0
+ * (cx / cy indexed by crop). */
+int pn2_crop_members(const double *points, int64_t sP, int64_t sC, int64_t P, const double *boxes_host, int K,
+                     int crop_id0, int32_t *counts, const int64_t *crop_offset, int64_t *slot_point,
+                     int32_t *slot_crop, void *stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "pn2_linear_wgrad_scratch_bytes": (_z, [_l, _i, _i]),
     "pn2_linear_bwd_weight": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
     "pn2_slice_cells": (_i, [_p, _l, _l, _l, _p, _p, _i, _p, _p, _i, _d, _d, _d, _d, _d, _p, _p, _p, _p, _p]),
+    "pn2_crop_members": (_i, [_p, _l, _l, _l, _p, _i, _i, _p, _p, _p, _p, _p]),
     "pn2_slice_pad": (_i, [_p, _p, _p, _p, _p, _l, _i, _p, _p, _p]),
     "pn2_slice_rows": (_i, [_p, _l, _l, _p, _p, _l, _l, _p, _i, _p, _p, _p, _p, _p, _i, _d, _d, _d, _l, _p, _p, _p, _p]),
     "pn2_rotate_z": (_i, [_p, _l, _l, _l, _p, _i, _i, _p]),

@@ -84,8 +84,9 @@ slice_rows_kernel(const double *__restrict__ pts, int64_t sP, int64_t sC, const 
         const int cell = slot_cell[s];
         const double x = pts[p * sP], y = pts[p * sP + sC], z = pts[p * sP + 2 * sC];
         float *r = rows + s * C;
-        r[0] = (float)__dsub_rn(x, cx[cell % gx]);                     // :221  data_batch[:, 0] - (s_x + block_size / 2.0)
-        r[1] = (float)__dsub_rn(y, cy[cell / gx]);
+        // gx > 0: grid of cells (centre column / row arrays); gx == 0: one centre per cell (the training crops)
+        r[0] = (float)__dsub_rn(x, gx > 0 ? cx[cell % gx] : cx[cell]);    // :221  data_batch[:, 0] - (s_x + block_size / 2.0)
+        r[1] = (float)__dsub_rn(y, gx > 0 ? cy[cell / gx] : cy[cell]);
         r[2] = (float)z;
         r[3] = (float)__ddiv_rn(x, max_x);                             // :217-219 normalised by the scene maximum
         r[4] = (float)__ddiv_rn(y, max_y);
@@ -100,9 +101,71 @@ slice_rows_kernel(const double *__restrict__ pts, int64_t sP, int64_t sC, const 
     }
 }
 
+// ---- the training crops (/root/reference/sem_seg_training.py:206-215, TrainCustomDataset.__getitem__): K candidate boxes
+// [lo_x, hi_x] x [lo_y, hi_y] (centre -+ block_size / 2 in float64), every point tested against every box with the reference's
+// comparisons; count pass / fill pass like slice_cells_kernel.  A box of a dense room holds 1e5+ points, so the per-box
+// counter is bumped once per WARP (ballot + popc), not once per point.
+constexpr int kMaxCrops = 64;
+struct CropBoxes {
+    double lo_x[kMaxCrops], hi_x[kMaxCrops], lo_y[kMaxCrops], hi_y[kMaxCrops];
+    int K;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+crop_members_kernel(const double *__restrict__ pts, int64_t sP, int64_t sC, int64_t P, const __grid_constant__ CropBoxes bx,
+                    int32_t *__restrict__ counts, const int64_t *__restrict__ crop_offset, int64_t *__restrict__ slot_point,
+                    int32_t *__restrict__ slot_crop, int crop_id0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < P; base += stride) {
+        const int64_t p = base + lane;
+        const bool live = p < P;
+        const double x = live ? pts[p * sP] : 0.0, y = live ? pts[p * sP + sC] : 0.0;
+        for (int k = 0; k < bx.K; ++k) {
+            const bool in = live && x >= bx.lo_x[k] && x <= bx.hi_x[k] && y >= bx.lo_y[k] && y <= bx.hi_y[k];
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (m == 0u) continue;
+            const int leader = __ffs(m) - 1;
+            int first = 0;
+            if (lane == leader) first = atomicAdd(counts + k, __popc(m));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if (FILL && in) {
+                const int64_t slot = crop_offset[k] + first + __popc(m & ((1u << lane) - 1u));
+                slot_point[slot] = p;
+                slot_crop[slot] = crop_id0 + k;
+            }
+        }
+    }
+}
+
 }  // namespace pn2
 
 using namespace pn2;
+
+extern "C" int pn2_crop_members(const double *points, int64_t sP, int64_t sC, int64_t P, const double *boxes_host, int K,
+                                int crop_id0, int32_t *counts, const int64_t *crop_offset, int64_t *slot_point,
+                                int32_t *slot_crop, void *stream) {
+    PN2_REQUIRE(P >= 0 && K >= 0 && K <= kMaxCrops, "crop_members: bad sizes P=%lld K=%d (<= %d boxes per call)", (long long)P, K, kMaxCrops);
+    if (P == 0 || K == 0) return PN2_OK;
+    PN2_REQUIRE(points && boxes_host && counts, "crop_members: null pointer");
+    PN2_REQUIRE(!crop_offset == !slot_point && !slot_point == !slot_crop, "crop_members: the fill pass needs crop_offset, slot_point and slot_crop");
+    CropBoxes bx;
+    bx.K = K;
+    for (int k = 0; k < K; ++k) {                 // boxes_host: [K][4] = lo_x, hi_x, lo_y, hi_y (HOST memory, float64)
+        bx.lo_x[k] = boxes_host[4 * k];
+        bx.hi_x[k] = boxes_host[4 * k + 1];
+        bx.lo_y[k] = boxes_host[4 * k + 2];
+        bx.hi_y[k] = boxes_host[4 * k + 3];
+    }
+    const int grid = grid_for(P, 256);
+    if (slot_point)
+        crop_members_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(points, sP, sC, P, bx, counts, crop_offset, slot_point, slot_crop, crop_id0);
+    else
+        crop_members_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(points, sP, sC, P, bx, counts, nullptr, nullptr, nullptr, crop_id0);
+    count_launch();
+    return check_launch("crop_members");
+}
 
 static SliceGrid make_grid(const double *lo_x, const double *hi_x, int gx, const double *lo_y, const double *hi_y, int gy,
                            double min_x, double min_y, double stride, double block_size, double padding) {
@@ -146,7 +209,7 @@ extern "C" int pn2_slice_rows(const double *points, int64_t sP, int64_t sC, cons
                               int64_t eP, const double *extra_div, int E, const float *labelweights, const int64_t *slot_point,
                               const int32_t *slot_cell, const double *cx, const double *cy, int gx, double max_x, double max_y,
                               double max_z, int64_t S, float *rows, int64_t *out_label, float *out_weight, void *stream) {
-    PN2_REQUIRE(S >= 0 && E >= 0 && gx >= 1, "slice_rows: bad sizes");
+    PN2_REQUIRE(S >= 0 && E >= 0 && gx >= 0, "slice_rows: bad sizes");
     if (S == 0) return PN2_OK;
     PN2_REQUIRE(points && slot_point && slot_cell && cx && cy && rows && out_label, "slice_rows: null pointer");
     PN2_REQUIRE(E == 0 || (extra && extra_div), "slice_rows: extra features without data");

@@ -432,3 +432,90 @@ def slice_scene(points, labels=None, extra=None, extra_names=(), labelweights=No
          ptr(out_weight), stream())
     nb = S // bp
     return rows.view(nb, bp, C), out_label.view(nb, bp), out_weight.view(nb, bp), slot_point.view(nb, bp)
+
+
+def sample_training_crops(points, labels, batch, extra=None, extra_names=(), coord_max=None, num_point=4096, block_size=1.0,
+                          min_points=1024, generator=None, max_rounds=50):
+    """`batch` items of TrainCustomDataset.__getitem__ (/root/reference/sem_seg_training.py:200-259) for one room, on the
+    device: random centre point, the block_size x block_size column around it, redrawn until it holds more than
+    `min_points` points (:206-215), `num_point` of them chosen without replacement when there are enough, with replacement
+    otherwise (:217-220), rows [x - cx, y - cy, z, x/max, y/max, z/max, extras (/255 for colours)] (:223-252).
+
+    points [N, 3] float64 CUDA, labels [N] int64 CUDA, extra [E, N] float64 CUDA.  Returns (features [batch, num_point,
+    6 + E] float32, labels [batch, num_point] int64, centre point index [batch] int64, selected point indices [batch,
+    num_point] int64), on the device.  Membership and rows are the reference's float64 arithmetic; all the choices are
+    random in the reference too (numpy's generator there, `generator` -- a CUDA torch.Generator -- here)."""
+    import ctypes
+    import numpy as np
+    require_cuda(points, "points", dtype=torch.float64)
+    require_cuda(labels, "labels", dtype=torch.int64)
+    dev, N = points.device, points.shape[0]
+    if points.dim() != 2 or points.shape[1] != 3 or N == 0:
+        raise ValueError("points must be a non-empty [N, 3] float64 tensor")
+    E = 0 if extra is None else extra.shape[0]
+    if E != len(extra_names):
+        raise ValueError("extra has %d rows but %d names were given" % (E, len(extra_names)))
+    cmax = points.amax(dim=0).cpu().numpy() if coord_max is None else np.asarray(coord_max, dtype=np.float64)
+    sP, sC = points.stride()
+    half = float(block_size) / 2.0
+    centre_idx = torch.empty(batch, dtype=torch.int64, device=dev)
+    centres = torch.empty(batch, 3, dtype=torch.float64, device=dev)
+    counts_all = torch.zeros(batch, dtype=torch.int64, device=dev)
+    todo = list(range(batch))
+
+    def boxes_of(c):                                   # :208-209 centre -+ [block_size / 2, block_size / 2, 0] in float64
+        c = c.cpu().numpy()
+        return np.ascontiguousarray(np.stack([c[:, 0] - half, c[:, 0] + half, c[:, 1] - half, c[:, 1] + half], axis=1))
+
+    def members(boxes, counts, offset, slot_point, slot_crop):
+        for k0 in range(0, boxes.shape[0], 64):        # <= 64 boxes per launch
+            bx = np.ascontiguousarray(boxes[k0:k0 + 64])
+            call("pn2_crop_members", ptr(points), sP, sC, N, bx.ctypes.data_as(ctypes.c_void_p), bx.shape[0], k0,
+                 ptr(counts[k0:]), ptr(None if offset is None else offset[k0:]), ptr(slot_point), ptr(slot_crop), stream())
+
+    for _ in range(max_rounds):                        # the reference's `while True` (:206), all pending crops per round
+        k = len(todo)
+        draw = torch.randint(0, N, (k,), device=dev, generator=generator)       # np.random.choice(N_points)
+        c = points[draw]
+        counts = torch.zeros(k, dtype=torch.int32, device=dev)
+        members(boxes_of(c), counts, None, None, None)
+        ok = (counts > min_points).cpu().numpy()
+        rows = torch.tensor(todo, device=dev)
+        good = torch.from_numpy(ok).to(dev)
+        centre_idx[rows[good]] = draw[good]
+        centres[rows[good]] = c[good]
+        counts_all[rows[good]] = counts[good].long()
+        todo = [t for t, g in zip(todo, ok) if not g]
+        if not todo:
+            break
+    else:
+        raise RuntimeError("no block with more than %d points found after %d rounds" % (min_points, max_rounds))
+    offset = torch.cumsum(counts_all, 0) - counts_all
+    total = int(counts_all.sum())
+    slot_point = torch.empty(total, dtype=torch.int64, device=dev)
+    slot_crop = torch.empty(total, dtype=torch.int32, device=dev)
+    cursor = torch.zeros(batch, dtype=torch.int32, device=dev)
+    members(boxes_of(centres), cursor, offset, slot_point, slot_crop)
+    # a random permutation of every crop's members; the first num_point of it = np.random.choice(..., replace=False)
+    key = torch.randint(0, 2 ** 31, (total,), device=dev, dtype=torch.int64, generator=generator)
+    order = torch.argsort((slot_crop.long() << 32) | key)
+    slot_point = slot_point[order]
+    j = torch.arange(num_point, device=dev).unsqueeze(0).expand(batch, num_point)
+    with_repl = torch.randint(0, 2 ** 62, (batch, num_point), device=dev, dtype=torch.int64, generator=generator) % counts_all.unsqueeze(1)
+    pick = torch.where((counts_all >= num_point).unsqueeze(1), j, with_repl)      # :217-220
+    sel = slot_point[(offset.unsqueeze(1) + pick).reshape(-1)].contiguous()
+    S = batch * num_point
+    C = 6 + E
+    feats = torch.empty(S, C, device=dev, dtype=torch.float32)
+    out_label = torch.empty(S, dtype=torch.int64, device=dev)
+    crop_of_slot = torch.arange(batch, device=dev, dtype=torch.int32).repeat_interleave(num_point)
+    div, eE, eP = None, 0, 0
+    if E:
+        require_cuda(extra, "extra", dtype=torch.float64)
+        div = torch.tensor([255.0 if nm in ("red", "green", "blue") else 1.0 for nm in extra_names], dtype=torch.float64, device=dev)
+        eE, eP = extra.stride()
+    cx, cy = centres[:, 0].contiguous(), centres[:, 1].contiguous()
+    call("pn2_slice_rows", ptr(points), sP, sC, ptr(labels.contiguous()), ptr(extra), eE, eP, ptr(div), E, None, ptr(sel),
+         ptr(crop_of_slot), ptr(cx), ptr(cy), 0, float(cmax[0]), float(cmax[1]), float(cmax[2]), S, ptr(feats), ptr(out_label),
+         None, stream())
+    return feats.view(batch, num_point, C), out_label.view(batch, num_point), centre_idx, sel.view(batch, num_point)

@@ -21,6 +21,7 @@ unless another file is named):
   vote_argmax          np.argmax(vote_label_pool, 1)   (localfunctions.py:405)
   rotate_z             rotate_point_cloud_z        (provider.py:66-84)
   slice_scene          TestCustomDataset.__getitem__  (sem_seg_testing.py:182-254)
+  train_crop           TrainCustomDataset.__getitem__ (sem_seg_training.py:200-259)
 
 The arithmetic itself lives in PyTorch (third party, un-pinned by the reference;
 effective pin torch 2.11.0+cu128 of this image), so this port issues the same
@@ -341,3 +342,37 @@ def slice_scene(points, labels, extra, extra_names, labelweights, block_size=1.0
     data_room = data_room.reshape((-1, block_points, data_room.shape[1]))
     return (data_room, label_room.reshape((-1, block_points)), sample_weight.reshape((-1, block_points)),
             index_room.reshape((-1, block_points)), cells)
+
+
+def train_crop(points, labels, extra, extra_names, coord_max, num_point=4096, block_size=1.0):
+    """sem_seg_training.py:200-259 for one item of one room: numpy restatement of TrainCustomDataset.__getitem__ making the
+    same calls to numpy's global generator in the same order (choice of the centre until the block holds > 1024 points, then
+    choice of num_point members), so under the same seed it reproduces the reference exactly.  Returns (features
+    [num_point, 6 + E] float64, labels [num_point], centre [3], selected point indices)."""
+    import numpy as np
+    N_points = points.shape[0]
+    while True:
+        center = points[np.random.choice(N_points)][:3]
+        block_min = center - [block_size / 2.0, block_size / 2.0, 0]
+        block_max = center + [block_size / 2.0, block_size / 2.0, 0]
+        idxs = np.where((points[:, 0] >= block_min[0]) & (points[:, 0] <= block_max[0]) & (points[:, 1] >= block_min[1]) &
+                        (points[:, 1] <= block_max[1]))[0]
+        if idxs.size > 1024:
+            break
+    sel = np.random.choice(idxs, num_point, replace=not (idxs.size >= num_point))
+    selected = points[sel, :]
+    cur = np.zeros((num_point, 6))
+    cur[:, 3] = selected[:, 0] / coord_max[0]
+    cur[:, 4] = selected[:, 1] / coord_max[1]
+    cur[:, 5] = selected[:, 2] / coord_max[2]
+    selected[:, 0] = selected[:, 0] - center[0]
+    selected[:, 1] = selected[:, 1] - center[1]
+    cur[:, 0:3] = selected
+    feats = np.zeros((num_point, 6 + len(extra_names)))
+    feats[:, :6] = cur
+    for i, name in enumerate(extra_names):
+        f = extra[i][sel]
+        if name in ("red", "blue", "green"):
+            f = f / 255
+        feats[:, 6 + i] = f
+    return feats, labels[sel], center, sel

@@ -342,8 +342,40 @@ def slicer():
     save("slicer.npz", out)
 
 
+def crops():
+    """TrainCustomDataset.__getitem__ (sem_seg_training.py:200-259), unmodified, on a synthetic room: a dataset object built
+    through the reference's own `las_file_list=None` constructor path and filled by hand (no LAS IO)."""
+    _reference_localfunctions()
+    import types
+    if "geofunction" not in sys.modules:
+        try:
+            import geofunction                                          # noqa: F401
+        except Exception:
+            sys.modules["geofunction"] = types.ModuleType("geofunction")
+            sys.modules["geofunction"].cal_geofeature = None
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    import sem_seg_training as T
+    sys.argv = argv
+    assert T.__file__.startswith(REF), T.__file__
+    out = {}
+    for tag, (P, seed, npnt, extent) in {"dense": (16000, 3, 1024, (2.5, 1.5, 3.0)), "thin": (6000, 4, 2048, (2.2, 1.4, 2.0))}.items():
+        pts, labels, extra, names = synthetic_scene(P, seed, extent)
+        ds = T.TrainCustomDataset(None, num_classes=18, num_point=npnt)
+        ds.room_points, ds.room_labels = [pts.copy()], [labels.astype(np.float64)]
+        ds.room_coord_min, ds.room_coord_max = [np.amin(pts, axis=0)], [np.amax(pts, axis=0)]
+        ds.num_extra_features, ds.feature_name, ds.extra_features_data = len(names), list(names), [extra]
+        ds.room_idxs = np.zeros(4, dtype=np.int64)
+        np.random.seed(70 + seed)
+        feats, labs = zip(*[ds[i] for i in range(4)])
+        out[tag + "_points"], out[tag + "_labels"], out[tag + "_extra"] = pts, labels, np.stack(extra)
+        out[tag + "_meta"] = np.array([npnt, 70 + seed])
+        out[tag + "_features"] = np.stack(feats)                              # float64, as the DataLoader would collate them
+        out[tag + "_item_labels"] = np.stack(labs).astype(np.int32)
+    save("crops.npz", out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes", "rotation", "slicer"]
+    which = sys.argv[1:] or ["ops_small", "ops_levels", "ops_large", "modules", "model", "votes", "rotation", "slicer", "crops"]
     for w in which:
         t = time.time()
         globals()[w]()

@@ -23,7 +23,7 @@ def _header_decls():
 def test_header_declares_the_hot_path():
     d = _header_decls()
     for name in ("pn2_farthest_point_sample", "pn2_query_ball_point", "pn2_square_distance", "pn2_index_points",
-                 "pn2_group_points", "pn2_linear_fwd", "pn2_linear_bwd_data", "pn2_linear_bwd_weight", "pn2_linear_bwd_weight_accum", "pn2_add_vote", "pn2_vote_argmax", "pn2_rotate_z", "pn2_slice_cells", "pn2_slice_pad", "pn2_slice_rows",
+                 "pn2_group_points", "pn2_linear_fwd", "pn2_linear_bwd_data", "pn2_linear_bwd_weight", "pn2_linear_bwd_weight_accum", "pn2_add_vote", "pn2_vote_argmax", "pn2_rotate_z", "pn2_slice_cells", "pn2_crop_members", "pn2_slice_pad", "pn2_slice_rows",
                  "pn2_bn_relu_max", "pn2_three_nn", "pn2_interp_concat", "pn2_interp_bwd", "pn2_last_error"):
         assert name in d
 

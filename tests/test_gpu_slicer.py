@@ -92,3 +92,56 @@ def test_slice_scene_larger_random_scene_and_degenerate_inputs(pn2):
         pn2.slice_scene(torch.from_numpy(pts).float().to(DEV))
     with pytest.raises(ValueError):
         pn2.slice_scene(torch.from_numpy(pts).to(DEV), extra=torch.zeros(2, P, dtype=torch.float64, device=DEV), extra_names=["red"])
+
+
+def _check_crops(pn2, pts, labels, extra, npnt, batch, seed):
+    """structure and rows of ops.sample_training_crops against the reference's rules (sem_seg_training.py:200-259)"""
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    d_pts = torch.from_numpy(pts).to(DEV)
+    feats, lab, centre_idx, sel = pn2.sample_training_crops(d_pts, torch.from_numpy(labels.astype(np.int64)).to(DEV), batch,
+                                                            torch.from_numpy(np.stack(extra)).to(DEV), NAMES, num_point=npnt,
+                                                            generator=gen)
+    feats, lab, centre_idx, sel = feats.cpu().numpy(), lab.cpu().numpy(), centre_idx.cpu().numpy(), sel.cpu().numpy()
+    assert feats.shape == (batch, npnt, 6 + len(NAMES)) and sel.shape == (batch, npnt)
+    cmax = pts.max(0)
+    for b in range(batch):
+        c = pts[centre_idx[b]]
+        lo, hi = c - [0.5, 0.5, 0], c + [0.5, 0.5, 0]
+        members = np.where((pts[:, 0] >= lo[0]) & (pts[:, 0] <= hi[0]) & (pts[:, 1] >= lo[1]) & (pts[:, 1] <= hi[1]))[0]
+        assert members.size > 1024                                          # :214 the accepted block is populated
+        assert np.isin(sel[b], members).all()                                # only points of the block
+        if members.size >= npnt:
+            assert np.unique(sel[b]).size == npnt                            # :218 replace=False
+        p = pts[sel[b]]
+        cols = [p[:, 0] - c[0], p[:, 1] - c[1], p[:, 2], p[:, 0] / cmax[0], p[:, 1] / cmax[1], p[:, 2] / cmax[2]]
+        for e, nm in zip(extra, NAMES):
+            cols.append(e[sel[b]] / 255 if nm in ("red", "blue", "green") else e[sel[b]])
+        assert np.array_equal(feats[b], torch.Tensor(np.stack(cols, axis=1)).numpy())   # bit-exact rows
+        assert np.array_equal(lab[b], labels[sel[b]])
+    return centre_idx, sel
+
+
+@pytest.mark.parametrize("tag", ["dense", "thin"])
+def test_training_crops_follow_reference_rules(pn2, golden, tag):
+    v = golden("crops")
+    npnt = int(v[tag + "_meta"][0])
+    pts, labels, extra = v[tag + "_points"], v[tag + "_labels"], list(v[tag + "_extra"])
+    c1, s1 = _check_crops(pn2, pts, labels, extra, npnt, 6, 1)
+    c2, s2 = _check_crops(pn2, pts, labels, extra, npnt, 6, 2)
+    assert not np.array_equal(c1, c2)                                        # different seeds, different crops
+    # the reference's own items obey the same rules the device sampler is checked against (fixture sanity)
+    f = v[tag + "_features"]
+    assert f.shape[1] == npnt and np.all(np.abs(f[:, :, 0]) <= 0.5 + 1e-9) and np.all(np.abs(f[:, :, 1]) <= 0.5 + 1e-9)
+
+
+def test_training_crops_large_room_many_crops(pn2):
+    g = np.random.RandomState(8)
+    P = 300_000
+    pts = np.stack([g.uniform(0, 8, P), g.normal(0, 0.3, P), g.uniform(0, 6, P)], axis=1) + np.array([500.0, 20.0, 1.0])
+    labels = g.randint(0, 18, P).astype(np.int32)
+    extra = [g.randint(0, 256, P).astype(np.float64) for _ in range(3)] + [g.normal(size=P)]
+    _check_crops(pn2, pts, labels, extra, 4096, 70, 5)                       # > 64 crops: two launches of the membership kernel
+    sparse = pts[:3000]                                                      # no block can hold 1025 points
+    with pytest.raises(RuntimeError):
+        pn2.sample_training_crops(torch.from_numpy(sparse).to(DEV), torch.zeros(3000, dtype=torch.int64, device=DEV), 2,
+                                  max_rounds=3)

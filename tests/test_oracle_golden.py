@@ -180,3 +180,15 @@ def test_slicer_oracle_reproduces_reference(golden, tag):
     assert np.array_equal(lab, v[tag + "_label"]) and np.array_equal(idx, v[tag + "_index"])
     assert np.array_equal(w.astype(np.float32), v[tag + "_weight"])
     assert sum(c[2] for c in cells) == data.shape[0] and len(cells) > 4
+
+
+@pytest.mark.parametrize("tag", ["dense", "thin"])
+def test_train_crop_oracle_reproduces_reference(golden, tag):
+    """oracle train_crop == TrainCustomDataset.__getitem__ (sem_seg_training.py:200-259) under the same numpy seed."""
+    v = golden("crops")
+    npnt, seed = int(v[tag + "_meta"][0]), int(v[tag + "_meta"][1])
+    pts, labels, extra = v[tag + "_points"], v[tag + "_labels"], list(v[tag + "_extra"])
+    np.random.seed(seed)
+    for i in range(v[tag + "_features"].shape[0]):
+        f, l, c, sel = O.train_crop(pts, labels, extra, ["red", "blue", "green", "planarity"], np.amax(pts, axis=0), num_point=npnt)
+        assert np.array_equal(f, v[tag + "_features"][i]) and np.array_equal(l, v[tag + "_item_labels"][i])
