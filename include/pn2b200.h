@@ -200,7 +200,9 @@ int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const f
  * conv bias (entries may be NULL), and the eval-mode scale / shift of pn2_bn_eval_fold.
  * xyz [B,N,3] strided; new_xyz [B,S,3] contiguous; feats [B,N,D] with row strides (fB,fN), element
  * stride 1 (NULL when D = 0); idx [B,S,32] int64 (out-of-range entries gather zeros);
- * out [B,S,N_{L-1}] fp32.  workspace: pn2_sa_fused_eval_workspace_bytes() bytes (0 = unsupported). */
+ * out [B,S,N_{L-1}] fp32.  workspace: pn2_sa_fused_eval_workspace_bytes() bytes (0 = unsupported).  W_host == NULL:
+ * the workspace still holds the weight images packed by a previous call for the same weights (inference with frozen
+ * parameters: no pack launches). */
 size_t pn2_sa_fused_eval_workspace_bytes(int D, int L, const int *widths_host);
 int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64_t sC, const float *new_xyz,
                       const float *feats, int64_t fB, int64_t fN, const int64_t *idx, int B, int N,

@@ -418,8 +418,9 @@ extern "C" int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64
                                  int nsample, int D, int L, const int *widths_host, const float *const *W_host,
                                  const float *const *bias_host, const float *const *scale_host,
                                  const float *const *shift_host, float *out, void *workspace, void *stream) {
-    PN2_REQUIRE(xyz && new_xyz && idx && out && workspace && widths_host && W_host && scale_host && shift_host && bias_host,
+    PN2_REQUIRE(xyz && new_xyz && idx && out && workspace && widths_host && scale_host && shift_host && bias_host,
                 "sa_fused_eval: null pointer");
+    const bool prepacked = W_host == nullptr;     // the workspace still holds the images a previous call packed from the same weights
     PN2_REQUIRE(B >= 0 && N > 0 && S >= 0 && D >= 0 && (D == 0 || feats), "sa_fused_eval: bad sizes B=%d N=%d S=%d D=%d", B, N, S, D);
     if (nsample != 32) {
         set_error("sa_fused_eval: nsample=%d (the fused kernel pools over exactly one warp of 32 samples)", nsample);
@@ -454,10 +455,10 @@ extern "C" int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64
     // weight images: layer 0 with its input columns rotated by 3 (the gather writes features first, xyz last)
     int K = D + 3;
     for (int l = 0; l < L; ++l) {
-        PN2_REQUIRE(W_host[l] && scale_host[l] && shift_host[l], "sa_fused_eval: null layer pointer");
+        PN2_REQUIRE((prepacked || W_host[l]) && scale_host[l] && shift_host[l], "sa_fused_eval: null layer pointer");
         const int Nl = widths_host[l], KC = (K + 63) / 64;
         int c = a.chunk_begin[l];
-        for (int n0 = 0; n0 < Nl; n0 += 256) {
+        for (int n0 = 0; n0 < Nl && !prepacked; n0 += 256) {
             const int nb = Nl - n0 < 256 ? Nl - n0 : 256, n_pad = sa_round_up(nb, 16);
             const int total = KC * n_pad * 8;
             pack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(W_host[l] + (int64_t)n0 * K, K, 1, nb, K, n_pad, KC,

@@ -11,6 +11,7 @@ read from them at call time, running statistics are written back).
 One autograd.Function per module: forward = FPS -> ball query -> gather -> MLP
 (-> max over nsample); backward is hand written on the same kernels.
 """
+import contextlib
 import ctypes
 import os
 
@@ -32,6 +33,61 @@ def _row_ld(k, dtype):
 
 class _LayerState:
     __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias", "wpack_bwd")
+
+
+_GRAD_MODE = [True]       # grad mode at the module's forward() (inside autograd.Function.forward it always reads False)
+
+
+def _note_grad_mode():
+    _GRAD_MODE[0] = torch.is_grad_enabled()
+
+
+def _want_backward(ctx):
+    """Will this forward be differentiated?  (ctx.needs_input_grad ignores torch.no_grad())"""
+    return _GRAD_MODE[0] and any(ctx.needs_input_grad)
+
+
+# Inference with FROZEN parameters (opt-in: `with frozen_parameters():`, used by trainer.SemSegPredictor): folded BatchNorm
+# (scale, shift) and packed weight images are a function of the parameters and running statistics only, so inside the
+# context they are computed once and reused.  It is opt-in because nothing can invalidate such a cache reliably: CUDA-graph
+# replays of a training step and this library's own kernels update parameters / running statistics without moving torch's
+# version counters.  Entering the (outermost) context starts from an empty cache; the version check below only catches
+# ordinary in-place updates made while the context is active.
+_EVAL_CACHE = {}
+_FROZEN = [0]
+
+
+@contextlib.contextmanager
+def frozen_parameters():
+    if _FROZEN[0] == 0:
+        _EVAL_CACHE.clear()
+    _FROZEN[0] += 1
+    try:
+        yield _EVAL_CACHE
+    finally:
+        _FROZEN[0] -= 1
+
+
+def _eval_key_versions(convs, bns):
+    ts = []
+    for conv, bn in zip(convs, bns):
+        ts += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    return tuple((None if t is None else (t.data_ptr(), t._version, t.device.index)) for t in ts) + tuple(float(bn.eps) for bn in bns)
+
+
+def _eval_cache_get(kind, convs, bns):
+    if not _FROZEN[0]:
+        return None
+    ent = _EVAL_CACHE.get((kind,) + tuple(id(c) for c in convs))
+    if ent is not None and ent[0] == _eval_key_versions(convs, bns):
+        return ent[1]
+    return None
+
+
+def _eval_cache_put(kind, convs, bns, payload):
+    # (tensors born inside a capture belong to that graph's pool: never cached)
+    if _FROZEN[0] and not torch.cuda.is_current_stream_capturing():
+        _EVAL_CACHE[(kind,) + tuple(id(c) for c in convs)] = (_eval_key_versions(convs, bns), payload)
 
 
 def _bn_trains(bn):
@@ -111,7 +167,14 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     Ns = Ks[1:] + [K]
     K = K0
     fwd_img = bwd_img = None
-    if dtype == torch.bfloat16:
+    # pure inference (every BatchNorm on running statistics, nothing to differentiate): folded (scale, shift) and the packed
+    # weight images depend on the parameters only -- reuse them until a parameter / running statistic changes
+    frozen = not want_bwd and not any(_bn_trains(bn) for bn in bns)
+    cached = _eval_cache_get(("mlp", dtype), convs, bns) if frozen else None
+    new_fold = []
+    if cached is not None:
+        fwd_img = cached[0]
+    elif dtype == torch.bfloat16:
         # every layer's weight image (and, for a backward pass, its transposed image for the data gradient) in one launch;
         # the first layer's data gradient is only needed when the MLP input wants a gradient -- pack it anyway, it is tiny
         n_l = len(Ws)
@@ -155,8 +218,12 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
                      float(momentum), ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
                      ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt), stream())
         else:
-            call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
-                 ptr(st.scale), ptr(st.shift), stream())
+            if cached is not None:
+                st.scale, st.shift = cached[1][l]
+            else:
+                call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), N,
+                     ptr(st.scale), ptr(st.shift), stream())
+                new_fold.append((st.scale, st.shift))
             if wpack is not None:
                 call("pn2_linear_fwd_prepacked", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), ptr(bias), M, K,
                      N, ptr(z), ldz, dt(z), None, ptr(wpack), None, stream())
@@ -171,6 +238,8 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
         layers.append(st)
         x, ldx, K = z, ldz, N
         in_scale, in_shift = st.scale, st.shift
+    if frozen and cached is None:
+        _eval_cache_put(("mlp", dtype), convs, bns, (fwd_img, new_fold))
     return layers
 
 
@@ -354,8 +423,12 @@ def sa_fused_eval(idx, convs, bns, new_xyz, xyz_r, pts_r):
     ws_bytes = lib.pn2_sa_fused_eval_workspace_bytes(D, L, c_widths)
     if ws_bytes == 0:
         raise ValueError("sa_fused_eval: unsupported level D=%d widths=%s" % (D, widths))
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    fold = torch.empty(L, 2, max(widths), device=dev, dtype=torch.float32)
+    cached = _eval_cache_get("sa_fused", convs, bns)
+    if cached is not None:
+        ws, fold = cached
+    else:
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        fold = torch.empty(L, 2, max(widths), device=dev, dtype=torch.float32)
     Ws, keep = [], []
     K = 3 + D
     for l, (conv, bn) in enumerate(zip(convs, bns)):
@@ -365,8 +438,9 @@ def sa_fused_eval(idx, convs, bns, new_xyz, xyz_r, pts_r):
             raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
         gamma = None if bn.weight is None else bn.weight.detach()
         beta = None if bn.bias is None else bn.bias.detach()
-        call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
-             widths[l], ptr(fold[l, 0]), ptr(fold[l, 1]), stream())
+        if cached is None:
+            call("pn2_bn_eval_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
+                 widths[l], ptr(fold[l, 0]), ptr(fold[l, 1]), stream())
         Ws.append(W)
         keep.append(None if conv.bias is None else conv.bias.detach())
         K = widths[l]
@@ -375,9 +449,12 @@ def sa_fused_eval(idx, convs, bns, new_xyz, xyz_r, pts_r):
     sB, sN, sC = xyz_r.stride()
     fB, fN = (0, 0) if feats is None else feats.stride()[:2]
     call("pn2_sa_fused_eval", ptr(xyz_r), sB, sN, sC, ptr(new_xyz), ptr(feats), fB, fN, ptr(idx), B, N, S, nsample, D, L,
-         c_widths, arr(*[w.data_ptr() for w in Ws]), arr(*[None if b is None else b.data_ptr() for b in keep]),
+         c_widths, None if cached is not None else arr(*[w.data_ptr() for w in Ws]),       # NULL: ws holds the packed images
+         arr(*[None if b is None else b.data_ptr() for b in keep]),
          arr(*[fold[l, 0].data_ptr() for l in range(L)]), arr(*[fold[l, 1].data_ptr() for l in range(L)]),
          ptr(out), ptr(ws), stream())
+    if cached is None:
+        _eval_cache_put("sa_fused", convs, bns, (ws, fold))
     return out
 
 
@@ -412,7 +489,7 @@ class _SetAbstractionFn(torch.autograd.Function):
         K0 = 3 + D
         x0 = ops.group_rows(xyz_r, new_xyz, feats, idx, _row_ld(K0, dtype), dtype)
         M = B * S * nsample
-        layers = mlp_forward(x0, K0, M, convs, bns, any(ctx.needs_input_grad))
+        layers = mlp_forward(x0, K0, M, convs, bns, _want_backward(ctx))
         last = layers[-1]
         out = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.float32)
         arg = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.int32)
@@ -446,7 +523,7 @@ class _GroupAllFn(torch.autograd.Function):
         ld = _row_ld(K0, dtype)
         x0 = torch.zeros(B * N, ld, device=x0_f32.device, dtype=dtype)
         x0[:, :K0] = x0_f32.reshape(B * N, K0)
-        layers = mlp_forward(x0, K0, B * N, convs, bns, any(ctx.needs_input_grad))
+        layers = mlp_forward(x0, K0, B * N, convs, bns, _want_backward(ctx))
         last = layers[-1]
         out = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.float32)
         arg = torch.empty(B, 1, last.N, device=x0.device, dtype=torch.int32)
@@ -484,7 +561,7 @@ class _FeaturePropagationFn(torch.autograd.Function):
         pB, pN, pD = (0, 0, 0) if p1_r is None else p1_r.stride()
         call("pn2_interp_concat", ptr(p1_r), pB, pN, pD, ptr(p2), S * D2, D2, 1, ptr(idx3), ptr(w3), B, N, S, D1, D2,
              ptr(x0), x0.shape[1], dt(x0), stream())
-        layers = mlp_forward(x0, K0, M, convs, bns, any(ctx.needs_input_grad))
+        layers = mlp_forward(x0, K0, M, convs, bns, _want_backward(ctx))
         last = layers[-1]
         out = torch.empty(B, N, last.N, device=p2.device, dtype=torch.float32)
         call("pn2_bn_relu", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), M, last.N,
@@ -532,7 +609,7 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
         pB, pN, pD = (0, 0, 0) if p1_r is None else p1_r.stride()
         call("pn2_interp_concat", ptr(p1_r), pB, pN, pD, ptr(p2), S * D2, D2, 1, ptr(idx3), ptr(w3), B, N, S, D1, D2,
              ptr(x0), x0.shape[1], dt(x0), stream())
-        want_bwd = any(ctx.needs_input_grad)
+        want_bwd = _want_backward(ctx)
         layers = mlp_forward(x0, K0, M, convs, bns, want_bwd)
         last = layers[-1]
         NC = conv2.out_channels
@@ -636,6 +713,7 @@ class PointNetSetAbstraction(nn.Module):
 
     def forward(self, xyz, points, geometry=None):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
+        _note_grad_mode()
         _check_module_inputs(xyz, points)
         xyz_r = xyz.permute(0, 2, 1)
         pts_r = None if points is None else points.permute(0, 2, 1)
@@ -695,6 +773,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.bn_blocks.append(bns)
 
     def forward(self, xyz, points):
+        _note_grad_mode()
         _check_module_inputs(xyz, points)
         xyz_r = xyz.permute(0, 2, 1)
         pts_r = None if points is None else points.permute(0, 2, 1)
@@ -739,6 +818,7 @@ class PointNetFeaturePropagation(nn.Module):
     def forward_with_head(self, xyz1, xyz2, points1, points2, conv1, bn1, dropout, conv2, neighbours=None):
         """This level followed by `log_softmax(conv2(dropout(relu(bn1(conv1(.))))))` (pointnet2_sem_seg.py:36-38) in one
         chain of rows; returns the log-probabilities [B, N, classes] (already permuted as :39 does)."""
+        _note_grad_mode()
         _check_module_inputs(xyz1, points1)
         _check_module_inputs(xyz2, points2)
         p = float(dropout.p) if (dropout is not None and dropout.training) else 0.0
@@ -753,6 +833,7 @@ class PointNetFeaturePropagation(nn.Module):
 
     def forward(self, xyz1, xyz2, points1, points2, neighbours=None):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        _note_grad_mode()
         _check_module_inputs(xyz1, points1)
         _check_module_inputs(xyz2, points2)
         if points2 is None:

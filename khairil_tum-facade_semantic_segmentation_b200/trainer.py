@@ -11,6 +11,7 @@ gradient buffer (~3.9 MB) over NCCL/NVLink per step.  BatchNorm statistics stay 
 import torch
 import torch.distributed as dist
 
+from . import modules
 from .sem_seg import get_loss, get_model
 
 
@@ -329,6 +330,9 @@ class SemSegPredictor:
     transpose, `classifier(torch_data)`, arg-max of the log-probabilities); the FPS start indices stay a
     fresh CPU-generator draw per forward (pointnet2_utils.py:75), staged through pinned buffers.
 
+    The parameters are frozen at construction (folded BatchNorm / packed weights are computed once, not per forward): build a
+    new predictor after changing them.
+
     pipeline=True: the graph additionally runs, on a forked branch, the coordinate-only index pipeline
     (get_model.geometry_all) of the batch just submitted while the main branch runs the feature path of the
     batch submitted one call earlier (see SemSegTrainer.enable_cuda_graph); use submit()/flush(), which hand
@@ -355,12 +359,26 @@ class SemSegPredictor:
             with torch.no_grad():
                 self._geo = self.model.geometry_all(self.points.transpose(2, 1)[:, :3, :])
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):
-                self._forward(self.points)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
+        # the parameters are FROZEN for this predictor: folded BatchNorm and packed weight images are computed once in the
+        # warm-up pass below (modules.frozen_parameters) and the captured graph reads them -- ~60 tiny launches fewer per
+        # forward.  Build a new predictor after changing the model's parameters or running statistics.
+        with modules.frozen_parameters() as cache:
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(max(1, warmup)):
+                    self._forward(self.points)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._frozen_tensors = list(cache.values())          # keep what the graph will read alive with the predictor
+            self.graph = torch.cuda.CUDAGraph()
+            self._capture(dev)
+        self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
+        if self.pipeline:     # host results travel through a two-slot pinned ring and are handed out one call after their replay
+            self._rb_host = [self._host_labels, torch.empty_like(self._host_labels).pin_memory()]
+            self._rb_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._rb_rows, self._rb_slot = [None, None], 0
+        torch.set_rng_state(rng_state)
+
+    def _capture(self, dev):
         with torch.no_grad(), torch.cuda.graph(self.graph):
             if self.pipeline:
                 main = torch.cuda.current_stream(dev)
@@ -373,12 +391,6 @@ class SemSegPredictor:
                 main.wait_stream(self._geo_stream)
                 self._shift(nxt)
                 del nxt
-        self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
-        if self.pipeline:     # host results travel through a two-slot pinned ring and are handed out one call after their replay
-            self._rb_host = [self._host_labels, torch.empty_like(self._host_labels).pin_memory()]
-            self._rb_ev = [torch.cuda.Event(), torch.cuda.Event()]
-            self._rb_rows, self._rb_slot = [None, None], 0
-        torch.set_rng_state(rng_state)
 
     def _forward(self, points):
         if self._geo is None:

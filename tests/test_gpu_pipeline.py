@@ -146,3 +146,34 @@ def test_predict_blocks_pipelined_equals_plain(pn2):
     assert (lo, hi) == (lo2, hi2) == (0, 11)
     assert torch.equal(got, want)
     pn2.set_precision("fp32")
+
+
+def test_predictor_cache_does_not_leak_into_later_forwards(pn2):
+    """SemSegPredictor computes folded BatchNorm / packed weights once (modules.frozen_parameters): its labels equal the eager
+    forward's at construction time; after a parameter change the eager forward (no cache outside the context) follows
+    immediately, and so does a NEW predictor (the old one must be rebuilt: part of what it reads is frozen, part is live)."""
+    pn2.set_precision("bf16")
+    torch.manual_seed(3)
+    net = I.randomize_module_(pn2.get_model(NC, C - 6), 31).to(DEV).eval()
+    x = I.facade_batch(B, N, C, 800)
+    start_seed = 21
+
+    def eager():
+        torch.manual_seed(start_seed)
+        with torch.no_grad():
+            return net(x.to(DEV).transpose(2, 1))[0].argmax(2).cpu()
+
+    pred = pn2.SemSegPredictor(net, B, N, C, DEV)
+    torch.manual_seed(start_seed)
+    first = pred.predict_host(x).clone()
+    assert torch.equal(first, eager())
+    with torch.no_grad():                                   # change the parameters the way training would
+        net.conv2.bias.add_(torch.linspace(-3, 3, NC, device=DEV))
+        net.fp1.mlp_bns[0].running_mean.mul_(-1.0)
+        net.sa1.mlp_convs[0].weight.mul_(1.5)
+    changed = eager()
+    assert not torch.equal(changed, first)                  # eager: recomputed from the live parameters
+    pred2 = pn2.SemSegPredictor(net, B, N, C, DEV)
+    torch.manual_seed(start_seed)
+    assert torch.equal(pred2.predict_host(x), changed)      # a new one sees the new parameters
+    pn2.set_precision("fp32")
