@@ -288,6 +288,18 @@ int pn2_head_tail_bwd(const float *dlogp, const float *logp, const float *W2, in
                       float drop_p, const int64_t *seed, void *dA, int ldda, void *dlogits_rows, int lddl,
                       double *db2_accum, float *db2, void *stream);
 
+/* ---- optimizer step of the training loop (sem_seg_training.py:576-582: torch.optim.Adam with L2 weight decay) ----
+ * One launch over the flat gradient buffer.  params[T]: device table of the parameter tensors' fp32 pointers;
+ * tensor_off[T] / tensor_n[T]: each tensor's first element in the three flat buffers (a multiple of 4) and its size;
+ * chunks[n_chunks]: (tensor, first element) pairs as int32x2, each covering <= chunk_elems (a multiple of 4)
+ * elements -- one CTA per chunk.  hyper[5] = {lr, beta1, beta2, eps, weight_decay} (fp64, DEVICE memory, read at run
+ * time); *step: fp32 count of finished steps, incremented by the call; *ticket: a zeroed uint32, left zero.
+ * Arithmetic of torch.optim.Adam (amsgrad / maximize off):  g += wd*p;  m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int pn2_adam_step(void *const *params, const int64_t *tensor_off, const int64_t *tensor_n, const void *chunks,
+                  int n_chunks, int chunk_elems, const float *grad_flat, float *exp_avg_flat, float *exp_avg_sq_flat,
+                  const double *hyper, float *step, void *ticket, void *stream);
+
 /* ---- layout helpers ------------------------------------------------------------
  * dst[r, c] (fp32, leading dim ldd) = src[r*sR + c*sC] for r < R, c < C: turns a
  * channel-major [C,R] slab into point-major rows (batched over B with strides). */

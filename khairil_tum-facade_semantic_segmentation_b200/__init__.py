@@ -11,11 +11,11 @@ from .modules import PointNetFeaturePropagation, PointNetSetAbstraction, PointNe
 from .ops import (add_vote, draw_rotation_angles, rotate_point_cloud_z_, farthest_point_sample, get_precision, index_points, new_vote_pool, query_ball_point,
                   sample_and_group, sample_and_group_all, sample_training_crops, set_precision, slice_scene, square_distance, three_nn, vote_argmax)
 from .sem_seg import get_loss, get_model
-from .trainer import FlatGradients, SemSegPredictor, SemSegTrainer, predict_blocks, predict_scene, shard_range
+from .trainer import FlatAdam, FlatGradients, SemSegPredictor, SemSegTrainer, predict_blocks, predict_scene, shard_range
 
 __all__ = [
     "PointNetSetAbstraction", "PointNetSetAbstractionMsg", "PointNetFeaturePropagation",
     "square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
     "sample_and_group_all", "three_nn", "add_vote", "vote_argmax", "slice_scene", "sample_training_crops", "rotate_point_cloud_z_", "draw_rotation_angles", "new_vote_pool", "predict_scene", "set_precision", "get_precision", "get_model", "get_loss",
-    "SemSegTrainer", "SemSegPredictor", "FlatGradients", "predict_blocks", "shard_range", "load", "launch_count", "Pn2Error", "SO_PATH", "EXPORTED_SYMBOLS",
+    "SemSegTrainer", "SemSegPredictor", "FlatGradients", "FlatAdam", "predict_blocks", "shard_range", "load", "launch_count", "Pn2Error", "SO_PATH", "EXPORTED_SYMBOLS",
 ]

@@ -79,6 +79,7 @@ class FlatGradients:
         for p in self.params:
             offsets.append(total)
             total += (p.numel() + 3) // 4 * 4
+        self.offsets = offsets
         self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
         self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, offsets)]
         if self.flat.is_cuda:
@@ -105,10 +106,116 @@ class FlatGradients:
             self.flat.div_(dist.get_world_size(group))
 
 
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (the reference's optimizer, /root/reference/sem_seg_training.py:576-582; amsgrad / maximize off)
+    as ONE kernel launch over a FlatGradients buffer (csrc/optim.cu: pn2_adam_step) instead of the six multi-tensor
+    launches of the fused PyTorch implementation.  The moments are two flat buffers laid out like the gradients;
+    ``state[p]`` holds views of them plus the shared step counter, so ``state_dict()`` has torch.optim.Adam's layout and
+    ``load_state_dict()`` accepts one of its checkpoints (localfunctions.py:322 saves optimizer.state_dict()).
+    Learning rate, betas, eps and weight decay live in DEVICE memory: ``param_groups[0]`` is re-read on every eager step
+    and by ``sync_hyper()`` (call it before replaying a captured graph after a schedule changed them), so a captured
+    step follows the reference's per-epoch learning-rate decay without re-capture.  One parameter group; CUDA fp32."""
+
+    CHUNK = 1024          # elements per CTA
+
+    def __init__(self, grads, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if not grads.flat.is_cuda:
+            raise ValueError("FlatAdam needs CUDA parameters (pn2-b200 has no CPU path)")
+        super().__init__(grads.params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.grads = grads
+        dev = grads.flat.device
+        for p in grads.params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
+                raise TypeError("FlatAdam: parameters must be contiguous fp32 tensors on %s" % dev)
+        self.exp_avg = torch.zeros_like(grads.flat)
+        self.exp_avg_sq = torch.zeros_like(grads.flat)
+        self.step_count = torch.zeros((), device=dev, dtype=torch.float32)
+        self._ticket = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._hyper = torch.zeros(5, device=dev, dtype=torch.float64)
+        self._hyper_host = torch.zeros(5, dtype=torch.float64).pin_memory()
+        self._hyper_seen = None
+        chunks = [(t, s) for t, p in enumerate(grads.params) for s in range(0, p.numel(), self.CHUNK)]
+        self._n_chunks = len(chunks)
+        self._chunks = torch.tensor(chunks, dtype=torch.int32).reshape(-1, 2).to(dev)
+        self._off = torch.tensor(grads.offsets, dtype=torch.int64).to(dev)
+        self._n = torch.tensor([p.numel() for p in grads.params], dtype=torch.int64).to(dev)
+        self._ptrs = torch.tensor([p.data_ptr() for p in grads.params], dtype=torch.int64).to(dev)
+        self._ptrs_host = [p.data_ptr() for p in grads.params]
+        self._bind_state()
+        self.sync_hyper()
+
+    def _bind_state(self):
+        for p, off in zip(self.grads.params, self.grads.offsets):
+            n = p.numel()
+            self.state[p] = {"step": self.step_count, "exp_avg": self.exp_avg[off:off + n].view_as(p),
+                             "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p)}
+
+    def sync_hyper(self):
+        """param_groups[0] -> the device copy the kernel reads (a 40-byte copy, only when something changed)."""
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam supports one parameter group")
+        g = self.param_groups[0]
+        now = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]))
+        if now != self._hyper_seen:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FlatAdam: hyper-parameters changed during CUDA-graph capture; call sync_hyper() before")
+            torch.cuda.synchronize(self._hyper.device)      # rare; the pinned source of the last change may still be in flight
+            self._hyper_host.copy_(torch.tensor(now, dtype=torch.float64))
+            self._hyper.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_seen = now
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise ValueError("FlatAdam.step takes no closure")
+        from ._lib import call, ptr, stream
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
+            if [p.data_ptr() for p in self.grads.params] != self._ptrs_host:
+                raise RuntimeError("FlatAdam: a parameter was re-allocated (model.to()/load with assign?) after the optimizer was built")
+        for p, v in zip(self.grads.params, self.grads.views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                raise RuntimeError("FlatAdam: a .grad is not its slice of the flat buffer; call FlatGradients.adopt() after backward")
+        call("pn2_adam_step", ptr(self._ptrs), ptr(self._off), ptr(self._n), ptr(self._chunks), self._n_chunks, self.CHUNK,
+             ptr(self.grads.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self._hyper), ptr(self.step_count),
+             ptr(self._ticket), stream())
+
+    def zero_grad(self, set_to_none=True):
+        self.grads.zero()
+
+    def reset_state(self):
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count.zero_()
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam (or FlatAdam) state_dict: the moments are copied INTO the flat buffers."""
+        super().load_state_dict(state_dict)
+        loaded = dict(self.state)
+        steps = [float(st["step"]) for st in loaded.values() if "step" in st]
+        with torch.no_grad():
+            self.reset_state()
+            for p, off in zip(self.grads.params, self.grads.offsets):
+                st = loaded.get(p)
+                if st:
+                    n = p.numel()
+                    self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            if steps:
+                if min(steps) != max(steps):
+                    raise ValueError("FlatAdam keeps ONE step counter; the checkpoint has %s..%s" % (min(steps), max(steps)))
+                self.step_count.fill_(steps[0])
+        self.state.clear()
+        self._bind_state()
+        self._hyper_seen = None
+        self.sync_hyper()
+
+
 class SemSegTrainer:
     def __init__(self, num_classes=18, num_extra_features=3, lr=1e-3, weight_decay=1e-4, device="cuda",
-                 class_weights=None, model=None, fused_optimizer=True, augment_rotate_z=False):
-        """augment_rotate_z: apply the training loop's augmentation (provider.rotate_point_cloud_z on points[:, :, :3],
+                 class_weights=None, model=None, fused_optimizer=True, augment_rotate_z=False, flat_optimizer=True):
+        """flat_optimizer: Adam as one launch of this library over the flat gradient buffer (FlatAdam) instead of
+        torch.optim.Adam.  augment_rotate_z: apply the training loop's augmentation (provider.rotate_point_cloud_z on points[:, :, :3],
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
         self._rot_staging = None
@@ -118,9 +225,12 @@ class SemSegTrainer:
         self.criterion = get_loss()
         self.grads = FlatGradients(self.model.parameters())
         on_gpu = self.device.type == "cuda"
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08,
-                                          weight_decay=weight_decay, fused=bool(fused_optimizer and on_gpu),
-                                          capturable=on_gpu)
+        if on_gpu and flat_optimizer:
+            self.optimizer = FlatAdam(self.grads, lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=weight_decay)
+        else:
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08,
+                                              weight_decay=weight_decay, fused=bool(fused_optimizer and on_gpu),
+                                              capturable=on_gpu)
         self.class_weights = (torch.ones(num_classes) if class_weights is None else class_weights).to(self.device)
         self._graph = None
 
@@ -142,7 +252,8 @@ class SemSegTrainer:
         CUDA graph replayed per step: the ~420 kernel launches of a step cost no host time any more.
         Inputs are copied into static buffers; the FPS start indices stay a fresh CPU-generator draw per
         step (drawn on the host before each replay into pinned buffers the graph's memcpy nodes read).
-        Re-capture after changing BatchNorm momentum or the learning-rate schedule's Python state.
+        Re-capture after changing BatchNorm momentum (FlatAdam reads the learning rate from device memory: no re-capture;
+        torch.optim.Adam bakes it in).
 
         pipeline=True software-pipelines consecutive batches inside that one graph: a forked branch runs the
         coordinate-only index pipeline (FPS, ball query, 3-NN: get_model.geometry_all) of the batch just SUBMITTED
@@ -239,10 +350,17 @@ class SemSegTrainer:
                 self._shift(self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :]))
             self._primed = True
             return None
-        for m in self._sa:
-            m.start_staging.draw()
+        self._pre_replay()
         self._graph.replay()
         return self._g_loss
+
+    def _pre_replay(self):
+        """host work a replay depends on: the reference's per-forward FPS start draws (module order) and, for FlatAdam,
+        the device copy of the optimizer's hyper-parameters (follows a learning-rate schedule without re-capture)"""
+        for m in self._sa:
+            m.start_staging.draw()
+        if isinstance(self.optimizer, FlatAdam):
+            self.optimizer.sync_hyper()
 
     def _take_loss(self, j):
         if not self._loss_valid[j]:
@@ -282,8 +400,7 @@ class SemSegTrainer:
         self._g_points.copy_(points, non_blocking=True)
         self._g_target.copy_(target.view(-1), non_blocking=True)
         self._augment(self._g_points)
-        for m in self._sa:                            # the reference's per-forward randint draws, in module order
-            m.start_staging.draw()
+        self._pre_replay()
         self._graph.replay()
         return self._g_loss
 
@@ -314,8 +431,7 @@ class SemSegTrainer:
             self._g_points.copy_(points_host, non_blocking=True)
             self._g_target.copy_(target_host.view(-1), non_blocking=True)
             self._augment(self._g_points)
-            for m in self._sa:
-                m.start_staging.draw()
+            self._pre_replay()
             self._graph.replay()
             return float(self._g_loss)
         points = points_host.to(self.device, non_blocking=True).float()

@@ -1,0 +1,155 @@
+"""csrc/optim.cu (pn2_adam_step through trainer.FlatAdam) against torch.optim.Adam -- the optimizer the reference's
+training loop builds (/root/reference/sem_seg_training.py:576-582) -- on the same parameters and gradients.
+
+Tolerance: both evaluate the same fp32 formula (bias corrections in fp64); the differences are FMA contraction and
+the order of two multiplications: parameters equal to rtol 2e-6 / atol 1e-7 after 6 steps."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SHAPES = [(32, 12, 1, 1), (32,), (7,), (64, 67, 1), (1,), (256, 259, 1, 1), (13, 5), (18, 128, 1), (18,), (3000,)]
+
+
+def _params(seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.nn.Parameter((torch.randn(*s, generator=g) * 0.3).to(DEV)) for s in SHAPES]
+
+
+def _grads(step, scale=1.0):
+    g = torch.Generator().manual_seed(1000 + step)
+    return [(torch.randn(*s, generator=g) * scale).to(DEV) for s in SHAPES]
+
+
+def _run_reference(params, n_steps, lr, wd, lr_after=None, first=0):
+    opt = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    for t in range(first, first + n_steps):
+        if lr_after is not None and t == first + 3:
+            opt.param_groups[0]["lr"] = lr_after
+        for p, g in zip(params, _grads(t)):
+            p.grad = g
+        opt.step()
+    return opt
+
+
+def _flat_step(pn2, grads, opt, t):
+    grads.zero()
+    for v, g in zip(grads.views, _grads(t)):
+        v.copy_(g)
+    grads.adopt()
+    opt.step()
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-4])
+def test_flat_adam_matches_torch_adam(pn2, wd):
+    ref = _params(1)
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    _run_reference(ref, 6, 1e-3, wd, lr_after=7e-4)
+    grads = pn2.FlatGradients(mine)
+    opt = pn2.FlatAdam(grads, lr=1e-3, weight_decay=wd)
+    for t in range(6):
+        if t == 3:
+            opt.param_groups[0]["lr"] = 7e-4          # the reference's per-epoch decay writes param_groups (localfunctions.py:172-177)
+        _flat_step(pn2, grads, opt, t)
+    assert float(opt.step_count) == 6.0
+    assert int(opt._ticket.item()) == 0
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), float((a - b).abs().max())
+    # padding elements between the slices never move
+    used = torch.zeros_like(grads.flat, dtype=torch.bool)
+    for p, off in zip(grads.params, grads.offsets):
+        used[off:off + p.numel()] = True
+    assert float(opt.exp_avg[~used].abs().sum()) == 0.0 and float(opt.exp_avg_sq[~used].abs().sum()) == 0.0
+
+
+def test_flat_adam_state_dict_round_trip_with_torch_adam(pn2):
+    """state_dict() has torch.optim.Adam's layout; a torch.optim.Adam checkpoint loads and training continues identically."""
+    ref = _params(2)
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    ref_opt = _run_reference(ref, 3, 1e-3, 1e-4)
+    sd = copy.deepcopy(ref_opt.state_dict())
+    with torch.no_grad():
+        for a, b in zip(mine, ref):
+            a.copy_(b)
+    grads = pn2.FlatGradients(mine)
+    opt = pn2.FlatAdam(grads, lr=5e-2, weight_decay=0.0)       # overwritten by the checkpoint's param_groups
+    opt.load_state_dict(sd)
+    assert float(opt.step_count) == 3.0 and opt.param_groups[0]["lr"] == 1e-3 and opt.param_groups[0]["weight_decay"] == 1e-4
+    for t in range(3, 6):
+        for p, g in zip(ref, _grads(t)):
+            p.grad = g
+        ref_opt.step()
+        _flat_step(pn2, grads, opt, t)
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
+    out = opt.state_dict()
+    assert set(out["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and len(out["state"]) == len(SHAPES)
+    fresh = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in mine], lr=1e-3)
+    fresh.load_state_dict(out)                                  # and back into torch.optim.Adam
+    st = fresh.state[fresh.param_groups[0]["params"][3]]
+    assert torch.equal(st["exp_avg"], opt.state[mine[3]]["exp_avg"]) and float(st["step"]) == 6.0
+
+
+def test_flat_adam_inside_cuda_graph_follows_lr_and_counts_steps(pn2):
+    mine = _params(3)
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    grads = pn2.FlatGradients(mine)
+    opt = pn2.FlatAdam(grads, lr=1e-3, weight_decay=1e-4)
+    for v, g in zip(grads.views, _grads(0)):
+        v.copy_(g)
+    grads.adopt()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph):
+            opt.step()
+    torch.cuda.current_stream().wait_stream(side)
+    ref_opt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    for t in range(4):
+        lr = 1e-3 * 0.7 ** t
+        opt.param_groups[0]["lr"] = ref_opt.param_groups[0]["lr"] = lr
+        opt.sync_hyper()
+        for v, p, g in zip(grads.views, ref, _grads(t)):
+            v.copy_(g)
+            p.grad = g
+        graph.replay()
+        ref_opt.step()
+    torch.cuda.synchronize()
+    assert float(opt.step_count) == 4.0
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_trainer_with_flat_adam_tracks_torch_adam(pn2):
+    """Two trainers from the same initial network, same batches, same FPS draws: the parameters after 3 steps agree
+    (bf16 rows make the gradients identical run to run only up to atomics order: compare loosely, Adam normalises
+    the update so a sign flip of a ~0 gradient moves a weight by 2*lr at most)."""
+    import _inputs as I
+    pn2.set_precision("bf16")
+    try:
+        nets = [I.randomize_module_(pn2.get_model(18, 3), 17).to(DEV) for _ in range(2)]
+        trainers = [pn2.SemSegTrainer(18, 3, device=DEV, model=nets[0], flat_optimizer=True),
+                    pn2.SemSegTrainer(18, 3, device=DEV, model=nets[1], flat_optimizer=False)]
+        assert isinstance(trainers[0].optimizer, pn2.FlatAdam) and isinstance(trainers[1].optimizer, torch.optim.Adam)
+        pts = I.facade_batch(4, 1024, 9, 5).to(DEV)
+        lab = I.labels(4, 1024, 18, 6).to(DEV)
+        losses = [[], []]
+        for i, tr in enumerate(trainers):
+            tr.model.drop1.p = 0.0
+            torch.manual_seed(99)
+            for _ in range(3):
+                losses[i].append(float(tr.step_device(pts, lab)))
+        assert abs(losses[0][0] - losses[1][0]) < 1e-3
+        assert abs(losses[0][2] - losses[1][2]) < 0.05 * abs(losses[1][2]) + 1e-3
+        moved = 0.0
+        for a, b in zip(nets[0].parameters(), nets[1].parameters()):
+            assert float((a - b).abs().max()) <= 2 * 3 * 1e-3 + 1e-6
+            if a.dim() > 1:                                    # biases ahead of a train-mode BatchNorm have pure-noise gradients
+                moved = max(moved, float((a - b).abs().mean()))
+        assert moved < 1.5e-3
+    finally:
+        pn2.set_precision("fp32")
