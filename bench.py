@@ -110,6 +110,11 @@ KERNEL_MODEL = {
     # head tail (csrc/head.cu): Z rows in, log-probabilities (+ the bf16 activation kept for backward) out / their gradients back
     "pn2_head_tail_fwd": lambda a: (a[6] * (a[1] * 2 + a[8] * 4 + (a[13] * 2 if a[12] else 0)), 2.0 * a[6] * a[7] * a[8], "hbm"),
     "pn2_head_tail_bwd": lambda a: (a[3] * (a[5] * 8 + a[9] * 2 + (a[11] * 2 if a[10] else 0)), 2.0 * a[3] * a[4] * a[5], "hbm"),
+    # ... fused with the weighted NLL: targets in, no dense [M, NC] gradient
+    "pn2_head_tail_loss_fwd": lambda a: (a[6] * (a[1] * 2 + a[8] * 4 + 8 + (a[15] * 2 if a[14] else 0)), 2.0 * a[6] * a[7] * a[8], "hbm"),
+    "pn2_head_tail_loss_bwd": lambda a: (a[6] * (a[8] * 4 + 8 + a[12] * 2 + (a[14] * 2 if a[13] else 0)), 2.0 * a[6] * a[7] * a[8], "hbm"),
+    # Adam over the flat gradient buffer (csrc/optim.cu): p, m, v read + written, g read (chunks x elements is an upper bound)
+    "pn2_adam_step": lambda a: (a[4] * a[5] * 28, 0.0, "hbm"),
 }
 # the launch-saving variants move the same bytes as the entry points they replace (same leading argument layout)
 for _alias, _base in (("pn2_linear_fwd_prepacked", "pn2_linear_fwd"), ("pn2_linear_bwd_data_prepacked", "pn2_linear_bwd_data"),

@@ -271,7 +271,7 @@ int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, co
 
 /* ---- segmentation head tail on rows (models/pointnet2_sem_seg.py:36-39) -----------
  * conv1 + bn1 run as one more pn2_linear_fwd layer; these two calls are what follows its pre-BatchNorm
- * product Z [M, C] (bf16 rows, C % 8 == 0, C <= 256):
+ * product Z [M, C] (bf16 rows, C % 32 == 0, C <= 256):
  *   forward : a = dropout(relu(Z*scale + shift)); logp[M, NC] = log_softmax(a.W2^T + b2)   (NC <= 32 classes,
  *             W2 [NC, C] fp32, b2 may be NULL); act_out (bf16 rows [M, ldo], may be NULL) receives a, which
  *             conv2's weight gradient needs.
@@ -280,13 +280,30 @@ int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, co
  *             the zeroed fp64 accumulator db2_accum[>= 32], left zero); dlogits_rows (bf16 [M, lddl], lddl % 8 == 0,
  *             may be NULL) receives dlogits for pn2_linear_bwd_weight (conv2's weight gradient).
  * Dropout keeps element (m, k) when hash(*seed, m*C + k) >= p (p quantised to 1/256; kept values scaled by
- * 1/(1-p)); *seed is an int64 in DEVICE memory read at run time; drop_p = 0 (eval mode) ignores it. */
+ * 1/(1-p)); *seed is an int64 in DEVICE memory read at run time; drop_p = 0 (eval mode) ignores it.
+ * C % 32 == 0 (the contraction runs on mma.sync m16n8k16 with bf16 hi+lo split operands, fp32-level accuracy).
+ *
+ * pn2_head_tail_loss_fwd / _bwd: the same tail FUSED with the loss of pointnet2_sem_seg.py:47-48,
+ * F.nll_loss(pred, target, weight) = -(sum_m w[t_m] logp[m, t_m]) / (sum_m w[t_m]):
+ *   forward : additionally reads target[M] (int64; values outside [0, NC), e.g. F.nll_loss's ignore_index -100,
+ *             contribute nothing) and class_weight[NC] (NULL = ones); loss_accum[2] is a zeroed fp64 scratch (left
+ *             zero); loss_out[0] = the loss, loss_out[1] = sum of the target weights (backward reads it).
+ *   backward: dlogits = (*dloss) * w[t]/loss_out[1] * (exp(logp) - onehot(t)) straight from the targets -- the dense
+ *             [M, NC] gradient tensor of pn2_head_tail_bwd does not exist; dloss (DEVICE, NULL = 1) is dL/dloss. */
 int pn2_head_tail_fwd(const void *Z, int ldz, const float *scale, const float *shift, const float *W2,
                       const float *b2, int64_t M, int C, int NC, float drop_p, const int64_t *seed,
                       float *logp, void *act_out, int ldo, void *stream);
 int pn2_head_tail_bwd(const float *dlogp, const float *logp, const float *W2, int64_t M, int C, int NC,
                       float drop_p, const int64_t *seed, void *dA, int ldda, void *dlogits_rows, int lddl,
                       double *db2_accum, float *db2, void *stream);
+int pn2_head_tail_loss_fwd(const void *Z, int ldz, const float *scale, const float *shift, const float *W2,
+                           const float *b2, int64_t M, int C, int NC, float drop_p, const int64_t *seed,
+                           const int64_t *target, const float *class_weight, float *logp, void *act_out, int ldo,
+                           double *loss_accum, float *loss_out, void *stream);
+int pn2_head_tail_loss_bwd(const float *logp, const int64_t *target, const float *class_weight, const float *loss_out,
+                           const float *dloss, const float *W2, int64_t M, int C, int NC, float drop_p,
+                           const int64_t *seed, void *dA, int ldda, void *dlogits_rows, int lddl, double *db2_accum,
+                           float *db2, void *stream);
 
 /* ---- optimizer step of the training loop (sem_seg_training.py:576-582: torch.optim.Adam with L2 weight decay) ----
  * One launch over the flat gradient buffer.  params[T]: device table of the parameter tensors' fp32 pointers;

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "pn2_interp_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pn2_head_tail_fwd": (_i, [_p, _i, _p, _p, _p, _p, _l, _i, _i, _f, _p, _p, _p, _i, _p]),
     "pn2_head_tail_bwd": (_i, [_p, _p, _p, _l, _i, _i, _f, _p, _p, _i, _p, _i, _p, _p, _p]),
+    "pn2_head_tail_loss_fwd": (_i, [_p, _i, _p, _p, _p, _p, _l, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
+    "pn2_head_tail_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _f, _p, _p, _i, _p, _i, _p, _p, _p]),
     "pn2_adam_step": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_to_rows": (_i, [_p, _l, _l, _l, _i, _l, _i, _p, _l, _i, _p]),
     "pn2_rows_to_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),

@@ -595,7 +595,10 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
     [B, N, classes].  SURVEY.md 8(f) n2; the modules keep owning every parameter."""
 
     @staticmethod
-    def forward(ctx, nn3, convs, bns, conv2, drop_p, seed, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+    def forward(ctx, nn3, convs, bns, conv2, drop_p, seed, loss_args, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+        """loss_args: None, or (target [B*N] int64, class_weight [NC] fp32 or None): then the weighted NLL of
+        pointnet2_sem_seg.py:47-48 is evaluated inside the head kernels and (logp, loss) is returned; logp is not
+        differentiable on that path (the gradient enters through the loss)."""
         B, N, _ = xyz1_r.shape
         S = xyz2_r.shape[1]
         dtype = ops.rows_dtype()
@@ -618,21 +621,33 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
         b2 = None if conv2.bias is None else conv2.bias.detach()
         logp = torch.empty(B, N, NC, device=p2.device, dtype=torch.float32)
         act = torch.empty(M, last.Z.shape[1], device=p2.device, dtype=torch.bfloat16) if want_bwd else None
-        call("pn2_head_tail_fwd", ptr(last.Z), last.Z.shape[1], ptr(last.scale), ptr(last.shift), ptr(W2), ptr(b2), M,
-             last.N, NC, float(drop_p), ptr(seed), ptr(logp), ptr(act), 0 if act is None else act.shape[1], stream())
-        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, float(drop_p), seed, logp, act)
-        return logp
+        loss = None
+        if loss_args is None:
+            call("pn2_head_tail_fwd", ptr(last.Z), last.Z.shape[1], ptr(last.scale), ptr(last.shift), ptr(W2), ptr(b2), M,
+                 last.N, NC, float(drop_p), ptr(seed), ptr(logp), ptr(act), 0 if act is None else act.shape[1], stream())
+        else:
+            target, cw = loss_args
+            loss = torch.empty(2, device=p2.device, dtype=torch.float32)          # [loss, sum of the target weights]
+            call("pn2_head_tail_loss_fwd", ptr(last.Z), last.Z.shape[1], ptr(last.scale), ptr(last.shift), ptr(W2), ptr(b2),
+                 M, last.N, NC, float(drop_p), ptr(seed), ptr(target), ptr(cw), ptr(logp), ptr(act),
+                 0 if act is None else act.shape[1], ptr(_stat_accum(p2.device)), ptr(loss), stream())
+        ctx.state = (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, float(drop_p), seed, logp, act,
+                     loss_args, loss)
+        if loss_args is None:
+            return logp
+        ctx.mark_non_differentiable(logp)
+        ctx.set_materialize_grads(False)          # no zero-filled [B, N, classes] gradient for the detached log-probabilities
+        return logp, loss[0]
 
     @staticmethod
-    def backward(ctx, dlogp):
-        layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, drop_p, seed, logp, act = ctx.state
+    def backward(ctx, dlogp, dloss=None):
+        (layers, x0, K0, M, idx3, w3, (B, N, S, D1, D2), convs, bns, conv2, W2, drop_p, seed, logp, act, loss_args,
+         loss) = ctx.state
         ctx.state = None
-        lib = load()
-        dev = dlogp.device
-        need1 = ctx.needs_input_grad[8] and D1 > 0
-        need2 = ctx.needs_input_grad[9]
+        dev = logp.device
+        need1 = ctx.needs_input_grad[9] and D1 > 0
+        need2 = ctx.needs_input_grad[10]
         NC, C = W2.shape
-        dlogp = dlogp.contiguous().view(M, NC)
         dA = torch.empty(M, act.shape[1], device=dev, dtype=torch.bfloat16)
         if dA.shape[1] != C:
             dA[:, C:].zero_()
@@ -641,8 +656,17 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
         db2 = _sink(conv2.bias)
         if db2 is None:
             db2 = torch.empty(NC, device=dev, dtype=torch.float32)
-        call("pn2_head_tail_bwd", ptr(dlogp), ptr(logp), ptr(W2), M, C, NC, drop_p, ptr(seed), ptr(dA), dA.shape[1],
-             ptr(dl_rows), lddl, ptr(_stat_accum(dev)), ptr(db2), stream())
+        if loss_args is None:
+            dlogp = dlogp.contiguous().view(M, NC)
+            call("pn2_head_tail_bwd", ptr(dlogp), ptr(logp), ptr(W2), M, C, NC, drop_p, ptr(seed), ptr(dA), dA.shape[1],
+                 ptr(dl_rows), lddl, ptr(_stat_accum(dev)), ptr(db2), stream())
+        else:
+            target, cw = loss_args
+            if dloss is None:
+                raise RuntimeError("fused head loss: backward reached the head without a gradient for the loss")
+            dloss = dloss.contiguous().float()
+            call("pn2_head_tail_loss_bwd", ptr(logp), ptr(target), ptr(cw), ptr(loss), ptr(dloss), ptr(W2), M, C, NC, drop_p,
+                 ptr(seed), ptr(dA), dA.shape[1], ptr(dl_rows), lddl, ptr(_stat_accum(dev)), ptr(db2), stream())
         dW2 = _weight_grad(dl_rows, act, act.shape[1], None, None, M, C, NC, conv2.weight, dev, stream(), [])
         grads, dx0 = mlp_backward(layers, x0, K0, M, dA, None, 1, need1 or need2, convs, bns)
         dp1 = dp2 = None
@@ -654,9 +678,9 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
             call("pn2_interp_bwd", ptr(dx0), dx0.shape[1], dt(dx0), ptr(idx3), ptr(w3), B, N, S, D1, D2, ptr(dp2),
                  stream())
         n_mlp = 4 * len(convs)
-        tail_needs = ctx.needs_input_grad[10 + n_mlp:]
+        tail_needs = ctx.needs_input_grad[11 + n_mlp:]
         tail = (dW2.view_as(conv2.weight) if tail_needs[0] else None, db2 if len(tail_needs) > 1 and tail_needs[1] else None)
-        return (None,) * 8 + (dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[10:10 + n_mlp]) + tail[:len(tail_needs)]
+        return (None,) * 9 + (dp1, dp2) + _param_grads(grads, convs, ctx.needs_input_grad[11:11 + n_mlp]) + tail[:len(tail_needs)]
 
 
 def _check_module_inputs(xyz, points):
@@ -812,12 +836,16 @@ class PointNetFeaturePropagation(nn.Module):
         return (ops.rows_dtype() == torch.bfloat16 and points2.is_cuda and isinstance(conv1, nn.Conv1d)
                 and isinstance(conv2, nn.Conv1d) and isinstance(bn1, nn.BatchNorm1d) and conv1.kernel_size == (1,)
                 and conv2.kernel_size == (1,) and conv1.in_channels == self.mlp_convs[-1].out_channels
-                and conv1.out_channels % 8 == 0 and conv1.out_channels <= 256 and conv2.in_channels == conv1.out_channels
+                and conv1.out_channels % 32 == 0 and conv1.out_channels <= 256 and conv2.in_channels == conv1.out_channels
                 and conv2.out_channels <= 32 and bn1.num_features == conv1.out_channels)
 
-    def forward_with_head(self, xyz1, xyz2, points1, points2, conv1, bn1, dropout, conv2, neighbours=None):
+    def forward_with_head(self, xyz1, xyz2, points1, points2, conv1, bn1, dropout, conv2, neighbours=None, loss_target=None,
+                          loss_weight=None):
         """This level followed by `log_softmax(conv2(dropout(relu(bn1(conv1(.))))))` (pointnet2_sem_seg.py:36-38) in one
-        chain of rows; returns the log-probabilities [B, N, classes] (already permuted as :39 does)."""
+        chain of rows; returns the log-probabilities [B, N, classes] (already permuted as :39 does).
+        loss_target [B*N] int64 (+ loss_weight [classes] fp32 or None): also evaluates F.nll_loss(pred, target, weight)
+        (pointnet2_sem_seg.py:47-48) inside the head kernels and returns (log-probabilities, loss); the log-probabilities
+        are then detached (the gradient enters through the loss)."""
         _note_grad_mode()
         _check_module_inputs(xyz1, points1)
         _check_module_inputs(xyz2, points2)
@@ -827,8 +855,20 @@ class PointNetFeaturePropagation(nn.Module):
             seed = torch.randint(0, 2 ** 31 - 1, (1,), device=points2.device, dtype=torch.int64)
         convs, bns = list(self.mlp_convs) + [conv1], list(self.mlp_bns) + [bn1]
         params = _flat_params(convs, bns) + [conv2.weight] + ([conv2.bias] if conv2.bias is not None else [])
+        loss_args = None
+        if loss_target is not None:
+            require_cuda(loss_target, "loss_target", torch.int64)
+            if loss_target.numel() != xyz1.shape[0] * xyz1.shape[2]:
+                raise ValueError("loss_target must hold one label per point (%d), got %d" % (xyz1.shape[0] * xyz1.shape[2],
+                                                                                         loss_target.numel()))
+            if loss_weight is not None:
+                require_cuda(loss_weight, "loss_weight")
+                if loss_weight.numel() != conv2.out_channels:
+                    raise ValueError("loss_weight must hold one weight per class")
+                loss_weight = loss_weight.contiguous()
+            loss_args = (loss_target.contiguous().view(-1), loss_weight)
         return _FeaturePropagationHeadFn.apply(
-            neighbours, convs, bns, conv2, p, seed, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
+            neighbours, convs, bns, conv2, p, seed, loss_args, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
             None if points1 is None else points1.permute(0, 2, 1), points2.permute(0, 2, 1), *params)
 
     def forward(self, xyz1, xyz2, points1, points2, neighbours=None):

@@ -95,6 +95,21 @@ class get_model(nn.Module):
         return [t for g in geo for t in g] + [t for n in nn3 for t in n]
 
     def forward(self, xyz, geometry=None):
+        return self._forward(xyz, geometry, None)
+
+    def forward_loss(self, xyz, target, weight=None, geometry=None):
+        """forward() followed by get_loss (pointnet2_sem_seg.py:47-48: F.nll_loss(pred, target, weight=weight)) ->
+        (loss, pred, l4_points).  With the fused head (bf16 rows) the loss and its gradient are evaluated inside the head
+        kernels (csrc/head.cu): no [B*N, classes] gradient tensor, none of the ~20 small loss kernels; `pred` is then
+        detached.  Otherwise the same value through get_loss on the ordinary forward."""
+        out = self._forward(xyz, geometry, (target, weight))
+        if len(out) == 3:
+            return out[2], out[0], out[1]
+        pred, l4_points = out
+        loss = get_loss()(pred.contiguous().view(-1, pred.shape[-1]), target.view(-1), l4_points, weight)
+        return loss, pred, l4_points
+
+    def _forward(self, xyz, geometry, loss_args):
         feats = [xyz]
         coords = [xyz[:, :3, :]]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
@@ -126,6 +141,11 @@ class get_model(nn.Module):
                 # the last level and the head as one chain of rows (csrc/head.cu); log-probabilities come out [B,N,classes]
                 if ahead:
                     main.wait_event(events[4 + i])
+                if loss_args is not None:
+                    pred, loss = fp.forward_with_head(coords[0], coords[1], skip, up, self.conv1, self.bn1, self.drop1,
+                                                      self.conv2, neighbours=nn3[i] if ahead else None,
+                                                      loss_target=loss_args[0], loss_weight=loss_args[1])
+                    return pred, l4_points, loss
                 pred = fp.forward_with_head(coords[0], coords[1], skip, up, self.conv1, self.bn1, self.drop1, self.conv2,
                                             neighbours=nn3[i] if ahead else None)
                 return pred, l4_points

@@ -213,11 +213,13 @@ class FlatAdam(torch.optim.Optimizer):
 
 class SemSegTrainer:
     def __init__(self, num_classes=18, num_extra_features=3, lr=1e-3, weight_decay=1e-4, device="cuda",
-                 class_weights=None, model=None, fused_optimizer=True, augment_rotate_z=False, flat_optimizer=True):
-        """flat_optimizer: Adam as one launch of this library over the flat gradient buffer (FlatAdam) instead of
+                 class_weights=None, model=None, fused_optimizer=True, augment_rotate_z=False, flat_optimizer=True, fused_loss=True):
+        """fused_loss: evaluate the loss through get_model.forward_loss (inside the head kernels when the fused head applies).
+        flat_optimizer: Adam as one launch of this library over the flat gradient buffer (FlatAdam) instead of
         torch.optim.Adam.  augment_rotate_z: apply the training loop's augmentation (provider.rotate_point_cloud_z on points[:, :, :3],
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
+        self.fused_loss = bool(fused_loss)
         self._rot_staging = None
         self.device = torch.device(device)
         self.num_classes = num_classes
@@ -236,11 +238,15 @@ class SemSegTrainer:
 
     def _step_impl(self, points, target, geometry=None):
         self.grads.zero()
-        if geometry is None:
-            pred, feat = self.model(points.transpose(2, 1))
+        if self.fused_loss and hasattr(self.model, "forward_loss"):
+            # forward + weighted NLL in one pass (the loss and its gradient come out of the head kernels when they apply)
+            loss, _, _ = self.model.forward_loss(points.transpose(2, 1), target, self.class_weights, geometry=geometry)
         else:
-            pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
-        loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
+            if geometry is None:
+                pred, feat = self.model(points.transpose(2, 1))
+            else:
+                pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
+            loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
         loss.backward()
         self.grads.adopt()
         self.grads.all_reduce_mean()

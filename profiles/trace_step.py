@@ -1,6 +1,6 @@
 """Kernel timeline of one CUDA-graph replay of the training step (or the inference forward) through torch.profiler
 (CUPTI): start, duration and stream of every kernel, written as CSV -- the overlap / gap picture ncu's serialised
-launch list cannot give.  Usage: python profiles/trace_step.py [train|forward] out.csv"""
+launch list cannot give.  Usage: python profiles/trace_step.py [train|forward] out.csv [--no-pipeline] [--replays=N]"""
 import importlib, json, os, sys
 import torch
 from torch.profiler import profile, ProfilerActivity
@@ -28,8 +28,10 @@ else:
 for _ in range(4):
     run()
 torch.cuda.synchronize()
+replays = int([a.split("=")[1] for a in sys.argv if a.startswith("--replays=")][0]) if any(a.startswith("--replays=") for a in sys.argv) else 1
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    run()
+    for _ in range(replays):       # > 1: back-to-back replays show the gap between consecutive graphs
+        run()
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 rows = []

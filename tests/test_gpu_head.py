@@ -2,8 +2,10 @@
 against a torch fp32/fp64 statement of /root/reference/models/pointnet2_sem_seg.py:36-39 on the same bf16 inputs, and
 the whole fp1+head chain (modules.PointNetFeaturePropagation.forward_with_head) against the PyTorch head.
 
-Tolerances: the kernels read bf16 Z and accumulate in fp32 -> log-probabilities to 1e-4 (absolute) of the torch
-evaluation of the same bf16 inputs; dA is stored as bf16 (2^-8 relative)."""
+Tolerances: the kernels read bf16 Z, multiply on mma.sync with bf16 hi+lo split operands (three products, fp32
+accumulation: 2^-16 relative per term) -> log-probabilities to 1e-4 (absolute) of the fp64 torch evaluation of the same
+bf16 inputs; dA is stored as bf16 (2^-8 relative).  The fused-loss entry points (pn2_head_tail_loss_fwd/_bwd) are checked
+against F.nll_loss(weight=..., ignore_index=-100) in fp64 and against the dense-gradient path."""
 import importlib
 
 import numpy as np
@@ -138,5 +140,99 @@ def test_fp1_with_fused_head_matches_pytorch_head(pn2):
             torch.manual_seed(5)
             eb, _ = net_b(x)
         assert float((ea - eb).abs().max()) < 0.05
+    finally:
+        pn2.set_precision("fp32")
+
+
+@pytest.mark.parametrize("M,C,NC,weighted", [(1000, 128, 18, True), (4099, 128, 13, False), (513, 64, 32, True), (77, 256, 2, True),
+                                              (131072, 128, 18, True)])
+def test_head_tail_fused_loss_matches_nll_loss(lib, M, C, NC, weighted):
+    """pn2_head_tail_loss_fwd/_bwd == pn2_head_tail_fwd -> F.nll_loss(weight, ignore_index=-100) -> pn2_head_tail_bwd."""
+    z, scale, shift, W2, b2 = _case(M, C, NC, 7 * M + NC)
+    g = torch.Generator().manual_seed(M)
+    target = torch.randint(0, NC, (M,), generator=g)
+    target[torch.rand(M, generator=g) < 0.1] = -100                     # F.nll_loss's default ignore_index
+    target = target.to(DEV)
+    cw = (0.25 + torch.rand(NC, generator=g)).to(DEV) if weighted else None
+    logp_a, logp_b = torch.empty(M, NC, device=DEV), torch.empty(M, NC, device=DEV)
+    act_a, act_b = (torch.empty(M, C, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+    lib.call("pn2_head_tail_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
+             None, lib.ptr(logp_a), lib.ptr(act_a), C, lib.stream())
+    accum = torch.zeros(64, device=DEV, dtype=torch.float64)
+    loss = torch.full((2,), float("nan"), device=DEV)
+    lib.call("pn2_head_tail_loss_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
+             None, lib.ptr(target), lib.ptr(cw), lib.ptr(logp_b), lib.ptr(act_b), C, lib.ptr(accum), lib.ptr(loss), lib.stream())
+    assert torch.equal(logp_a, logp_b) and torch.equal(act_a, act_b)
+    assert float(accum.abs().sum()) == 0.0
+    lp = logp_a.double().requires_grad_(True)
+    want = torch.nn.functional.nll_loss(lp, target, weight=None if cw is None else cw.double())
+    assert abs(float(loss[0]) - float(want)) <= 1e-5 * abs(float(want)) + 1e-6
+    wsum = float((cw[target.clamp(min=0)] * (target >= 0)).sum()) if weighted else float((target >= 0).sum())
+    assert abs(float(loss[1]) - wsum) <= 1e-5 * wsum
+    # backward with dL/dloss = 0.7: dense path fed with autograd's gradient of nll_loss vs the fused path
+    (0.7 * want).backward()
+    dlogp = lp.grad.float().contiguous()
+    lddl = (NC + 7) // 8 * 8
+    outs = []
+    for fused in (False, True):
+        dA = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+        dl = torch.full((M, lddl), float("nan"), device=DEV, dtype=torch.bfloat16)
+        db2 = torch.empty(NC, device=DEV)
+        if fused:
+            dloss = torch.tensor(0.7, device=DEV)
+            lib.call("pn2_head_tail_loss_bwd", lib.ptr(logp_a), lib.ptr(target), lib.ptr(cw), lib.ptr(loss), lib.ptr(dloss),
+                     lib.ptr(W2), M, C, NC, 0.0, None, lib.ptr(dA), C, lib.ptr(dl), lddl, lib.ptr(accum), lib.ptr(db2),
+                     lib.stream())
+        else:
+            lib.call("pn2_head_tail_bwd", lib.ptr(dlogp), lib.ptr(logp_a), lib.ptr(W2), M, C, NC, 0.0, None, lib.ptr(dA), C,
+                     lib.ptr(dl), lddl, lib.ptr(accum), lib.ptr(db2), lib.stream())
+        outs.append((dA.double(), dl.double(), db2.double()))
+    assert float(accum.abs().sum()) == 0.0
+    (dA0, dl0, db0), (dA1, dl1, db1) = outs
+    dlogits = dlogp.double() - logp_a.double().exp() * dlogp.double().sum(1, keepdim=True)      # exact statement
+    assert float((dl1[:, :NC] - dlogits).abs().max()) <= 2.0 ** -7 * float(dlogits.abs().max())
+    assert float(dl1[:, NC:].abs().max() if lddl > NC else 0.0) == 0.0
+    want_dA = dlogits @ W2.double()
+    assert float((dA1 - want_dA).abs().max()) <= 2.0 ** -7 * float(want_dA.abs().max())
+    assert float((dA1 - dA0).abs().max()) <= 2.0 ** -7 * float(want_dA.abs().max())
+    assert torch.allclose(db1, dlogits.sum(0), rtol=1e-4, atol=1e-6)
+    ignored = (target < 0)
+    assert float(dA1[ignored].abs().max()) == 0.0 and float(dl1[ignored].abs().max()) == 0.0     # ignored points: no gradient
+
+
+def test_forward_loss_matches_forward_plus_get_loss(pn2):
+    """get_model.forward_loss (loss inside the head kernels) == forward() + get_loss on the same network: loss value and
+    every parameter gradient (both run the fused head; the only difference is where the loss gradient is formed)."""
+    pn2.set_precision("bf16")
+    try:
+        nets = [I.randomize_module_(pn2.get_model(18, 3), 61).to(DEV).train() for _ in range(2)]
+        for net in nets:
+            net.drop1.p = 0.0
+        x = I.facade_batch(2, 2048, 9, 3).to(DEV).transpose(2, 1)
+        target = I.labels(2, 2048, 18, 7).to(DEV)
+        target[5] = -100
+        w = torch.linspace(0.5, 1.5, 18).to(DEV)
+        torch.manual_seed(72)
+        loss_a, pred_a, _ = nets[0].forward_loss(x, target, w)
+        assert not pred_a.requires_grad and loss_a.requires_grad
+        loss_a.backward()
+        torch.manual_seed(72)
+        pred_b, _ = nets[1](x)
+        loss_b = pn2.get_loss()(pred_b.contiguous().view(-1, 18), target, None, w)
+        loss_b.backward()
+        assert float((pred_a - pred_b).abs().max()) < 1e-5
+        assert abs(float(loss_a) - float(loss_b)) < 1e-5
+        for (n, pa), (_, pb) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+            if n.endswith("bias") and ("mlp_convs" in n or n == "conv1.bias"):
+                continue                                   # cancelled by train-mode batch norm (rounding noise only)
+            a, b = pa.grad.double().flatten(), pb.grad.double().flatten()
+            assert float((a - b).norm() / (b.norm() + 1e-30)) < 2e-2, n
+        # eval / no_grad: same value, no graph
+        nets[0].eval()
+        with torch.no_grad():
+            torch.manual_seed(5)
+            loss_e, pred_e, _ = nets[0].forward_loss(x, target, w)
+            want = pn2.get_loss()(pred_e.contiguous().view(-1, 18), target, None, w)
+        assert abs(float(loss_e) - float(want)) < 1e-5
     finally:
         pn2.set_precision("fp32")
