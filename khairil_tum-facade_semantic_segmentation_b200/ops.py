@@ -6,6 +6,8 @@ indices), CUDA float32 only.  Every function below is a thin argument-checking
 wrapper around one or two entry points of libpn2b200.so; torch supplies device
 memory and the current stream, nothing else.
 """
+import contextlib
+
 import torch
 
 from . import _lib
@@ -83,6 +85,95 @@ def index_points(points, idx):
     return _IndexPoints.apply(points, idx)
 
 
+class _OutputArena:
+    def __init__(self, tensors=None):
+        self.replay = tensors is not None
+        self.tensors = list(tensors) if self.replay else []
+        self.i = 0
+
+
+_ARENA = None
+
+
+def _out(shape, dtype, device):
+    """Output tensor of an index operator: a fresh one, or -- inside reuse_outputs() -- the next tensor of the arena."""
+    a = _ARENA
+    if a is None:
+        return torch.empty(shape, device=device, dtype=dtype)
+    if not a.replay:
+        t = torch.empty(shape, device=device, dtype=dtype)
+        a.tensors.append(t)
+        return t
+    if a.i >= len(a.tensors):
+        raise RuntimeError("reuse_outputs: more operator outputs than recorded tensors")
+    t = a.tensors[a.i]
+    a.i += 1
+    if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        raise RuntimeError("reuse_outputs: output %d is %s %s, recorded %s %s" % (a.i - 1, tuple(shape), dtype, tuple(t.shape), t.dtype))
+    return t
+
+
+@contextlib.contextmanager
+def record_outputs():
+    """Collect, in call order, every output tensor the index operators (farthest_point_sample, query_ball_point,
+    three_nn) allocate inside the block: `with record_outputs() as rec: ...; rec.tensors`."""
+    global _ARENA
+    prev, _ARENA = _ARENA, _OutputArena()
+    try:
+        yield _ARENA
+    finally:
+        _ARENA = prev
+
+
+@contextlib.contextmanager
+def reuse_outputs(tensors):
+    """Run the same sequence of index operators again, writing into `tensors` (from record_outputs) instead of new
+    allocations -- the two geometry slots of a software-pipelined CUDA graph pair (trainer.py) are filled this way, so no
+    copy is needed to hand a batch's indices from the index pipeline to the feature path."""
+    global _ARENA
+    prev, _ARENA = _ARENA, _OutputArena(tensors)
+    try:
+        yield _ARENA
+        if _ARENA.i != len(_ARENA.tensors):
+            raise RuntimeError("reuse_outputs: %d of %d recorded outputs were produced" % (_ARENA.i, len(_ARENA.tensors)))
+    finally:
+        _ARENA = prev
+
+
+class StartIndexGroup:
+    """The start-index stagings of several call sites (the four set-abstraction levels) behind ONE pinned ring and ONE
+    device buffer: draw() makes the reference's draws in module order and sends them with a single host->device copy
+    instead of one per level (each ~6 us of serial stream time ahead of a replay).  Built after the members exist and
+    BEFORE the graph that reads their device buffers is captured (the members' buffers become views of the group's)."""
+    SLOTS = 8
+
+    def __init__(self, members):
+        self.members = list(members)
+        dev = self.members[0].dev.device
+        total = sum(m.B for m in self.members)
+        self.host = torch.empty(self.SLOTS, total, dtype=torch.int64).pin_memory()
+        self.dev = torch.empty(total, dtype=torch.int64, device=dev)
+        off = 0
+        for m in self.members:
+            self.dev[off:off + m.B].copy_(m.dev)
+            m.dev = self.dev[off:off + m.B]
+            m.group, m.group_off = self, off
+            off += m.B
+        self._events = [None] * self.SLOTS
+        self._slot = 0
+
+    def draw(self):
+        j = self._slot
+        self._slot = (j + 1) % self.SLOTS
+        if self._events[j] is not None:
+            self._events[j].synchronize()
+        for m in self.members:          # the reference's per-forward draws, in module order (:75)
+            self.host[j, m.group_off:m.group_off + m.B].copy_(torch.randint(0, m.N, (m.B,), dtype=torch.long))
+        self.dev.copy_(self.host[j], non_blocking=True)
+        ev = self._events[j] = self._events[j] or torch.cuda.Event()
+        ev.record()
+
+
 class StartIndexStaging:
     """Host ring + ONE static device buffer for the FPS start indices of one call site.  A captured CUDA graph reads the
     device buffer; before every replay draw() makes the reference's torch.randint draw (:75) into the next pinned ring
@@ -133,8 +224,8 @@ def farthest_point_sample(xyz, npoint, start=None, return_xyz=False, staging=Non
         if start.shape != (B,) or start.dtype != torch.int64:
             raise ValueError("start must be int64 [B]")
         start = start.to(xyz.device, non_blocking=True)
-    out = torch.empty(B, npoint, device=xyz.device, dtype=torch.int64)
-    new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32) if return_xyz else None
+    out = _out((B, npoint), torch.int64, xyz.device)
+    new_xyz = _out((B, npoint, 3), torch.float32, xyz.device) if return_xyz else None
     sB, sN, sC = xyz.stride()
     call("pn2_farthest_point_sample", ptr(xyz), sB, sN, sC, B, N, npoint, ptr(start), ptr(out), ptr(new_xyz), stream())
     return (out, new_xyz) if return_xyz else out
@@ -152,8 +243,8 @@ def query_ball_point(radius, nsample, xyz, new_xyz, return_count=False):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     nsample = int(nsample)
-    out = torch.empty(B, S, nsample, device=xyz.device, dtype=torch.int64)
-    cnt = torch.empty(B, S, device=xyz.device, dtype=torch.int32) if return_count else None
+    out = _out((B, S, nsample), torch.int64, xyz.device)
+    cnt = _out((B, S), torch.int32, xyz.device) if return_count else None
     sB, sN, sC = xyz.stride()
     qB, qN, qC = new_xyz.stride()
     call("pn2_query_ball_point", ptr(xyz), sB, sN, sC, ptr(new_xyz), qB, qN, qC, B, N, S, radius_sq(radius),
@@ -166,8 +257,8 @@ def three_nn(xyz1, xyz2):
     _xyz3(xyz1, "xyz1"), _xyz3(xyz2, "xyz2")
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
-    idx = torch.empty(B, N, 3, device=xyz1.device, dtype=torch.int64)
-    w = torch.empty(B, N, 3, device=xyz1.device, dtype=torch.float32)
+    idx = _out((B, N, 3), torch.int64, xyz1.device)
+    w = _out((B, N, 3), torch.float32, xyz1.device)
     aB, aN, aC = xyz1.stride()
     cB, cN, cC = xyz2.stride()
     call("pn2_three_nn", ptr(xyz1), aB, aN, aC, ptr(xyz2), cB, cN, cC, B, N, S, ptr(idx), ptr(w), stream())

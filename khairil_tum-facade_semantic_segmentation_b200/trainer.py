@@ -255,23 +255,26 @@ class SemSegTrainer:
 
     def enable_cuda_graph(self, batch_clouds, npoint, channels, warmup=3, pipeline=False):
         """Capture the whole training step (forward, loss, backward, gradient all-reduce, Adam) into ONE
-        CUDA graph replayed per step: the ~420 kernel launches of a step cost no host time any more.
+        CUDA graph replayed per step: the ~300 kernel launches of a step cost no host time any more.
         Inputs are copied into static buffers; the FPS start indices stay a fresh CPU-generator draw per
-        step (drawn on the host before each replay into pinned buffers the graph's memcpy nodes read).
+        step (drawn on the host before each replay into a pinned ring, one host->device copy ahead of the replay).
         Re-capture after changing BatchNorm momentum (FlatAdam reads the learning rate from device memory: no re-capture;
         torch.optim.Adam bakes it in).
 
-        pipeline=True software-pipelines consecutive batches inside that one graph: a forked branch runs the
+        pipeline=True software-pipelines consecutive batches inside the graph: a forked branch runs the
         coordinate-only index pipeline (FPS, ball query, 3-NN: get_model.geometry_all) of the batch just SUBMITTED
         while the main branch runs forward/backward/Adam of the batch submitted one call earlier with the indices
-        computed for it during the previous replay; after the join the new indices and inputs are shifted into the
-        "current" slot.  The FPS dependency chain (0.5 ms on 32 of 148 SMs) thereby leaves the critical path.
+        computed for it during the previous replay.  The FPS dependency chain (0.5 ms on 32 of 148 SMs) thereby leaves
+        the critical path.  Inputs and indices live in TWO slots and there are two captured graphs (sharing one memory
+        pool): graph k trains on slot k while its index branch fills slot 1-k (ops.reuse_outputs), and consecutive calls
+        alternate between them -- nothing is copied from a "next" to a "current" slot.
         step_device() then returns the loss of the PREVIOUS batch (None on the first call).  step() -- host buffers --
         adds two more stages: the host->device copy of the batch handed in runs on a copy stream beside the replay that
         works on the two batches before it, and the loss of a replay is read back by the NEXT call (the host never waits on
         the replay it has just launched), so it returns the loss of the batch handed in THREE calls earlier (None 3 times).
         flush() finishes what is in flight and returns the remaining losses in batch order.  Same arithmetic per batch
         as pipeline=False."""
+        from . import ops
         from .modules import PointNetSetAbstraction
         dev = self.device
         rng_state = torch.get_rng_state()     # warm-up / capture must not advance the CPU generator the FPS start draws use
@@ -279,28 +282,37 @@ class SemSegTrainer:
         self._sa = [m for m in self.model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
         for m in self._sa:
             m.use_static_start_buffers(True)
-        self._g_points = torch.zeros(batch_clouds, npoint, channels, device=dev)
-        self._g_target = torch.zeros(batch_clouds * npoint, dtype=torch.int64, device=dev)
-        self._g_points.uniform_(-0.5, 0.5)
-        self._pipeline, self._primed, self._geo = bool(pipeline), False, None
+        self._pipeline, self._primed, self._parity, self._start_group = bool(pipeline), False, 0, None
+        n_slots = 2 if pipeline else 1
+        self._pts = [torch.zeros(batch_clouds, npoint, channels, device=dev).uniform_(-0.5, 0.5) for _ in range(n_slots)]
+        self._tgt = [torch.zeros(batch_clouds * npoint, dtype=torch.int64, device=dev) for _ in range(n_slots)]
+        self._g_points, self._g_target = self._pts[0], self._tgt[0]       # the slot of the batch submitted last
+        self._slots = [None] * n_slots           # pipeline: (geometry, its tensors in allocation order) per slot
         side = torch.cuda.Stream(device=dev)
         if pipeline:
-            self._n_points = self._g_points.clone()
-            self._n_target = self._g_target.clone()
             self._geo_stream = torch.cuda.Stream(device=dev)
-            self._stager = _HostStager([self._g_points, self._g_target], dev)
+            self._stager = _HostStager([self._pts[0], self._tgt[0]], dev)
             self._loss_host = torch.zeros(2).pin_memory()            # step(): losses come back through a pinned ring,
             self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]  # read one call after their replay was launched
             self._loss_valid, self._loss_slot = [False, False], 0
-            with torch.no_grad():       # persistent "current batch" index tensors (outside any graph pool)
-                self._geo = self.model.geometry_all(self._g_points.transpose(2, 1)[:, :3, :])
+            with torch.no_grad():       # persistent index tensors of the two slots (outside any graph pool)
+                for k in range(2):
+                    with ops.record_outputs() as rec:
+                        geo = self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
+                    self._slots[k] = (geo, rec.tensors)
         side.wait_stream(torch.cuda.current_stream(dev))
         saved = [(p.detach().clone()) for p in self.model.state_dict().values()]
+        geo0 = self._slots[0][0] if pipeline else None
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._step_impl(self._g_points, self._g_target, self._geo)
+                self._step_impl(self._pts[0], self._tgt[0], geo0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # one pinned ring / one host->device copy for the start indices of all levels (their device buffers become views of
+        # the group's: must happen before the capture)
+        stagings = [m.start_staging for m in self._sa]
+        if stagings and all(isinstance(st, ops.StartIndexStaging) for st in stagings):
+            self._start_group = ops.StartIndexGroup(stagings)
         # the warm-up steps must not count as training: restore parameters/buffers and optimizer moments
         with torch.no_grad():
             for t, s in zip(self.model.state_dict().values(), saved):
@@ -309,23 +321,27 @@ class SemSegTrainer:
                 for v in st.values():
                     if torch.is_tensor(v):
                         v.zero_()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            if pipeline:
-                main = torch.cuda.current_stream(dev)
-                self._geo_stream.wait_stream(main)
-                with torch.cuda.stream(self._geo_stream), torch.no_grad():
-                    nxt = self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :])
-                self._g_loss = self._step_impl(self._g_points, self._g_target, self._geo)
-                main.wait_stream(self._geo_stream)
-                self._shift(nxt)
-                del nxt
-            else:
-                self._g_loss = self._step_impl(self._g_points, self._g_target)
+        self._graphs, self._g_losses = [], []
+        for k in range(n_slots):
+            graph = torch.cuda.CUDAGraph()
+            pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}     # never replayed concurrently
+            with torch.cuda.graph(graph, **pool):
+                if pipeline:
+                    main = torch.cuda.current_stream(dev)
+                    self._geo_stream.wait_stream(main)
+                    with torch.cuda.stream(self._geo_stream), torch.no_grad():
+                        with ops.reuse_outputs(self._slots[1 - k][1]):
+                            self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :])
+                    loss = self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])
+                    main.wait_stream(self._geo_stream)
+                else:
+                    loss = self._step_impl(self._pts[0], self._tgt[0])
+            self._graphs.append(graph)
+            self._g_losses.append(loss)
         with torch.no_grad():                         # capture does not execute, but keep the state pristine anyway
             for t, s in zip(self.model.state_dict().values(), saved):
                 t.copy_(s)
-        self._graph = graph
+        self._graph, self._g_loss = self._graphs[0], self._g_losses[0]
         torch.set_rng_state(rng_state)
         return self
 
@@ -338,33 +354,33 @@ class SemSegTrainer:
             ops.rotate_point_cloud_z_(points, ops.draw_rotation_angles(points.shape[0]), staging=self._rot_staging)
         return points
 
-    def _shift(self, nxt):
-        """next-batch indices and inputs -> the "current" slot the feature path reads (a few multi-tensor copies)."""
-        cur, new = get_model.geometry_tensors(self._geo), get_model.geometry_tensors(nxt)
-        for dt in (torch.int64, torch.float32):
-            torch._foreach_copy_([c for c in cur if c.dtype == dt], [n for n in new if n.dtype == dt])
-        self._g_points.copy_(self._n_points)
-        self._g_target.copy_(self._n_target)
-
     def _submit(self, points, target):
-        """pipeline mode: stage the new batch, run its index pipeline next to the previous batch's feature path."""
-        self._n_points.copy_(points, non_blocking=True)
-        self._n_target.copy_(target.view(-1), non_blocking=True)
-        self._augment(self._n_points)
+        """pipeline mode: put the new batch into the free slot, run its index pipeline next to the previous batch's
+        feature path (the graph that trains on the other slot)."""
+        from . import ops
+        k = self._parity
+        self._parity = k ^ 1
+        self._g_points, self._g_target = self._pts[k], self._tgt[k]
+        self._pts[k].copy_(points, non_blocking=True)
+        self._tgt[k].copy_(target.view(-1), non_blocking=True)
+        self._augment(self._pts[k])
         if not self._primed:                          # first batch: only its index pipeline, eagerly
-            with torch.no_grad():
-                self._shift(self.model.geometry_all(self._n_points.transpose(2, 1)[:, :3, :]))
+            with torch.no_grad(), ops.reuse_outputs(self._slots[k][1]):
+                self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
             self._primed = True
             return None
         self._pre_replay()
-        self._graph.replay()
-        return self._g_loss
+        self._graphs[k ^ 1].replay()                  # trains on slot k^1 (the batch before), indexes slot k
+        return self._g_losses[k ^ 1]
 
     def _pre_replay(self):
         """host work a replay depends on: the reference's per-forward FPS start draws (module order) and, for FlatAdam,
         the device copy of the optimizer's hyper-parameters (follows a learning-rate schedule without re-capture)"""
-        for m in self._sa:
-            m.start_staging.draw()
+        if self._start_group is not None:
+            self._start_group.draw()
+        else:
+            for m in self._sa:
+                m.start_staging.draw()
         if isinstance(self.optimizer, FlatAdam):
             self.optimizer.sync_hyper()
 
@@ -393,7 +409,8 @@ class SemSegTrainer:
                 out.append(float(loss))
         if self._primed:
             self._primed = False
-            out.append(float(self._step_impl(self._g_points, self._g_target, self._geo)))
+            k = self._parity ^ 1                      # the slot of the batch submitted last: indexed, not yet trained on
+            out.append(float(self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])))
         return out
 
     def step_device(self, points, target):
@@ -470,29 +487,38 @@ class SemSegPredictor:
         self._sa = [m for m in model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
         for m in self._sa:
             m.use_static_start_buffers(True)
-        self.points = torch.zeros(batch_clouds, npoint, channels, device=dev)
-        self.points.uniform_(-0.5, 0.5)
-        self._geo, self._pending = None, None
+        from . import ops
+        n_slots = 2 if self.pipeline else 1
+        self._pts = [torch.zeros(batch_clouds, npoint, channels, device=dev).uniform_(-0.5, 0.5) for _ in range(n_slots)]
+        self.points = self._pts[0]
+        self._slots, self._pending, self._parity, self._start_group = [None] * n_slots, None, 0, None
         side = torch.cuda.Stream(device=dev)
         if self.pipeline:
-            self.next_points = self.points.clone()
             self._geo_stream = torch.cuda.Stream(device=dev)
             self._stager = _HostStager([self.points], dev)
-            with torch.no_grad():
-                self._geo = self.model.geometry_all(self.points.transpose(2, 1)[:, :3, :])
+            with torch.no_grad():       # persistent index tensors of the two slots (outside any graph pool)
+                for k in range(2):
+                    with ops.record_outputs() as rec:
+                        geo = self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
+                    self._slots[k] = (geo, rec.tensors)
         side.wait_stream(torch.cuda.current_stream(dev))
         # the parameters are FROZEN for this predictor: folded BatchNorm and packed weight images are computed once in the
-        # warm-up pass below (modules.frozen_parameters) and the captured graph reads them -- ~60 tiny launches fewer per
+        # warm-up pass below (modules.frozen_parameters) and the captured graphs read them -- ~60 tiny launches fewer per
         # forward.  Build a new predictor after changing the model's parameters or running statistics.
         with modules.frozen_parameters() as cache:
             with torch.cuda.stream(side), torch.no_grad():
                 for _ in range(max(1, warmup)):
-                    self._forward(self.points)
+                    self._forward(0)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            self._frozen_tensors = list(cache.values())          # keep what the graph will read alive with the predictor
-            self.graph = torch.cuda.CUDAGraph()
-            self._capture(dev)
+            stagings = [m.start_staging for m in self._sa]
+            if all(isinstance(st, ops.StartIndexStaging) for st in stagings):
+                self._start_group = ops.StartIndexGroup(stagings)      # one host->device copy for the four levels' start draws
+            self._frozen_tensors = list(cache.values())          # keep what the graphs will read alive with the predictor
+            self._graphs, self._log_probs, self._labels = [], [], []
+            for k in range(n_slots):
+                self._capture(dev, k)
+        self.graph, self.log_probs, self.labels = self._graphs[0], self._log_probs[0], self._labels[0]
         self._host_labels = torch.empty(batch_clouds, npoint, dtype=torch.int64).pin_memory()
         if self.pipeline:     # host results travel through a two-slot pinned ring and are handed out one call after their replay
             self._rb_host = [self._host_labels, torch.empty_like(self._host_labels).pin_memory()]
@@ -500,35 +526,38 @@ class SemSegPredictor:
             self._rb_rows, self._rb_slot = [None, None], 0
         torch.set_rng_state(rng_state)
 
-    def _capture(self, dev):
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+    def _capture(self, dev, k):
+        """graph k: feature path of slot k; pipelined: beside it the index pipeline of the batch waiting in slot 1-k"""
+        from . import ops
+        graph = torch.cuda.CUDAGraph()
+        pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}         # never replayed concurrently
+        with torch.no_grad(), torch.cuda.graph(graph, **pool):
             if self.pipeline:
                 main = torch.cuda.current_stream(dev)
                 self._geo_stream.wait_stream(main)
-                with torch.cuda.stream(self._geo_stream):
-                    nxt = self.model.geometry_all(self.next_points.transpose(2, 1)[:, :3, :])
-            self.log_probs, _ = self._forward(self.points)                     # [B, npoint, classes]
-            self.labels = self.log_probs.argmax(dim=2)
+                with torch.cuda.stream(self._geo_stream), ops.reuse_outputs(self._slots[1 - k][1]):
+                    self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :])
+            log_probs, _ = self._forward(k)                                    # [B, npoint, classes]
+            labels = log_probs.argmax(dim=2)
             if self.pipeline:
                 main.wait_stream(self._geo_stream)
-                self._shift(nxt)
-                del nxt
+        self._graphs.append(graph)
+        self._log_probs.append(log_probs)
+        self._labels.append(labels)
 
-    def _forward(self, points):
-        if self._geo is None:
-            return self.model(points.transpose(2, 1))
-        return self.model(points.transpose(2, 1), geometry=self._geo)
+    def _forward(self, k):
+        if not self.pipeline:
+            return self.model(self._pts[k].transpose(2, 1))
+        return self.model(self._pts[k].transpose(2, 1), geometry=self._slots[k][0])
 
-    def _shift(self, nxt):
-        cur, new = get_model.geometry_tensors(self._geo), get_model.geometry_tensors(nxt)
-        for dt in (torch.int64, torch.float32):
-            torch._foreach_copy_([c for c in cur if c.dtype == dt], [n for n in new if n.dtype == dt])
-        self.points.copy_(self.next_points)
-
-    def _replay(self):
-        for m in self._sa:
-            m.start_staging.draw()
-        self.graph.replay()
+    def _replay(self, k=0):
+        if self._start_group is not None:
+            self._start_group.draw()
+        else:
+            for m in self._sa:
+                m.start_staging.draw()
+        self._graphs[k].replay()
+        self.log_probs, self.labels = self._log_probs[k], self._labels[k]      # outputs of the replay just launched
 
     def forward_device(self, points):
         """points [b <= batch, npoint, C] on the device -> (log_probs, labels) views of the static outputs."""
@@ -571,14 +600,17 @@ class SemSegPredictor:
         return out
 
     def _advance(self, points, to_host):
+        from . import ops
         b = points.shape[0]
-        self.next_points[:b].copy_(points, non_blocking=True)
+        k = self._parity
+        self._parity = k ^ 1
+        self._pts[k][:b].copy_(points, non_blocking=True)
         prev, self._pending = self._pending, b
         if prev is None:                           # first batch: only its index pipeline, eagerly
-            with torch.no_grad():
-                self._shift(self.model.geometry_all(self.next_points.transpose(2, 1)[:, :3, :]))
+            with torch.no_grad(), ops.reuse_outputs(self._slots[k][1]):
+                self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
             return None
-        self._replay()
+        self._replay(k ^ 1)                        # feature path of slot k^1 (the batch before), index pipeline of slot k
         return self._read(prev, to_host)
 
     def flush_one(self, to_host=True):
@@ -592,7 +624,9 @@ class SemSegPredictor:
                 self._stager.release(pend[0])
             elif self._pending is not None:
                 prev, self._pending = self._pending, None
-                self._replay()                     # the index branch re-runs on the stale "next" slot: harmless
+                k = self._parity                   # the last batch sits in slot k^1; the index branch re-runs on the stale
+                self._parity = k ^ 1               # slot k: harmless
+                self._replay(k ^ 1)
                 r = self._read(prev, to_host)
             else:
                 for j in (self._rb_slot, self._rb_slot ^ 1):          # queued read-backs, older first
