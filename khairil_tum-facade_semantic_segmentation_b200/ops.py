@@ -157,8 +157,8 @@ class StartIndexGroup:
         for m in self.members:
             self.dev[off:off + m.B].copy_(m.dev)
             m.dev = self.dev[off:off + m.B]
-            m.group, m.group_off = self, off
-            off += m.B
+            m.group_off = off          # no back-reference to the group: a reference cycle would leave the pinned rings to the
+            off += m.B                 # cyclic collector, which may run (and free pinned memory) in the middle of a capture
         self._events = [None] * self.SLOTS
         self._slot = 0
 

@@ -8,11 +8,28 @@ decay 1e-4).  Multi-GPU is pure data parallelism over point-cloud blocks, one pr
 GPU: inference needs no collective; training all-reduces ONE flat fp32
 gradient buffer (~3.9 MB) over NCCL/NVLink per step.  BatchNorm statistics stay per rank.
 """
+import contextlib
+import gc
+
 import torch
 import torch.distributed as dist
 
 from . import modules
 from .sem_seg import get_loss, get_model
+
+
+@contextlib.contextmanager
+def _no_gc():
+    """No cyclic garbage collection inside a CUDA-graph capture: collecting an object that owns pinned host memory makes
+    the host allocator record events on the streams that used it -- an invalid operation on a capturing stream."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 def shard_range(n_items, rank, world):
@@ -325,7 +342,7 @@ class SemSegTrainer:
         for k in range(n_slots):
             graph = torch.cuda.CUDAGraph()
             pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}     # never replayed concurrently
-            with torch.cuda.graph(graph, **pool):
+            with _no_gc(), torch.cuda.graph(graph, **pool):
                 if pipeline:
                     main = torch.cuda.current_stream(dev)
                     self._geo_stream.wait_stream(main)
@@ -531,7 +548,7 @@ class SemSegPredictor:
         from . import ops
         graph = torch.cuda.CUDAGraph()
         pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}         # never replayed concurrently
-        with torch.no_grad(), torch.cuda.graph(graph, **pool):
+        with _no_gc(), torch.no_grad(), torch.cuda.graph(graph, **pool):
             if self.pipeline:
                 main = torch.cuda.current_stream(dev)
                 self._geo_stream.wait_stream(main)
