@@ -274,7 +274,8 @@ int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, co
  * product Z [M, C] (bf16 rows, C % 32 == 0, C <= 256):
  *   forward : a = dropout(relu(Z*scale + shift)); logp[M, NC] = log_softmax(a.W2^T + b2)   (NC <= 32 classes,
  *             W2 [NC, C] fp32, b2 may be NULL); act_out (bf16 rows [M, ldo], may be NULL) receives a, which
- *             conv2's weight gradient needs.
+ *             conv2's weight gradient needs; labels (int64 [M], may be NULL) receives argmax_c logp[m, c] (first
+ *             maximum, as torch.argmax -- localfunctions.py:400 takes it with numpy on the host).
  *   backward: dlogits = dlogp - exp(logp)*rowsum(dlogp);  dA[M, C] (bf16) = (dlogits.W2) * keep/(1-p), i.e. the
  *             gradient w.r.t. relu(bn1(.)) that pn2_bn_relu_bwd_* take; db2[NC] = column sums of dlogits (through
  *             the zeroed fp64 accumulator db2_accum[>= 32], left zero); dlogits_rows (bf16 [M, lddl], lddl % 8 == 0,
@@ -292,7 +293,7 @@ int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_t *idx3, co
  *             [M, NC] gradient tensor of pn2_head_tail_bwd does not exist; dloss (DEVICE, NULL = 1) is dL/dloss. */
 int pn2_head_tail_fwd(const void *Z, int ldz, const float *scale, const float *shift, const float *W2,
                       const float *b2, int64_t M, int C, int NC, float drop_p, const int64_t *seed,
-                      float *logp, void *act_out, int ldo, void *stream);
+                      float *logp, void *act_out, int ldo, int64_t *labels, void *stream);
 int pn2_head_tail_bwd(const float *dlogp, const float *logp, const float *W2, int64_t M, int C, int NC,
                       float drop_p, const int64_t *seed, void *dA, int ldda, void *dlogits_rows, int lddl,
                       double *db2_accum, float *db2, void *stream);

@@ -123,7 +123,7 @@ head_tail_fwd_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const float *
                      int64_t M, int C, int NC, const int64_t *__restrict__ seed_ptr, uint32_t thresh8, float keep_scale,
                      float *__restrict__ logp, __nv_bfloat16 *__restrict__ act_out, int ldo,
                      const int64_t *__restrict__ target, const float *__restrict__ class_weight,
-                     double *__restrict__ loss_accum) {
+                     double *__restrict__ loss_accum, int64_t *__restrict__ labels) {
     extern __shared__ __align__(16) unsigned char head_smem[];
     const int KS = C >> 4, nfrag = KS * NT * 32;
     uint2 *bhi = reinterpret_cast<uint2 *>(head_smem), *blo = bhi + nfrag;
@@ -234,6 +234,8 @@ head_tail_fwd_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const float *
             }
             if (q == 0) den += w0 + w1;
         }
+        float bv0 = -INFINITY, bv1 = -INFINITY;       // arg-max of the STORED log-probabilities, first maximum (torch.argmax)
+        int bc0 = 0, bc1 = 0;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
 #pragma unroll
@@ -245,8 +247,21 @@ head_tail_fwd_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const float *
                     if (v1) logp[r1 * NC + col] = l1;
                     if (col == t0) num = fmaf(w0, l0, num);
                     if (col == t1) num = fmaf(w1, l1, num);
+                    if (l0 > bv0) { bv0 = l0; bc0 = col; }
+                    if (l1 > bv1) { bv1 = l1; bc1 = col; }
                 }
             }
+        }
+        if (labels) {          // uniform
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ov0 = __shfl_xor_sync(0xffffffffu, bv0, o), ov1 = __shfl_xor_sync(0xffffffffu, bv1, o);
+                const int oc0 = __shfl_xor_sync(0xffffffffu, bc0, o), oc1 = __shfl_xor_sync(0xffffffffu, bc1, o);
+                if (ov0 > bv0 || (ov0 == bv0 && oc0 < bc0)) { bv0 = ov0; bc0 = oc0; }
+                if (ov1 > bv1 || (ov1 == bv1 && oc1 < bc1)) { bv1 = ov1; bc1 = oc1; }
+            }
+            if (q == 0 && v0) labels[r0] = bc0;
+            if (q == 0 && v1) labels[r1] = bc1;
         }
     }
     if (target) {       // uniform across the block
@@ -459,7 +474,8 @@ static int head_grid(Kernel kernel, size_t smem, int64_t M) {
 
 static int head_fwd_launch(const void *Z, int ldz, const float *scale, const float *shift, const float *W2, const float *b2,
                            int64_t M, int C, int NC, float drop_p, const int64_t *seed, float *logp, void *act_out, int ldo,
-                           const int64_t *target, const float *class_weight, double *loss_accum, cudaStream_t stream) {
+                           const int64_t *target, const float *class_weight, double *loss_accum, int64_t *labels,
+                           cudaStream_t stream) {
     const int nt = (NC + 7) / 8;
     const uint32_t thr = drop_threshold(drop_p);
     const float ks = thr ? 256.0f / (float)(256 - (int)thr) : 1.0f;
@@ -467,7 +483,7 @@ static int head_fwd_launch(const void *Z, int ldz, const float *scale, const flo
 #define PN2_HEAD_FWD(NT)                                                                                                \
     head_tail_fwd_kernel<NT><<<head_grid(head_tail_fwd_kernel<NT>, smem, M), kHeadThreads, smem, stream>>>((const __nv_bfloat16 *)Z, ldz, scale, shift, W2, b2, M, C, \
                                                                    NC, seed, thr, ks, logp, (__nv_bfloat16 *)act_out, ldo,  \
-                                                                   target, class_weight, loss_accum)
+                                                                   target, class_weight, loss_accum, labels)
     switch (nt) {
         case 1: PN2_HEAD_FWD(1); break;
         case 2: PN2_HEAD_FWD(2); break;
@@ -521,11 +537,11 @@ using namespace pn2;
 
 extern "C" int pn2_head_tail_fwd(const void *Z, int ldz, const float *scale, const float *shift, const float *W2,
                                  const float *b2, int64_t M, int C, int NC, float drop_p, const int64_t *seed,
-                                 float *logp, void *act_out, int ldo, void *stream) {
+                                 float *logp, void *act_out, int ldo, int64_t *labels, void *stream) {
     PN2_HEAD_FWD_CHECKS("head_tail_fwd");
     if (M == 0) return PN2_OK;
     head_fwd_launch(Z, ldz, scale, shift, W2, b2, M, C, NC, drop_p, seed, logp, act_out, ldo, nullptr, nullptr, nullptr,
-                    (cudaStream_t)stream);
+                    labels, (cudaStream_t)stream);
     return check_launch("head_tail_fwd");
 }
 
@@ -548,7 +564,7 @@ extern "C" int pn2_head_tail_loss_fwd(const void *Z, int ldz, const float *scale
     PN2_REQUIRE(target && loss_accum && loss_out, "head_tail_loss_fwd: null pointer");
     if (M > 0)
         head_fwd_launch(Z, ldz, scale, shift, W2, b2, M, C, NC, drop_p, seed, logp, act_out, ldo, target, class_weight,
-                        loss_accum, (cudaStream_t)stream);
+                        loss_accum, nullptr, (cudaStream_t)stream);
     head_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_accum, loss_out);
     count_launch();
     return check_launch("head_tail_loss_fwd");

@@ -373,8 +373,8 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
         if l > 0 or need_dx0:
             ldd = _row_ld(st.K, dtype) if l > 0 else x0.shape[1]
             dA = torch.empty(M, ldd, device=dev, dtype=dtype)
-            if ldd != st.K:
-                dA[:, st.K:].zero_()
+            # (padding columns st.K..ldd of the first layer's input gradient are never read: its consumers --
+            # pn2_group_points_bwd, pn2_rows_to_f32, pn2_interp_bwd, _GroupAllFn -- address columns < st.K only)
             if st.wpack_bwd is not None:
                 call("pn2_linear_bwd_data_prepacked", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd,
                      dt(dA), ptr(st.wpack_bwd), stream())
@@ -595,10 +595,13 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
     [B, N, classes].  SURVEY.md 8(f) n2; the modules keep owning every parameter."""
 
     @staticmethod
-    def forward(ctx, nn3, convs, bns, conv2, drop_p, seed, loss_args, xyz1_r, xyz2_r, p1_r, p2_r, *params):
-        """loss_args: None, or (target [B*N] int64, class_weight [NC] fp32 or None): then the weighted NLL of
+    def forward(ctx, nn3, convs, bns, conv2, drop_p, seed, extras, xyz1_r, xyz2_r, p1_r, p2_r, *params):
+        """extras: None or a dict.  "loss": (target [B*N] int64, class_weight [NC] fp32 or None) -- the weighted NLL of
         pointnet2_sem_seg.py:47-48 is evaluated inside the head kernels and (logp, loss) is returned; logp is not
-        differentiable on that path (the gradient enters through the loss)."""
+        differentiable on that path (the gradient enters through the loss).  "labels": an int64 [B, N] tensor that
+        receives argmax(logp, dim=2) from the same kernel (inference; localfunctions.py:400)."""
+        loss_args = None if extras is None else extras.get("loss")
+        labels = None if extras is None else extras.get("labels")
         B, N, _ = xyz1_r.shape
         S = xyz2_r.shape[1]
         dtype = ops.rows_dtype()
@@ -624,7 +627,8 @@ class _FeaturePropagationHeadFn(torch.autograd.Function):
         loss = None
         if loss_args is None:
             call("pn2_head_tail_fwd", ptr(last.Z), last.Z.shape[1], ptr(last.scale), ptr(last.shift), ptr(W2), ptr(b2), M,
-                 last.N, NC, float(drop_p), ptr(seed), ptr(logp), ptr(act), 0 if act is None else act.shape[1], stream())
+                 last.N, NC, float(drop_p), ptr(seed), ptr(logp), ptr(act), 0 if act is None else act.shape[1], ptr(labels),
+                 stream())
         else:
             target, cw = loss_args
             loss = torch.empty(2, device=p2.device, dtype=torch.float32)          # [loss, sum of the target weights]
@@ -735,6 +739,17 @@ class PointNetSetAbstraction(nn.Module):
         idx = ops.query_ball_point(self.radius, self.nsample, xyz_r, new_xyz)
         return new_xyz, idx
 
+    def sample(self, xyz):
+        """FPS half of geometry(): xyz [B,3,N] -> new_xyz [B,S,3] (:124-125)."""
+        _check_module_inputs(xyz, None)
+        _, new_xyz = ops.farthest_point_sample(xyz.permute(0, 2, 1), self.npoint, return_xyz=True,
+                                               staging=self._staging(xyz.shape[0], xyz.shape[2], xyz.device))
+        return new_xyz
+
+    def ball_query(self, xyz, new_xyz):
+        """ball-query half of geometry(): xyz [B,3,N], new_xyz [B,S,3] -> idx [B,S,nsample] int64 (:126)."""
+        return ops.query_ball_point(self.radius, self.nsample, xyz.permute(0, 2, 1), new_xyz)
+
     def forward(self, xyz, points, geometry=None):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,D',S]."""
         _note_grad_mode()
@@ -840,12 +855,14 @@ class PointNetFeaturePropagation(nn.Module):
                 and conv2.out_channels <= 32 and bn1.num_features == conv1.out_channels)
 
     def forward_with_head(self, xyz1, xyz2, points1, points2, conv1, bn1, dropout, conv2, neighbours=None, loss_target=None,
-                          loss_weight=None):
+                          loss_weight=None, labels_out=None):
         """This level followed by `log_softmax(conv2(dropout(relu(bn1(conv1(.))))))` (pointnet2_sem_seg.py:36-38) in one
         chain of rows; returns the log-probabilities [B, N, classes] (already permuted as :39 does).
         loss_target [B*N] int64 (+ loss_weight [classes] fp32 or None): also evaluates F.nll_loss(pred, target, weight)
         (pointnet2_sem_seg.py:47-48) inside the head kernels and returns (log-probabilities, loss); the log-probabilities
-        are then detached (the gradient enters through the loss)."""
+        are then detached (the gradient enters through the loss).
+        labels_out: a contiguous int64 [B, N] CUDA tensor that receives argmax(log-probabilities, dim=2) from the same kernel
+        (not together with loss_target)."""
         _note_grad_mode()
         _check_module_inputs(xyz1, points1)
         _check_module_inputs(xyz2, points2)
@@ -855,7 +872,12 @@ class PointNetFeaturePropagation(nn.Module):
             seed = torch.randint(0, 2 ** 31 - 1, (1,), device=points2.device, dtype=torch.int64)
         convs, bns = list(self.mlp_convs) + [conv1], list(self.mlp_bns) + [bn1]
         params = _flat_params(convs, bns) + [conv2.weight] + ([conv2.bias] if conv2.bias is not None else [])
-        loss_args = None
+        extras = None
+        if labels_out is not None:
+            require_cuda(labels_out, "labels_out", torch.int64)
+            if loss_target is not None or not labels_out.is_contiguous() or labels_out.numel() != xyz1.shape[0] * xyz1.shape[2]:
+                raise ValueError("labels_out must be a contiguous int64 [B, N] tensor (and excludes loss_target)")
+            extras = {"labels": labels_out}
         if loss_target is not None:
             require_cuda(loss_target, "loss_target", torch.int64)
             if loss_target.numel() != xyz1.shape[0] * xyz1.shape[2]:
@@ -866,9 +888,9 @@ class PointNetFeaturePropagation(nn.Module):
                 if loss_weight.numel() != conv2.out_channels:
                     raise ValueError("loss_weight must hold one weight per class")
                 loss_weight = loss_weight.contiguous()
-            loss_args = (loss_target.contiguous().view(-1), loss_weight)
+            extras = {"loss": (loss_target.contiguous().view(-1), loss_weight)}
         return _FeaturePropagationHeadFn.apply(
-            neighbours, convs, bns, conv2, p, seed, loss_args, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
+            neighbours, convs, bns, conv2, p, seed, extras, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1),
             None if points1 is None else points1.permute(0, 2, 1), points2.permute(0, 2, 1), *params)
 
     def forward(self, xyz1, xyz2, points1, points2, neighbours=None):

@@ -7,6 +7,8 @@ The reference file itself also runs unchanged on top of ``models/pointnet2_utils
 copy exists because the reference tree is not present on the GPU box.  The head and the loss
 are ordinary PyTorch (they are outside the hot path).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -28,6 +30,17 @@ def _geometry_stream(dev):
     if s is None:
         s = _GEO_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
     return s
+
+
+_GEO_HELPERS = {}
+
+
+def _geometry_helpers(dev):
+    """two helper streams per device for get_model.geometry_all(fork=True)"""
+    h = _GEO_HELPERS.get(dev.index)
+    if h is None:
+        h = _GEO_HELPERS[dev.index] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return h
 
 
 class _NoWait:
@@ -73,19 +86,48 @@ class get_model(nn.Module):
                 events.append(side.record_event())
         return geo, nn3, events, main
 
-    def geometry_all(self, xyz0):
-        """The whole coordinate-only index pipeline of one batch on the CURRENT stream: (geo, nn3) as forward() takes
-        them through `geometry=`.  A pipelined caller (trainer.SemSegTrainer / SemSegPredictor with pipeline=True)
+    fork_geometry = os.environ.get("PN2_FORK_GEOMETRY", "1") != "0"      # geometry_all: ball queries and 3-NN searches on helper streams beside the FPS chain
+
+    def geometry_all(self, xyz0, fork=None):
+        """The whole coordinate-only index pipeline of one batch, issued from the CURRENT stream: (geo, nn3) as forward()
+        takes them through `geometry=`.  A pipelined caller (trainer.SemSegTrainer / SemSegPredictor with pipeline=True)
         runs it for batch i+1 while the feature path of batch i is still busy -- the 1 360-iteration FPS chain keeps
-        only B of the 148 SMs busy, so it hides completely behind the MLPs of the previous batch."""
-        geo, nn3 = [], []
+        only B of the 148 SMs busy, so it hides behind the MLPs of the previous batch.
+
+        fork (default: self.fork_geometry): only the four FPS calls depend on each other (level l+1 samples level l's
+        centroids); the ball query of level l and the 3-NN search between levels l and l+1 need FPS l only.  They are
+        issued on two helper streams that fork after each FPS and join at the end, so the branch takes
+        FPS1 + max(ball queries, 3-NN searches) ~ 0.58 ms instead of the 0.97 ms sum -- which had become the length of
+        the pipelined inference forward.  Same kernels, same results."""
+        fork = self.fork_geometry if fork is None else fork
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        if not (fork and xyz0.is_cuda):
+            geo, nn3 = [], []
+            coords = [xyz0]
+            for sa in sas:
+                g = sa.geometry(coords[-1])
+                geo.append(g)
+                coords.append(g[0].permute(0, 2, 1))
+            for fine, coarse in ((3, 4), (2, 3), (1, 2), (0, 1)):
+                nn3.append(PointNetFeaturePropagation.neighbours(coords[fine], coords[coarse]))
+            return geo, nn3
+        dev = xyz0.device
+        cur = torch.cuda.current_stream(dev)
+        balls, knn = _geometry_helpers(dev)
+        geo, nn3 = [None] * 4, [None] * 4
         coords = [xyz0]
-        for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
-            g = sa.geometry(coords[-1])
-            geo.append(g)
-            coords.append(g[0].permute(0, 2, 1))
-        for fine, coarse in ((3, 4), (2, 3), (1, 2), (0, 1)):
-            nn3.append(PointNetFeaturePropagation.neighbours(coords[fine], coords[coarse]))
+        for level, sa in enumerate(sas):
+            new_xyz = sa.sample(coords[-1])                      # FPS on the issuing stream: the dependent chain
+            coords.append(new_xyz.permute(0, 2, 1))
+            ready = cur.record_event()
+            balls.wait_event(ready)
+            with torch.cuda.stream(balls):
+                geo[level] = (new_xyz, sa.ball_query(coords[level], new_xyz))
+            knn.wait_event(ready)
+            with torch.cuda.stream(knn):                         # nn3 is ordered fp4 .. fp1: (fine, coarse) = (level, level + 1)
+                nn3[3 - level] = PointNetFeaturePropagation.neighbours(coords[level], coords[level + 1])
+        cur.wait_stream(balls)
+        cur.wait_stream(knn)
         return geo, nn3
 
     @staticmethod
@@ -109,7 +151,20 @@ class get_model(nn.Module):
         loss = get_loss()(pred.contiguous().view(-1, pred.shape[-1]), target.view(-1), l4_points, weight)
         return loss, pred, l4_points
 
-    def _forward(self, xyz, geometry, loss_args):
+    def forward_labels(self, xyz, geometry=None):
+        """forward() plus the arg-max labels the test loop takes from it (localfunctions.py:398-400:
+        `seg_pred.contiguous().cpu().data.max(2)[1]`) -> (labels [B, N] int64, pred, l4_points).  With the fused head the
+        labels come out of the head kernel itself (no separate arg-max pass over the [B, N, classes] log-probabilities)."""
+        if xyz.is_cuda:
+            labels = torch.empty(xyz.shape[0], xyz.shape[2], device=xyz.device, dtype=torch.int64)
+            out = self._forward(xyz, geometry, None, labels)
+            if len(out) == 3:
+                return labels, out[0], out[1]
+        else:
+            out = self._forward(xyz, geometry, None)
+        return out[0].argmax(dim=2), out[0], out[1]
+
+    def _forward(self, xyz, geometry, loss_args, labels_out=None):
         feats = [xyz]
         coords = [xyz[:, :3, :]]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
@@ -146,6 +201,10 @@ class get_model(nn.Module):
                                                       self.conv2, neighbours=nn3[i] if ahead else None,
                                                       loss_target=loss_args[0], loss_weight=loss_args[1])
                     return pred, l4_points, loss
+                if labels_out is not None:
+                    pred = fp.forward_with_head(coords[0], coords[1], skip, up, self.conv1, self.bn1, self.drop1, self.conv2,
+                                                neighbours=nn3[i] if ahead else None, labels_out=labels_out)
+                    return pred, l4_points, labels_out
                 pred = fp.forward_with_head(coords[0], coords[1], skip, up, self.conv1, self.bn1, self.drop1, self.conv2,
                                             neighbours=nn3[i] if ahead else None)
                 return pred, l4_points

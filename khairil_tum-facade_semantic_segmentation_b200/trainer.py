@@ -554,8 +554,7 @@ class SemSegPredictor:
                 self._geo_stream.wait_stream(main)
                 with torch.cuda.stream(self._geo_stream), ops.reuse_outputs(self._slots[1 - k][1]):
                     self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :])
-            log_probs, _ = self._forward(k)                                    # [B, npoint, classes]
-            labels = log_probs.argmax(dim=2)
+            labels, log_probs, _ = self._forward(k)                            # [B, npoint], [B, npoint, classes]
             if self.pipeline:
                 main.wait_stream(self._geo_stream)
         self._graphs.append(graph)
@@ -563,9 +562,13 @@ class SemSegPredictor:
         self._labels.append(labels)
 
     def _forward(self, k):
-        if not self.pipeline:
-            return self.model(self._pts[k].transpose(2, 1))
-        return self.model(self._pts[k].transpose(2, 1), geometry=self._slots[k][0])
+        """(labels, log-probabilities, l4 features) of slot k; the labels come out of the head kernel when it is fused"""
+        x = self._pts[k].transpose(2, 1)
+        geometry = self._slots[k][0] if self.pipeline else None
+        if hasattr(self.model, "forward_labels"):
+            return self.model.forward_labels(x, geometry=geometry)
+        pred, feat = self.model(x) if geometry is None else self.model(x, geometry=geometry)
+        return pred.argmax(dim=2), pred, feat
 
     def _replay(self, k=0):
         if self._start_group is not None:

@@ -36,8 +36,10 @@ def test_head_tail_forward_backward_no_dropout(lib, M, C, NC):
     z, scale, shift, W2, b2 = _case(M, C, NC, M + NC)
     logp = torch.empty(M, NC, device=DEV)
     act = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    labels = torch.full((M,), -1, device=DEV, dtype=torch.int64)
     lib.call("pn2_head_tail_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
-             None, lib.ptr(logp), lib.ptr(act), C, lib.stream())
+             None, lib.ptr(logp), lib.ptr(act), C, lib.ptr(labels), lib.stream())
+    assert torch.equal(labels, logp.argmax(dim=1))                      # fused arg-max == torch.argmax of the stored values
     a = torch.relu(z.double() * scale.double() + shift.double()).requires_grad_(True)
     want = torch.log_softmax(a @ W2.double().t() + b2.double(), dim=1)
     assert float((logp.double() - want).abs().max()) < 1e-4
@@ -71,7 +73,7 @@ def test_head_tail_dropout_is_consistent_and_unbiased(lib):
         logp = torch.empty(M, NC, device=DEV)
         act = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
         lib.call("pn2_head_tail_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.5,
-                 lib.ptr(seed), lib.ptr(logp), lib.ptr(act), C, lib.stream())
+                 lib.ptr(seed), lib.ptr(logp), lib.ptr(act), C, None, lib.stream())
         outs.append((logp, act, seed))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])      # same seed, same mask
     assert not torch.equal(outs[0][1], outs[2][1])                                           # another seed, another mask
@@ -157,7 +159,7 @@ def test_head_tail_fused_loss_matches_nll_loss(lib, M, C, NC, weighted):
     logp_a, logp_b = torch.empty(M, NC, device=DEV), torch.empty(M, NC, device=DEV)
     act_a, act_b = (torch.empty(M, C, device=DEV, dtype=torch.bfloat16) for _ in range(2))
     lib.call("pn2_head_tail_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
-             None, lib.ptr(logp_a), lib.ptr(act_a), C, lib.stream())
+             None, lib.ptr(logp_a), lib.ptr(act_a), C, None, lib.stream())
     accum = torch.zeros(64, device=DEV, dtype=torch.float64)
     loss = torch.full((2,), float("nan"), device=DEV)
     lib.call("pn2_head_tail_loss_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
@@ -240,3 +242,19 @@ def test_forward_loss_matches_forward_plus_get_loss(pn2):
         assert abs(float(loss_e) - float(want)) < 1e-5
     finally:
         pn2.set_precision("fp32")
+
+
+def test_head_tail_argmax_takes_first_maximum_on_ties(lib):
+    """Rows whose logits tie exactly (identical W2 rows / zero activations): labels == torch.argmax (lowest index)."""
+    M, C, NC = 300, 64, 18
+    z, scale, shift, W2, b2 = _case(M, C, NC, 11)
+    W2[7] = W2[3]
+    W2[12] = W2[3]
+    b2[7] = b2[12] = b2[3] = 2.5                      # classes 3, 7, 12 always tie, and usually win
+    z[100:200] = -50.0                               # relu -> all-zero activations: logits == b2 exactly
+    logp = torch.empty(M, NC, device=DEV)
+    labels = torch.full((M,), -1, device=DEV, dtype=torch.int64)
+    lib.call("pn2_head_tail_fwd", lib.ptr(z), C, lib.ptr(scale), lib.ptr(shift), lib.ptr(W2), lib.ptr(b2), M, C, NC, 0.0,
+             None, lib.ptr(logp), None, 0, lib.ptr(labels), lib.stream())
+    assert torch.equal(labels, logp.argmax(dim=1))
+    assert int((labels == 3).sum()) > 100 and int((labels == 7).sum()) == 0 and int((labels == 12).sum()) == 0
