@@ -10,6 +10,7 @@ gradient buffer (~3.9 MB) over NCCL/NVLink per step.  BatchNorm statistics stay 
 """
 import contextlib
 import gc
+import os
 
 import torch
 import torch.distributed as dist
@@ -30,6 +31,15 @@ def _no_gc():
     finally:
         if was:
             gc.enable()
+
+
+def _capture_stream(dev):
+    """The stream a step / forward graph is captured on: HIGH priority, so its kernel nodes win the block scheduler
+    against the index-pipeline branch (captured from default-priority streams).  Without it the big-grid ball-query and
+    3-NN kernels of the next batch, once launched, keep every free block slot until their last wave and the feature
+    path's next kernel waits ~0.1 ms behind them although it is the critical path.  PN2_MAIN_PRIORITY=0 switches it off."""
+    prio = int(os.environ.get("PN2_MAIN_PRIORITY", "-1"))
+    return torch.cuda.Stream(device=dev, priority=prio)
 
 
 def shard_range(n_items, rank, world):
@@ -300,6 +310,9 @@ class SemSegTrainer:
         for m in self._sa:
             m.use_static_start_buffers(True)
         self._pipeline, self._primed, self._parity, self._start_group = bool(pipeline), False, 0, None
+        # training hides the whole index branch behind ~3 ms of feature work: issuing it as ONE chain disturbs the feature
+        # path least (measured: 3.02 vs 3.05 ms per step with the branch forked over helper streams); PN2_TRAIN_FORK=1 forks
+        self._fork = os.environ.get("PN2_TRAIN_FORK", "0") != "0"
         n_slots = 2 if pipeline else 1
         self._pts = [torch.zeros(batch_clouds, npoint, channels, device=dev).uniform_(-0.5, 0.5) for _ in range(n_slots)]
         self._tgt = [torch.zeros(batch_clouds * npoint, dtype=torch.int64, device=dev) for _ in range(n_slots)]
@@ -315,7 +328,7 @@ class SemSegTrainer:
             with torch.no_grad():       # persistent index tensors of the two slots (outside any graph pool)
                 for k in range(2):
                     with ops.record_outputs() as rec:
-                        geo = self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
+                        geo = self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :], fork=self._fork)
                     self._slots[k] = (geo, rec.tensors)
         side.wait_stream(torch.cuda.current_stream(dev))
         saved = [(p.detach().clone()) for p in self.model.state_dict().values()]
@@ -342,13 +355,13 @@ class SemSegTrainer:
         for k in range(n_slots):
             graph = torch.cuda.CUDAGraph()
             pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}     # never replayed concurrently
-            with _no_gc(), torch.cuda.graph(graph, **pool):
+            with _no_gc(), torch.cuda.graph(graph, stream=_capture_stream(dev), **pool):
                 if pipeline:
                     main = torch.cuda.current_stream(dev)
                     self._geo_stream.wait_stream(main)
                     with torch.cuda.stream(self._geo_stream), torch.no_grad():
                         with ops.reuse_outputs(self._slots[1 - k][1]):
-                            self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :])
+                            self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :], fork=self._fork)
                     loss = self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])
                     main.wait_stream(self._geo_stream)
                 else:
@@ -383,7 +396,7 @@ class SemSegTrainer:
         self._augment(self._pts[k])
         if not self._primed:                          # first batch: only its index pipeline, eagerly
             with torch.no_grad(), ops.reuse_outputs(self._slots[k][1]):
-                self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :])
+                self.model.geometry_all(self._pts[k].transpose(2, 1)[:, :3, :], fork=self._fork)
             self._primed = True
             return None
         self._pre_replay()
@@ -548,7 +561,7 @@ class SemSegPredictor:
         from . import ops
         graph = torch.cuda.CUDAGraph()
         pool = {} if not self._graphs else {"pool": self._graphs[0].pool()}         # never replayed concurrently
-        with _no_gc(), torch.no_grad(), torch.cuda.graph(graph, **pool):
+        with _no_gc(), torch.no_grad(), torch.cuda.graph(graph, stream=_capture_stream(dev), **pool):
             if self.pipeline:
                 main = torch.cuda.current_stream(dev)
                 self._geo_stream.wait_stream(main)
