@@ -28,8 +28,9 @@ ENTRY = [
     (r"interp_bwd_kernel", "pn2_interp_bwd"),
     (r"group_points_bwd", "pn2_group_points_bwd"),
     (r"group_points", "pn2_group_points"),
-    (r"head_tail_fwd_kernel", "pn2_head_tail_fwd"),
-    (r"head_tail_bwd_kernel", "pn2_head_tail_bwd"),
+    (r"head_tail_fwd_kernel", "pn2_head_tail_loss_fwd"),       # the training step calls the tail fused with the loss
+    (r"head_tail_bwd_kernel", "pn2_head_tail_loss_bwd"),
+    (r"adam_flat_kernel", "pn2_adam_step"),
     (r"rows_to_f32_kernel", "pn2_rows_to_f32"),
     (r"pack_weights", "pn2_pack_weights"),
 ]

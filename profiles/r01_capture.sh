@@ -18,6 +18,7 @@ full bn_bwd_sa1 'bn_bwd_(dz|reduce)_vec8' 32 4
 full linear_tc2_fp1 'linear_tc2_kernel' 14 4
 full geometry 'fps_kernel|ball_query_kernel|three_nn_kernel' 0 3
 full pool_tail 'pool_bwd_dz|bn_relu_max' 0 2
+full head_adam 'head_tail_fwd_kernel|head_tail_bwd_kernel|adam_flat_kernel' 0 3
 python profiles/trace_step.py train gpurun_out/r01_trace_train_pipelined.csv
 python profiles/trace_step.py forward gpurun_out/r01_trace_forward_pipelined.csv
 ls -la gpurun_out/r01_*
