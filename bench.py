@@ -283,7 +283,7 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # =================================================================================================
@@ -372,7 +372,7 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
                              % (b * S * N / (ball_ms * 1e-3) / 1e12, fps_ms, fps_ms * 1e3 / S, 16)},
         "cpu_baseline": cpu, "kernel_ms": {"fps": fps_ms, "ball_query": ball_ms},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
@@ -470,7 +470,7 @@ def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
                 "d2h_bytes_per_step": int(P / n_batches), "ms_per_step": ms / n_batches},
         "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_facade(args, rank, world, dev, pn2, barrier, sampler):
@@ -553,10 +553,33 @@ def run_facade(args, rank, world, dev, pn2, barrier, sampler):
                 "d2h_bytes_per_step": int(n_scene * 8 / n_batches), "ms_per_step": ms / n_batches},
         "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything a library writes to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG=VERSION is
+    in the environment) goes to stderr; the ONE JSON line of the contract is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -789,7 +812,7 @@ def main():
     if unpipelined_ms is not None:
         line["unpipelined"] = {"ms_per_step": unpipelined_ms.item(), "value": points_per_step / (unpipelined_ms.item() * 1e-3), "unit": UNIT,
                                "what": "the same graph-replayed train step without overlapping consecutive batches (resident inputs)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     shutdown(world, trainer)
 
 

@@ -14,6 +14,6 @@ net = pn2.get_model(18, 3).cuda().eval()
 x = I.facade_batch(B, 4096, 9, 3).cuda().transpose(2, 1)
 with torch.no_grad():
     for _ in range(iters):
-        pred, _ = net(x)
+        labels, pred, _ = net.forward_labels(x)      # the test loop's forward + arg-max (localfunctions.py:398-400)
 torch.cuda.synchronize()
 print("ok", tuple(pred.shape))
