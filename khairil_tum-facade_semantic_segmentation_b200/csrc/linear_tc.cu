@@ -59,7 +59,7 @@ __global__ void pack_weight_kernel(const float *__restrict__ W, int64_t w_sn, in
 
 // One launch packs up to kPackJobs weights (every layer of an MLP, both orientations): job j owns blocks
 // [first_block[j], first_block[j+1]); its image is the concatenation over 256-row blocks of N of [KC][n_pad][128 B].
-constexpr int kPackJobs = 16;
+constexpr int kPackJobs = 48;      // the whole network (23 layers x 2 orientations) in one launch
 struct PackJobs {
     int n;
     const float *W[kPackJobs];

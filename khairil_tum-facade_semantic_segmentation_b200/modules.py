@@ -146,6 +146,54 @@ def _pack_weights(Ws, Ks, Ns, transposed, dev):
     return imgs
 
 
+_STEP_IMAGES = {}          # tuple(id(conv) for conv in an MLP) -> (forward images, data-gradient images) packed by prepack_mlps
+
+
+def _mlp_weights(convs, K0=None):
+    """([W [N, K] fp32 views], [K per layer], [N per layer]) of a conv chain; K0 checks the first layer's input width."""
+    Ws, Ks = [], []
+    K = K0
+    for conv in convs:
+        N = conv.out_channels
+        W = conv.weight.detach().reshape(N, -1)
+        if not W.is_contiguous():
+            W = W.contiguous()
+        if K is None:
+            K = W.shape[1]
+        if W.shape[1] != K or W.dtype != torch.float32:
+            raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
+        Ws.append(W)
+        Ks.append(K)
+        K = N
+    return Ws, Ks, Ks[1:] + [K]
+
+
+def prepack_mlps(chains):
+    """The bf16 tensor-core weight images (both orientations) of SEVERAL MLPs in ONE launch, ahead of a training step:
+    `chains` lists the conv chains the coming forward will run (get_model.training_chains()).  mlp_forward picks its
+    images up from here instead of packing per MLP (8 launches of 2-6 us each on the feature path's critical path).
+    Images are valid for ONE forward: call again after the parameters changed (every optimizer step)."""
+    _STEP_IMAGES.clear()
+    if ops.rows_dtype() != torch.bfloat16:
+        return
+    Ws, Ks, Ns, tr, spans = [], [], [], [], []
+    for convs in chains:
+        convs = list(convs)
+        if not convs or not convs[0].weight.is_cuda:
+            continue
+        w, k, n = _mlp_weights(convs)
+        spans.append((tuple(id(c) for c in convs), len(Ws), len(w)))
+        Ws += w + w
+        Ks += k + k
+        Ns += n + n
+        tr += [0] * len(w) + [1] * len(w)
+    if not Ws:
+        return
+    imgs = _pack_weights(Ws, Ks, Ns, tr, Ws[0].device)
+    for key, first, n_l in spans:
+        _STEP_IMAGES[key] = (imgs[first:first + n_l], imgs[first + n_l:first + 2 * n_l])
+
+
 def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     """relu(bn(conv(.))) chain on rows (pointnet2_utils.py:196-198 / :311-314) up to the last
     layer's pre-BN product; the caller applies the last BN+ReLU fused with its tail."""
@@ -153,18 +201,7 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     x, ldx, K = x0, x0.shape[1], K0
     in_scale = in_shift = None
     layers = []
-    Ws, Ks = [], []
-    for conv in convs:
-        N = conv.out_channels
-        W = conv.weight.detach().reshape(N, -1)
-        if not W.is_contiguous():
-            W = W.contiguous()
-        if W.shape[1] != K or W.dtype != torch.float32:
-            raise ValueError("conv weight %s does not match %d input channels (fp32)" % (tuple(conv.weight.shape), K))
-        Ws.append(W)
-        Ks.append(K)
-        K = N
-    Ns = Ks[1:] + [K]
+    Ws, Ks, Ns = _mlp_weights(convs, K0)
     K = K0
     fwd_img = bwd_img = None
     # pure inference (every BatchNorm on running statistics, nothing to differentiate): folded (scale, shift) and the packed
@@ -174,6 +211,8 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
     new_fold = []
     if cached is not None:
         fwd_img = cached[0]
+    elif dtype == torch.bfloat16 and want_bwd and tuple(id(c) for c in convs) in _STEP_IMAGES:
+        fwd_img, bwd_img = _STEP_IMAGES.pop(tuple(id(c) for c in convs))      # packed for the whole network by prepack_mlps
     elif dtype == torch.bfloat16:
         # every layer's weight image (and, for a backward pass, its transposed image for the data gradient) in one launch;
         # the first layer's data gradient is only needed when the MLP input wants a gradient -- pack it anyway, it is tiny

@@ -151,6 +151,15 @@ class get_model(nn.Module):
         loss = get_loss()(pred.contiguous().view(-1, pred.shape[-1]), target.view(-1), l4_points, weight)
         return loss, pred, l4_points
 
+    def training_chains(self):
+        """The conv chains forward() will run as MLPs, for modules.prepack_mlps (one weight-pack launch per step)."""
+        chains = [m.mlp_convs for m in (self.sa1, self.sa2, self.sa3, self.sa4, self.fp4, self.fp3, self.fp2)]
+        fp1 = self.fp1
+        fused = self.fused_head and type(fp1) is PointNetFeaturePropagation and fp1.head_applies(
+            self.conv1, self.bn1, self.conv2, self.conv1.weight)
+        chains.append(list(fp1.mlp_convs) + [self.conv1] if fused else fp1.mlp_convs)
+        return chains
+
     def forward_labels(self, xyz, geometry=None):
         """forward() plus the arg-max labels the test loop takes from it (localfunctions.py:398-400:
         `seg_pred.contiguous().cpu().data.max(2)[1]`) -> (labels [B, N] int64, pred, l4_points).  With the fused head the

@@ -247,6 +247,7 @@ class SemSegTrainer:
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
         self.fused_loss = bool(fused_loss)
+        self.prepack = os.environ.get("PN2_PREPACK", "1") != "0"
         self._rot_staging = None
         self.device = torch.device(device)
         self.num_classes = num_classes
@@ -265,6 +266,8 @@ class SemSegTrainer:
 
     def _step_impl(self, points, target, geometry=None):
         self.grads.zero()
+        if self.prepack and hasattr(self.model, "training_chains") and points.is_cuda:
+            modules.prepack_mlps(self.model.training_chains())      # every MLP's weight images in one launch
         if self.fused_loss and hasattr(self.model, "forward_loss"):
             # forward + weighted NLL in one pass (the loss and its gradient come out of the head kernels when they apply)
             loss, _, _ = self.model.forward_loss(points.transpose(2, 1), target, self.class_weights, geometry=geometry)
@@ -274,6 +277,7 @@ class SemSegTrainer:
             else:
                 pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
             loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
+        modules._STEP_IMAGES.clear()          # images a forward did not pick up must not outlive the parameters they were packed from
         loss.backward()
         self.grads.adopt()
         self.grads.all_reduce_mean()
