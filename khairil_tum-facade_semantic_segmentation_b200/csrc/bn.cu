@@ -593,6 +593,69 @@ extern "C" int pn2_bn_bwd_finalize(double *accum, int C, float *dgamma, float *d
     return check_launch("bn_bwd_finalize");
 }
 
+// Dense bf16 dA / Z / dZ with C % 8 == 0 and 256 % (C/8) == 0 (every layer width of the network): a thread owns 8 channels --
+// its 32 coefficients (sc, sh, a, b) stay in REGISTERS for the whole kernel -- of every (256 / (C/8))-th row of the block's
+// contiguous row range, U rows (2U 16-byte loads) in flight.  bn_bwd_dz_vec8_kernel re-reads the four coefficients of every
+// element from shared memory (~26 LDS per 16 bytes of dZ: half of the issue slots on the 1 M-row layers, ncu: 51 % issue,
+// mio_throttle) and keeps one row in flight per thread.  dZ may alias dA (a thread reads its chunks before it writes them).
+template <int U>
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_dz_rows_kernel(const __nv_bfloat16 *dA, int ldda, const __nv_bfloat16 *__restrict__ Z, int ldz,
+                      const float *__restrict__ scale, const float *__restrict__ shift,
+                      const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                      const float *__restrict__ dgamma, const float *__restrict__ dbeta, int64_t M, int C, float inv_m,
+                      __nv_bfloat16 *dZ, int lddz) {
+    const int cpr = C >> 3;
+    const int c8 = threadIdx.x % cpr, rl = threadIdx.x / cpr, rstep = 256 / cpr;
+    const int c0 = c8 << 3;
+    float sc[8], sh[8], ca[8], cb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = scale[c0 + e];
+        sh[e] = shift[c0 + e];
+        ca[e] = cb[e] = 0.0f;
+        if (save_mean) {
+            ca[e] = -sc[e] * dgamma[c0 + e] * save_invstd[c0 + e] * inv_m;
+            cb[e] = -sc[e] * dbeta[c0 + e] * inv_m - ca[e] * save_mean[c0 + e];
+        }
+    }
+    const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(M, r_begin + rows_per_block);
+    for (int64_t r = r_begin + rl; r < r_end; r += (int64_t)rstep * U) {
+        uint4 zr[U], gr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = r + (int64_t)u * rstep;
+            if (rr < r_end) {
+                zr[u] = *reinterpret_cast<const uint4 *>(Z + rr * ldz + c0);
+                gr[u] = *reinterpret_cast<const uint4 *>(dA + rr * ldda + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t rr = r + (int64_t)u * rstep;
+            if (rr >= r_end) break;
+            const uint32_t *zw = reinterpret_cast<const uint32_t *>(&zr[u]);
+            const uint32_t *gw = reinterpret_cast<const uint32_t *>(&gr[u]);
+            uint4 out;
+            uint32_t *ow = reinterpret_cast<uint32_t *>(&out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&zw[i]));
+                const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gw[i]));
+                const float g0 = (fmaf(z.x, sc[2 * i], sh[2 * i]) > 0.0f) ? g.x : 0.0f;
+                const float g1 = (fmaf(z.y, sc[2 * i + 1], sh[2 * i + 1]) > 0.0f) ? g.y : 0.0f;
+                const float d0 = fmaf(sc[2 * i], g0, fmaf(ca[2 * i], z.x, cb[2 * i]));
+                const float d1 = fmaf(sc[2 * i + 1], g1, fmaf(ca[2 * i + 1], z.y, cb[2 * i + 1]));
+                const __nv_bfloat162 o = __floats2bfloat162_rn(d0, d1);
+                ow[i] = *reinterpret_cast<const uint32_t *>(&o);
+            }
+            *reinterpret_cast<uint4 *>(dZ + rr * lddz + c0) = out;
+        }
+    }
+}
+
 // Pooled variant of bn_bwd_dz_vec8_kernel with the group's gradient and arg-max map loaded ONCE per thread for KU samples:
 // the per-sample form re-reads 64 bytes of (dOut, arg) from L2 for every 16 bytes of Z, which made it L2-bound (1.8 TB/s of
 // HBM traffic on sa1); here the ratio is 64 : 16*KU and the KU row loads are in flight together.
@@ -680,6 +743,17 @@ static int dz_dispatch(const void *dA, int ldda, int da_dtype, const int32_t *ar
                 nsample, C, inv_m, (__nv_bfloat16 *)dZ, lddz);
             count_launch();
             return check_launch("pool_bwd_dz_vec8");
+        }
+        if (!POOL && 256 % (C / 8) == 0) {
+            constexpr int U = 3;
+            const int per_pass = (256 / (C / 8)) * U;
+            const int64_t want = (M + per_pass - 1) / per_pass;
+            const int rgrid = (int)(want < 1 ? 1 : (want > 3 * kNumSMs ? 3 * kNumSMs : want));
+            bn_bwd_dz_rows_kernel<U><<<rgrid, 256, 0, st>>>((const __nv_bfloat16 *)dA, ldda, (const __nv_bfloat16 *)Z, ldz, scale,
+                                                            shift, save_mean, save_invstd, dgamma, dbeta, M, C, inv_m,
+                                                            (__nv_bfloat16 *)dZ, lddz);
+            count_launch();
+            return check_launch("bn_bwd_dz_rows");
         }
         const int vgrid = grid_for(M * (C / 8), 256, kNumSMs * 8);
         bn_bwd_dz_vec8_kernel<POOL><<<vgrid, 256, sizeof(float) * 4 * C, st>>>(

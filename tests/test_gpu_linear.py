@@ -239,6 +239,11 @@ def test_bn_relu_backward_kernels(lib, M, C, mode, train, ns):
         want = scale.double() * gm
     err = ((dZ[:, :C].double() - want).abs() / (want.abs() + 1.0)).max().item()
     assert err <= (2.0 ** -7 if dzt == torch.bfloat16 else 1e-5), err
+    if mode == "bf16":                       # in place (dZ aliases dA), as modules.mlp_backward calls it: same bits
+        lib.call("pn2_bn_relu_bwd_dz", lib.ptr(dA), ldda, lib.dt(dA), lib.ptr(Z), ldz, lib.dt(Z), lib.ptr(scale),
+                 lib.ptr(shift), mu_p, is_p, lib.ptr(dgb[0]), lib.ptr(dgb[1]), M, C, lib.ptr(dA), ldda, lib.dt(dA),
+                 lib.stream())
+        assert torch.equal(dA[:, :C], dZ[:, :C])
 
 
 # ---- the launch-saving variants: one pack launch for many weights, prepacked layer calls with the train-mode
