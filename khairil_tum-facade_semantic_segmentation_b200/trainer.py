@@ -247,7 +247,7 @@ class SemSegTrainer:
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
         self.fused_loss = bool(fused_loss)
-        self.prepack = os.environ.get("PN2_PREPACK", "1") != "0"
+        self.prepack = True                  # every MLP's weight images in one launch per step (modules.prepack_mlps)
         self._rot_staging = None
         self.device = torch.device(device)
         self.num_classes = num_classes
