@@ -795,7 +795,7 @@ def main():
                    "parallelism": "dp%d (blocks sharded, flat-gradient NCCL all-reduce)" % world,
                    "l2": "256 MiB buffer written between timed steps (L2 flush), outside the per-step events",
                    "optimizer": "Adam(lr 1e-3, wd 1e-4) inside the step",
-                   "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
+                   "launch": ("whole step replayed as one CUDA graph" + (" (two captured graphs alternate over two input/index slots)" if pipelined else "")) if graphed else "eager launches",
                    "pipeline": ("depth 2: inside the graph the index pipeline (FPS, ball query, 3-NN) of the batch submitted by this call runs "
                                 "beside forward/backward/Adam of the batch submitted by the previous call; every step does one batch of each; "
                                 "the loss read back is the previous batch's; e2e adds two stages: the host->device copy of a batch runs on a copy "

@@ -139,7 +139,7 @@ def test_trainer_rotation_augmentation_uses_reference_draws(pn2):
         want = O.rotate_z(pts[:, :, :3].cpu().numpy(), ang)
         if mode == "eager":
             continue                                                        # (the rotated clone is not kept)
-        seen = tr._g_points if mode == "graph" else tr._g_points            # pipeline: shifted into the current slot
+        seen = tr._g_points                                                 # the slot of the batch submitted last (both modes)
         if mode == "pipeline":
             torch.cuda.synchronize()
         assert np.array_equal(seen[:, :, :3].cpu().numpy(), want), mode
