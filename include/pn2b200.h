@@ -129,13 +129,16 @@ int pn2_pack_weights(int n, const float *const *W_host, const int *K_host, const
                      const int *transposed_host, void *const *wpack_host, void *stream);
 /* Train-mode BatchNorm finalize fused into the layer kernel: the CTA that draws the last ticket does what
  * pn2_bn_train_finalize does (same fields) and leaves stat_accum and *ticket zeroed.  ticket: a zero-initialised
- * uint32 in device memory, reusable by consecutive calls on one stream. */
+ * uint32 in device memory, reusable by consecutive calls on one stream.  momentum_dev (may be NULL): a float in DEVICE
+ * memory read at run time instead of `momentum`, so that a captured CUDA graph follows the reference's per-epoch
+ * BatchNorm-momentum schedule (localfunctions.py:191-195) without re-capture. */
 typedef struct pn2_bn_finalize {
     uint32_t *ticket;
     const float *gamma, *beta, *conv_bias;
     float eps, momentum;
     float *running_mean, *running_var, *scale, *shift, *save_mean, *save_invstd;
     int64_t *num_batches_tracked;
+    const float *momentum_dev;
 } pn2_bn_finalize;
 /* pn2_linear_fwd with wpack ALREADY holding the image (pn2_pack_weights) and, when fin_host (a HOST struct of device
  * pointers) is non-NULL, the BatchNorm finalize of the layer's statistics fused in (stat_accum required). */

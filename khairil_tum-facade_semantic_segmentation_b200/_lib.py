@@ -82,7 +82,7 @@ class BnFinalize(ctypes.Structure):
     """pn2_bn_finalize of include/pn2b200.h (a HOST struct of device pointers)."""
     _fields_ = [("ticket", _p), ("gamma", _p), ("beta", _p), ("conv_bias", _p), ("eps", _f), ("momentum", _f),
                 ("running_mean", _p), ("running_var", _p), ("scale", _p), ("shift", _p), ("save_mean", _p),
-                ("save_invstd", _p), ("num_batches_tracked", _p)]
+                ("save_invstd", _p), ("num_batches_tracked", _p), ("momentum_dev", _p)]
 
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -145,6 +145,7 @@ extern "C" int pn2_linear_fwd_prepacked(const void *X, int ldx, int x_dtype, con
     int rc = simt_linear_nt(X, ldx, x_dtype, in_scale, in_shift, W, K, 1, bias, M, K, N, Z, ldz, z_dtype, stat_accum,
                             (cudaStream_t)stream);
     if (rc != PN2_OK || !fin_host) return rc;
+    PN2_REQUIRE(!fin.momentum_dev, "linear_fwd_prepacked: momentum_dev needs the fused (tensor-core) finalize");
     return pn2_bn_train_finalize(stat_accum, M, N, fin.gamma, fin.beta, fin.conv_bias, fin.eps, fin.momentum,
                                  fin.running_mean, fin.running_var, fin.scale, fin.shift, fin.save_mean, fin.save_invstd,
                                  (int64_t *)fin.num_batches_tracked, stream);

@@ -78,6 +78,7 @@ struct BnFinalize {           // device pointers; mirrors pn2_bn_finalize of inc
     float eps, momentum;
     float *running_mean, *running_var, *scale, *shift, *save_mean, *save_invstd;
     long long *num_batches_tracked;
+    const float *momentum_dev;     // when non-null: the momentum, read at run time (graph replays follow a schedule)
 };
 __device__ __forceinline__ void bn_finalize_channel(double s1, double s2, int64_t M, int c, const float *gamma,
                                                     const float *beta, const float *conv_bias, float eps, float momentum,

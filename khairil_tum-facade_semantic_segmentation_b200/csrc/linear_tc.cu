@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                             acc[a.stat_ld + c] = 0.0;
                         }
                         bn_finalize_channel(s1, s2, a.M, b_stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
-                                            a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
+                                            a.fin.momentum_dev ? __ldg(a.fin.momentum_dev) : a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
                                             a.fin.save_mean, a.fin.save_invstd);
                     }
                     if (tid == 0) {
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                             acc[a.stat_ld + c] = 0.0;
                         }
                         bn_finalize_channel(s1, s2, a.M, b_stat_off + c, a.fin.gamma, a.fin.beta, a.fin.conv_bias, a.fin.eps,
-                                            a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
+                                            a.fin.momentum_dev ? __ldg(a.fin.momentum_dev) : a.fin.momentum, a.fin.running_mean, a.fin.running_var, a.fin.scale, a.fin.shift,
                                             a.fin.save_mean, a.fin.save_invstd);
                     }
                     if (tid == 0) {

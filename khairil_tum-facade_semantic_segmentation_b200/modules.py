@@ -14,6 +14,7 @@ One autograd.Function per module: forward = FPS -> ball query -> gather -> MLP
 import contextlib
 import ctypes
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -146,6 +147,18 @@ def _pack_weights(Ws, Ks, Ns, transposed, dev):
     return imgs
 
 
+_MOMENTUM_DEV = weakref.WeakKeyDictionary()      # BatchNorm module -> 1-element fp32 CUDA tensor holding its momentum
+
+
+def set_momentum_buffers(mapping):
+    """mapping: {BatchNorm module: 1-element fp32 CUDA tensor}.  The fused BatchNorm finalize of a train-mode layer then
+    reads the momentum from that tensor at run time instead of baking `bn.momentum` into the launch, so a captured
+    training step follows the reference's per-epoch momentum schedule (localfunctions.py:191-195) without re-capture.
+    The owner (trainer.SemSegTrainer) keeps the tensors in step with `bn.momentum`."""
+    for bn, t in mapping.items():
+        _MOMENTUM_DEV[bn] = t
+
+
 _STEP_IMAGES = {}          # tuple(id(conv) for conv in an MLP) -> (forward images, data-gradient images) packed by prepack_mlps
 
 
@@ -245,9 +258,10 @@ def mlp_forward(x0, K0, M, convs, bns, want_bwd=True):
                 nbt = None
             update = bn.training and bn.running_mean is not None
             if wpack is not None:     # tensor-core rows: statistics -> scale/shift fused into the layer kernel
+                mom_dev = _MOMENTUM_DEV.get(bn) if (update and bn.momentum is not None) else None
                 fin = BnFinalize(ptr(_ticket(dev)), ptr(gamma), ptr(beta), ptr(bias), float(bn.eps), float(momentum),
                                  ptr(bn.running_mean) if update else None, ptr(bn.running_var) if update else None,
-                                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt))
+                                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), ptr(nbt), ptr(mom_dev))
                 call("pn2_linear_fwd_prepacked", ptr(x), ldx, dt(x), ptr(in_scale), ptr(in_shift), ptr(W), None, M, K, N,
                      ptr(z), ldz, dt(z), ptr(accum), ptr(wpack), ctypes.addressof(fin), stream())
             else:

@@ -90,6 +90,31 @@ class _HostStager:
         return [k for k in order if self.rows[k] is not None]
 
 
+class _BnMomentum:
+    """Every BatchNorm's momentum in ONE device tensor the fused finalize kernels read at run time
+    (modules.set_momentum_buffers), kept in step with `bn.momentum` by sync(): the reference's per-epoch schedule
+    (/root/reference/localfunctions.py:191-195, `m.momentum = momentum` on every BatchNorm1d/2d) reaches a captured
+    training step without re-capture, the way the learning rate does through FlatAdam's device hyper-parameters."""
+
+    def __init__(self, model, device):
+        self.bns = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        self.dev = torch.zeros(max(1, len(self.bns)), device=device, dtype=torch.float32)
+        self.host = torch.zeros(max(1, len(self.bns)), dtype=torch.float32).pin_memory()
+        self.seen = None
+        modules.set_momentum_buffers({bn: self.dev[i:i + 1] for i, bn in enumerate(self.bns)})
+        self.sync()
+
+    def sync(self):
+        now = tuple(-1.0 if bn.momentum is None else float(bn.momentum) for bn in self.bns)
+        if now != self.seen:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("BatchNorm momentum changed during CUDA-graph capture")
+            torch.cuda.synchronize(self.dev.device)          # rare (once per schedule step); the last copy may be in flight
+            self.host[:len(now)].copy_(torch.tensor(now, dtype=torch.float32))
+            self.dev.copy_(self.host, non_blocking=True)
+            self.seen = now
+
+
 class FlatGradients:
     """One flat fp32 buffer holding every parameter gradient, so data-parallel training needs a single
     all-reduce per step (no bucketing: the buffer is latency-, not bandwidth-bound).  The buffer is also the
@@ -250,11 +275,18 @@ class SemSegTrainer:
         self.prepack = True                  # every MLP's weight images in one launch per step (modules.prepack_mlps)
         self._rot_staging = None
         self.device = torch.device(device)
+        on_gpu = self.device.type == "cuda"
+        if on_gpu:
+            # one GPU per process: the library launches on the CURRENT device's streams (include/pn2b200.h takes a stream, not
+            # a device), so the trainer's device becomes the current one
+            torch.cuda.set_device(self.device)
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_classes = num_classes
         self.model = (model if model is not None else get_model(num_classes, num_extra_features)).to(self.device)
         self.criterion = get_loss()
+        self.broadcast_state()
         self.grads = FlatGradients(self.model.parameters())
-        on_gpu = self.device.type == "cuda"
+        self._bn_momentum = _BnMomentum(self.model, self.device) if on_gpu else None
         if on_gpu and flat_optimizer:
             self.optimizer = FlatAdam(self.grads, lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=weight_decay)
         else:
@@ -264,7 +296,28 @@ class SemSegTrainer:
         self.class_weights = (torch.ones(num_classes) if class_weights is None else class_weights).to(self.device)
         self._graph = None
 
+    def broadcast_state(self):
+        """Data-parallel replicas start (and, after a checkpoint load on rank 0, restart) from rank 0's parameters and
+        BatchNorm buffers -- DDP's construction-time broadcast.  Afterwards the replicas only exchange gradients; the running
+        statistics stay per rank and rank 0's are the ones a checkpoint should save.  No-op without an
+        initialised process group."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            with torch.no_grad():
+                for t in self.model.state_dict().values():
+                    dist.broadcast(t, src=0)
+
+    def release_graphs(self):
+        """Drop every captured graph (and what only they keep alive).  NCCL requires the graphs that captured a
+        communicator's collectives to be destroyed before the communicator is."""
+        self.__dict__.pop("_graphs", None)
+        self.__dict__.pop("_g_losses", None)
+        self._graph = self._g_loss = None
+        self._slots = []
+        gc.collect()
+
     def _step_impl(self, points, target, geometry=None):
+        if self._bn_momentum is not None and not torch.cuda.is_current_stream_capturing():
+            self._bn_momentum.sync()
         self.grads.zero()
         if self.prepack and hasattr(self.model, "training_chains") and points.is_cuda:
             modules.prepack_mlps(self.model.training_chains())      # every MLP's weight images in one launch
@@ -289,8 +342,10 @@ class SemSegTrainer:
         CUDA graph replayed per step: the ~300 kernel launches of a step cost no host time any more.
         Inputs are copied into static buffers; the FPS start indices stay a fresh CPU-generator draw per
         step (drawn on the host before each replay into a pinned ring, one host->device copy ahead of the replay).
-        Re-capture after changing BatchNorm momentum (FlatAdam reads the learning rate from device memory: no re-capture;
-        torch.optim.Adam bakes it in).
+        The reference's per-epoch schedules need no re-capture with bf16 rows: FlatAdam reads the learning rate and the fused
+        BatchNorm finalize reads each module's momentum from device memory (torch.optim.Adam / fp32 rows bake them in:
+        re-capture after changing them).  Re-capturing keeps the optimizer state (moments, step counter) and the parameters;
+        it refuses to run while pipelined batches are in flight (flush() first).
 
         pipeline=True software-pipelines consecutive batches inside the graph: a forked branch runs the
         coordinate-only index pipeline (FPS, ball query, 3-NN: get_model.geometry_all) of the batch just SUBMITTED
@@ -308,6 +363,8 @@ class SemSegTrainer:
         from . import ops
         from .modules import PointNetSetAbstraction
         dev = self.device
+        if getattr(self, "_pipeline", False) and (self._primed or self._stager.pending() or any(self._loss_valid)):
+            raise RuntimeError("enable_cuda_graph: batches are still in flight in the pipeline; call flush() first")
         rng_state = torch.get_rng_state()     # warm-up / capture must not advance the CPU generator the FPS start draws use
         self.model.train()
         self._sa = [m for m in self.model.modules() if isinstance(m, PointNetSetAbstraction) and not m.group_all]
@@ -336,6 +393,10 @@ class SemSegTrainer:
                     self._slots[k] = (geo, rec.tensors)
         side.wait_stream(torch.cuda.current_stream(dev))
         saved = [(p.detach().clone()) for p in self.model.state_dict().values()]
+        # ... nor as optimizer steps: the moments and the step counter (a loaded checkpoint's, or those of the epochs trained
+        # so far when the caller re-captures) come back exactly as they were
+        saved_opt = {p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in self.optimizer.state.items()}
         geo0 = self._slots[0][0] if pipeline else None
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -351,10 +412,14 @@ class SemSegTrainer:
         with torch.no_grad():
             for t, s in zip(self.model.state_dict().values(), saved):
                 t.copy_(s)
-            for st in self.optimizer.state.values():
-                for v in st.values():
+            for p, st in self.optimizer.state.items():
+                old = saved_opt.get(p)
+                for k, v in st.items():
                     if torch.is_tensor(v):
-                        v.zero_()
+                        if old is not None and torch.is_tensor(old.get(k)):
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()              # state created by the warm-up itself: a zero state is a fresh state
         self._graphs, self._g_losses = [], []
         for k in range(n_slots):
             graph = torch.cuda.CUDAGraph()
@@ -417,6 +482,8 @@ class SemSegTrainer:
                 m.start_staging.draw()
         if isinstance(self.optimizer, FlatAdam):
             self.optimizer.sync_hyper()
+        if self._bn_momentum is not None:
+            self._bn_momentum.sync()
 
     def _take_loss(self, j):
         if not self._loss_valid[j]:

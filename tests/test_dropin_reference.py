@@ -1,34 +1,34 @@
-"""The reference's own models/pointnet2_sem_seg.py, UNCHANGED, on top of this repo's
-models/pointnet2_utils.py.  Needs /root/reference (authoring container only); the GPU half
-additionally needs a device, so it only runs where both exist."""
-import importlib
-import os
-import sys
+"""The reference's own files, UNCHANGED, on top of this repo's models/pointnet2_utils.py.
 
+The reference tree is /root/reference in the authoring container and the copy staged under oracle/_ref/ by
+oracle/fetch_reference.py (git-ignored, travels to the GPU box) everywhere else -- so these tests run on the B200 box:
+
+* the unchanged `get_model` (/root/reference/models/pointnet2_sem_seg.py:22-40) builds on our operators, loads a reference
+  state_dict and reproduces the fixture written by the unmodified reference;
+* the unchanged `modelTraining` (/root/reference/localfunctions.py:159-334: learning-rate / BatchNorm-momentum schedule,
+  rotate, `.cuda()`, forward, weighted NLL, backward, Adam, checkpoint, evaluation pass) runs a whole epoch on our
+  operators and agrees with the same function driving the PURE reference model (its eager CUDA path);
+* the unchanged `modelTesting` (:349-479: batching with stale rows, forward, arg-max, the Python add_vote loop, label
+  file) does the same, and its label file agrees with pn2.predict_scene on the same blocks.
+"""
+import logging
+import os
+import types
+
+import numpy as np
 import pytest
 import torch
 
-REF = "/root/reference"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+import _inputs as I
+from oracle import ref_env as E
 
-
-def _import_reference_model():
-    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("models", "pointnet2_sem_seg")}
-    for k in saved_mods:
-        del sys.modules[k]
-    sys.path[:0] = [ROOT, os.path.join(REF, "models")]     # OUR models/pointnet2_utils.py, THEIR pointnet2_sem_seg.py
-    try:
-        mod = importlib.import_module("pointnet2_sem_seg")
-        utils = importlib.import_module("models.pointnet2_utils")
-    finally:
-        sys.path[:] = saved_path
-    return mod, utils
+pytestmark = pytest.mark.skipif(E.reference_root() is None,
+                                reason="no reference tree (/root/reference or oracle/_ref staged by build())")
 
 
 def test_unchanged_reference_model_builds_on_our_operators(pn2, golden):
-    mod, utils = _import_reference_model()
-    assert mod.__file__.startswith(REF) and utils.__file__.startswith(ROOT)
+    mod, utils = E.load_model_module(ours=True)
+    assert mod.__file__.startswith(E.reference_root()) and utils.__file__.startswith(E.ROOT)
     net = mod.get_model(18, 3)
     assert isinstance(net.sa1, pn2.PointNetSetAbstraction) and isinstance(net.fp1, pn2.PointNetFeaturePropagation)
     assert sorted(net.state_dict().keys()) == list(golden("model")["state_keys"])
@@ -39,15 +39,187 @@ def test_unchanged_reference_model_builds_on_our_operators(pn2, golden):
         assert hasattr(utils, name), name
 
 
+def test_staged_copy_is_the_unmodified_reference():
+    """oracle/_ref (what travels to the GPU box) is byte-identical to the mounted tree, where both exist."""
+    staged = os.path.join(E.HERE, "_ref")
+    if not (os.path.isdir("/root/reference") and os.path.isdir(staged)):
+        pytest.skip("needs both the mounted reference and the staged copy")
+    from oracle import fetch_reference as F
+    for rel in F.FILES:
+        assert F._sha(os.path.join("/root/reference", rel)) == F._sha(os.path.join(staged, rel)), rel
+
+
+def test_reference_loops_import_with_stand_ins():
+    lf = E.load_localfunctions()
+    assert callable(lf.modelTraining) and callable(lf.modelTesting) and callable(lf.add_vote)
+    assert hasattr(E.load_script("sem_seg_testing"), "TestCustomDataset")
+    assert hasattr(E.load_script("sem_seg_training"), "TrainCustomDataset")
+
+
 @pytest.mark.gpu
-def test_unchanged_reference_model_runs_on_gpu(pn2, golden):
-    import numpy as np
-    import _inputs as I
-    mod, _ = _import_reference_model()
+@pytest.mark.parametrize("precision,atol", [("fp32", 1e-3), ("bf16", 0.15)])
+def test_unchanged_reference_model_runs_on_gpu(pn2, golden, precision, atol):
+    pn2.set_precision(precision)
+    mod, _ = E.load_model_module(ours=True)
     net = I.randomize_module_(mod.get_model(18, 3), 61).cuda().eval()
     g = golden("model")
     x = I.facade_batch(2, 2048, 9, int(g["facade_seed"])).cuda().transpose(2, 1)
     torch.manual_seed(71)
     with torch.no_grad():
         pred, _ = net(x)
-    assert np.abs(pred.cpu().numpy() - g["facade_eval_pred"]).max() < 1e-3
+    assert np.abs(pred.cpu().numpy() - g["facade_eval_pred"]).max() < atol
+    pn2.set_precision("fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# script level: the unchanged loops
+# ---------------------------------------------------------------------------------------------------------------------
+B, N, NC = 4, 2048, 18
+
+
+class _Log(logging.Handler):
+    def __init__(self):
+        super().__init__()
+        self.lines = []
+
+    def emit(self, record):
+        self.lines.append(record.getMessage())
+
+    def value(self, prefix):
+        hits = [ln for ln in self.lines if ln.startswith(prefix)]
+        assert hits, (prefix, self.lines)
+        return float(hits[-1][len(prefix):])
+
+
+def _loaders():
+    train = [(I.facade_batch(B, N, 9, 300 + i), I.labels(B, N, NC, 400 + i).view(B, N)) for i in range(3)]
+    test = [(I.facade_batch(B, N, 9, 350 + i), I.labels(B, N, NC, 450 + i).view(B, N)) for i in range(2)]
+    return train, test
+
+
+def _run_training(lf, mod, tmp, tag):
+    """One epoch of the UNCHANGED modelTraining (localfunctions.py:159-334) on `mod.get_model`."""
+    classifier = I.randomize_module_(mod.get_model(NC, 3), 61).cuda()
+    classifier.drop1.p = 0.0                      # the dropout mask is generator specific; everything else is deterministic
+    optimizer = torch.optim.Adam(classifier.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+    criterion = mod.get_loss().cuda()
+    weights = torch.linspace(0.5, 1.5, NC).cuda()
+    ckpt = tmp / tag
+    ckpt.mkdir()
+    logger = logging.getLogger("dropin_" + tag)
+    logger.setLevel(logging.INFO)
+    log = _Log()
+    logger.addHandler(log)
+    train, test = _loaders()
+    torch.manual_seed(7)                          # FPS start draws (pointnet2_utils.py:75)
+    np.random.seed(7)                             # rotation angles (provider.py:76)
+    seg_label_to_cat = {i: "class%d" % i for i in range(NC)}
+    charts = lf.modelTraining(0, 1, 1e-3, 0.7, 10, B, N, NC, train, test, classifier, optimizer, criterion, weights,
+                              str(ckpt), "/best_model.pth", seg_label_to_cat, logger)
+    logger.removeHandler(log)
+    assert os.path.exists(str(ckpt) + "/model.pth") and os.path.exists(str(ckpt) + "/best_model.pth")
+    saved = torch.load(str(ckpt) + "/model.pth", map_location="cpu")
+    assert set(saved) == {"epoch", "model_state_dict", "optimizer_state_dict"}
+    return charts, log, classifier, saved
+
+
+@pytest.mark.gpu
+def test_unchanged_modelTraining_epoch_on_our_operators(pn2, tmp_path):
+    lf = E.load_localfunctions()
+    pn2.set_precision("fp32")
+    ours_mod, _ = E.load_model_module(ours=True)
+    ref_mod, ref_utils = E.load_model_module(ours=False)
+    assert ref_utils.__file__.startswith(E.reference_root())
+    (acc_o, ml_o, iou_o), log_o, net_o, saved_o = _run_training(lf, ours_mod, tmp_path, "ours")
+    assert isinstance(net_o.sa1, pn2.PointNetSetAbstraction)
+    (acc_r, ml_r, iou_r), log_r, net_r, saved_r = _run_training(lf, ref_mod, tmp_path, "ref")
+    assert not isinstance(net_r.sa1, pn2.PointNetSetAbstraction)
+    # the reference itself runs its eager CUDA path here (TF32 convolutions by default, its own CUDA rounding of the
+    # distance matrices): agreement is therefore bounded by the reference's CPU-vs-CUDA difference, not by ours
+    tl_o, tl_r = log_o.value("Training mean loss: "), log_r.value("Training mean loss: ")
+    assert abs(tl_o - tl_r) <= 2e-2 * abs(tl_r), (tl_o, tl_r)
+    assert abs(ml_o[0] - ml_r[0]) <= 2e-2 * abs(ml_r[0]), (ml_o, ml_r)
+    assert abs(acc_o[0] - acc_r[0]) <= 0.02, (acc_o, acc_r)
+    assert abs(log_o.value("Training accuracy: ") - log_r.value("Training accuracy: ")) <= 0.02
+    # same checkpoint layout; the BatchNorm-momentum schedule (:191-195) reached our modules; running statistics moved alike
+    assert sorted(saved_o["model_state_dict"]) == sorted(saved_r["model_state_dict"])
+    assert all(m.momentum == 0.1 for m in net_o.modules() if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)))
+    for k, v in saved_r["model_state_dict"].items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            w = saved_o["model_state_dict"][k]
+            assert torch.allclose(w, v, rtol=5e-2, atol=5e-3), (k, float((w - v).abs().max()))
+    assert int(saved_o["model_state_dict"]["sa1.mlp_bns.0.num_batches_tracked"]) == 3
+    # three Adam steps at lr 1e-3 move every weight by at most ~3e-3; both runs must have moved the same way overall
+    moved = torch.cat([(saved_o["model_state_dict"][k] - saved_r["model_state_dict"][k]).flatten()
+                       for k in saved_r["model_state_dict"] if k.endswith("weight")])
+    assert float(moved.abs().max()) <= 6.5e-3
+
+
+class _Scene:
+    """What modelTesting reads from its dataset (sem_seg_testing.TestCustomDataset): built through the reference's own
+    `las_file_list=None` constructor path and filled with a synthetic scene."""
+
+    @staticmethod
+    def make(points=12000, seed=3):
+        T = E.load_script("sem_seg_testing")
+        g = np.random.RandomState(seed)
+        pts = np.stack([g.uniform(0, 2.6, points), np.clip(g.normal(0.6, 0.15, points), 0, 1.2), g.uniform(0, 3.0, points)], 1)
+        pts += np.array([690000.25, 5335000.5, 0.0])       # (z stays absolute in the blocks: keep it small, as r = 0.1 needs)
+        labels = g.randint(0, NC, points).astype(np.int32)
+        extra = [g.randint(0, 256, points).astype(np.float64) for _ in range(3)]
+        ds = T.TestCustomDataset(None, las_file_list=None, num_classes=NC, block_points=N)
+        ds.file_list = ["scene0.las"]
+        ds.scene_points_list, ds.semantic_labels_list = [pts], [labels.astype(np.float64)]
+        ds.num_extra_features, ds.feature_name, ds.extra_features_data = 3, ["red", "blue", "green"], [extra]
+        lw = np.histogram(labels, range(NC + 1))[0].astype(np.float32)
+        lw = lw / np.sum(lw)
+        ds.labelweights = np.power(np.amax(lw) / lw, 1 / 3.0)
+        return ds
+
+
+def _run_testing(lf, classifier, ds, tmp, tag):
+    out = tmp / tag
+    out.mkdir()
+    lines = []
+    args = types.SimpleNamespace(num_votes=1, visual=False)
+    torch.manual_seed(9)
+    np.random.seed(9)                            # the slicer's padding / shuffle draws (sem_seg_testing.py:207-209)
+    with torch.no_grad():
+        lf.modelTesting(ds, NC, N, 3, args, lf.tz, 9, lines.append, str(out), classifier.eval(),
+                        {i: "class%d" % i for i in range(NC)}, False, False)
+    labels = np.loadtxt(str(out / "scene0.txt"), dtype=np.int64)
+    return labels, lines
+
+
+@pytest.mark.gpu
+def test_unchanged_modelTesting_scene_on_our_operators(pn2, tmp_path):
+    lf = E.load_localfunctions()
+    pn2.set_precision("fp32")
+    ours_mod, _ = E.load_model_module(ours=True)
+    ref_mod, _ = E.load_model_module(ours=False)
+    ds = _Scene.make()
+    net_o = I.randomize_module_(ours_mod.get_model(NC, 3), 61).cuda()
+    net_r = I.randomize_module_(ref_mod.get_model(NC, 3), 61).cuda()
+    lab_o, lines_o = _run_testing(lf, net_o, ds, tmp_path, "ours")
+    lab_r, lines_r = _run_testing(lf, net_r, ds, tmp_path, "ref")
+    P = ds.scene_points_list[0].shape[0]
+    assert lab_o.shape == (P,) and lab_r.shape == (P,)
+    assert any(ln.startswith("eval whole scene point accuracy") for ln in lines_o)
+    agree = float((lab_o == lab_r).mean())
+    assert agree >= 0.985, agree               # bounded by the reference's own TF32 / CUDA-rounding path
+    # the same scene through this repo's drivers: device slicer is generator-specific, so feed the reference's blocks
+    np.random.seed(9)
+    data, _, smpw, pidx = ds[0]
+    ours = I.randomize_module_(pn2.get_model(NC, 3), 61).cuda().eval()
+    ours.load_state_dict(net_o.state_dict())
+    torch.manual_seed(9)
+    nb = data.shape[0]
+    pad = (-nb) % 3                            # modelTesting's last batch keeps stale rows: make the batches identical
+    blocks = torch.Tensor(data)
+    labels, pool = pn2.predict_scene(ours, blocks, torch.from_numpy(pidx), torch.from_numpy(smpw), P, NC, batch_size=3,
+                                     pipeline=False)
+    assert int(pool.sum()) == int((smpw != 0).sum())
+    if pad == 0:                               # identical batches and start draws: identical forward, identical votes
+        assert float((labels.numpy() == lab_o).mean()) >= 0.999
+    else:
+        assert float((labels.numpy() == lab_o).mean()) >= 0.97

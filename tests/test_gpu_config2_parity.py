@@ -1,0 +1,106 @@
+"""BASELINE.json configs[1] at its TRUE size, in the configuration bench.py measures: bf16 rows on the tcgen05 kernels,
+fused head + fused weighted NLL, flat gradient buffer, one-launch Adam, the whole step replayed as a CUDA graph with
+consecutive batches software-pipelined -- one training step on facade_batch(32, 4096, 9) against the oracle on the same
+batch, parameters and FPS start draws:
+
+* sampling / grouping / neighbour indices of all four levels bit-exact vs the C oracle (pointnet2_utils.py:63-107,
+  :296-302), read from the geometry slot the captured graph filled;
+* the loss within 2e-2 of the torch-CPU port's (models/pointnet2_sem_seg.py:22-50 in fp32);
+* every parameter gradient, read from trainer.FlatGradients, against the port's: cosine >= the bound stated below.
+
+Dropout is switched off on both sides (its mask comes from generator-specific draws); everything else is the benched path.
+"""
+import numpy as np
+import pytest
+import torch
+
+import _inputs as I
+from oracle import c_oracle as C
+from oracle import pn2_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, N, CH, NC = 32, 4096, 9, 18
+LEVELS = ((1024, 0.1), (256, 0.2), (64, 0.4), (16, 0.8))
+# bf16 storage of every activation (9 layers deep behind sa1) bounds how well the first levels' gradients can agree with an
+# fp32 evaluation; measured on B200 (profiles/r02_config2_parity.txt): worst tensor 0.99+ from sa2 on, sa1 >= 0.97
+COS_BOUND = {"sa1": 0.95}
+COS_DEFAULT = 0.98
+
+
+def _oracle_geometry(xyz0, seed):
+    """The four levels' (new_xyz, ball idx) and the four 3-NN (idx, w) from the C oracle with the reference's draws."""
+    torch.manual_seed(seed)
+    geo, coords = [], [xyz0]
+    for (S, r) in LEVELS:
+        cur = coords[-1]
+        start = torch.randint(0, cur.shape[1], (B,), dtype=torch.long).numpy()      # pointnet2_utils.py:75
+        fps = C.fps(cur, S, start)
+        new_xyz = np.ascontiguousarray(np.take_along_axis(cur, fps[:, :, None].repeat(3, 2), 1))
+        geo.append((new_xyz, C.ball_query(r, 32, cur, new_xyz)))
+        coords.append(new_xyz)
+    nn3 = []
+    for fine, coarse in ((3, 4), (2, 3), (1, 2), (0, 1)):
+        idx, _, w = C.three_nn(coords[fine], coords[coarse])
+        nn3.append((idx, w))
+    return geo, nn3
+
+
+def test_config2_trainer_step_matches_oracle(pn2):
+    pn2.set_precision("bf16")
+    torch.manual_seed(1234)
+    trainer = pn2.SemSegTrainer(NC, CH - 6, device=DEV)
+    trainer.model.drop1.p = 0.0
+    ref = O.OracleSemSeg(NC, CH - 6).train()
+    ref.load_state_dict(trainer.model.state_dict())
+    ref.drop1.p = 0.0
+    trainer.enable_cuda_graph(B, N, CH, pipeline=True)
+    batch, target = I.facade_batch(B, N, CH, 11), I.labels(B, N, NC, 111)
+    other = I.facade_batch(B, N, CH, 12)
+    seed = 4321
+    torch.manual_seed(seed)
+    assert trainer.step_device(batch.to(DEV), target.to(DEV)) is None          # primes: index pipeline of the batch only
+    k = trainer._parity ^ 1                                                    # the slot that batch went into
+    geo_d, nn3_d = trainer._slots[k][0]
+    loss = trainer.step_device(other.to(DEV), target.to(DEV))                  # replay: trains on `batch`
+    torch.cuda.synchronize()
+    loss = float(loss)
+
+    # ---- indices: bit-exact --------------------------------------------------------------------------------------
+    geo_o, nn3_o = _oracle_geometry(batch[:, :, :3].contiguous().numpy(), seed)
+    for lvl, ((nx_d, idx_d), (nx_o, idx_o)) in enumerate(zip(geo_d, geo_o), 1):
+        assert np.array_equal(nx_d.cpu().numpy(), nx_o), "FPS centroids of level %d" % lvl
+        assert np.array_equal(idx_d.cpu().numpy(), idx_o), "ball-query indices of level %d" % lvl
+    for i, ((idx_d, w_d), (idx_o, w_o)) in enumerate(zip(nn3_d, nn3_o)):
+        same = idx_d.cpu().numpy() == idx_o
+        # exactly tied distances (duplicated points): the reference's unstable sort leaves their order open
+        assert same.mean() > 0.999, "3-NN indices of fp%d" % (4 - i)
+        rows = same.all(-1)
+        assert np.array_equal(w_d.cpu().numpy()[rows], w_o[rows]), "3-NN weights of fp%d" % (4 - i)
+
+    # ---- loss and gradients vs the fp32 port ---------------------------------------------------------------------
+    torch.manual_seed(seed)
+    pred, _ = ref(batch.transpose(2, 1))
+    rloss = O.nll(pred.contiguous().view(-1, NC), target, torch.ones(NC))
+    rloss.backward()
+    assert abs(loss - rloss.item()) <= 2e-2, (loss, rloss.item())
+    views = {id(p): v for p, v in zip(trainer.grads.params, trainer.grads.views)}
+    report, worst = [], {}
+    for (n, p), (_, rp) in zip(trainer.model.named_parameters(), ref.named_parameters()):
+        if n.endswith("bias") and ("mlp_convs" in n or n == "conv1.bias"):
+            continue          # a conv bias in front of a train-mode BatchNorm: its gradient is rounding noise in both
+        g = views[id(p)].detach().double().cpu().flatten()
+        rg = rp.grad.double().flatten()
+        assert torch.isfinite(g).all(), n
+        cos = float(torch.nn.functional.cosine_similarity(g, rg, dim=0))
+        ratio = float(g.norm() / rg.norm())
+        report.append("%-28s cos %.5f  |g|/|g_ref| %.4f" % (n, cos, ratio))
+        top = n.split(".")[0]
+        worst[top] = min(worst.get(top, 1.0), cos)
+        assert cos >= COS_BOUND.get(top, COS_DEFAULT), "\n".join(report)
+        assert 0.9 <= ratio <= 1.1, "\n".join(report)
+    print("config-2 parity: loss %.6f vs oracle %.6f; worst gradient cosine per module: %s" % (
+        loss, rloss.item(), ", ".join("%s %.4f" % kv for kv in sorted(worst.items()))))
+    print("\n".join(report))
+    trainer.flush()
+    pn2.set_precision("fp32")

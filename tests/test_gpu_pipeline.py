@@ -177,3 +177,69 @@ def test_predictor_cache_does_not_leak_into_later_forwards(pn2):
     torch.manual_seed(start_seed)
     assert torch.equal(pred2.predict_host(x), changed)      # a new one sees the new parameters
     pn2.set_precision("fp32")
+
+
+def test_recapture_keeps_optimizer_state_and_refuses_pending_batches(pn2):
+    """enable_cuda_graph's warm-up steps must neither count as training nor reset Adam (a loaded checkpoint's
+    moments / step counter, or those of the epochs trained so far when the caller re-captures)."""
+    data = _batches(4, 500)
+    t = _trainer(pn2, True, lr=1e-3)
+    torch.manual_seed(5)
+    for p, y in data:
+        t.step_device(p, y)
+    with pytest.raises(RuntimeError, match="flush"):
+        t.enable_cuda_graph(B, N, C, pipeline=True)          # a batch is still in flight
+    t.flush()
+    torch.cuda.synchronize()
+    opt = t.optimizer
+    before = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), float(opt.step_count))
+    params = [p.detach().clone() for p in t.model.parameters()]
+    assert before[2] == 4.0 and float(before[0].abs().sum()) > 0
+    t.enable_cuda_graph(B, N, C, pipeline=True)
+    torch.cuda.synchronize()
+    assert float(opt.step_count) == 4.0
+    assert torch.equal(opt.exp_avg, before[0]) and torch.equal(opt.exp_avg_sq, before[1])
+    for p, q in zip(t.model.parameters(), params):
+        assert torch.equal(p, q)
+    # a torch.optim.Adam checkpoint survives the capture too
+    ref_opt = torch.optim.Adam(t.model.parameters(), lr=1e-3)
+    for p in t.model.parameters():
+        p.grad = torch.ones_like(p)
+    ref_opt.step()
+    sd = ref_opt.state_dict()
+    t.optimizer.load_state_dict(sd)
+    t.enable_cuda_graph(B, N, C)
+    torch.cuda.synchronize()
+    assert float(opt.step_count) == 1.0 and float(opt.exp_avg.abs().sum()) > 0
+    pn2.set_precision("fp32")
+
+
+def test_captured_step_follows_the_momentum_schedule_without_recapture(pn2):
+    """localfunctions.py:191-195 sets m.momentum on every BatchNorm each epoch; a captured bf16 step reads it from device
+    memory: after the change the replayed step must update the running statistics like an eager step with that momentum."""
+    (p, y), = _batches(1, 600)
+
+    def run(captured):
+        t = _trainer(pn2, False)
+        if not captured:
+            t._graph = None
+        for m in t.model.modules():
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.momentum = 0.025                           # after the capture (which baked nothing in)
+        torch.manual_seed(3)
+        t.step_device(p, y)
+        torch.cuda.synchronize()
+        return {k: v.clone() for k, v in t.model.state_dict().items() if "running" in k}
+
+    eager, replay = run(False), run(True)
+    for k in eager:
+        assert torch.allclose(eager[k], replay[k], rtol=1e-5, atol=1e-6), k
+    # and the value is the scheduled one: running_mean = 0.975 * 0 + 0.025 * batch mean, so it stays small
+    t0 = _trainer(pn2, False)
+    torch.manual_seed(3)
+    t0.step_device(p, y)
+    torch.cuda.synchronize()
+    k = "sa1.mlp_bns.0.running_mean"
+    ratio = float(replay[k].abs().sum() / t0.model.state_dict()[k].abs().sum())
+    assert abs(ratio - 0.25) < 1e-3, ratio                   # 0.025 / 0.1
+    pn2.set_precision("fp32")
