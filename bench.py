@@ -217,35 +217,189 @@ def synthetic_batches(n, seed):
     return out
 
 
-def cpu_train_step_rate(batch_clouds, steps, warmup, threads, budget_s=150.0):
-    """The oracle port (torch-CPU restatement of the reference modules) timed on the host cores.
-    Stops early once `budget_s` of timed work is spent; returns (points/s from the median step, s/step, steps)."""
+def reference_model_module():
+    """(module with get_model / get_loss, kind): the UNMODIFIED reference (models/pointnet2_sem_seg.py on its own
+    models/pointnet2_utils.py) from /root/reference or the copy staged under oracle/_ref by build(); the oracle port only
+    if neither exists."""
+    from oracle import ref_env as E
+    if E.reference_root() is not None:
+        mod, _ = E.load_model_module(ours=False)
+        return mod, "reference", "unmodified reference (%s)" % E.reference_kind()
     from oracle import pn2_oracle as O
+
+    class _Port:
+        get_model = staticmethod(lambda nc, e: O.OracleSemSeg(nc, e))
+        get_loss = staticmethod(lambda: (lambda pred, target, feat, w: O.nll(pred, target, w)))
+    return _Port, "port", "oracle port of the reference (no reference tree staged)"
+
+
+def cpu_train_step_rate(batch_clouds, steps, warmup, threads, budget_s=150.0):
+    """The reference's own train step (localfunctions.py:203-218: zero_grad, forward, weighted NLL, backward, Adam of
+    sem_seg_training.py:576-582) on the host cores.  Stops early once `budget_s` of timed work is spent; returns
+    (points/s from the median step, s/step, timed steps, warm-up steps, kind, description)."""
     import _inputs as I
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    net = O.OracleSemSeg(NUM_CLASSES, CHANNELS - 6).train()
+    mod, kind, what = reference_model_module()
+    net = mod.get_model(NUM_CLASSES, CHANNELS - 6).train()
+    crit = mod.get_loss()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
     w = torch.ones(NUM_CLASSES)
     x = I.facade_batch(batch_clouds, NPOINT, CHANNELS, 11)
     y = I.labels(batch_clouds, NPOINT, NUM_CLASSES, 111)
-    times = []
-    for i in range(warmup + steps):
+    def one():
         t = time.perf_counter()
         opt.zero_grad()
         pred, feat = net(x.transpose(2, 1))
-        loss = O.nll(pred.contiguous().view(-1, NUM_CLASSES), y, w)
+        loss = crit(pred.contiguous().view(-1, NUM_CLASSES), y, feat, w)
         loss.backward()
         opt.step()
-        if i >= warmup:
-            times.append(time.perf_counter() - t)
-            if sum(times) > budget_s:
-                break
+        return time.perf_counter() - t
+
+    t_begin, warm_done, times = time.perf_counter(), 0, []
+    while warm_done < warmup and time.perf_counter() - t_begin < budget_s / 3:       # the driver's --warmup, bounded in time
+        one()
+        warm_done += 1
+    warmup = warm_done
+    while len(times) < steps and sum(times) < budget_s:
+        times.append(one())
     med = sorted(times)[len(times) // 2]
-    return batch_clouds * NPOINT / med, med, len(times)
+    return batch_clouds * NPOINT / med, med, len(times), warmup, kind, what
 
 
-def shutdown(world, trainer):
+def cpu_forward_rate(batch_clouds, threads, reps=2):
+    """BASELINE.json configs[0]: eval-mode forward of `batch_clouds` x 4096 x 9 on the host cores (the reference itself when
+    staged).  Returns (points/s, s per forward, kind, description)."""
+    import _inputs as I
+    torch.set_num_threads(threads)
+    mod, kind, what = reference_model_module()
+    torch.manual_seed(0)
+    net = mod.get_model(NUM_CLASSES, CHANNELS - 6).eval()
+    x = I.facade_batch(batch_clouds, NPOINT, CHANNELS, 21).transpose(2, 1)
+    best = None
+    with torch.no_grad():
+        net(x[:2])
+        for _ in range(reps):
+            t = time.perf_counter()
+            net(x)
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+    return batch_clouds * NPOINT / best, best, kind, what
+
+
+def torch_gpu_baseline(dev, steps=3):
+    """The reference's own code path with `.cuda()` (localfunctions.py:208: eager PyTorch, cuBLAS / cuDNN / cub library kernels,
+    cuDNN's default TF32 convolutions) on THIS GPU: eval forward and train step at the headline shape -- SURVEY 2b's
+    "PyTorch-on-B200 bar".  Returns a dict (ms per forward / step, points/s)."""
+    import _inputs as I
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True        # torch's defaults
+    out = {}
+    try:
+        mod, kind, what = reference_model_module()
+        torch.manual_seed(0)
+        net = mod.get_model(NUM_CLASSES, CHANNELS - 6).to(dev)
+        crit = mod.get_loss()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+        w = torch.ones(NUM_CLASSES, device=dev)
+        x = I.facade_batch(B_PER_GPU, NPOINT, CHANNELS, 11).to(dev)
+        y = I.labels(B_PER_GPU, NPOINT, NUM_CLASSES, 111).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        def train_step():
+            opt.zero_grad()
+            pred, feat = net(x.transpose(2, 1))
+            loss = crit(pred.contiguous().view(-1, NUM_CLASSES), y, feat, w)
+            loss.backward()
+            opt.step()
+
+        def forward():
+            with torch.no_grad():
+                net(x.transpose(2, 1))
+
+        net.train()
+        ms_train = timed(train_step)
+        net.eval()
+        ms_fwd = timed(forward)
+        pts = B_PER_GPU * NPOINT
+        out = {"kind": kind, "what": what + ", eager on cuda, torch default precision (fp32 matmul, TF32 cuDNN convolutions), "
+               "resident inputs, %d timed iterations after 1 warm-up" % steps,
+               "train_ms_per_step": ms_train, "train_points_per_s": pts / (ms_train * 1e-3),
+               "forward_ms_per_batch": ms_fwd, "forward_points_per_s": pts / (ms_fwd * 1e-3), "unit": UNIT}
+        del net, opt
+    except Exception as exc:
+        out = {"unavailable": repr(exc)[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+        torch.cuda.empty_cache()
+    return out
+
+
+def dropin_rates(pn2, dev, host, steps=5):
+    """Drop-in mode as a user of the reference gets it: the reference's UNCHANGED get_model / get_loss on top of this repo's
+    models/pointnet2_utils.py, torch.optim.Adam, the eager batch body of localfunctions.py:203-220 (zero_grad, host->device
+    copy, transpose, forward, loss, backward, step, `seg_pred.cpu()`), no CUDA graph, no fused head, no pipeline -- every
+    operator call pays the Python + ctypes path.  ms per step for fp32 rows (the default precision) and bf16 rows."""
+    from oracle import ref_env as E
+    out = {}
+    before = pn2.get_precision()
+    try:
+        if E.reference_root() is not None:
+            mod, _ = E.load_model_module(ours=True)
+            what = "unmodified reference get_model/get_loss on this repo's operators"
+        else:
+            mod = pn2
+            what = "this repo's sem_seg.get_model (reference tree not staged)"
+        for precision in ("fp32", "bf16"):
+            pn2.set_precision(precision)
+            torch.manual_seed(0)
+            net = mod.get_model(NUM_CLASSES, CHANNELS - 6).to(dev).train()
+            crit = mod.get_loss()
+            opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+            w = torch.ones(NUM_CLASSES, device=dev)
+
+            def body(points, target):
+                opt.zero_grad()
+                points, target = points.float().to(dev, non_blocking=True), target.long().to(dev, non_blocking=True)
+                pred, feat = net(points.transpose(2, 1))
+                pred = pred.contiguous().view(-1, NUM_CLASSES)
+                loss = crit(pred, target.view(-1), feat, w)
+                loss.backward()
+                opt.step()
+                return pred.cpu().data.max(1)[1]
+
+            launches0 = pn2.launch_count()
+            for i in range(2):
+                body(*host[i % len(host)])
+            torch.cuda.synchronize()
+            per_step = (pn2.launch_count() - launches0) // 2
+            t = time.perf_counter()
+            for i in range(steps):
+                body(*host[i % len(host)])
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t) * 1e3 / steps
+            out[precision] = {"ms_per_step": ms, "points_per_s": B_PER_GPU * NPOINT / (ms * 1e-3), "pn2_entry_calls_per_step": per_step}
+            del net, opt
+        out["what"] = what + "; eager, torch.optim.Adam, host batch in, seg_pred.cpu() out (localfunctions.py:203-220); wall clock over %d steps" % steps
+    except Exception as exc:
+        out["unavailable"] = repr(exc)[:200]
+    finally:
+        pn2.set_precision(before)
+        torch.cuda.empty_cache()
+    return out
+
+
+def shutdown(world, *trainers):
     """Multi-rank exit.  NCCL requires every CUDA graph that captured a communicator's collectives to be destroyed
     before the communicator is (otherwise the destroy blocks for ever): drop the captured training step first, give
     the process-group teardown a bounded time, then leave without running further destructors."""
@@ -254,8 +408,9 @@ def shutdown(world, trainer):
     import gc
     import torch.distributed as dist
     sys.stdout.flush()
-    trainer._graph = None
-    trainer._g_loss = None
+    for trainer in trainers:
+        if trainer is not None:
+            trainer.release_graphs()         # every reference to the captured graphs (they hold NCCL nodes)
     gc.collect()
     torch.cuda.synchronize()
     t = threading.Thread(target=dist.destroy_process_group, daemon=True)
@@ -271,14 +426,14 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     sample_clouds = args.ref_sample_clouds
-    rate, sec, done = cpu_train_step_rate(sample_clouds, args.steps, min(args.warmup, 1), threads)
+    rate, sec, done, warm, kind, what = cpu_train_step_rate(sample_clouds, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "oracle port of the reference modules (torch CPU ops in the reference's order), "
-                   "fp32, %d of the batch's 32 clouds per step; median step; at most 150 s of timed steps" % sample_clouds},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        "config": {"workload": WORKLOAD, "note": "%s on the host cores (torch CPU, fp32), %d of the batch's 32 clouds per step; "
+                   "median step; at most 150 s of timed steps" % (what, sample_clouds)},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": "%d x %d-point clouds per step (train step: fwd+bwd+Adam)" % (sample_clouds, NPOINT)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -337,7 +492,7 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
     e2e = _rank_max(torch.tensor([e0.elapsed_time(e1) / max(1, args.steps // 4)], device=dev, dtype=torch.float64), world).item()
     clocks = sampler.stop() if sampler else None
     if rank != 0:
-        return
+        return None
     pk, pk_kind = peaks()
     by = {n: (a, t) for n, a, t in calls}
     fps_ms, ball_ms = by["pn2_farthest_point_sample"][1], by["pn2_query_ball_point"][1]
@@ -372,7 +527,7 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
                              % (b * S * N / (ball_ms * 1e-3) / 1e12, fps_ms, fps_ms * 1e3 / S, 16)},
         "cpu_baseline": cpu, "kernel_ms": {"fps": fps_ms, "ball_query": ball_ms},
     }
-    emit(line)
+    return line
 
 
 def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
@@ -429,7 +584,7 @@ def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
     ms = _rank_max(torch.tensor([total_ms], device=dev, dtype=torch.float64), world).item()
     clocks = sampler.stop() if sampler else None
     if rank != 0:
-        return
+        return None
     assert votes_total == nb * NPOINT, (votes_total, nb * NPOINT)
     lo, hi = pn2.shard_range(nb, 0, world)
     n_batches = (hi - lo + batch - 1) // batch
@@ -470,7 +625,7 @@ def run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler):
                 "d2h_bytes_per_step": int(P / n_batches), "ms_per_step": ms / n_batches},
         "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
     }
-    emit(line)
+    return line
 
 
 def run_facade(args, rank, world, dev, pn2, barrier, sampler):
@@ -518,7 +673,7 @@ def run_facade(args, rank, world, dev, pn2, barrier, sampler):
     clocks = sampler.stop() if sampler else None
     votes_total = int(pool.sum().item())
     if rank != 0:
-        return
+        return None
     assert votes_total == nb_total * NPOINT, (votes_total, nb_total * NPOINT)       # every (slot, point) pair voted once
     pts = nb_total * NPOINT
     cpu = None
@@ -553,7 +708,138 @@ def run_facade(args, rank, world, dev, pn2, barrier, sampler):
                 "d2h_bytes_per_step": int(n_scene * 8 / n_batches), "ms_per_step": ms / n_batches},
         "gpu_launches": pn2.launch_count(), "clocks": clocks, "roofline": None, "cpu_baseline": cpu,
     }
-    emit(line)
+    return line
+
+
+def _compact(line):
+    """the few keys of another workload's full line that the headline line carries under `other_workloads`"""
+    if line is None:
+        return None
+    keep = {k: line.get(k) for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "dtype")}
+    keep["workload"] = line["config"]["workload"]
+    keep["e2e_value"] = (line.get("e2e") or {}).get("value")
+    for k in ("kernel_ms",):
+        if k in line:
+            keep[k] = line[k]
+    for k in ("slice_ms", "total_ms", "blocks"):
+        if k in line["config"]:
+            keep[k] = line["config"][k]
+    return keep
+
+
+def other_workloads(args, rank, world, dev, pn2, lib_mod, barrier):
+    """BASELINE.json configs[2], [3] and [4] at the current N, in short form (the full lines: --workload fps_ball / facade
+    --from-scene, --channels 6).  No CPU legs here; every rank takes part (the shards and the vote merge need all of them)."""
+    import argparse as _ap
+    out = {}
+    sub = _ap.Namespace(**vars(args))
+    sub.no_cpu_baseline, sub.steps, sub.warmup = True, 3, 3
+    try:
+        out["fps_ball"] = _compact(run_fps_ball(sub, rank, world, dev, pn2, lib_mod, barrier, None))
+    except Exception as exc:
+        out["fps_ball"] = {"unavailable": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        out["facade_from_scene"] = _compact(run_facade_from_scene(sub, rank, world, dev, pn2, barrier, None))
+    except Exception as exc:
+        out["facade_from_scene"] = {"unavailable": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def train_rate_other_channels(pn2, dev, world, channels, steps, warmup, barrier, rank):
+    """The headline measurement for another input width (--RGB_OFF: 6 channels, BASELINE.json configs[4]): ms per step
+    resident and from host buffers, through the same pipelined graph."""
+    import _inputs as I
+    torch.manual_seed(1234)
+    trainer = pn2.SemSegTrainer(NUM_CLASSES, channels - 6, device=dev)
+    host = []
+    for i in range(4):
+        pts = I.facade_batch(B_PER_GPU, NPOINT, channels, 1000 * rank + 51 + i).pin_memory()
+        lab = I.labels(B_PER_GPU, NPOINT, NUM_CLASSES, 1000 * rank + 151 + i).pin_memory()
+        host.append((pts, lab))
+    resident = [(p.to(dev), t.to(dev)) for p, t in host]
+    trainer.enable_cuda_graph(B_PER_GPU, NPOINT, channels, pipeline=True)
+    for i in range(warmup + 1):
+        trainer.step_device(*resident[i % 4])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        trainer.step_device(*resident[i % 4])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    trainer.flush()
+    for i in range(4):
+        trainer.step(*host[i % 4])
+    barrier()
+    e0.record()
+    for i in range(steps):
+        trainer.step(*host[i % 4])
+    e1.record()
+    barrier()
+    e2e = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    trainer.flush()
+    _rank_max(ms, world), _rank_max(e2e, world)
+    pts = world * B_PER_GPU * NPOINT
+    return trainer, {"workload": "sem_seg train step, %dx%dx%dch per GPU (--RGB_OFF), %d classes" % (B_PER_GPU, NPOINT, channels, NUM_CLASSES),
+                     "n_gpus": world, "ms_per_step": ms.item(), "value": pts / (ms.item() * 1e-3), "e2e_ms_per_step": e2e.item(),
+                     "e2e_value": pts / (e2e.item() * 1e-3), "unit": UNIT, "scaling": "weak", "dtype": "bf16",
+                     "note": "L2 not flushed between these steps (short form); graph + pipeline as the headline"}
+
+
+def data_parallel_check(pn2, trainer, resident, world, rank, dev):
+    """SURVEY.md 8(e) on the GPUs: (1) the all-reduced flat gradient equals the mean of the ranks' local gradients
+    (all-gathered and averaged in fp64); (2) a rank's local gradient is what a single GPU computes: every rank runs RANK 0's
+    batch with the collective switched off and the results are compared across the ranks (fp32 atomics order is the only
+    freedom).  Eager steps; parameters, buffers and optimizer state are restored afterwards."""
+    import torch.distributed as dist
+    model, opt = trainer.model, trainer.optimizer
+    saved = [t.detach().clone() for t in model.state_dict().values()]
+    saved_opt = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count.clone()) if hasattr(opt, "exp_avg") else None
+    graph, trainer._graph = trainer._graph, None
+    out = {}
+    try:
+        trainer.grads.check_next = True
+        torch.manual_seed(77 + rank)
+        trainer.step_device(*resident[0])
+        torch.cuda.synchronize()
+        out["allreduce_vs_mean_of_rank_gradients"] = trainer.grads.last_check
+        # (2) rank 0's batch everywhere, no collective
+        pts, tgt = resident[0][0].clone(), resident[0][1].clone()
+        dist.broadcast(pts, src=0)
+        dist.broadcast(tgt, src=0)
+        with torch.no_grad():
+            for t, sv in zip(model.state_dict().values(), saved):
+                t.copy_(sv)
+        overlap, trainer.overlap_allreduce = trainer.overlap_allreduce, False
+        real = trainer.grads.all_reduce_mean
+        trainer.grads.all_reduce_mean = lambda *a, **k: None
+        try:
+            torch.manual_seed(99)
+            trainer.step_device(pts, tgt)
+            torch.cuda.synchronize()
+        finally:
+            trainer.grads.all_reduce_mean = real
+            trainer.overlap_allreduce = overlap
+        local = trainer.grads.flat.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        ref = gathered[0].double()
+        worst = max(float((g.double() - ref).norm() / ref.norm().clamp_min(1e-30)) for g in gathered)
+        out["rank_local_vs_rank0_on_the_same_batch"] = {"max_rel_l2": worst, "world": world,
+                                                        "note": "no collective in this step; differences = fp32 atomic order only"}
+    except Exception as exc:
+        out["error"] = repr(exc)[:300]
+    finally:
+        with torch.no_grad():
+            for t, sv in zip(model.state_dict().values(), saved):
+                t.copy_(sv)
+            if saved_opt is not None:
+                opt.exp_avg.copy_(saved_opt[0]), opt.exp_avg_sq.copy_(saved_opt[1]), opt.step_count.copy_(saved_opt[2])
+        trainer._graph = graph
+    return out
 
 
 _REAL_STDOUT = None
@@ -602,6 +888,8 @@ def main():
                          "the device (pn2.slice_scene) inside the timed region, instead of starting from ready host blocks")
     ap.add_argument("--scene-points", type=int, default=10_000_000, help="facade --from-scene: points of the synthetic scene")
     ap.add_argument("--batch", type=int, default=128, help="facade workload: blocks per forward")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="train workload: skip the extra legs (other_workloads, torch_gpu_baseline, dropin) -- for profiling runs")
     args = ap.parse_args()
     global CHANNELS, WORKLOAD
     CHANNELS = args.channels
@@ -635,11 +923,13 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if args.workload != "train":
         if args.workload == "fps_ball":
-            run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler)
+            line = run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler)
         elif args.from_scene:
-            run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler)
+            line = run_facade_from_scene(args, rank, world, dev, pn2, barrier, sampler)
         else:
-            run_facade(args, rank, world, dev, pn2, barrier, sampler)
+            line = run_facade(args, rank, world, dev, pn2, barrier, sampler)
+        if line is not None:
+            emit(line)
         if world > 1:
             sys.stdout.flush()
             t = threading.Thread(target=dist.destroy_process_group, daemon=True)
@@ -742,8 +1032,20 @@ def main():
         dist.all_reduce(fwd_ms, op=dist.ReduceOp.MAX)
         if unpipelined_ms is not None:
             dist.all_reduce(unpipelined_ms, op=dist.ReduceOp.MAX)
+    # ---- the rest of the measurement contract, outside the timed regions above ---------------------------------------
+    dp_check = data_parallel_check(pn2, trainer, resident, world, rank, dev) if world > 1 else None
+    trainer6, other = None, None
+    if not args.headline_only:
+        other = other_workloads(args, rank, world, dev, pn2, lib_mod, barrier)
+        pn2.set_precision(args.precision)
+        try:
+            trainer6, ch6 = train_rate_other_channels(pn2, dev, world, 6, 10, 3, barrier, rank)
+        except Exception as exc:
+            ch6 = {"unavailable": repr(exc)[:200]}
+        if other is not None:
+            other["train_6ch"] = ch6
     if rank != 0:
-        return shutdown(world, trainer)
+        return shutdown(world, trainer, trainer6)
 
     points_per_step = world * B_PER_GPU * NPOINT
     ms_per_step = total_ms.item() / args.steps
@@ -763,11 +1065,12 @@ def main():
         # DRAM traffic of the same entry point from the committed ncu pass (profiles/make_traffic.py), per call like `achieved`
         traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+            tname = next(n for n in ("r02_dram_traffic.json", "r01_dram_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", n)))
+            with open(os.path.join(ROOT, "profiles", tname)) as f:
                 tj = json.load(f)
             if top["entry"] in tj:
                 traffic = tj[top["entry"]]["dram_bytes_per_step"] / top["calls_per_step"]
-                traffic_src = "profiles/r01_dram_traffic.json: " + tj.get("_source", "")
+                traffic_src = "profiles/%s: " % tname + tj.get("_source", "")
         except Exception:
             pass
         roof = {"kernel": top["entry"] + " (all %d launches of a step; the largest share of kernel time among the streaming kernels)" % round(top["calls_per_step"]),
@@ -778,13 +1081,20 @@ def main():
                 "note": "achieved = sum of algorithmic bytes / sum of CUDA-event durations over the launches of %d eager steps; "
                         "the FPS dependency chain (pn2_farthest_point_sample) is latency-bound and listed under kernels" % kernel_steps}
 
-    cpu = None
+    cpu = cpu_fwd = gpu_base = dropin = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        rate, sec, done = cpu_train_step_rate(B_PER_GPU, 5, 1, threads, budget_s=25.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d timed train steps on the whole %d x %d-point batch (oracle port of the reference, fp32, fwd+bwd+Adam), "
-                         "%.1f s/step, median" % (done, B_PER_GPU, NPOINT, sec)}
+        rate, sec, done, warm, kind, what = cpu_train_step_rate(B_PER_GPU, 5, 1, threads, budget_s=25.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d timed train steps (after %d warm-up) on the whole %d x %d-point batch (%s, torch CPU fp32, fwd+bwd+Adam), "
+                         "%.1f s/step, median" % (done, warm, B_PER_GPU, NPOINT, what, sec)}
+        # BASELINE.json configs[0]: eval forward 16 x 4096 x 9 on the host cores
+        rate_f, sec_f, kind_f, what_f = cpu_forward_rate(16, threads)
+        cpu_fwd = {"value": rate_f, "unit": UNIT, "cores": threads, "kind": kind_f, "s_per_forward": sec_f,
+                   "sample": "eval-mode forward of 16 x %d x %d ch under no_grad (%s), best of 2" % (NPOINT, CHANNELS, what_f)}
+    if not args.headline_only and world == 1:
+        gpu_base = torch_gpu_baseline(dev)
+        dropin = dropin_rates(pn2, dev, host)
 
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
     line = {
@@ -809,11 +1119,24 @@ def main():
                             "inputs, e2e: pinned host points in, arg-max labels read back to the host"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
     }
+    if cpu_fwd is not None:
+        line["cpu_baseline_forward"] = cpu_fwd
+    if gpu_base is not None:
+        line["torch_gpu_baseline"] = gpu_base
+        if "train_ms_per_step" in gpu_base:
+            line["torch_gpu_baseline"]["speedup_train"] = gpu_base["train_ms_per_step"] / ms_per_step
+            line["torch_gpu_baseline"]["speedup_forward"] = gpu_base["forward_ms_per_batch"] / fwd_ms[0].item()
+    if dropin is not None:
+        line["dropin"] = dropin
+    if other is not None:
+        line["other_workloads"] = other
+    if dp_check is not None:
+        line["data_parallel_check"] = dp_check
     if unpipelined_ms is not None:
         line["unpipelined"] = {"ms_per_step": unpipelined_ms.item(), "value": points_per_step / (unpipelined_ms.item() * 1e-3), "unit": UNIT,
                                "what": "the same graph-replayed train step without overlapping consecutive batches (resident inputs)"}
     emit(line)
-    shutdown(world, trainer)
+    shutdown(world, trainer, trainer6)
 
 
 if __name__ == "__main__":

@@ -195,6 +195,9 @@ class get_model(nn.Module):
             else:
                 c, f = sa(coords[-1], feats[-1])
             coords.append(c)
+            hook = self.feature_grad_hooks.get(i + 1) if self.feature_grad_hooks else None
+            if hook is not None and f.requires_grad:
+                f.register_hook(hook)
             feats.append(f)
         l4_points = feats[4]
         up = feats[4]
@@ -224,6 +227,8 @@ class get_model(nn.Module):
                 up = fp(coords[fine], coords[fine + 1], skip, up)
         return self._head(up), l4_points
 
+    feature_grad_hooks = None    # {level 1..4: hook}: registered on that set-abstraction level's output features when they
+                                 # carry a gradient (trainer.SemSegTrainer: early all-reduce of finished gradient buckets)
     fused_head = True     # bf16 mode: fp1 + head as one chain of rows on this library's kernels
     rows_head = True      # otherwise: the PyTorch head on point-major rows (no layout copies)
 

@@ -124,6 +124,13 @@ class FlatGradients:
 
     def __init__(self, params):
         from . import modules
+        params = list(params)
+        if params and isinstance(params[0], tuple):          # named_parameters(): names enable bucket_of()
+            self.names = [n for n, p in params if p.requires_grad]
+            params = [p for _, p in params]
+        else:
+            self.names = ["p%d" % i for i, p in enumerate(params) if p.requires_grad]
+        self.check_next, self.last_check = False, None
         self.params = [p for p in params if p.requires_grad]
         # every parameter's slice starts on a 16-byte boundary (the weight-gradient kernels add into it with
         # red.global.add.v4.f32); the few padding elements stay zero
@@ -152,10 +159,40 @@ class FlatGradients:
                 v.copy_(g)
                 p.grad = v
 
-    def all_reduce_mean(self, group=None):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+    def bucket_of(self, names):
+        """[lo, hi) of the flat buffer covered by the parameters whose qualified name starts with one of `names`
+        (they must be contiguous in parameter order); used to all-reduce a finished part of the gradient early."""
+        idx = [i for i, n in enumerate(self.names) if any(n == m or n.startswith(m + ".") for m in names)]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            raise ValueError("bucket %s is not a contiguous run of parameters" % (names,))
+        hi = self.offsets[idx[-1]] + (self.params[idx[-1]].numel() + 3) // 4 * 4
+        return self.offsets[idx[0]], hi
+
+    def all_reduce_mean(self, group=None, lo=0, hi=None):
+        """Mean over the ranks of flat[lo:hi) (default: the whole buffer): ONE collective, averaged inside NCCL
+        (ReduceOp.AVG -- no separate scale kernel); gloo (CPU tests) sums and scales.  With `check_next` set, the next
+        whole-buffer call also all-gathers the ranks' LOCAL gradients and records how far the reduced buffer is from their
+        mean (`last_check`) -- SURVEY.md 8(e)'s contract, reported by bench.py at N > 1."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        world = dist.get_world_size(group)
+        part = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+        check = self.check_next and lo == 0 and hi is None and not (self.flat.is_cuda and torch.cuda.is_current_stream_capturing())
+        local = self.flat.clone() if check else None
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(part, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+            part.div_(world)
+        if check:
+            gathered = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(gathered, local, group=group)
+            mean = torch.stack(gathered).double().mean(0)
+            err = float((self.flat.double() - mean).abs().max())
+            self.last_check = {"world": world, "max_abs_err": err, "max_abs_mean": float(mean.abs().max()),
+                               "rel_l2": float((self.flat.double() - mean).norm() / mean.norm().clamp_min(1e-30)),
+                               "rank_gradients_differ": bool(world > 1 and not torch.equal(gathered[0], gathered[-1]))}
+            self.check_next = False
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -271,6 +308,7 @@ class SemSegTrainer:
         torch.optim.Adam.  augment_rotate_z: apply the training loop's augmentation (provider.rotate_point_cloud_z on points[:, :, :3],
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
+        self.overlap_allreduce = os.environ.get("PN2_OVERLAP_ALLREDUCE", "1") != "0"
         self.fused_loss = bool(fused_loss)
         self.prepack = True                  # every MLP's weight images in one launch per step (modules.prepack_mlps)
         self._rot_staging = None
@@ -279,13 +317,14 @@ class SemSegTrainer:
         if on_gpu:
             # one GPU per process: the library launches on the CURRENT device's streams (include/pn2b200.h takes a stream, not
             # a device), so the trainer's device becomes the current one
-            torch.cuda.set_device(self.device)
+            if self.device.index is not None:
+                torch.cuda.set_device(self.device)
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_classes = num_classes
         self.model = (model if model is not None else get_model(num_classes, num_extra_features)).to(self.device)
         self.criterion = get_loss()
         self.broadcast_state()
-        self.grads = FlatGradients(self.model.parameters())
+        self.grads = FlatGradients(self.model.named_parameters())
         self._bn_momentum = _BnMomentum(self.model, self.device) if on_gpu else None
         if on_gpu and flat_optimizer:
             self.optimizer = FlatAdam(self.grads, lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=weight_decay)
@@ -315,25 +354,69 @@ class SemSegTrainer:
         self._slots = []
         gc.collect()
 
+    def _early_buckets(self):
+        """Data-parallel overlap: which parts of the flat gradient are final before backward ends.  Backward runs
+        head -> fp1 .. fp4 -> sa4 .. sa1 and the library's kernels write every weight / BatchNorm gradient of those modules
+        straight into the flat buffer (the gradient sink), so [fp4 .. fp1, head] is final when the gradient of sa4's output
+        arrives and [sa3, sa4] when the gradient of sa2's output is complete; only [sa1, sa2] (80 KB) is left for the
+        all-reduce on the critical path after the last backward kernel.  Returns {feature level: (lo, hi)} or None when
+        some gradient of those buckets is produced outside the sink (PyTorch head, fp32 rows, custom modules)."""
+        from . import ops
+        m = self.model
+        if not (self.overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        if not (self.fused_loss and hasattr(m, "forward_loss") and getattr(m, "fused_head", False) and self.device.type == "cuda"
+                and ops.rows_dtype() == torch.bfloat16 and type(m).__name__ == "get_model" and hasattr(m, "feature_grad_hooks")):
+            return None
+        try:
+            return {4: self.grads.bucket_of(["fp4", "fp3", "fp2", "fp1", "conv1", "bn1", "conv2"]),
+                    2: self.grads.bucket_of(["sa3", "sa4"]), 0: self.grads.bucket_of(["sa1", "sa2"])}
+        except ValueError:
+            return None
+
     def _step_impl(self, points, target, geometry=None):
         if self._bn_momentum is not None and not torch.cuda.is_current_stream_capturing():
             self._bn_momentum.sync()
         self.grads.zero()
         if self.prepack and hasattr(self.model, "training_chains") and points.is_cuda:
             modules.prepack_mlps(self.model.training_chains())      # every MLP's weight images in one launch
-        if self.fused_loss and hasattr(self.model, "forward_loss"):
-            # forward + weighted NLL in one pass (the loss and its gradient come out of the head kernels when they apply)
-            loss, _, _ = self.model.forward_loss(points.transpose(2, 1), target, self.class_weights, geometry=geometry)
-        else:
-            if geometry is None:
-                pred, feat = self.model(points.transpose(2, 1))
+        buckets = None if self.grads.check_next else self._early_buckets()
+        if buckets is not None:
+            main = torch.cuda.current_stream(self.device)
+            comm = self._comm_stream = getattr(self, "_comm_stream", None) or torch.cuda.Stream(device=self.device)
+
+            def reduce_when_ready(level):
+                lo, hi = buckets[level]
+
+                def hook(grad):          # fires when the gradient w.r.t. that level's features is complete
+                    comm.wait_stream(main)
+                    with torch.cuda.stream(comm):
+                        self.grads.all_reduce_mean(lo=lo, hi=hi)
+                    return grad
+                return hook
+
+            self.model.feature_grad_hooks = {4: reduce_when_ready(4), 2: reduce_when_ready(2)}
+        try:
+            if self.fused_loss and hasattr(self.model, "forward_loss"):
+                # forward + weighted NLL in one pass (the loss and its gradient come out of the head kernels when they apply)
+                loss, _, _ = self.model.forward_loss(points.transpose(2, 1), target, self.class_weights, geometry=geometry)
             else:
-                pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
-            loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
+                if geometry is None:
+                    pred, feat = self.model(points.transpose(2, 1))
+                else:
+                    pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
+                loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
+        finally:
+            if buckets is not None:
+                self.model.feature_grad_hooks = None
         modules._STEP_IMAGES.clear()          # images a forward did not pick up must not outlive the parameters they were packed from
         loss.backward()
         self.grads.adopt()
-        self.grads.all_reduce_mean()
+        if buckets is not None:
+            self.grads.all_reduce_mean(lo=buckets[0][0], hi=buckets[0][1])      # what is left: sa1 + sa2
+            main.wait_stream(comm)
+        else:
+            self.grads.all_reduce_mean()
         self.optimizer.step()
         return loss.detach()
 

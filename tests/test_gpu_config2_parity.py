@@ -5,8 +5,8 @@ batch, parameters and FPS start draws:
 
 * sampling / grouping / neighbour indices of all four levels bit-exact vs the C oracle (pointnet2_utils.py:63-107,
   :296-302), read from the geometry slot the captured graph filled;
-* the loss within 2e-2 of the torch-CPU port's (models/pointnet2_sem_seg.py:22-50 in fp32);
-* every parameter gradient, read from trainer.FlatGradients, against the port's: cosine >= the bound stated below.
+* the loss within 2e-3 (bf16 rows) / 1e-4 (fp32 rows) of the torch-CPU port's (models/pointnet2_sem_seg.py:22-50 in fp32);
+* every parameter gradient, read from trainer.FlatGradients, against the port's: cosine >= the bounds stated below.
 
 Dropout is switched off on both sides (its mask comes from generator-specific draws); everything else is the benched path.
 """
@@ -22,10 +22,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 B, N, CH, NC = 32, 4096, 9, 18
 LEVELS = ((1024, 0.1), (256, 0.2), (64, 0.4), (16, 0.8))
-# bf16 storage of every activation (9 layers deep behind sa1) bounds how well the first levels' gradients can agree with an
-# fp32 evaluation; measured on B200 (profiles/r02_config2_parity.txt): worst tensor 0.99+ from sa2 on, sa1 >= 0.97
-COS_BOUND = {"sa1": 0.95}
-COS_DEFAULT = 0.98
+# Gradient bars.  fp32 rows: every tensor's cosine with the fp32 port >= 0.999 (measured >= 0.9998).  bf16 rows: rounding every
+# activation AND every activation gradient to bf16 costs correlation layer by layer on the way back (15 BatchNorm layers
+# deep at sa1), for PyTorch's own mixed precision exactly as for these kernels -- profiles/r02_gradcheck_bf16_32x4096.txt:
+# head 0.999, fp1 0.8-0.98, sa1 0.45-0.55 with random labels for BOTH.  The bar is therefore the reference itself under
+# torch.autocast(bfloat16) on the same batch (cuDNN / cuBLAS bf16 kernels): per tensor not worse than that by more than 0.3
+# (single tensors scatter by +-0.25 either way), on average not worse at all, plus absolute floors where bf16 still resolves
+# the gradient (head, fp1).
+FLOORS = {"conv2.weight": 0.995, "conv2.bias": 0.999, "bn1.weight": 0.995, "bn1.bias": 0.995, "conv1.weight": 0.95,
+          "fp1.mlp_convs.2.weight": 0.9, "fp1.mlp_convs.1.weight": 0.8}
 
 
 def _oracle_geometry(xyz0, seed):
@@ -46,14 +51,40 @@ def _oracle_geometry(xyz0, seed):
     return geo, nn3
 
 
-def test_config2_trainer_step_matches_oracle(pn2):
-    pn2.set_precision("bf16")
+def _port_autocast_gradients(state, batch, target, seed):
+    """The oracle port on the GPU under torch.autocast(bfloat16) -- what PyTorch's own mixed precision makes of the
+    reference -- with the geometry kept in fp32; returns {name: flat fp64 gradient}."""
+    saved = O.pairwise_sqdist
+
+    def sqdist_fp32(src, dst):
+        with torch.autocast("cuda", enabled=False):
+            return saved(src.float(), dst.float())
+
+    O.pairwise_sqdist = sqdist_fp32
+    try:
+        net = O.OracleSemSeg(NC, CH - 6).to(DEV).train()
+        net.load_state_dict(state)
+        net.drop1.p = 0.0
+        torch.manual_seed(seed)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred, _ = net(batch.to(DEV).transpose(2, 1))
+        loss = O.nll(pred.float().contiguous().view(-1, NC), target.to(DEV), torch.ones(NC, device=DEV))
+        loss.backward()
+        return {n: p.grad.detach().double().cpu().flatten() for n, p in net.named_parameters()}
+    finally:
+        O.pairwise_sqdist = saved
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_config2_trainer_step_matches_oracle(pn2, precision):
+    pn2.set_precision(precision)
     torch.manual_seed(1234)
     trainer = pn2.SemSegTrainer(NC, CH - 6, device=DEV)
     trainer.model.drop1.p = 0.0
     ref = O.OracleSemSeg(NC, CH - 6).train()
     ref.load_state_dict(trainer.model.state_dict())
     ref.drop1.p = 0.0
+    state = {k: v.detach().cpu().clone() for k, v in trainer.model.state_dict().items()}
     trainer.enable_cuda_graph(B, N, CH, pipeline=True)
     batch, target = I.facade_batch(B, N, CH, 11), I.labels(B, N, NC, 111)
     other = I.facade_batch(B, N, CH, 12)
@@ -83,9 +114,10 @@ def test_config2_trainer_step_matches_oracle(pn2):
     pred, _ = ref(batch.transpose(2, 1))
     rloss = O.nll(pred.contiguous().view(-1, NC), target, torch.ones(NC))
     rloss.backward()
-    assert abs(loss - rloss.item()) <= 2e-2, (loss, rloss.item())
+    assert abs(loss - rloss.item()) <= (2e-3 if precision == "bf16" else 1e-4), (loss, rloss.item())
+    cmp = _port_autocast_gradients(state, batch, target, seed) if precision == "bf16" else None
     views = {id(p): v for p, v in zip(trainer.grads.params, trainer.grads.views)}
-    report, worst = [], {}
+    report, ours, theirs = [], [], []
     for (n, p), (_, rp) in zip(trainer.model.named_parameters(), ref.named_parameters()):
         if n.endswith("bias") and ("mlp_convs" in n or n == "conv1.bias"):
             continue          # a conv bias in front of a train-mode BatchNorm: its gradient is rounding noise in both
@@ -94,13 +126,20 @@ def test_config2_trainer_step_matches_oracle(pn2):
         assert torch.isfinite(g).all(), n
         cos = float(torch.nn.functional.cosine_similarity(g, rg, dim=0))
         ratio = float(g.norm() / rg.norm())
-        report.append("%-28s cos %.5f  |g|/|g_ref| %.4f" % (n, cos, ratio))
-        top = n.split(".")[0]
-        worst[top] = min(worst.get(top, 1.0), cos)
-        assert cos >= COS_BOUND.get(top, COS_DEFAULT), "\n".join(report)
-        assert 0.9 <= ratio <= 1.1, "\n".join(report)
-    print("config-2 parity: loss %.6f vs oracle %.6f; worst gradient cosine per module: %s" % (
-        loss, rloss.item(), ", ".join("%s %.4f" % kv for kv in sorted(worst.items()))))
+        tcos = float(torch.nn.functional.cosine_similarity(cmp[n], rg, dim=0)) if cmp is not None else float("nan")
+        report.append("%-28s cos %.5f  torch-autocast-bf16 %.5f  |g|/|g_ref| %.4f" % (n, cos, tcos, ratio))
+        ours.append(cos)
+        theirs.append(tcos)
+        if precision == "fp32":
+            assert cos >= 0.999 and 0.99 <= ratio <= 1.01, report[-1]
+        else:
+            assert cos >= min(0.98, tcos - 0.3) and cos >= FLOORS.get(n, -1.0), report[-1]
+            assert 0.8 <= ratio <= 1.25, report[-1]
+    print("config-2 parity (%s rows): loss %.6f vs oracle %.6f" % (precision, loss, rloss.item()))
     print("\n".join(report))
+    if precision == "bf16":
+        mean_o, mean_t = sum(ours) / len(ours), sum(theirs) / len(theirs)
+        print("mean cosine: ours %.4f, torch autocast bf16 %.4f" % (mean_o, mean_t))
+        assert mean_o >= mean_t - 0.02, (mean_o, mean_t)
     trainer.flush()
     pn2.set_precision("fp32")
