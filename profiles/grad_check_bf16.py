@@ -32,8 +32,12 @@ _sqdist = O.pairwise_sqdist
 
 def _sqdist_fp32(src, dst):
     """geometry stays fp32 under autocast (indices are not what is being compared here)"""
-    with torch.autocast("cuda", enabled=False):
-        return _sqdist(src.float(), dst.float())
+    tf32, torch.backends.cuda.matmul.allow_tf32 = torch.backends.cuda.matmul.allow_tf32, False
+    try:
+        with torch.autocast("cuda", enabled=False):
+            return _sqdist(src.float(), dst.float())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
 O.pairwise_sqdist = _sqdist_fp32
