@@ -166,6 +166,35 @@ int pn2_linear_bwd_weight_accum(const void *dZ, int lddz, int dz_dtype, const vo
                                 int x_dtype, const float *in_scale, const float *in_shift, int64_t M,
                                 int K, int N, float *dW, void *stream);
 
+/* ---- one backward step of an MLP layer, fused (bf16 rows, tcgen05) -----------------------------------------------
+ * Autograd through relu(bn_l(conv_l(act_{l-1}))) (:196-198, :311-314) for layer l in ONE launch instead of the
+ * reduce / dz / data-gradient / weight-gradient launches above:
+ *     dZ_l      = BatchNorm+ReLU backward of layer l applied to dA_l while the tile is in shared memory (never stored)
+ *     dX        = dZ_l . W_l, masked by layer l-1's ReLU when prev_* are given (so its consumer passes da_mode 1)
+ *     dW       += dZ_l^T . act(X),  act = relu(prev_scale . X + prev_shift) or X itself (the MLP's input rows)
+ *     dgamma_prev, dbeta_prev of layer l-1's BatchNorm from dX (when prev_* are given; "last CTA finalizes")
+ * da_mode: 0 = dA dense, layer l's ReLU mask applied here; 1 = dA already masked by the call that produced it;
+ *          3 = `dA` IS dZ_l (Z / scale / ... unused).  mean == NULL: frozen statistics (dZ = scale . mask . dA).
+ * dW is ADDED to (zero it first; L2 reductions, order varies run to run); K % 4 != 0 needs `scratch`
+ * (pn2_mlp_bwd_layer_scratch_bytes) for a fixed-order partial sum instead.  dX / dW may be NULL (not wanted).
+ * HOST struct of device pointers; pn2_mlp_bwd_layer_supported tells whether the kernel takes a layer
+ * (N, ldx <= 128, row pitches % 8 == 0, shared / tensor memory) -- otherwise use the per-step entry points. */
+typedef struct pn2_bwd_layer {
+    const void *dA; int ldda; int da_mode;
+    const void *Z; int ldz;
+    const float *scale, *shift, *mean, *invstd, *dgamma, *dbeta;
+    const void *wpack_t;
+    const void *X; int ldx;
+    const float *prev_scale, *prev_shift, *prev_mean, *prev_invstd;
+    void *dX; int lddx;
+    float *dW; void *scratch;
+    double *stat_accum; uint32_t *ticket; float *dgamma_prev, *dbeta_prev;
+    int64_t M; int K, N;
+} pn2_bwd_layer;
+int pn2_mlp_bwd_layer_supported(int64_t M, int K, int N, int ldx, int lddx, int da_mode, int has_prev, int want_dx, int want_dw);
+size_t pn2_mlp_bwd_layer_scratch_bytes(int64_t M, int K, int N);
+int pn2_mlp_bwd_layer(const pn2_bwd_layer *layer_host, void *stream);
+
 /* ---- BatchNorm (train statistics / eval fold) ---------------------------------
  * Train (:198 with module.training): turns the [PN2_STAT_REPLICAS][2][N] fp64 sums of pn2_linear_fwd
  * into mean / biased variance over M rows (and zeroes the accumulator), writes

@@ -51,6 +51,9 @@ _SIGNATURES = {
     "pn2_add_vote": (_i, [_p, _p, _p, _i, _l, _l, _i, _p, _p, _p]),
     "pn2_vote_argmax": (_i, [_p, _l, _i, _p, _i, _p]),
     "pn2_linear_bwd_weight_accum": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _l, _i, _i, _p, _p]),
+    "pn2_mlp_bwd_layer_supported": (_i, [_l, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "pn2_mlp_bwd_layer_scratch_bytes": (_z, [_l, _i, _i]),
+    "pn2_mlp_bwd_layer": (_i, [_p, _p]),
     "pn2_bn_train_finalize": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_bn_eval_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "pn2_bn_relu_max": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
@@ -83,6 +86,17 @@ class BnFinalize(ctypes.Structure):
     _fields_ = [("ticket", _p), ("gamma", _p), ("beta", _p), ("conv_bias", _p), ("eps", _f), ("momentum", _f),
                 ("running_mean", _p), ("running_var", _p), ("scale", _p), ("shift", _p), ("save_mean", _p),
                 ("save_invstd", _p), ("num_batches_tracked", _p), ("momentum_dev", _p)]
+
+
+class BwdLayer(ctypes.Structure):
+    """pn2_bwd_layer of include/pn2b200.h (a HOST struct of device pointers)."""
+    _fields_ = [("dA", _p), ("ldda", _i), ("da_mode", _i), ("Z", _p), ("ldz", _i),
+                ("scale", _p), ("shift", _p), ("mean", _p), ("invstd", _p), ("dgamma", _p), ("dbeta", _p),
+                ("wpack_t", _p), ("X", _p), ("ldx", _i),
+                ("prev_scale", _p), ("prev_shift", _p), ("prev_mean", _p), ("prev_invstd", _p),
+                ("dX", _p), ("lddx", _i), ("dW", _p), ("scratch", _p),
+                ("stat_accum", _p), ("ticket", _p), ("dgamma_prev", _p), ("dbeta_prev", _p),
+                ("M", _l), ("K", _i), ("N", _i)]
 
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

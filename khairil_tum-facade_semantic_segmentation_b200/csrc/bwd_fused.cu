@@ -1,0 +1,580 @@
+// bwd_fused.cu -- one backward step of an MLP layer on bf16 rows as ONE tcgen05 kernel.
+//
+// Reference semantics: autograd through relu(bn(conv(x))) of PointNetSetAbstraction / PointNetFeaturePropagation
+// (/root/reference/models/pointnet2_utils.py:196-198, :311-314).  For layer l with input X (the previous layer's
+// pre-BatchNorm product Z_{l-1}, or the MLP's input rows) the layer-by-layer path ran five launches over [M, C] rows:
+//
+//     reduce(l-1)  dgamma_{l-1}, dbeta_{l-1} = sum_m mask.dA_{l-1}.zhat, sum_m mask.dA_{l-1}            (reads dA, Z)
+//     dz(l)        dZ_l = gamma.invstd.(mask.dA_l - dbeta/M - zhat.dgamma/M)                              (reads dA, Z; writes dZ)
+//     dgrad(l)     dA_{l-1} = dZ_l . W_l                                                                 (reads dZ; writes dA)
+//     wgrad(l)     dW_l = dZ_l^T . relu(bn(Z_{l-1}))                                                     (reads dZ, Z_{l-1})
+//
+// Here a CTA owns 128-row tiles and does all of it while the tile is in shared / tensor memory:
+//   * TMA loads the (dA_l, Z_l, X) tiles; dZ_l is formed IN PLACE on the dA tile (never stored);
+//   * the X tile becomes relu(bn(.)) (the weight gradient's operand) and zhat (the statistics' operand);
+//   * tcgen05.mma: dA_{l-1} = dZ.W (K-major A, resident W image), dW += dZ^T.act (both operands MN-major straight from
+//     the row tiles, accumulated in tensor memory over ALL tiles of the CTA, added to dW with L2 reductions at the end);
+//   * epilogue: dA_{l-1} leaves tensor memory once, is masked by layer l-1's ReLU, rounded to bf16, staged and stored by
+//     TMA; the staged tile is also the MN-major A operand of two more MMAs that accumulate
+//         S2[k,k'] += sum_m dA'[m,k] zhat[m,k']   (its diagonal is dgamma_{l-1})   and   S1[k,.] += sum_m dA'[m,k] . 1
+//     in tensor memory -- the column statistics cost no issue slots on the FMA pipes;
+//   * the CTA that draws the last ticket turns the fp64 accumulators into dgamma_{l-1} / dbeta_{l-1}.
+// HBM traffic per layer: dA_l + Z_l + X read, dA_{l-1} written (4 passes over [M, C] instead of 10), one launch instead of 4-5.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pn2 {
+
+using namespace tc;
+
+int tc_wgrad_reduce(const float *scratch, int splits, int N, int K, int K_ld, float *dW, cudaStream_t st);   // linear_tc.cu
+
+constexpr int kBfBM = 128;
+constexpr int kBfSlab = kBfBM * 128;          // one 64-column slab of a 128-row tile: 16 KB (SW128 box layout)
+constexpr int kBfCompute = 256;               // warps 0-7: transforms, MMA issue (thread 0), epilogues
+constexpr int kBfThreads = kBfCompute + 32;   // warp 8: TMA producer
+constexpr int kBfMaxC = 128;                  // widest layer (N) / input (K_ld) this kernel takes
+
+struct BwdFusedArgs {
+    CUtensorMap tm_da, tm_z, tm_x, tm_dx;
+    const float *scale, *shift, *mean, *invstd, *dgamma, *dbeta;   // layer l; mean == null: frozen statistics
+    const float *p_scale, *p_shift, *p_mean, *p_invstd;            // layer l-1 (X = Z_{l-1}); null: X is the plain MLP input
+    const uint8_t *Wimg;         // transposed image of W_l: [nS chunks][K_pad rows][128 B] (tc_pack_weights, transposed)
+    int64_t M;
+    int K, N, K_pad, k_store;    // K_pad = round_up(K, 16); k_store = columns of dX written (round_up(K, 8) <= lddx)
+    int nS, kS;                  // 64-column slabs of the dA / Z tiles and of the X tile
+    int da_mode;                 // 0: dA dense, mask applied here; 1: dA already masked by its producer; 3: dZ_l given
+    int want_dx, want_dw, want_stats;
+    int ones_col;                // >= 0: the statistics' ones live in columns [ones_col, ones_col + 16) of the zhat tile; < 0: own tile
+    int s2_cols;                 // N extent of the S2 product
+    float *dW;                   // accumulate target [N, K] (L2 reductions) or null when scratch is used
+    float *scratch;              // [gridDim.x][N][K_ld4] fp32 partial blocks (K % 4 != 0) or null
+    int dw_vec4, K_ld4;
+    double *stat_accum;          // [replicas][2][K] fp64
+    unsigned *ticket;
+    float *dgamma_prev, *dbeta_prev;
+    float inv_m;
+    int tmem_cols, off_dw, off_s2, off_s1;
+    // shared-memory byte offsets from the 1024-aligned base
+    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_bytes;
+    int coef_ld;
+};
+
+__device__ __forceinline__ void bf_red_add_f32(float *p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void bf_red_add_v4_f32(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Which 16-byte unit of a 64-column slab a thread owns in iteration i, for a tile whose rows hold `nch` valid chunks.
+//   nch == 8 (or anything else): physical unit q = tid + 256 i: row q >> 3, logical chunk (q & 7) ^ (row & 7) -- constant per
+//            thread, every thread busy, conflict free (4 iterations per slab);
+//   nch == 4: only half of every 128-byte row is data.  A warp takes one 8-row swizzle atom per iteration; its four 8-thread
+//            phases take the row pairs (p, p + 4): logical chunks 0-3 of row p sit in the physical chunks {0..3} ^ p and those
+//            of row p + 4 in the complementary half, so a phase touches all 32 banks once (2 iterations per slab).
+struct UnitMap {
+    int chunk;        // logical 16-byte chunk (8 columns) inside the slab, constant per thread
+    int row0, rstep;  // rows row0 + rstep * i
+    int iters;
+};
+__device__ __forceinline__ UnitMap unit_map(int tid, int nch) {
+    UnitMap m;
+    if (nch == 4) {
+        const int w = tid >> 5, l = tid & 31;
+        m.chunk = l & 3;
+        m.row0 = 8 * w + (l >> 3) + 4 * ((l >> 2) & 1);
+        m.rstep = 64;
+        m.iters = 2;
+    } else {
+        m.chunk = (tid & 7) ^ ((tid >> 3) & 7);
+        m.row0 = tid >> 3;
+        m.rstep = 32;
+        m.iters = 4;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_constant__ BwdFusedArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    uint8_t *const s_w = smem + a.o_w, *const s_da = smem + a.o_da, *const s_z = smem + a.o_z, *const s_x = smem + a.o_x;
+    uint8_t *const s_act = smem + a.o_act, *const s_stage = smem + a.o_stage, *const s_ones = smem + a.o_ones;
+    // per-column coefficients: layer l  dz = sc.g + cb.z + cc (mask test sc.z + sh > 0), layer l-1  act = relu(psc.z + psh),
+    // zhat = pis.z + pmi (pmi = -mean.invstd)
+    float *const coef = reinterpret_cast<float *>(smem + a.o_coef);
+    const int cl = a.coef_ld;
+    float *const c_sc = coef, *const c_sh = coef + cl, *const c_b = coef + 2 * cl, *const c_c = coef + 3 * cl;
+    float *const p_sc = coef + 4 * cl, *const p_sh = coef + 5 * cl, *const p_is = coef + 6 * cl, *const p_mi = coef + 7 * cl;
+    const bool prev = a.p_scale != nullptr;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bar_full, 1);
+        mbar_init(&bar_empty, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_init_fence();
+    }
+    for (int c = tid; c < cl; c += kBfThreads) {
+        float sc = 0.f, sh = 0.f, cb = 0.f, cc = 0.f;
+        if (c < a.N && a.da_mode != 3) {
+            sc = a.scale[c];
+            sh = a.shift[c];
+            if (a.mean) {      // train: dz = sc.(g - dbeta/M - zhat.dgamma/M) = sc.g + cb.z + cc
+                cb = -sc * a.dgamma[c] * a.invstd[c] * a.inv_m;
+                cc = -sc * a.dbeta[c] * a.inv_m - cb * a.mean[c];
+            }
+        }
+        c_sc[c] = sc; c_sh[c] = sh; c_b[c] = cb; c_c[c] = cc;
+        float ps = 0.f, ph = 0.f, pi = 0.f, pm = 0.f;
+        if (prev && c < a.K) { ps = a.p_scale[c]; ph = a.p_shift[c]; pi = a.p_invstd[c]; pm = -a.p_mean[c] * pi; }
+        p_sc[c] = ps; p_sh[c] = ph; p_is[c] = pi; p_mi[c] = pm;
+    }
+    if (a.want_stats && a.ones_col < 0)     // the all-ones K-major B operand of the S1 product: [16 n-rows x 128 k] bf16 = 4 KB
+        for (int i = tid; i < 4096 / 4; i += kBfThreads) reinterpret_cast<uint32_t *>(s_ones)[i] = 0x3f803f80u;
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const int64_t m_tiles = (a.M + kBfBM - 1) / kBfBM;
+    const uint32_t w_chunk_bytes = (uint32_t)a.K_pad * 128u;
+
+    if (warp == kBfCompute / 32) {
+        // ---- producer: the tile's row boxes (and, once, the weight image) by TMA ----
+        if (lane == 0) {
+            tma_prefetch_desc(&a.tm_da);
+            tma_prefetch_desc(&a.tm_x);
+            uint32_t t = 0;
+            for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+                if (t > 0) mbar_wait(&bar_empty, (t - 1) & 1u);
+                const int m0 = (int)(tile * kBfBM);
+                uint32_t bytes = a.stage_bytes;
+                if (t == 0 && a.want_dx) bytes += (uint32_t)a.nS * w_chunk_bytes;
+                mbar_expect_tx(&bar_full, bytes);
+                if (t == 0 && a.want_dx)
+                    for (int j = 0; j < a.nS; ++j) bulk_g2s(s_w + (size_t)j * w_chunk_bytes, a.Wimg + (size_t)j * w_chunk_bytes, w_chunk_bytes, &bar_full);
+                for (int j = 0; j < a.nS; ++j) tma_load_2d(s_da + (size_t)j * kBfSlab, &a.tm_da, 64 * j, m0, &bar_full);
+                if (a.da_mode != 3)
+                    for (int j = 0; j < a.nS; ++j) tma_load_2d(s_z + (size_t)j * kBfSlab, &a.tm_z, 64 * j, m0, &bar_full);
+                if (a.want_dw || prev)
+                    for (int j = 0; j < a.kS; ++j) tma_load_2d(s_x + (size_t)j * kBfSlab, &a.tm_x, 64 * j, m0, &bar_full);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int row = tid & 127, half = tid >> 7;                // epilogue: row of the tile, column half
+        const int wq = warp & 3;                                  // tensor-memory lane quarter of this warp
+        // MN-major operands of a one-slab tile: the M = 128 product reads "the next slab" through LBO; 0 makes it the same slab
+        // again (rows 64-127 of those products are never used)
+        const uint32_t lbo_n = a.nS > 1 ? (uint32_t)kBfSlab : 0u, lbo_k = a.kS > 1 ? (uint32_t)kBfSlab : 0u;
+        const uint32_t idesc_dx = make_idesc_bf16(kBfBM, a.K_pad, 0, 0);      // dA = dZ . W      (A, B K-major)
+        const uint32_t idesc_dw = make_idesc_bf16(kBfBM, a.K_pad, 1, 1);      // dW = dZ^T . act  (A, B MN-major)
+        const uint32_t idesc_s2 = make_idesc_bf16(kBfBM, a.s2_cols, 1, 1);    // S2 = dA'^T . [zhat | ones]
+        const uint32_t idesc_s1 = make_idesc_bf16(kBfBM, 16, 1, 0);           // S1 = dA'^T . ones (B K-major, own tile)
+        // valid 16-byte chunks per row of a slab (the last slab of a tile may be narrower)
+        uint32_t t = 0;
+        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+            const int64_t m0 = tile * kBfBM;
+            const int rows_valid = (int)min((int64_t)kBfBM, a.M - m0);
+            mbar_wait(&bar_full, t & 1u);
+            // ---- T1: dZ_l in place on the dA tile ----
+            if (a.da_mode != 3) {
+                for (int j = 0; j < a.nS; ++j) {
+                    const int nch = min(8, (a.N - 64 * j) >> 3);
+                    const UnitMap um = unit_map(tid, nch);
+                    const int c0 = 64 * j + 8 * um.chunk;
+                    if (um.chunk >= nch) continue;
+                    float sc[8], sh[8], cb[8], cc[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sc[e] = c_sc[c0 + e]; sh[e] = c_sh[c0 + e]; cb[e] = c_b[c0 + e]; cc[e] = c_c[c0 + e]; }
+#pragma unroll 2
+                    for (int i = 0; i < um.iters; ++i) {
+                        const int r = um.row0 + um.rstep * i;
+                        const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(r, um.chunk);
+                        uint4 g4 = *reinterpret_cast<const uint4 *>(s_da + off);
+                        const uint4 z4 = *reinterpret_cast<const uint4 *>(s_z + off);
+                        uint32_t *gw = reinterpret_cast<uint32_t *>(&g4);
+                        const uint32_t *zw = reinterpret_cast<const uint32_t *>(&z4);
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            float2 g = unpack_bf16x2(gw[e2]);
+                            const float2 z = unpack_bf16x2(zw[e2]);
+                            if (a.da_mode == 0) {
+                                if (!(fmaf(z.x, sc[2 * e2], sh[2 * e2]) > 0.0f)) g.x = 0.0f;
+                                if (!(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]) > 0.0f)) g.y = 0.0f;
+                            }
+                            const float dx = fmaf(sc[2 * e2], g.x, fmaf(cb[2 * e2], z.x, cc[2 * e2]));
+                            const float dy = fmaf(sc[2 * e2 + 1], g.y, fmaf(cb[2 * e2 + 1], z.y, cc[2 * e2 + 1]));
+                            gw[e2] = pack_bf16x2(dx, dy);
+                        }
+                        if (r >= rows_valid) g4 = make_uint4(0u, 0u, 0u, 0u);      // rows past M (zero-filled loads) must stay zero
+                        *reinterpret_cast<uint4 *>(s_da + off) = g4;
+                    }
+                }
+            }
+            // ---- T2: X tile -> act (weight-gradient operand) and zhat in place (statistics operand) ----
+            if (prev) {
+                for (int j = 0; j < a.kS; ++j) {
+                    const int nch = min(8, (a.K - 64 * j) >> 3);
+                    const UnitMap um = unit_map(tid, nch);
+                    const int c0 = 64 * j + 8 * um.chunk;
+                    if (um.chunk >= nch) continue;
+                    float sc[8], sh[8], is[8], mi[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sc[e] = p_sc[c0 + e]; sh[e] = p_sh[c0 + e]; is[e] = p_is[c0 + e]; mi[e] = p_mi[c0 + e]; }
+#pragma unroll 2
+                    for (int i = 0; i < um.iters; ++i) {
+                        const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
+                        uint4 z4 = *reinterpret_cast<const uint4 *>(s_x + off);
+                        uint4 a4;
+                        uint32_t *zw = reinterpret_cast<uint32_t *>(&z4), *aw = reinterpret_cast<uint32_t *>(&a4);
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const float2 z = unpack_bf16x2(zw[e2]);
+                            aw[e2] = pack_bf16x2(fmaxf(fmaf(z.x, sc[2 * e2], sh[2 * e2]), 0.0f), fmaxf(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f));
+                            zw[e2] = pack_bf16x2(fmaf(z.x, is[2 * e2], mi[2 * e2]), fmaf(z.y, is[2 * e2 + 1], mi[2 * e2 + 1]));
+                        }
+                        *reinterpret_cast<uint4 *>(s_act + off) = a4;
+                        *reinterpret_cast<uint4 *>(s_x + off) = z4;
+                    }
+                }
+                if (a.ones_col >= 0) {
+                    // the statistics' ones: 16 columns of the zhat tile past its data (the TMA load zero-filled them): 256 units
+                    const int r = tid >> 1, ch = ((a.ones_col & 63) >> 3) + (tid & 1);
+                    *reinterpret_cast<uint4 *>(s_x + (size_t)(a.ones_col >> 6) * kBfSlab + sw128_offset(r, ch)) =
+                        make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                }
+            }
+            fence_proxy_async();
+            named_bar_sync(1, kBfCompute);
+            // ---- MMAs of the tile: data gradient and weight gradient ----
+            if (tid == 0) {
+                fence_after_sync();
+                if (a.want_dx) {
+                    for (int j = 0; j < a.nS; ++j) {
+                        const int n_left = a.N - 64 * j;
+                        const int nk = n_left >= 64 ? 4 : (n_left + 15) / 16;
+                        const uint32_t a_base = smem_addr(s_da + (size_t)j * kBfSlab), b_base = smem_addr(s_w + (size_t)j * w_chunk_bytes);
+                        for (int kk = 0; kk < nk; ++kk)
+                            umma_bf16(tmem, make_desc(a_base + 32 * kk, 0, 1024), make_desc(b_base + 32 * kk, 0, 1024), idesc_dx,
+                                      (uint32_t)((j | kk) != 0));
+                    }
+                }
+                if (a.want_dw) {
+                    const uint32_t a_base = smem_addr(s_da), b_base = smem_addr(prev ? s_act : s_x);
+                    for (int r = 0; r < kBfBM / 16; ++r)
+                        umma_bf16(tmem + (uint32_t)a.off_dw, make_desc(a_base + 2048 * r, lbo_n, 1024),
+                                  make_desc(b_base + 2048 * r, lbo_k, 1024), idesc_dw, (uint32_t)((t | (uint32_t)r) != 0));
+                }
+                if (a.want_dx) umma_commit(&bar_mma);
+                else umma_commit(&bar_empty);           // nothing else reads the tile: the producer may refill it
+            }
+            if (!a.want_dx) continue;
+            mbar_wait(&bar_mma, t & 1u);
+            fence_after_sync();
+            // ---- epilogue: dA_{l-1} row `row`, this warp group's 16-column chunks -> mask of layer l-1 -> bf16 -> staging ----
+            {
+                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+                for (int c0 = 16 * half; c0 < a.k_store; c0 += 32) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    const int ch = (c0 & 63) >> 3;
+                    const uint32_t o_lo = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(row, ch);
+                    const uint32_t o_hi = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(row, ch + 1);
+                    const bool two = c0 + 8 < a.k_store;
+                    if (prev) {
+                        const uint4 m_lo = *reinterpret_cast<const uint4 *>(s_act + o_lo);
+                        uint4 m_hi = make_uint4(0u, 0u, 0u, 0u);
+                        if (two) m_hi = *reinterpret_cast<const uint4 *>(s_act + o_hi);
+                        const uint32_t mw[8] = {m_lo.x, m_lo.y, m_lo.z, m_lo.w, m_hi.x, m_hi.y, m_hi.z, m_hi.w};
+#pragma unroll
+                        for (int e2 = 0; e2 < 8; ++e2) {
+                            // act is relu(.) >= 0 in bf16: positive <=> its 15 magnitude bits are non-zero
+                            if (!(mw[e2] & 0x00007fffu)) v[2 * e2] = 0.0f;
+                            if (!(mw[e2] & 0x7fff0000u)) v[2 * e2 + 1] = 0.0f;
+                        }
+                    }
+                    uint4 lo, hi;
+                    lo.x = pack_bf16x2(v[0], v[1]);   lo.y = pack_bf16x2(v[2], v[3]);
+                    lo.z = pack_bf16x2(v[4], v[5]);   lo.w = pack_bf16x2(v[6], v[7]);
+                    hi.x = pack_bf16x2(v[8], v[9]);   hi.y = pack_bf16x2(v[10], v[11]);
+                    hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+                    *reinterpret_cast<uint4 *>(s_stage + o_lo) = lo;
+                    if (two) *reinterpret_cast<uint4 *>(s_stage + o_hi) = hi;
+                }
+            }
+            fence_before_sync();
+            fence_proxy_async();
+            named_bar_sync(1, kBfCompute);
+            if (tid == 0) {
+                for (int j = 0; j < a.kS; ++j)
+                    if (64 * j < a.k_store) tma_store_2d(&a.tm_dx, 64 * j, (int)m0, s_stage + (size_t)j * kBfSlab);
+                if (a.want_stats) {
+                    fence_after_sync();
+                    const uint32_t a_base = smem_addr(s_stage), b2 = smem_addr(s_x), b1 = smem_addr(s_ones);
+                    for (int r = 0; r < kBfBM / 16; ++r) {
+                        const uint32_t acc = (uint32_t)((t | (uint32_t)r) != 0);
+                        umma_bf16(tmem + (uint32_t)a.off_s2, make_desc(a_base + 2048 * r, lbo_k, 1024), make_desc(b2 + 2048 * r, lbo_k, 1024),
+                                  idesc_s2, acc);
+                        if (a.ones_col < 0)
+                            umma_bf16(tmem + (uint32_t)a.off_s1, make_desc(a_base + 2048 * r, lbo_k, 1024),
+                                      make_desc(b1 + (uint32_t)(r >> 2) * 2048u + (uint32_t)(r & 3) * 32u, 0, 1024), idesc_s1, acc);
+                    }
+                }
+                tma_store_wait_read();
+                umma_commit(&bar_empty);      // every MMA that reads the tile / the staging is done -> refill
+            }
+        }
+        if (tid == 0) tma_store_wait_all();
+        // ---- end of the CTA: drain the accumulators that lived in tensor memory across all its tiles ----
+        const uint32_t n_my = (uint32_t)(((m_tiles - 1 - (int64_t)blockIdx.x) / (int64_t)gridDim.x) + 1);   // tiles this CTA did (>= 1)
+        // the last commit of the loop went to bar_empty (phase n_my - 1): wait for it here -- the producer only waits for
+        // phases 0 .. n_my - 2
+        mbar_wait(&bar_empty, (n_my - 1) & 1u);
+        fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+        if (a.want_dw && wq * 32 < a.N) {      // (tensor-memory loads are warp-collective: whole warps take part, stores are per row)
+            float *acc = a.dW ? a.dW + (size_t)row * a.K : nullptr;
+            float *part = a.scratch ? a.scratch + ((size_t)blockIdx.x * a.N + row) * a.K_ld4 : nullptr;
+            const bool mine = row < a.N;
+            for (int c0 = 16 * half; c0 < a.K_pad; c0 += 32) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)a.off_dw + c0, v);
+                if (!mine) continue;
+                if (part) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        if (c0 + i < a.K_ld4) *reinterpret_cast<float4 *>(part + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else if (a.dw_vec4) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        if (c0 + i < a.K) bf_red_add_v4_f32(acc + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.K) bf_red_add_f32(acc + c0 + i, v[i]);
+                }
+            }
+        }
+        if (a.want_stats) {
+            // S2's diagonal (row k, column k) and S1 (row k, the ones column): lanes 0-15 need chunk 2 * wq, lanes 16-31 the next
+            if (half == 0 && wq * 32 < a.K) {
+                float v0[16], v1[16], w[16];
+                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(wq * 32), v0);
+                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(wq * 32 + 16), v1);
+                tmem_ld16(taddr + (uint32_t)(a.ones_col >= 0 ? a.off_s2 + a.ones_col : a.off_s1), w);
+                float s2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((lane & 15) == i) s2 = lane < 16 ? v0[i] : v1[i];
+                if (row < a.K) {
+                    double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.K;
+                    atomicAdd(acc + row, (double)w[0]);
+                    atomicAdd(acc + a.K + row, (double)s2);
+                }
+            }
+            // "last CTA finalizes" (as bn.cu: bn_bwd_last_block_finalize, among the compute threads)
+            __threadfence();
+            named_bar_sync(1, kBfCompute);
+            if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+            named_bar_sync(1, kBfCompute);
+            if (s_last) {
+                __threadfence();
+                for (int c = tid; c < a.K; c += kBfCompute) {
+                    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < kStatReplicas; ++r) {
+                        double *acc = a.stat_accum + (size_t)r * 2 * a.K;
+                        t1 += __ldcg(acc + c);
+                        t2 += __ldcg(acc + a.K + c);
+                        acc[c] = 0.0;
+                        acc[a.K + c] = 0.0;
+                    }
+                    a.dbeta_prev[c] = (float)t1;
+                    a.dgamma_prev[c] = (float)t2;
+                }
+                if (tid == 0) *a.ticket = 0u;
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, (uint32_t)a.tmem_cols);
+}
+
+static int bf_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct BwdFusedPlan {
+    bool ok;
+    int nS, kS, K_pad, k_store, tmem_cols, off_dw, off_s2, off_s1, ctas_per_sm, ones_col, s2_cols, coef_ld;
+    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_bytes;
+    size_t dyn_smem;
+};
+
+static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode, bool prev, bool want_dx, bool want_dw) {
+    BwdFusedPlan p;
+    memset(&p, 0, sizeof(p));
+    if (N < 8 || N > kBfMaxC || N % 8 != 0 || K < 1 || ldx > kBfMaxC || ldx % 8 != 0 || bf_round_up(K, 16) > kBfMaxC) return p;
+    if (!want_dx && !want_dw) return p;
+    if (prev && (!want_dx || K % 8 != 0)) return p;       // statistics of layer l-1 come out of the data-gradient epilogue
+    p.nS = (N + 63) / 64;
+    p.kS = (ldx + 63) / 64;
+    p.K_pad = bf_round_up(K, 16);
+    p.k_store = bf_round_up(K, 8);
+    if (want_dx && p.k_store > lddx) p.k_store = lddx;
+    // the statistics' ones: inside the zhat tile when its last slab has 16 spare columns, else a 4 KB tile of their own
+    p.ones_col = -1;
+    p.s2_cols = p.kS * 64;
+    if (prev && p.K_pad + 16 <= p.kS * 64) { p.ones_col = p.K_pad; p.s2_cols = p.K_pad + 16; }
+    else if (prev) p.s2_cols = p.K_pad;
+    uint32_t o = 0;
+    p.o_w = o;
+    if (want_dx) o += (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024);
+    p.o_da = o; o += (uint32_t)p.nS * kBfSlab;
+    p.stage_bytes = (uint32_t)p.nS * kBfSlab;
+    p.o_z = o;
+    if (da_mode != 3) { o += (uint32_t)p.nS * kBfSlab; p.stage_bytes += (uint32_t)p.nS * kBfSlab; }
+    p.o_x = o;
+    if (want_dw || prev) { o += (uint32_t)p.kS * kBfSlab; p.stage_bytes += (uint32_t)p.kS * kBfSlab; }
+    p.o_act = o;
+    if (prev) o += (uint32_t)p.kS * kBfSlab;
+    // the staged dA_{l-1} tile: over the Z tile when there is one and it is big enough (Z is dead once dZ is formed)
+    if (want_dx && da_mode != 3 && p.nS >= p.kS) p.o_stage = p.o_z;
+    else { p.o_stage = o; if (want_dx) o += (uint32_t)p.kS * kBfSlab; }
+    p.o_ones = o;
+    if (prev && p.ones_col < 0) o += 4096;
+    p.coef_ld = bf_round_up(N > p.kS * 64 ? N : p.kS * 64, 8);
+    if (p.coef_ld < bf_round_up(N, 64)) p.coef_ld = bf_round_up(N, 64);
+    p.o_coef = o;
+    o += (uint32_t)(8 * p.coef_ld * sizeof(float));
+    p.dyn_smem = (size_t)o + 1024;
+    // tensor memory: [dA_{l-1}: K_pad][dW: K_pad][S2: s2_cols][S1: 16 when the ones have their own tile]
+    int cols = 0;
+    if (want_dx) cols += p.K_pad;
+    p.off_dw = cols;
+    if (want_dw) cols += p.K_pad;
+    p.off_s2 = cols;
+    if (prev) cols += p.s2_cols;
+    p.off_s1 = cols;
+    if (prev && p.ones_col < 0) cols += 16;
+    int alloc = 32;
+    while (alloc < cols) alloc <<= 1;
+    if (alloc > 512) return p;
+    p.tmem_cols = alloc;
+    if (p.dyn_smem > 227 * 1024 - 1024) return p;
+    int per_sm = (int)((233472 - 1024) / (p.dyn_smem + 1024 + 512));
+    if (per_sm > 512 / alloc) per_sm = 512 / alloc;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) return p;
+    p.ctas_per_sm = per_sm;
+    p.ok = true;
+    return p;
+}
+
+static bool bwd_fused_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("PN2_FUSED_BWD");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+        const char *t = getenv("PN2_DISABLE_TC");
+        if (t && atoi(t) != 0) on = 0;
+    }
+    return on != 0;
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_mlp_bwd_layer_supported(int64_t M, int K, int N, int ldx, int lddx, int da_mode, int has_prev, int want_dx,
+                                           int want_dw) {
+    if (!bwd_fused_enabled() || M < 1) return 0;
+    return bwd_fused_plan(K, N, ldx, lddx, da_mode, has_prev != 0, want_dx != 0, want_dw != 0).ok ? 1 : 0;
+}
+
+extern "C" size_t pn2_mlp_bwd_layer_scratch_bytes(int64_t M, int K, int N) {
+    // fp32 partial blocks of the weight gradient when K % 4 != 0 (rows of dW are not 16-byte aligned: no vector reductions)
+    if (K % 4 == 0) return 0;
+    const int64_t m_tiles = (M + kBfBM - 1) / kBfBM;
+    const int64_t grid = m_tiles < 4 * kNumSMs ? m_tiles : 4 * kNumSMs;
+    return (size_t)grid * (size_t)N * (size_t)bf_round_up(K, 4) * sizeof(float) + 16;
+}
+
+extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
+    PN2_REQUIRE(L, "mlp_bwd_layer: null argument block");
+    PN2_REQUIRE(L->dA && L->M >= 1 && L->K >= 1 && L->N >= 1, "mlp_bwd_layer: bad sizes");
+    PN2_REQUIRE(L->da_mode == 0 || L->da_mode == 1 || L->da_mode == 3, "mlp_bwd_layer: da_mode must be 0, 1 or 3");
+    PN2_REQUIRE(L->da_mode == 3 || (L->Z && L->scale && L->shift), "mlp_bwd_layer: layer l's Z / scale / shift are required");
+    PN2_REQUIRE(L->da_mode == 3 || !L->mean || (L->invstd && L->dgamma && L->dbeta), "mlp_bwd_layer: train-mode BatchNorm needs invstd, dgamma, dbeta");
+    const bool prev = L->prev_scale != nullptr, want_dx = L->dX != nullptr, want_dw = L->dW != nullptr;
+    PN2_REQUIRE(!prev || (L->prev_shift && L->prev_mean && L->prev_invstd && L->stat_accum && L->ticket && L->dgamma_prev && L->dbeta_prev),
+                "mlp_bwd_layer: the statistics of layer l-1 need shift, mean, invstd, accumulator, ticket, dgamma_prev, dbeta_prev");
+    PN2_REQUIRE(!(want_dw || prev) || L->X, "mlp_bwd_layer: X is required");
+    PN2_REQUIRE(!want_dx || L->wpack_t, "mlp_bwd_layer: the data gradient needs the transposed weight image");
+    PN2_REQUIRE(L->ldda >= L->N && (L->da_mode == 3 || L->ldz >= L->N) && (!L->X || L->ldx >= L->K) && (!want_dx || L->lddx >= L->K),
+                "mlp_bwd_layer: leading dimensions");
+    PN2_REQUIRE(L->ldda % 8 == 0 && (L->da_mode == 3 || L->ldz % 8 == 0) && (!L->X || L->ldx % 8 == 0) && (!want_dx || L->lddx % 8 == 0),
+                "mlp_bwd_layer: bf16 rows need a 16-byte row pitch");
+    const BwdFusedPlan p = bwd_fused_plan(L->K, L->N, L->X ? L->ldx : bf_round_up(L->K, 8), want_dx ? L->lddx : 0, L->da_mode, prev, want_dx, want_dw);
+    if (!p.ok || !bwd_fused_enabled()) {
+        set_error("mlp_bwd_layer: layer K=%d N=%d is not supported by the fused kernel (see pn2_mlp_bwd_layer_supported)", L->K, L->N);
+        return PN2_ERR_UNSUPPORTED;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+        if (e != cudaSuccess) {
+            set_error("mlp_bwd_layer: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return PN2_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    BwdFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    bool ok = make_rows_tensor_map(&a.tm_da, L->dA, L->M, bf_round_up(L->N, 8) <= L->ldda ? bf_round_up(L->N, 8) : L->ldda, L->ldda, kBfBM);
+    if (L->da_mode != 3) ok = ok && make_rows_tensor_map(&a.tm_z, L->Z, L->M, bf_round_up(L->N, 8) <= L->ldz ? bf_round_up(L->N, 8) : L->ldz, L->ldz, kBfBM);
+    else a.tm_z = a.tm_da;
+    if (want_dw || prev) ok = ok && make_rows_tensor_map(&a.tm_x, L->X, L->M, L->ldx, L->ldx, kBfBM);
+    else a.tm_x = a.tm_da;
+    if (want_dx) ok = ok && make_rows_tensor_map(&a.tm_dx, L->dX, L->M, p.k_store, L->lddx, kBfBM);
+    else a.tm_dx = a.tm_da;
+    if (!ok) {
+        set_error("mlp_bwd_layer: cuTensorMapEncodeTiled failed (M=%lld N=%d K=%d)", (long long)L->M, L->N, L->K);
+        return PN2_ERR_CUDA;
+    }
+    a.scale = L->scale; a.shift = L->shift; a.mean = L->mean; a.invstd = L->invstd; a.dgamma = L->dgamma; a.dbeta = L->dbeta;
+    a.p_scale = L->prev_scale; a.p_shift = L->prev_shift; a.p_mean = L->prev_mean; a.p_invstd = L->prev_invstd;
+    a.Wimg = (const uint8_t *)L->wpack_t;
+    a.M = L->M; a.K = L->K; a.N = L->N; a.K_pad = p.K_pad; a.k_store = p.k_store; a.nS = p.nS; a.kS = p.kS;
+    a.da_mode = L->da_mode; a.want_dx = want_dx; a.want_dw = want_dw; a.want_stats = prev;
+    const int64_t m_tiles = (L->M + kBfBM - 1) / kBfBM;
+    int64_t grid = (int64_t)p.ctas_per_sm * kNumSMs;
+    if (grid > m_tiles) grid = m_tiles;
+    a.K_ld4 = bf_round_up(L->K, 4);
+    if (want_dw) {
+        if (L->K % 4 == 0 && ((uintptr_t)L->dW & 15) == 0) { a.dW = L->dW; a.dw_vec4 = 1; }
+        else if (L->scratch) a.scratch = (float *)(((uintptr_t)L->scratch + 15) & ~(uintptr_t)15);
+        else a.dW = L->dW;                                   // scalar L2 reductions
+    }
+    a.stat_accum = L->stat_accum; a.ticket = L->ticket; a.dgamma_prev = L->dgamma_prev; a.dbeta_prev = L->dbeta_prev;
+    a.inv_m = 1.0f / (float)L->M;
+    a.tmem_cols = p.tmem_cols; a.off_dw = p.off_dw; a.off_s2 = p.off_s2; a.off_s1 = p.off_s1;
+    a.ones_col = p.ones_col; a.s2_cols = p.s2_cols; a.o_coef = p.o_coef; a.coef_ld = p.coef_ld;
+    a.o_w = p.o_w; a.o_da = p.o_da; a.o_z = p.o_z; a.o_x = p.o_x; a.o_act = p.o_act; a.o_stage = p.o_stage; a.o_ones = p.o_ones;
+    a.stage_bytes = p.stage_bytes;
+    bwd_fused_kernel<<<(unsigned)grid, kBfThreads, p.dyn_smem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    int rc = check_launch("mlp_bwd_layer");
+    if (rc != PN2_OK || !a.scratch) return rc;
+    return tc_wgrad_reduce(a.scratch, (int)grid, L->N, L->K, a.K_ld4, L->dW, (cudaStream_t)stream);
+}

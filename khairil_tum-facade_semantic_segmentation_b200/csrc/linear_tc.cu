@@ -1063,6 +1063,14 @@ __global__ void wgrad_reduce_kernel2(const float *__restrict__ scratch, int spli
     }
 }
 
+// fixed-order sum of `splits` fp32 partial blocks [splits][N][K_ld] into dW[N][K] (also used by bwd_fused.cu)
+int tc_wgrad_reduce(const float *scratch, int splits, int N, int K, int K_ld, float *dW, cudaStream_t st) {
+    const int64_t NK = (int64_t)N * K;
+    wgrad_reduce_kernel2<<<(unsigned)((NK + 31) / 32), dim3(32, 8), 0, st>>>(scratch, splits, N, K, K_ld, dW);
+    count_launch();
+    return check_launch("wgrad_reduce");
+}
+
 struct WgradPlan {
     int splits, nblk_n, nblk_k, a_slabs, b_slabs, R, K_ld;
     int64_t rows_per_split;

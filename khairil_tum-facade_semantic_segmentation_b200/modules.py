@@ -33,7 +33,7 @@ def _row_ld(k, dtype):
 
 
 class _LayerState:
-    __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias", "wpack_bwd")
+    __slots__ = ("W", "K", "N", "Z", "scale", "shift", "mean", "invstd", "train", "has_bias", "wpack_bwd", "dgamma", "dbeta")
 
 
 _GRAD_MODE = [True]       # grad mode at the module's forward() (inside autograd.Function.forward it always reads False)
@@ -352,68 +352,181 @@ def _side_stream(dev):
     return s
 
 
+FUSED_BWD = True          # bf16 rows: one fused kernel per layer (csrc/bwd_fused.cu) wherever the library takes the layer
+
+
+def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dtype, keep):
+    """One launch of pn2_mlp_bwd_layer for layer `st` (see include/pn2b200.h), or None when the library does not take it.
+    cur / mode: the incoming gradient -- "dA" (dense, unmasked), "dA_masked" or "dZ".  Returns (dW, dA_prev, dgamma_prev,
+    dbeta_prev)."""
+    from ._lib import BwdLayer
+    lib = load()
+    if not FUSED_BWD or dtype != torch.bfloat16 or cur.dtype != torch.bfloat16 or st.wpack_bwd is None and want_dx:
+        return None
+    xin = x0 if prev is None else prev.Z
+    ldx = xin.shape[1]
+    ldd = (_row_ld(st.K, dtype) if prev is not None else x0.shape[1]) if want_dx else 0
+    da_mode = {"dA": 0, "dA_masked": 1, "dZ": 3}[mode]
+    if xin.dtype != torch.bfloat16 or not lib.pn2_mlp_bwd_layer_supported(M, st.K, st.N, ldx, ldd, da_mode, int(prev is not None),
+                                                                          int(want_dx), 1):
+        return None
+    param = getattr(conv, "weight", None)
+    dW = _sink(param, (st.N, st.K))
+    scratch = None
+    nbytes = lib.pn2_mlp_bwd_layer_scratch_bytes(M, st.K, st.N)
+    if nbytes:                                   # K % 4 != 0: fixed-order partials, the reduce launch WRITES dW
+        scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        if dW is None:
+            dW = torch.empty(st.N, st.K, device=dev, dtype=torch.float32)
+    elif dW is None:
+        dW = torch.zeros(st.N, st.K, device=dev, dtype=torch.float32)      # (a sink is zeroed once per step by its owner)
+    dA_prev = torch.empty(M, ldd, device=dev, dtype=dtype) if want_dx else None
+    dgamma_prev = dbeta_prev = None
+    if prev is not None:
+        dgamma_prev = _sink(bn_prev.weight) if bn_prev is not None else None
+        dbeta_prev = _sink(bn_prev.bias) if bn_prev is not None else None
+        if dgamma_prev is None or dbeta_prev is None:
+            dgb = torch.empty(2, st.K, device=dev, dtype=torch.float32)
+            dgamma_prev, dbeta_prev = dgb[0], dgb[1]
+    L = BwdLayer()
+    L.dA, L.ldda, L.da_mode = ptr(cur), cur.shape[1], da_mode
+    if da_mode != 3:
+        L.Z, L.ldz = ptr(st.Z), st.Z.shape[1]
+        L.scale, L.shift = ptr(st.scale), ptr(st.shift)
+        if st.train:
+            L.mean, L.invstd, L.dgamma, L.dbeta = ptr(st.mean), ptr(st.invstd), ptr(st.dgamma), ptr(st.dbeta)
+    L.wpack_t = ptr(st.wpack_bwd) if want_dx else None
+    L.X, L.ldx = ptr(xin), ldx
+    if prev is not None:
+        L.prev_scale, L.prev_shift, L.prev_mean, L.prev_invstd = ptr(prev.scale), ptr(prev.shift), ptr(prev.mean), ptr(prev.invstd)
+        L.stat_accum, L.ticket = ptr(_stat_accum(dev)), ptr(_ticket(dev))
+        L.dgamma_prev, L.dbeta_prev = ptr(dgamma_prev), ptr(dbeta_prev)
+    L.dX, L.lddx = ptr(dA_prev), ldd
+    L.dW, L.scratch = ptr(dW), ptr(scratch)
+    L.M, L.K, L.N = M, st.K, st.N
+    call("pn2_mlp_bwd_layer", ctypes.addressof(L), stream())
+    keep.append(scratch)
+    return dW, dA_prev, dgamma_prev, dbeta_prev
+
+
 def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bns=None):
     """Backward of mlp_forward + tail.  dout: [G, C] fp32 pooled gradient with arg-max map `arg`
-    (set abstraction) or [M, C] fp32 dense gradient (feature propagation, arg None).
-    Returns (per-layer (dW, dbias, dgamma, dbeta), dX0 or None)."""
+    (set abstraction) or [M, C] dense gradient (feature propagation: fp32; head: bf16), arg None.
+    Returns (per-layer (dW, dbias, dgamma, dbeta), dX0 or None).
+
+    Per layer, from the top: the gradient w.r.t. the layer's activation arrives as "dA" (dense), "dA_masked" (dense, already
+    multiplied by the layer's ReLU mask, its BatchNorm gradients known) or "dZ" (gradient w.r.t. the pre-BatchNorm product).
+    bf16 rows: ONE fused launch per layer (csrc/bwd_fused.cu: dZ on the fly, data gradient, weight gradient and the
+    BatchNorm gradients of the layer below) wherever the library takes the layer; otherwise the per-step kernels
+    (reduce / dz / data gradient / weight gradient on a side stream)."""
     lib = load()
     dev, dtype = x0.device, x0.dtype
     L = len(layers)
     grads = [None] * L
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev) if OVERLAP_WGRAD else None
+    side_used = False
     keep = []                 # operands of side-stream kernels stay alive until the streams are joined
 
-    def bn_grads(l, dA, ldda):
-        """dgamma/dbeta of layer l from the gradient w.r.t. its activation, then dZ."""
-        st = layers[l]
-        C = st.N
-        accum = _stat_accum(dev)
+    def bn_params(l):
+        """(dgamma, dbeta) targets of layer l: the parameters' gradient-sink views when there are any"""
         dgamma = _sink(bns[l].weight) if bns is not None else None
         dbeta = _sink(bns[l].bias) if bns is not None else None
         if dgamma is None or dbeta is None:
-            dgb = torch.empty(2, C, device=dev, dtype=torch.float32)
+            dgb = torch.empty(2, layers[l].N, device=dev, dtype=torch.float32)
             dgamma, dbeta = dgb[0], dgb[1]
-        mean_train = ptr(st.mean) if st.train else None
-        if arg is not None and dA is dout:
-            G = M // nsample
+        return dgamma, dbeta
+
+    def bn_reduce(l, dA, ldda, pooled):
+        """dgamma / dbeta of layer l from the gradient w.r.t. its activation"""
+        st = layers[l]
+        st.dgamma, st.dbeta = bn_params(l)
+        if pooled:
             call("pn2_pool_bn_relu_bwd_reduce_finalize", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z),
-                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), G, nsample, C, ptr(accum),
-                 ptr(_ticket(dev)), ptr(dgamma), ptr(dbeta), stream())
-            dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
-            call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgamma), ptr(dbeta), G, nsample, C, ptr(dZ),
-                 dZ.shape[1], dt(dZ), stream())
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M // nsample, nsample, st.N, ptr(_stat_accum(dev)),
+                 ptr(_ticket(dev)), ptr(st.dgamma), ptr(st.dbeta), stream())
         else:
             call("pn2_bn_relu_bwd_reduce_finalize", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z),
-                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, C, ptr(accum), ptr(_ticket(dev)),
-                 ptr(dgamma), ptr(dbeta), stream())
-            if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
-                dZ = dA                                   # element-wise update in place (never on autograd's grad)
-            else:
-                dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
-            call("pn2_bn_relu_bwd_dz", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
-                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(dgamma), ptr(dbeta), M, C, ptr(dZ), dZ.shape[1],
-                 dt(dZ), stream())
-        return dZ, dgamma, dbeta
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M, st.N, ptr(_stat_accum(dev)), ptr(_ticket(dev)),
+                 ptr(st.dgamma), ptr(st.dbeta), stream())
 
-    dZ, dgamma, dbeta = bn_grads(L - 1, dout, dout.shape[1])
+    def bn_dz(l, dA, ldda, pooled):
+        """dZ of layer l (its dgamma / dbeta known)"""
+        st = layers[l]
+        C = st.N
+        mean_train = ptr(st.mean) if st.train else None
+        if pooled:
+            dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
+            call("pn2_pool_bn_relu_bwd_dz", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+                 ptr(st.shift), mean_train, ptr(st.invstd), ptr(st.dgamma), ptr(st.dbeta), M // nsample, nsample, C, ptr(dZ),
+                 dZ.shape[1], dt(dZ), stream())
+            return dZ
+        if dA is not dout and dA.dtype == dtype and ldda == _row_ld(C, dtype):
+            dZ = dA                                   # element-wise update in place (never on autograd's grad)
+        else:
+            dZ = torch.empty(M, _row_ld(C, dtype), device=dev, dtype=dtype)
+        call("pn2_bn_relu_bwd_dz", ptr(dA), ldda, dt(dA), ptr(st.Z), st.Z.shape[1], dt(st.Z), ptr(st.scale),
+             ptr(st.shift), mean_train, ptr(st.invstd), ptr(st.dgamma), ptr(st.dbeta), M, C, ptr(dZ), dZ.shape[1],
+             dt(dZ), stream())
+        return dZ
+
+    # ---- the top layer: its BatchNorm gradients always come from a reduction over the incoming gradient ----
+    top = L - 1
+    pooled = arg is not None
+    bn_reduce(top, dout, dout.shape[1], pooled)
+    if not pooled and dout.dtype == torch.bfloat16 and dtype == torch.bfloat16:
+        cur, mode = dout, "dA"                        # (the head's bf16 gradient: dZ is formed inside the fused layer kernel)
+    else:
+        cur, mode = bn_dz(top, dout, dout.shape[1], pooled), "dZ"
     dx0 = None
     for l in range(L - 1, -1, -1):
         st = layers[l]
-        if l == 0:
-            xin, ldx, sc, sh = x0, x0.shape[1], None, None
-        else:
-            prev = layers[l - 1]
-            xin, ldx, sc, sh = prev.Z, prev.Z.shape[1], prev.scale, prev.shift
+        prev = layers[l - 1] if l > 0 else None
         conv = convs[l] if convs is not None else None
-        if side is not None:          # dZ is complete on the main stream here; the side stream picks it up
-            side.wait_stream(main)
-            with torch.cuda.stream(side):     # (allocations of this call belong to the side stream)
-                dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, side.cuda_stream, keep)
-            keep += [dZ, xin, sc, sh]
+        want_dx = l > 0 or need_dx0
+        fused = _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bns[l - 1] if (bns is not None and l > 0) else None,
+                                 want_dx, dev, dtype, keep)
+        if fused is not None:
+            dW, dA, dgp, dbp = fused
+            if prev is not None:
+                prev.dgamma, prev.dbeta = dgp, dbp
+            next_mode = "dA_masked"
         else:
-            dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, stream(), keep)
+            if mode == "dA_masked":
+                cur = bn_dz(l, cur, cur.shape[1], False)
+            elif mode == "dA":
+                cur = bn_dz(l, cur, cur.shape[1], False)     # (its reduction ran when the gradient was produced / at the top)
+            dZ = cur
+            if l == 0:
+                xin, ldx, sc, sh = x0, x0.shape[1], None, None
+            else:
+                xin, ldx, sc, sh = prev.Z, prev.Z.shape[1], prev.scale, prev.shift
+            if side is not None:          # dZ is complete on the main stream here; the side stream picks it up
+                side.wait_stream(main)
+                with torch.cuda.stream(side):     # (allocations of this call belong to the side stream)
+                    dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, side.cuda_stream, keep)
+                keep += [dZ, xin, sc, sh]
+                side_used = True
+            else:
+                dW = _weight_grad(dZ, xin, ldx, sc, sh, M, st.K, st.N, getattr(conv, "weight", None), dev, stream(), keep)
+            dA = None
+            if want_dx:
+                ldd = _row_ld(st.K, dtype) if l > 0 else x0.shape[1]
+                dA = torch.empty(M, ldd, device=dev, dtype=dtype)
+                # (padding columns st.K..ldd of the first layer's input gradient are never read: its consumers --
+                # pn2_group_points_bwd, pn2_rows_to_f32, pn2_interp_bwd, _GroupAllFn -- address columns < st.K only)
+                if st.wpack_bwd is not None:
+                    call("pn2_linear_bwd_data_prepacked", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd,
+                         dt(dA), ptr(st.wpack_bwd), stream())
+                else:
+                    wpack = None
+                    if dtype == torch.bfloat16:
+                        wpack = torch.empty(lib.pn2_linear_wpack_bytes(st.N, st.K), device=dev, dtype=torch.uint8)
+                    call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
+                         ptr(wpack), stream())
+                if l > 0:
+                    bn_reduce(l - 1, dA, ldd, False)
+            next_mode = "dA"
         if not st.has_bias:
             dbias = None
         elif st.train:      # batch-norm's mean subtraction cancels the conv bias exactly
@@ -421,27 +534,13 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
             if dbias is None:
                 dbias = torch.zeros(st.N, device=dev, dtype=torch.float32)
         else:               # frozen statistics: sum_m dz = scale * dbeta
-            dbias = st.scale * dbeta
-        grads[l] = (dW, dbias, dgamma, dbeta)
-        if l > 0 or need_dx0:
-            ldd = _row_ld(st.K, dtype) if l > 0 else x0.shape[1]
-            dA = torch.empty(M, ldd, device=dev, dtype=dtype)
-            # (padding columns st.K..ldd of the first layer's input gradient are never read: its consumers --
-            # pn2_group_points_bwd, pn2_rows_to_f32, pn2_interp_bwd, _GroupAllFn -- address columns < st.K only)
-            if st.wpack_bwd is not None:
-                call("pn2_linear_bwd_data_prepacked", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd,
-                     dt(dA), ptr(st.wpack_bwd), stream())
-            else:
-                wpack = None
-                if dtype == torch.bfloat16:
-                    wpack = torch.empty(lib.pn2_linear_wpack_bytes(st.N, st.K), device=dev, dtype=torch.uint8)
-                call("pn2_linear_bwd_data", ptr(dZ), dZ.shape[1], dt(dZ), ptr(st.W), M, st.K, st.N, ptr(dA), ldd, dt(dA),
-                     ptr(wpack), stream())
-            if l > 0:
-                dZ, dgamma, dbeta = bn_grads(l - 1, dA, ldd)
-            else:
-                dx0 = dA
-    if side is not None:
+            dbias = st.scale * st.dbeta
+        grads[l] = (dW, dbias, st.dgamma, st.dbeta)
+        if l > 0:
+            cur, mode = dA, next_mode
+        else:
+            dx0 = dA
+    if side_used:
         main.wait_stream(side)
     del keep
     return grads, dx0
