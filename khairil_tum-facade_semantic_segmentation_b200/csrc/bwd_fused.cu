@@ -34,9 +34,11 @@ int tc_wgrad_reduce(const float *scratch, int splits, int N, int K, int K_ld, fl
 
 constexpr int kBfBM = 128;
 constexpr int kBfSlab = kBfBM * 128;          // one 64-column slab of a 128-row tile: 16 KB (SW128 box layout)
-constexpr int kBfCompute = 256;               // warps 0-7: transforms, MMA issue (thread 0), epilogues
-constexpr int kBfThreads = kBfCompute + 32;   // warp 8: TMA producer
+constexpr int kBfEpi = 128;                   // warps 0-3 : epilogue group (tensor-memory lane quarters), statistics MMAs
+constexpr int kBfXf = 256;                    // warps 4-11: transform group; its thread 0 issues the data / weight-gradient MMAs
+constexpr int kBfThreads = kBfEpi + kBfXf + 32;   // warp 12: TMA producer
 constexpr int kBfMaxC = 128;                  // widest layer (N) / input (K_ld) this kernel takes
+constexpr int kBfMaxStages = 4;
 
 struct BwdFusedArgs {
     CUtensorMap tm_da, tm_z, tm_x, tm_dx;
@@ -47,7 +49,7 @@ struct BwdFusedArgs {
     int K, N, K_pad, k_store;    // K_pad = round_up(K, 16); k_store = columns of dX written (round_up(K, 8) <= lddx)
     int nS, kS;                  // 64-column slabs of the dA / Z tiles and of the X tile
     int da_mode;                 // 0: dA dense, mask applied here; 1: dA already masked by its producer; 3: dZ_l given
-    int want_dx, want_dw, want_stats;
+    int want_dx, want_dw, want_stats, load_x;
     int ones_col;                // >= 0: the statistics' ones live in columns [ones_col, ones_col + 16) of the zhat tile; < 0: own tile
     int s2_cols;                 // N extent of the S2 product
     float *dW;                   // accumulate target [N, K] (L2 reductions) or null when scratch is used
@@ -57,10 +59,13 @@ struct BwdFusedArgs {
     unsigned *ticket;
     float *dgamma_prev, *dbeta_prev;
     float inv_m;
-    int tmem_cols, off_dw, off_s2, off_s1;
-    // shared-memory byte offsets from the 1024-aligned base
-    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_bytes;
+    int tmem_cols, acc_bufs, off_dw, off_s2, off_s1;
+    int stages, alias_act;       // alias_act: act lives in the (dead) Z tile -> the transform group syncs between T1 and T2
+    // shared-memory byte offsets from the 1024-aligned base; per-stage buffers are stage_stride apart
+    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
     int coef_ld;
+    long long *dbg_buf;
+    int dbg;                     // PN2_BWD_DBG bit mask (profiling experiments): 1 skip wgrad MMAs, 2 skip statistics MMAs, 4 skip T1/T2
 };
 
 __device__ __forceinline__ void bf_red_add_f32(float *p, float v) {
@@ -69,8 +74,18 @@ __device__ __forceinline__ void bf_red_add_f32(float *p, float v) {
 __device__ __forceinline__ void bf_red_add_v4_f32(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void bf_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 
-// Which 16-byte unit of a 64-column slab a thread owns in iteration i, for a tile whose rows hold `nch` valid chunks.
+// PN2_BWD_DBG & 32: CTA 0 stamps clock64 at the phase boundaries of its first 24 tiles into `scratch` ([24][16] int64)
+#define BF_STAMP(slot)                                                                                   \
+    do {                                                                                                 \
+        if ((a.dbg & 32) && blockIdx.x == 0 && t < 24 && a.dbg_buf)                                      \
+            a.dbg_buf[t * 16 + (slot)] = clock64();                                                      \
+    } while (0)
+
+// Which 16-byte unit of a 64-column slab a transform thread owns in iteration i, for a tile whose rows hold `nch` valid chunks.
 //   nch == 8 (or anything else): physical unit q = tid + 256 i: row q >> 3, logical chunk (q & 7) ^ (row & 7) -- constant per
 //            thread, every thread busy, conflict free (4 iterations per slab);
 //   nch == 4: only half of every 128-byte row is data.  A warp takes one 8-row swizzle atom per iteration; its four 8-thread
@@ -98,16 +113,22 @@ __device__ __forceinline__ UnitMap unit_map(int tid, int nch) {
     return m;
 }
 
-__global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_constant__ BwdFusedArgs a) {
+// Three warp-specialised roles pipelined over the CTA's tiles (one CTA per SM):
+//   producer  : TMA loads of tile t+1 (t+2) while tile t is worked on -- group A = (dA, Z) is released as soon as the data /
+//               weight-gradient MMAs have read it, group B = (X, act, staging) when the statistics MMAs have;
+//   transform : dZ in place, X -> (act, zhat), then ONE thread issues the tile's data- and weight-gradient MMAs;
+//   epilogue  : dA_{l-1} out of tensor memory -> ReLU mask -> bf16 -> staging -> TMA store, then ONE thread issues the
+//               statistics MMAs on the staged tile.  The data-gradient accumulator is double buffered when it fits.
+__global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_constant__ BwdFusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_mma;
+    __shared__ __align__(8) uint64_t full_a[kBfMaxStages], full_b[kBfMaxStages], empty[kBfMaxStages], act_rdy[kBfMaxStages],
+        acc_full[2], acc_empty[2], bar_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-    uint8_t *const s_w = smem + a.o_w, *const s_da = smem + a.o_da, *const s_z = smem + a.o_z, *const s_x = smem + a.o_x;
-    uint8_t *const s_act = smem + a.o_act, *const s_stage = smem + a.o_stage, *const s_ones = smem + a.o_ones;
+    uint8_t *const s_w = smem + a.o_w, *const s_ones = smem + a.o_ones;
     // per-column coefficients: layer l  dz = sc.g + cb.z + cc (mask test sc.z + sh > 0), layer l-1  act = relu(psc.z + psh),
     // zhat = pis.z + pmi (pmi = -mean.invstd)
     float *const coef = reinterpret_cast<float *>(smem + a.o_coef);
@@ -115,12 +136,15 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
     float *const c_sc = coef, *const c_sh = coef + cl, *const c_b = coef + 2 * cl, *const c_c = coef + 3 * cl;
     float *const p_sc = coef + 4 * cl, *const p_sh = coef + 5 * cl, *const p_is = coef + 6 * cl, *const p_mi = coef + 7 * cl;
     const bool prev = a.p_scale != nullptr;
+    const int S = a.stages, AB = a.acc_bufs;
 
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
     if (tid == 0) {
-        mbar_init(&bar_full, 1);
-        mbar_init(&bar_empty, 1);
-        mbar_init(&bar_mma, 1);
+        for (int i = 0; i < kBfMaxStages; ++i) {
+            mbar_init(&full_a[i], 1); mbar_init(&full_b[i], 1); mbar_init(&empty[i], 1); mbar_init(&act_rdy[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1); }
+        mbar_init(&bar_done, 2);
         mbar_init_fence();
     }
     for (int c = tid; c < cl; c += kBfThreads) {
@@ -146,51 +170,58 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
     fence_after_sync();
     const uint32_t tmem = tmem_base_s;
     const int64_t m_tiles = (a.M + kBfBM - 1) / kBfBM;
+    const uint32_t n_my = (uint32_t)(((m_tiles - 1 - (int64_t)blockIdx.x) / (int64_t)gridDim.x) + 1);   // tiles of this CTA (>= 1)
     const uint32_t w_chunk_bytes = (uint32_t)a.K_pad * 128u;
+    // MN-major operands of a one-slab tile: the M = 128 product reads "the next slab" through LBO; 0 makes it the same slab
+    // again (rows 64-127 of those products are never used)
+    const uint32_t lbo_n = a.nS > 1 ? (uint32_t)kBfSlab : 0u, lbo_k = a.kS > 1 ? (uint32_t)kBfSlab : 0u;
 
-    if (warp == kBfCompute / 32) {
-        // ---- producer: the tile's row boxes (and, once, the weight image) by TMA ----
+    if (warp == (kBfEpi + kBfXf) / 32) {
+        // ================= producer =================
         if (lane == 0) {
             tma_prefetch_desc(&a.tm_da);
             tma_prefetch_desc(&a.tm_x);
-            uint32_t t = 0;
-            for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
-                if (t > 0) mbar_wait(&bar_empty, (t - 1) & 1u);
-                const int m0 = (int)(tile * kBfBM);
-                uint32_t bytes = a.stage_bytes;
+            for (uint32_t t = 0; t < n_my; ++t) {
+                const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S;
+                const int m0 = (int)(((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM);
+                uint8_t *st = smem + (size_t)s * a.stage_stride;
+                BF_STAMP(0);
+                if (u > 0) mbar_wait(&empty[s], (u - 1) & 1u);     // the whole stage is released at once (its buffers are re-used
+                uint32_t bytes = a.bytes_a;                        // inside a tile: staging over dZ, act over Z)
+                BF_STAMP(1);
                 if (t == 0 && a.want_dx) bytes += (uint32_t)a.nS * w_chunk_bytes;
-                mbar_expect_tx(&bar_full, bytes);
+                mbar_expect_tx(&full_a[s], bytes);
                 if (t == 0 && a.want_dx)
-                    for (int j = 0; j < a.nS; ++j) bulk_g2s(s_w + (size_t)j * w_chunk_bytes, a.Wimg + (size_t)j * w_chunk_bytes, w_chunk_bytes, &bar_full);
-                for (int j = 0; j < a.nS; ++j) tma_load_2d(s_da + (size_t)j * kBfSlab, &a.tm_da, 64 * j, m0, &bar_full);
+                    for (int j = 0; j < a.nS; ++j) bulk_g2s(s_w + (size_t)j * w_chunk_bytes, a.Wimg + (size_t)j * w_chunk_bytes, w_chunk_bytes, &full_a[s]);
+                for (int j = 0; j < a.nS; ++j) tma_load_2d(st + a.o_da + (size_t)j * kBfSlab, &a.tm_da, 64 * j, m0, &full_a[s]);
                 if (a.da_mode != 3)
-                    for (int j = 0; j < a.nS; ++j) tma_load_2d(s_z + (size_t)j * kBfSlab, &a.tm_z, 64 * j, m0, &bar_full);
-                if (a.want_dw || prev)
-                    for (int j = 0; j < a.kS; ++j) tma_load_2d(s_x + (size_t)j * kBfSlab, &a.tm_x, 64 * j, m0, &bar_full);
+                    for (int j = 0; j < a.nS; ++j) tma_load_2d(st + a.o_z + (size_t)j * kBfSlab, &a.tm_z, 64 * j, m0, &full_a[s]);
+                if (a.load_x) {
+                    mbar_expect_tx(&full_b[s], a.bytes_b);
+                    for (int j = 0; j < a.kS; ++j) tma_load_2d(st + a.o_x + (size_t)j * kBfSlab, &a.tm_x, 64 * j, m0, &full_b[s]);
+                }
             }
         }
         __syncwarp();
-    } else {
-        const int row = tid & 127, half = tid >> 7;                // epilogue: row of the tile, column half
-        const int wq = warp & 3;                                  // tensor-memory lane quarter of this warp
-        // MN-major operands of a one-slab tile: the M = 128 product reads "the next slab" through LBO; 0 makes it the same slab
-        // again (rows 64-127 of those products are never used)
-        const uint32_t lbo_n = a.nS > 1 ? (uint32_t)kBfSlab : 0u, lbo_k = a.kS > 1 ? (uint32_t)kBfSlab : 0u;
+    } else if (warp >= kBfEpi / 32) {
+        // ================= transform group (+ data / weight-gradient MMA issue) =================
+        const int ttid = tid - kBfEpi;
         const uint32_t idesc_dx = make_idesc_bf16(kBfBM, a.K_pad, 0, 0);      // dA = dZ . W      (A, B K-major)
         const uint32_t idesc_dw = make_idesc_bf16(kBfBM, a.K_pad, 1, 1);      // dW = dZ^T . act  (A, B MN-major)
-        const uint32_t idesc_s2 = make_idesc_bf16(kBfBM, a.s2_cols, 1, 1);    // S2 = dA'^T . [zhat | ones]
-        const uint32_t idesc_s1 = make_idesc_bf16(kBfBM, 16, 1, 0);           // S1 = dA'^T . ones (B K-major, own tile)
-        // valid 16-byte chunks per row of a slab (the last slab of a tile may be narrower)
-        uint32_t t = 0;
-        for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
-            const int64_t m0 = tile * kBfBM;
+        for (uint32_t t = 0; t < n_my; ++t) {
+            const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S, b = t % (uint32_t)AB;
+            const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
             const int rows_valid = (int)min((int64_t)kBfBM, a.M - m0);
-            mbar_wait(&bar_full, t & 1u);
+            uint8_t *st = smem + (size_t)s * a.stage_stride;
+            uint8_t *const s_da = st + a.o_da, *const s_z = st + a.o_z, *const s_x = st + a.o_x, *const s_act = st + a.o_act;
+            if (ttid == 0) BF_STAMP(2);
+            mbar_wait(&full_a[s], u & 1u);
+            if (ttid == 0) BF_STAMP(3);
             // ---- T1: dZ_l in place on the dA tile ----
-            if (a.da_mode != 3) {
+            if (a.da_mode != 3 && !(a.dbg & 4)) {
                 for (int j = 0; j < a.nS; ++j) {
                     const int nch = min(8, (a.N - 64 * j) >> 3);
-                    const UnitMap um = unit_map(tid, nch);
+                    const UnitMap um = unit_map(ttid, nch);
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], cb[8], cc[8];
@@ -221,11 +252,14 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
                     }
                 }
             }
+            if (ttid == 0) BF_STAMP(4);
+            if (a.load_x) mbar_wait(&full_b[s], u & 1u);
+            if (a.alias_act) named_bar_sync(1, kBfXf);       // every thread is done reading Z before act overwrites it
             // ---- T2: X tile -> act (weight-gradient operand) and zhat in place (statistics operand) ----
-            if (prev) {
+            if (prev && !(a.dbg & 4)) {
                 for (int j = 0; j < a.kS; ++j) {
                     const int nch = min(8, (a.K - 64 * j) >> 3);
-                    const UnitMap um = unit_map(tid, nch);
+                    const UnitMap um = unit_map(ttid, nch);
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], is[8], mi[8];
@@ -249,47 +283,72 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
                 }
                 if (a.ones_col >= 0) {
                     // the statistics' ones: 16 columns of the zhat tile past its data (the TMA load zero-filled them): 256 units
-                    const int r = tid >> 1, ch = ((a.ones_col & 63) >> 3) + (tid & 1);
+                    const int r = ttid >> 1, ch = ((a.ones_col & 63) >> 3) + (ttid & 1);
                     *reinterpret_cast<uint4 *>(s_x + (size_t)(a.ones_col >> 6) * kBfSlab + sw128_offset(r, ch)) =
                         make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
                 }
             }
+            if (ttid == 0) BF_STAMP(5);
             fence_proxy_async();
-            named_bar_sync(1, kBfCompute);
-            // ---- MMAs of the tile: data gradient and weight gradient ----
-            if (tid == 0) {
+            named_bar_sync(1, kBfXf);
+            if (ttid == 0) BF_STAMP(6);
+            // ---- MMAs of the tile: data gradient (accumulator buffer b) and weight gradient (lives across all tiles) ----
+            if (ttid == 0) {
+                if (a.want_dx) bf_mbar_arrive(&act_rdy[s]);      // (release: the epilogue group may read act[s])
+                if (a.want_dx && t >= (uint32_t)AB) mbar_wait(&acc_empty[b], ((t / (uint32_t)AB) - 1) & 1u);
+                BF_STAMP(7);
                 fence_after_sync();
+                // (descriptors: the start address sits in the low 14 bits in 16-byte units -- stepping through a tile is an
+                //  integer add on a descriptor built once; building each one from scratch cost ~170 cycles per MMA of dependent
+                //  64-bit arithmetic in this single thread)
                 if (a.want_dx) {
+                    const uint32_t d_acc = tmem + b * (uint32_t)a.K_pad;
                     for (int j = 0; j < a.nS; ++j) {
                         const int n_left = a.N - 64 * j;
                         const int nk = n_left >= 64 ? 4 : (n_left + 15) / 16;
-                        const uint32_t a_base = smem_addr(s_da + (size_t)j * kBfSlab), b_base = smem_addr(s_w + (size_t)j * w_chunk_bytes);
-                        for (int kk = 0; kk < nk; ++kk)
-                            umma_bf16(tmem, make_desc(a_base + 32 * kk, 0, 1024), make_desc(b_base + 32 * kk, 0, 1024), idesc_dx,
-                                      (uint32_t)((j | kk) != 0));
+                        const uint64_t ad = make_desc(smem_addr(s_da + (size_t)j * kBfSlab), 0, 1024);
+                        const uint64_t bd = make_desc(smem_addr(s_w + (size_t)j * w_chunk_bytes), 0, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk < nk) umma_bf16(d_acc, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc_dx, (uint32_t)((j | kk) != 0));
                     }
                 }
-                if (a.want_dw) {
-                    const uint32_t a_base = smem_addr(s_da), b_base = smem_addr(prev ? s_act : s_x);
-                    for (int r = 0; r < kBfBM / 16; ++r)
-                        umma_bf16(tmem + (uint32_t)a.off_dw, make_desc(a_base + 2048 * r, lbo_n, 1024),
-                                  make_desc(b_base + 2048 * r, lbo_k, 1024), idesc_dw, (uint32_t)((t | (uint32_t)r) != 0));
+                if (a.want_dw && !(a.dbg & 1)) {
+                    const uint64_t ad = make_desc(smem_addr(s_da), lbo_n, 1024), bd = make_desc(smem_addr(prev ? s_act : s_x), lbo_k, 1024);
+                    const uint32_t d_w = tmem + (uint32_t)a.off_dw;
+                    umma_bf16(d_w, ad, bd, idesc_dw, (uint32_t)(t != 0));
+#pragma unroll
+                    for (int r = 1; r < kBfBM / 16; ++r) umma_bf16(d_w, ad + (uint64_t)(128 * r), bd + (uint64_t)(128 * r), idesc_dw, 1u);
                 }
-                if (a.want_dx) umma_commit(&bar_mma);
-                else umma_commit(&bar_empty);           // nothing else reads the tile: the producer may refill it
+                if (a.want_dx) umma_commit(&acc_full[b]);
+                else umma_commit(&empty[s]);                      // no epilogue: the stage may be refilled
+                if (t == n_my - 1) umma_commit(&bar_done);
+                BF_STAMP(8);
             }
-            if (!a.want_dx) continue;
-            mbar_wait(&bar_mma, t & 1u);
-            fence_after_sync();
-            // ---- epilogue: dA_{l-1} row `row`, this warp group's 16-column chunks -> mask of layer l-1 -> bf16 -> staging ----
-            {
-                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
-                for (int c0 = 16 * half; c0 < a.k_store; c0 += 32) {
+        }
+    } else {
+        // ================= epilogue group (+ statistics MMA issue) =================
+        const uint32_t idesc_s2 = make_idesc_bf16(kBfBM, a.s2_cols, 1, 1);    // S2 = dA'^T . [zhat | ones]
+        const uint32_t idesc_s1 = make_idesc_bf16(kBfBM, 16, 1, 0);           // S1 = dA'^T . ones (B K-major, own tile)
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        if (a.want_dx) {
+            for (uint32_t t = 0; t < n_my; ++t) {
+                const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S, b = t % (uint32_t)AB;
+                const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
+                uint8_t *st = smem + (size_t)s * a.stage_stride;
+                uint8_t *const s_x = st + a.o_x, *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
+                if (tid == 0) BF_STAMP(9);
+                mbar_wait(&acc_full[b], (t / (uint32_t)AB) & 1u);
+                mbar_wait(&act_rdy[s], u & 1u);
+                if (tid == 0) BF_STAMP(10);
+                fence_after_sync();
+                const uint32_t taddr = tmem + b * (uint32_t)a.K_pad + lane_addr;
+                for (int c0 = 0; c0 < a.k_store; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
                     const int ch = (c0 & 63) >> 3;
-                    const uint32_t o_lo = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(row, ch);
-                    const uint32_t o_hi = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(row, ch + 1);
+                    const uint32_t o_lo = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(tid, ch);
+                    const uint32_t o_hi = (uint32_t)(c0 >> 6) * kBfSlab + sw128_offset(tid, ch + 1);
                     const bool two = c0 + 8 < a.k_store;
                     if (prev) {
                         const uint4 m_lo = *reinterpret_cast<const uint4 *>(s_act + o_lo);
@@ -311,42 +370,48 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
                     *reinterpret_cast<uint4 *>(s_stage + o_lo) = lo;
                     if (two) *reinterpret_cast<uint4 *>(s_stage + o_hi) = hi;
                 }
-            }
-            fence_before_sync();
-            fence_proxy_async();
-            named_bar_sync(1, kBfCompute);
-            if (tid == 0) {
-                for (int j = 0; j < a.kS; ++j)
-                    if (64 * j < a.k_store) tma_store_2d(&a.tm_dx, 64 * j, (int)m0, s_stage + (size_t)j * kBfSlab);
-                if (a.want_stats) {
-                    fence_after_sync();
-                    const uint32_t a_base = smem_addr(s_stage), b2 = smem_addr(s_x), b1 = smem_addr(s_ones);
-                    for (int r = 0; r < kBfBM / 16; ++r) {
-                        const uint32_t acc = (uint32_t)((t | (uint32_t)r) != 0);
-                        umma_bf16(tmem + (uint32_t)a.off_s2, make_desc(a_base + 2048 * r, lbo_k, 1024), make_desc(b2 + 2048 * r, lbo_k, 1024),
-                                  idesc_s2, acc);
-                        if (a.ones_col < 0)
-                            umma_bf16(tmem + (uint32_t)a.off_s1, make_desc(a_base + 2048 * r, lbo_k, 1024),
-                                      make_desc(b1 + (uint32_t)(r >> 2) * 2048u + (uint32_t)(r & 3) * 32u, 0, 1024), idesc_s1, acc);
+                fence_before_sync();      // this thread's tensor-memory reads are complete
+                fence_proxy_async();      // staging writes -> visible to the TMA store / the statistics MMAs
+                if (tid == 0) BF_STAMP(11);
+                named_bar_sync(2, kBfEpi);
+                if (tid == 0) {
+                    BF_STAMP(12);
+                    bf_mbar_arrive(&acc_empty[b]);       // the data-gradient MMAs of tile t + AB may overwrite this buffer
+                    for (int j = 0; j < a.kS; ++j)
+                        if (64 * j < a.k_store) tma_store_2d(&a.tm_dx, 64 * j, (int)m0, s_stage + (size_t)j * kBfSlab);
+                    if (a.want_stats && !(a.dbg & 2)) {
+                        fence_after_sync();
+                        const uint64_t ad = make_desc(smem_addr(s_stage), lbo_k, 1024), b2 = make_desc(smem_addr(s_x), lbo_k, 1024);
+                        const uint64_t b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                        const uint32_t d2 = tmem + (uint32_t)a.off_s2, d1 = tmem + (uint32_t)a.off_s1;
+                        const bool own_ones = a.ones_col < 0;
+#pragma unroll
+                        for (int r = 0; r < kBfBM / 16; ++r) {
+                            const uint32_t acc = r ? 1u : (uint32_t)(t != 0);
+                            umma_bf16(d2, ad + (uint64_t)(128 * r), b2 + (uint64_t)(128 * r), idesc_s2, acc);
+                            if (own_ones) umma_bf16(d1, ad + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, acc);
+                        }
                     }
+                    BF_STAMP(13);
+                    tma_store_wait_read();        // (the staging tile may sit in this stage's dA buffer: the refill must wait for it)
+                    BF_STAMP(14);
+                    umma_commit(&empty[s]);       // every MMA that reads the stage is done -> refill
+                    if (t == n_my - 1) umma_commit(&bar_done);
                 }
-                tma_store_wait_read();
-                umma_commit(&bar_empty);      // every MMA that reads the tile / the staging is done -> refill
             }
+            if (tid == 0) tma_store_wait_all();
+        } else if (tid == 0) {
+            bf_mbar_arrive(&bar_done);
         }
-        if (tid == 0) tma_store_wait_all();
         // ---- end of the CTA: drain the accumulators that lived in tensor memory across all its tiles ----
-        const uint32_t n_my = (uint32_t)(((m_tiles - 1 - (int64_t)blockIdx.x) / (int64_t)gridDim.x) + 1);   // tiles this CTA did (>= 1)
-        // the last commit of the loop went to bar_empty (phase n_my - 1): wait for it here -- the producer only waits for
-        // phases 0 .. n_my - 2
-        mbar_wait(&bar_empty, (n_my - 1) & 1u);
+        mbar_wait(&bar_done, 0);
         fence_after_sync();
-        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
-        if (a.want_dw && wq * 32 < a.N) {      // (tensor-memory loads are warp-collective: whole warps take part, stores are per row)
-            float *acc = a.dW ? a.dW + (size_t)row * a.K : nullptr;
-            float *part = a.scratch ? a.scratch + ((size_t)blockIdx.x * a.N + row) * a.K_ld4 : nullptr;
-            const bool mine = row < a.N;
-            for (int c0 = 16 * half; c0 < a.K_pad; c0 += 32) {
+        const uint32_t taddr = tmem + lane_addr;
+        if (a.want_dw && warp * 32 < a.N && !(a.dbg & 8)) {      // (tensor-memory loads are warp-collective: whole warps take part, stores are per row)
+            float *acc = a.dW ? a.dW + (size_t)tid * a.K : nullptr;
+            float *part = a.scratch ? a.scratch + ((size_t)blockIdx.x * a.N + tid) * a.K_ld4 : nullptr;
+            const bool mine = tid < a.N;
+            for (int c0 = 0; c0 < a.K_pad; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)a.off_dw + c0, v);
                 if (!mine) continue;
@@ -366,30 +431,30 @@ __global__ void __launch_bounds__(kBfThreads) bwd_fused_kernel(const __grid_cons
             }
         }
         if (a.want_stats) {
-            // S2's diagonal (row k, column k) and S1 (row k, the ones column): lanes 0-15 need chunk 2 * wq, lanes 16-31 the next
-            if (half == 0 && wq * 32 < a.K) {
+            // S2's diagonal (row k, column k) and S1 (row k, the ones column): lanes 0-15 need chunk 2 * warp, lanes 16-31 the next
+            if (warp * 32 < a.K) {
                 float v0[16], v1[16], w[16];
-                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(wq * 32), v0);
-                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(wq * 32 + 16), v1);
+                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(warp * 32), v0);
+                tmem_ld16(taddr + (uint32_t)a.off_s2 + (uint32_t)(warp * 32 + 16), v1);
                 tmem_ld16(taddr + (uint32_t)(a.ones_col >= 0 ? a.off_s2 + a.ones_col : a.off_s1), w);
                 float s2 = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if ((lane & 15) == i) s2 = lane < 16 ? v0[i] : v1[i];
-                if (row < a.K) {
+                if (tid < a.K) {
                     double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.K;
-                    atomicAdd(acc + row, (double)w[0]);
-                    atomicAdd(acc + a.K + row, (double)s2);
+                    atomicAdd(acc + tid, (double)w[0]);
+                    atomicAdd(acc + a.K + tid, (double)s2);
                 }
             }
-            // "last CTA finalizes" (as bn.cu: bn_bwd_last_block_finalize, among the compute threads)
+            // "last CTA finalizes" (as bn.cu: bn_bwd_last_block_finalize, among the epilogue threads)
             __threadfence();
-            named_bar_sync(1, kBfCompute);
+            named_bar_sync(2, kBfEpi);
             if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
-            named_bar_sync(1, kBfCompute);
+            named_bar_sync(2, kBfEpi);
             if (s_last) {
                 __threadfence();
-                for (int c = tid; c < a.K; c += kBfCompute) {
+                for (int c = tid; c < a.K; c += kBfEpi) {
                     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
                     for (int r = 0; r < kStatReplicas; ++r) {
@@ -415,8 +480,8 @@ static int bf_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct BwdFusedPlan {
     bool ok;
-    int nS, kS, K_pad, k_store, tmem_cols, off_dw, off_s2, off_s1, ctas_per_sm, ones_col, s2_cols, coef_ld;
-    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_bytes;
+    int nS, kS, K_pad, k_store, tmem_cols, acc_bufs, off_dw, off_s2, off_s1, ones_col, s2_cols, coef_ld, stages, load_x, alias_act;
+    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
     size_t dyn_smem;
 };
 
@@ -431,35 +496,45 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     p.K_pad = bf_round_up(K, 16);
     p.k_store = bf_round_up(K, 8);
     if (want_dx && p.k_store > lddx) p.k_store = lddx;
+    p.load_x = (want_dw || prev) ? 1 : 0;
     // the statistics' ones: inside the zhat tile when its last slab has 16 spare columns, else a 4 KB tile of their own
     p.ones_col = -1;
     p.s2_cols = p.kS * 64;
     if (prev && p.K_pad + 16 <= p.kS * 64) { p.ones_col = p.K_pad; p.s2_cols = p.K_pad + 16; }
     else if (prev) p.s2_cols = p.K_pad;
+    // one stage: [dA | Z | X | act | staging]; inside a tile dZ (the dA buffer) is dead once the data / weight-gradient MMAs
+    // are done -- the staged dA_{l-1} tile takes its place -- and Z is dead once dZ is formed -- act takes its place
     uint32_t o = 0;
-    p.o_w = o;
-    if (want_dx) o += (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024);
     p.o_da = o; o += (uint32_t)p.nS * kBfSlab;
-    p.stage_bytes = (uint32_t)p.nS * kBfSlab;
     p.o_z = o;
-    if (da_mode != 3) { o += (uint32_t)p.nS * kBfSlab; p.stage_bytes += (uint32_t)p.nS * kBfSlab; }
+    if (da_mode != 3) o += (uint32_t)p.nS * kBfSlab;
+    p.bytes_a = o;
     p.o_x = o;
-    if (want_dw || prev) { o += (uint32_t)p.kS * kBfSlab; p.stage_bytes += (uint32_t)p.kS * kBfSlab; }
-    p.o_act = o;
-    if (prev) o += (uint32_t)p.kS * kBfSlab;
-    // the staged dA_{l-1} tile: over the Z tile when there is one and it is big enough (Z is dead once dZ is formed)
-    if (want_dx && da_mode != 3 && p.nS >= p.kS) p.o_stage = p.o_z;
+    if (p.load_x) o += (uint32_t)p.kS * kBfSlab;
+    p.bytes_b = o - p.bytes_a;
+    p.alias_act = (prev && da_mode != 3 && p.kS <= p.nS) ? 1 : 0;
+    p.o_act = p.alias_act ? p.o_z : o;
+    if (prev && !p.alias_act) o += (uint32_t)p.kS * kBfSlab;
+    if (want_dx && p.kS <= p.nS) p.o_stage = p.o_da;
     else { p.o_stage = o; if (want_dx) o += (uint32_t)p.kS * kBfSlab; }
-    p.o_ones = o;
-    if (prev && p.ones_col < 0) o += 4096;
-    p.coef_ld = bf_round_up(N > p.kS * 64 ? N : p.kS * 64, 8);
-    if (p.coef_ld < bf_round_up(N, 64)) p.coef_ld = bf_round_up(N, 64);
-    p.o_coef = o;
-    o += (uint32_t)(8 * p.coef_ld * sizeof(float));
+    p.stage_stride = o;
+    const uint32_t w_bytes = want_dx ? (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024) : 0u;
+    const uint32_t ones_bytes = (prev && p.ones_col < 0) ? 4096u : 0u;
+    p.coef_ld = bf_round_up(N > p.kS * 64 ? N : p.kS * 64, 64);
+    const uint32_t coef_bytes = (uint32_t)(8 * p.coef_ld * sizeof(float));
+    const uint32_t budget = 227 * 1024 - 2048;                 // (static shared: barriers; 1 KB alignment slack)
+    p.stages = kBfMaxStages;
+    while (p.stages > 1 && (size_t)p.stages * p.stage_stride + w_bytes + ones_bytes + coef_bytes + 1024 > budget) --p.stages;
+    if ((size_t)p.stage_stride + w_bytes + ones_bytes + coef_bytes + 1024 > budget) return p;
+    o = (uint32_t)p.stages * p.stage_stride;
+    p.o_w = o; o += w_bytes;
+    p.o_ones = o; o += ones_bytes;
+    p.o_coef = o; o += coef_bytes;
     p.dyn_smem = (size_t)o + 1024;
-    // tensor memory: [dA_{l-1}: K_pad][dW: K_pad][S2: s2_cols][S1: 16 when the ones have their own tile]
-    int cols = 0;
-    if (want_dx) cols += p.K_pad;
+    // tensor memory: [dA_{l-1}: acc_bufs x K_pad][dW: K_pad][S2: s2_cols][S1: 16 when the ones have their own tile]
+    const int rest = (want_dw ? p.K_pad : 0) + (prev ? p.s2_cols + (p.ones_col < 0 ? 16 : 0) : 0);
+    p.acc_bufs = (want_dx && 2 * p.K_pad + rest <= 512) ? 2 : 1;
+    int cols = want_dx ? p.acc_bufs * p.K_pad : 0;
     p.off_dw = cols;
     if (want_dw) cols += p.K_pad;
     p.off_s2 = cols;
@@ -470,12 +545,6 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     while (alloc < cols) alloc <<= 1;
     if (alloc > 512) return p;
     p.tmem_cols = alloc;
-    if (p.dyn_smem > 227 * 1024 - 1024) return p;
-    int per_sm = (int)((233472 - 1024) / (p.dyn_smem + 1024 + 512));
-    if (per_sm > 512 / alloc) per_sm = 512 / alloc;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) return p;
-    p.ctas_per_sm = per_sm;
     p.ok = true;
     return p;
 }
@@ -505,7 +574,7 @@ extern "C" size_t pn2_mlp_bwd_layer_scratch_bytes(int64_t M, int K, int N) {
     // fp32 partial blocks of the weight gradient when K % 4 != 0 (rows of dW are not 16-byte aligned: no vector reductions)
     if (K % 4 == 0) return 0;
     const int64_t m_tiles = (M + kBfBM - 1) / kBfBM;
-    const int64_t grid = m_tiles < 4 * kNumSMs ? m_tiles : 4 * kNumSMs;
+    const int64_t grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
     return (size_t)grid * (size_t)N * (size_t)bf_round_up(K, 4) * sizeof(float) + 16;
 }
 
@@ -531,7 +600,7 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+        cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
         if (e != cudaSuccess) {
             set_error("mlp_bwd_layer: shared-memory opt-in failed: %s", cudaGetErrorString(e));
             cudaGetLastError();
@@ -558,7 +627,7 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.M = L->M; a.K = L->K; a.N = L->N; a.K_pad = p.K_pad; a.k_store = p.k_store; a.nS = p.nS; a.kS = p.kS;
     a.da_mode = L->da_mode; a.want_dx = want_dx; a.want_dw = want_dw; a.want_stats = prev;
     const int64_t m_tiles = (L->M + kBfBM - 1) / kBfBM;
-    int64_t grid = (int64_t)p.ctas_per_sm * kNumSMs;
+    int64_t grid = kNumSMs;                                  // one CTA per SM, pipelined over its tiles
     if (grid > m_tiles) grid = m_tiles;
     a.K_ld4 = bf_round_up(L->K, 4);
     if (want_dw) {
@@ -571,7 +640,10 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.tmem_cols = p.tmem_cols; a.off_dw = p.off_dw; a.off_s2 = p.off_s2; a.off_s1 = p.off_s1;
     a.ones_col = p.ones_col; a.s2_cols = p.s2_cols; a.o_coef = p.o_coef; a.coef_ld = p.coef_ld;
     a.o_w = p.o_w; a.o_da = p.o_da; a.o_z = p.o_z; a.o_x = p.o_x; a.o_act = p.o_act; a.o_stage = p.o_stage; a.o_ones = p.o_ones;
-    a.stage_bytes = p.stage_bytes;
+    a.stage_stride = p.stage_stride; a.bytes_a = p.bytes_a; a.bytes_b = p.bytes_b; a.stages = p.stages; a.acc_bufs = p.acc_bufs;
+    a.load_x = p.load_x; a.alias_act = p.alias_act;
+    { const char *e = getenv("PN2_BWD_DBG"); a.dbg = e ? atoi(e) : 0; }
+    if ((a.dbg & 32) && L->scratch && L->K % 4 == 0) a.dbg_buf = (long long *)L->scratch;
     bwd_fused_kernel<<<(unsigned)grid, kBfThreads, p.dyn_smem, (cudaStream_t)stream>>>(a);
     count_launch();
     int rc = check_launch("mlp_bwd_layer");

@@ -61,7 +61,8 @@ def main():
         dX = torch.empty(M, ld(K), device=DEV, dtype=torch.bfloat16) if want_dx else None
         dW = torch.zeros(N, K, device=DEV)
         nbytes = lib.pn2_mlp_bwd_layer_scratch_bytes(M, K, N)
-        scratch = torch.empty(max(nbytes, 16), device=DEV, dtype=torch.uint8)
+        dbg = int(os.environ.get("PN2_BWD_DBG", "0"))
+        scratch = torch.zeros(max(nbytes, 24 * 16 * 8), device=DEV, dtype=torch.uint8)
         accum = torch.zeros(8 * 2 * 4096, device=DEV, dtype=torch.float64)
         ticket = torch.zeros(4, device=DEV, dtype=torch.int32)
         dgb = torch.zeros(2, 128, device=DEV)
@@ -75,7 +76,7 @@ def main():
             a.prev_scale, a.prev_shift, a.prev_mean, a.prev_invstd = (coef[6 + i].data_ptr() for i in range(4))
             a.stat_accum, a.ticket, a.dgamma_prev, a.dbeta_prev = accum.data_ptr(), ticket.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr()
         a.dX, a.lddx = (dX.data_ptr(), dX.shape[1]) if want_dx else (None, 0)
-        a.dW, a.scratch = dW.data_ptr(), (scratch.data_ptr() if nbytes else None)
+        a.dW, a.scratch = dW.data_ptr(), (scratch.data_ptr() if (nbytes or dbg & 32) else None)
         a.M, a.K, a.N = M, K, N
 
         def fn():
@@ -98,6 +99,14 @@ def main():
         nbytes_alg = 2 * M * (ld(N) * (1 if da_mode == 3 else 2) + ld(K) + (ld(K) if want_dx else 0))
         out[name] = {"M": M, "K": K, "N": N, "us": round(ms * 1e3, 1), "GBps": round(nbytes_alg / ms / 1e6, 1)}
         print("%-11s M %8d K %4d N %4d prev %d dx %d mode %d: %7.1f us  %7.1f GB/s" % (name, M, K, N, has_prev, want_dx, da_mode, ms * 1e3, nbytes_alg / ms / 1e6))
+    if int(os.environ.get("PN2_BWD_DBG", "0")) & 32:
+        st = scratch[:24 * 16 * 8].view(torch.int64).view(24, 16).cpu()
+        base = int(st[st > 0].min())
+        names = ["P:top", "P:emptyOK", "T:top", "T:fullA", "T:T1done", "T:T2done", "T:bar", "T:acc_emptyOK", "T:issued", "E:top", "E:acc_full", "E:epi_done", "E:bar", "E:stored+stats", "E:store_read"]
+        print("clock64 stamps of CTA 0 (cycles since the first stamp), one row per tile:")
+        print("tile " + " ".join("%13s" % n for n in names))
+        for t in range(24):
+            print("%4d " % t + " ".join("%13d" % (int(st[t, i]) - base if int(st[t, i]) else -1) for i in range(15)))
     print(json.dumps(out))
 
 
