@@ -60,6 +60,8 @@ struct BwdFusedArgs {
     float *dgamma_prev, *dbeta_prev;
     float inv_m;
     int tmem_cols, acc_bufs, off_dw, off_s2, off_s1;
+    int defer_store_wait;
+    int combined;                // one product [dZ | dA']^T . [act | zhat | ones] gives the weight gradient AND the statistics
     int stages, alias_act;       // alias_act: act lives in the (dead) Z tile -> the transform group syncs between T1 and T2
     // shared-memory byte offsets from the 1024-aligned base; per-stage buffers are stage_stride apart
     uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t *const s_w = smem + a.o_w, *const s_ones = smem + a.o_ones;
     // per-column coefficients: layer l  dz = sc.g + cb.z + cc (mask test sc.z + sh > 0), layer l-1  act = relu(psc.z + psh),
@@ -227,29 +229,37 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     float sc[8], sh[8], cb[8], cc[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { sc[e] = c_sc[c0 + e]; sh[e] = c_sh[c0 + e]; cb[e] = c_b[c0 + e]; cc[e] = c_c[c0 + e]; }
-#pragma unroll 2
-                    for (int i = 0; i < um.iters; ++i) {
-                        const int r = um.row0 + um.rstep * i;
-                        const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(r, um.chunk);
-                        uint4 g4 = *reinterpret_cast<const uint4 *>(s_da + off);
-                        const uint4 z4 = *reinterpret_cast<const uint4 *>(s_z + off);
-                        uint32_t *gw = reinterpret_cast<uint32_t *>(&g4);
-                        const uint32_t *zw = reinterpret_cast<const uint32_t *>(&z4);
+                    // (all of the thread's units are loaded before any arithmetic: 2 x <= 4 LDS.128 in flight instead of a
+                    //  load -> compute -> store chain per unit; the loop bodies are fully unrolled and predicated on um.iters)
+                    uint4 g4[4], z4[4];
 #pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) {
-                            float2 g = unpack_bf16x2(gw[e2]);
-                            const float2 z = unpack_bf16x2(zw[e2]);
-                            if (a.da_mode == 0) {
-                                if (!(fmaf(z.x, sc[2 * e2], sh[2 * e2]) > 0.0f)) g.x = 0.0f;
-                                if (!(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]) > 0.0f)) g.y = 0.0f;
-                            }
-                            const float dx = fmaf(sc[2 * e2], g.x, fmaf(cb[2 * e2], z.x, cc[2 * e2]));
-                            const float dy = fmaf(sc[2 * e2 + 1], g.y, fmaf(cb[2 * e2 + 1], z.y, cc[2 * e2 + 1]));
-                            gw[e2] = pack_bf16x2(dx, dy);
+                    for (int i = 0; i < 4; ++i)
+                        if (i < um.iters) {
+                            const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
+                            g4[i] = *reinterpret_cast<const uint4 *>(s_da + off);
+                            z4[i] = *reinterpret_cast<const uint4 *>(s_z + off);
                         }
-                        if (r >= rows_valid) g4 = make_uint4(0u, 0u, 0u, 0u);      // rows past M (zero-filled loads) must stay zero
-                        *reinterpret_cast<uint4 *>(s_da + off) = g4;
-                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < um.iters) {
+                            const int r = um.row0 + um.rstep * i;
+                            uint32_t *gw = reinterpret_cast<uint32_t *>(&g4[i]);
+                            const uint32_t *zw = reinterpret_cast<const uint32_t *>(&z4[i]);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float2 g = unpack_bf16x2(gw[e2]);
+                                const float2 z = unpack_bf16x2(zw[e2]);
+                                if (a.da_mode == 0) {
+                                    if (!(fmaf(z.x, sc[2 * e2], sh[2 * e2]) > 0.0f)) g.x = 0.0f;
+                                    if (!(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]) > 0.0f)) g.y = 0.0f;
+                                }
+                                const float dx = fmaf(sc[2 * e2], g.x, fmaf(cb[2 * e2], z.x, cc[2 * e2]));
+                                const float dy = fmaf(sc[2 * e2 + 1], g.y, fmaf(cb[2 * e2 + 1], z.y, cc[2 * e2 + 1]));
+                                gw[e2] = pack_bf16x2(dx, dy);
+                            }
+                            if (r >= rows_valid) g4[i] = make_uint4(0u, 0u, 0u, 0u);      // rows past M (zero-filled loads) must stay zero
+                            *reinterpret_cast<uint4 *>(s_da + (uint32_t)j * kBfSlab + sw128_offset(r, um.chunk)) = g4[i];
+                        }
                 }
             }
             if (ttid == 0) BF_STAMP(4);
@@ -265,21 +275,26 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     float sc[8], sh[8], is[8], mi[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { sc[e] = p_sc[c0 + e]; sh[e] = p_sh[c0 + e]; is[e] = p_is[c0 + e]; mi[e] = p_mi[c0 + e]; }
-#pragma unroll 2
-                    for (int i = 0; i < um.iters; ++i) {
-                        const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
-                        uint4 z4 = *reinterpret_cast<const uint4 *>(s_x + off);
-                        uint4 a4;
-                        uint32_t *zw = reinterpret_cast<uint32_t *>(&z4), *aw = reinterpret_cast<uint32_t *>(&a4);
+                    uint4 x4[4];
 #pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) {
-                            const float2 z = unpack_bf16x2(zw[e2]);
-                            aw[e2] = pack_bf16x2(fmaxf(fmaf(z.x, sc[2 * e2], sh[2 * e2]), 0.0f), fmaxf(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f));
-                            zw[e2] = pack_bf16x2(fmaf(z.x, is[2 * e2], mi[2 * e2]), fmaf(z.y, is[2 * e2 + 1], mi[2 * e2 + 1]));
+                    for (int i = 0; i < 4; ++i)
+                        if (i < um.iters)
+                            x4[i] = *reinterpret_cast<const uint4 *>(s_x + (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < um.iters) {
+                            const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
+                            uint4 a4;
+                            uint32_t *zw = reinterpret_cast<uint32_t *>(&x4[i]), *aw = reinterpret_cast<uint32_t *>(&a4);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                const float2 z = unpack_bf16x2(zw[e2]);
+                                aw[e2] = pack_bf16x2(fmaxf(fmaf(z.x, sc[2 * e2], sh[2 * e2]), 0.0f), fmaxf(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f));
+                                zw[e2] = pack_bf16x2(fmaf(z.x, is[2 * e2], mi[2 * e2]), fmaf(z.y, is[2 * e2 + 1], mi[2 * e2 + 1]));
+                            }
+                            *reinterpret_cast<uint4 *>(s_act + off) = a4;
+                            *reinterpret_cast<uint4 *>(s_x + off) = x4[i];
                         }
-                        *reinterpret_cast<uint4 *>(s_act + off) = a4;
-                        *reinterpret_cast<uint4 *>(s_x + off) = z4;
-                    }
                 }
                 if (a.ones_col >= 0) {
                     // the statistics' ones: 16 columns of the zhat tile past its data (the TMA load zero-filled them): 256 units
@@ -293,11 +308,12 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             named_bar_sync(1, kBfXf);
             if (ttid == 0) BF_STAMP(6);
             // ---- MMAs of the tile: data gradient (accumulator buffer b) and weight gradient (lives across all tiles) ----
-            if (ttid == 0) {
-                if (a.want_dx) bf_mbar_arrive(&act_rdy[s]);      // (release: the epilogue group may read act[s])
+            if (warp == kBfEpi / 32) {          // the group's first warp, converged: one elected lane issues (see elect_one_sync)
                 if (a.want_dx && t >= (uint32_t)AB) mbar_wait(&acc_empty[b], ((t / (uint32_t)AB) - 1) & 1u);
-                BF_STAMP(7);
                 fence_after_sync();
+              if (elect_one_sync()) {
+                if (a.want_dx) bf_mbar_arrive(&act_rdy[s]);      // (release: the epilogue group may read act[s])
+                BF_STAMP(7);
                 // (descriptors: the start address sits in the low 14 bits in 16-byte units -- stepping through a tile is an
                 //  integer add on a descriptor built once; building each one from scratch cost ~170 cycles per MMA of dependent
                 //  64-bit arithmetic in this single thread)
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                             if (kk < nk) umma_bf16(d_acc, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc_dx, (uint32_t)((j | kk) != 0));
                     }
                 }
-                if (a.want_dw && !(a.dbg & 1)) {
+                if (a.want_dw && !a.combined && !(a.dbg & 1)) {
                     const uint64_t ad = make_desc(smem_addr(s_da), lbo_n, 1024), bd = make_desc(smem_addr(prev ? s_act : s_x), lbo_k, 1024);
                     const uint32_t d_w = tmem + (uint32_t)a.off_dw;
                     umma_bf16(d_w, ad, bd, idesc_dw, (uint32_t)(t != 0));
@@ -324,6 +340,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 else umma_commit(&empty[s]);                      // no epilogue: the stage may be refilled
                 if (t == n_my - 1) umma_commit(&bar_done);
                 BF_STAMP(8);
+              }
+              __syncwarp();
             }
         }
     } else {
@@ -373,13 +391,36 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 fence_before_sync();      // this thread's tensor-memory reads are complete
                 fence_proxy_async();      // staging writes -> visible to the TMA store / the statistics MMAs
                 if (tid == 0) BF_STAMP(11);
+                // staging in a buffer of its own (not over dZ) and >= 2 stages: the previous tile's store had a whole tile to read
+                // its buffer -- make sure of it here, before anyone passes into the next epilogue, instead of stalling behind
+                // every store
+                if (a.defer_store_wait && warp == 0 && elect_one_sync()) tma_store_wait_read();
                 named_bar_sync(2, kBfEpi);
-                if (tid == 0) {
+                if (warp == 0) {
+                  if (elect_one_sync()) {
                     BF_STAMP(12);
                     bf_mbar_arrive(&acc_empty[b]);       // the data-gradient MMAs of tile t + AB may overwrite this buffer
                     for (int j = 0; j < a.kS; ++j)
                         if (64 * j < a.k_store) tma_store_2d(&a.tm_dx, 64 * j, (int)m0, s_stage + (size_t)j * kBfSlab);
-                    if (a.want_stats && !(a.dbg & 2)) {
+                    if (a.combined) {
+                        // A = [dZ slab | staged dA' slab] (M = 128 through LBO), B = [act slab | zhat (+ ones) slab] (N through LBO):
+                        // D[0:64, 0:64] = dZ^T.act = dW, D[64:128, 64:] = dA'^T.[zhat | ones] = the statistics; 8 MMAs instead of 16
+                        fence_after_sync();
+                        const uint64_t ad = make_desc(smem_addr(st + a.o_da), a.o_stage - a.o_da, 1024);
+                        const uint64_t bd = make_desc(smem_addr(s_act), a.o_x - a.o_act, 1024);
+                        const uint32_t idesc_c = make_idesc_bf16(kBfBM, 64 + a.s2_cols, 1, 1);
+                        const uint32_t d_c = tmem + (uint32_t)a.off_dw;
+#pragma unroll
+                        for (int r = 0; r < kBfBM / 16; ++r)
+                            umma_bf16(d_c, ad + (uint64_t)(128 * r), bd + (uint64_t)(128 * r), idesc_c, r ? 1u : (uint32_t)(t != 0));
+                        if (a.ones_col < 0) {
+                            const uint64_t as = make_desc(smem_addr(s_stage), 0, 1024), b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                            const uint32_t d1 = tmem + (uint32_t)a.off_s1;
+#pragma unroll
+                            for (int r = 0; r < kBfBM / 16; ++r)
+                                umma_bf16(d1, as + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, r ? 1u : (uint32_t)(t != 0));
+                        }
+                    } else if (a.want_stats && !(a.dbg & 2)) {
                         fence_after_sync();
                         const uint64_t ad = make_desc(smem_addr(s_stage), lbo_k, 1024), b2 = make_desc(smem_addr(s_x), lbo_k, 1024);
                         const uint64_t b1 = make_desc(smem_addr(s_ones), 0, 1024);
@@ -393,13 +434,15 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                         }
                     }
                     BF_STAMP(13);
-                    tma_store_wait_read();        // (the staging tile may sit in this stage's dA buffer: the refill must wait for it)
+                    if (!a.defer_store_wait) tma_store_wait_read();   // (staging sits in this stage's dA buffer: the refill must wait)
                     BF_STAMP(14);
                     umma_commit(&empty[s]);       // every MMA that reads the stage is done -> refill
                     if (t == n_my - 1) umma_commit(&bar_done);
+                  }
+                  __syncwarp();
                 }
             }
-            if (tid == 0) tma_store_wait_all();
+            if (warp == 0 && elect_one_sync()) tma_store_wait_all();
         } else if (tid == 0) {
             bf_mbar_arrive(&bar_done);
         }
@@ -430,7 +473,26 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 }
             }
         }
-        if (a.want_stats) {
+        if (a.want_stats && a.combined) {
+            // statistics block of the combined product: row 64 + k, columns 64 + k (S2's diagonal) and 64 + ones_col (S1)
+            if (warp >= 2 && (warp - 2) * 32 < a.K) {
+                const int k = tid - 64;
+                float v0[16], v1[16], w[16];
+                const uint32_t c_stat = (uint32_t)a.off_dw + 64u;
+                tmem_ld16(taddr + c_stat + (uint32_t)((warp - 2) * 32), v0);
+                tmem_ld16(taddr + c_stat + (uint32_t)((warp - 2) * 32 + 16), v1);
+                tmem_ld16(taddr + (a.ones_col >= 0 ? c_stat + (uint32_t)a.ones_col : (uint32_t)a.off_s1), w);
+                float s2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((lane & 15) == i) s2 = lane < 16 ? v0[i] : v1[i];
+                if (k < a.K) {
+                    double *acc = a.stat_accum + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.K;
+                    atomicAdd(acc + k, (double)w[0]);
+                    atomicAdd(acc + a.K + k, (double)s2);
+                }
+            }
+        } else if (a.want_stats) {
             // S2's diagonal (row k, column k) and S1 (row k, the ones column): lanes 0-15 need chunk 2 * warp, lanes 16-31 the next
             if (warp * 32 < a.K) {
                 float v0[16], v1[16], w[16];
@@ -447,6 +509,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     atomicAdd(acc + a.K + tid, (double)s2);
                 }
             }
+        }
+        if (a.want_stats) {
             // "last CTA finalizes" (as bn.cu: bn_bwd_last_block_finalize, among the epilogue threads)
             __threadfence();
             named_bar_sync(2, kBfEpi);
@@ -480,7 +544,7 @@ static int bf_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct BwdFusedPlan {
     bool ok;
-    int nS, kS, K_pad, k_store, tmem_cols, acc_bufs, off_dw, off_s2, off_s1, ones_col, s2_cols, coef_ld, stages, load_x, alias_act;
+    int nS, kS, K_pad, k_store, tmem_cols, acc_bufs, off_dw, off_s2, off_s1, ones_col, s2_cols, coef_ld, stages, load_x, alias_act, combined;
     uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
     size_t dyn_smem;
 };
@@ -512,10 +576,20 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     p.o_x = o;
     if (p.load_x) o += (uint32_t)p.kS * kBfSlab;
     p.bytes_b = o - p.bytes_a;
+    // narrow layers: ONE product gives the weight gradient and the statistics (the tensor pipe takes ~170 cycles per
+    // tcgen05.mma of these tiny shapes whatever it holds, so the MMA COUNT is what matters); it needs dZ alive next to the staged
+    // tile and act next to zhat: [dZ][Z -> act][X -> zhat][staging]
+    p.combined = (prev && want_dw && want_dx && p.nS == 1 && p.kS == 1) ? 1 : 0;
     p.alias_act = (prev && da_mode != 3 && p.kS <= p.nS) ? 1 : 0;
-    p.o_act = p.alias_act ? p.o_z : o;
-    if (prev && !p.alias_act) o += (uint32_t)p.kS * kBfSlab;
-    if (want_dx && p.kS <= p.nS) p.o_stage = p.o_da;
+    if (p.combined && !p.alias_act) {            // (dZ given: no Z tile -- act gets its own slab BEFORE X so that LBO(act -> zhat) > 0)
+        p.o_act = p.o_x;
+        p.o_x = o;
+        o += (uint32_t)p.kS * kBfSlab;
+    } else {
+        p.o_act = p.alias_act ? p.o_z : o;
+        if (prev && !p.alias_act) o += (uint32_t)p.kS * kBfSlab;
+    }
+    if (want_dx && p.kS <= p.nS && !p.combined) p.o_stage = p.o_da;
     else { p.o_stage = o; if (want_dx) o += (uint32_t)p.kS * kBfSlab; }
     p.stage_stride = o;
     const uint32_t w_bytes = want_dx ? (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024) : 0u;
@@ -532,13 +606,15 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     p.o_coef = o; o += coef_bytes;
     p.dyn_smem = (size_t)o + 1024;
     // tensor memory: [dA_{l-1}: acc_bufs x K_pad][dW: K_pad][S2: s2_cols][S1: 16 when the ones have their own tile]
-    const int rest = (want_dw ? p.K_pad : 0) + (prev ? p.s2_cols + (p.ones_col < 0 ? 16 : 0) : 0);
+    const int rest = p.combined ? 64 + p.s2_cols + (p.ones_col < 0 ? 16 : 0)
+                                : (want_dw ? p.K_pad : 0) + (prev ? p.s2_cols + (p.ones_col < 0 ? 16 : 0) : 0);
     p.acc_bufs = (want_dx && 2 * p.K_pad + rest <= 512) ? 2 : 1;
     int cols = want_dx ? p.acc_bufs * p.K_pad : 0;
     p.off_dw = cols;
-    if (want_dw) cols += p.K_pad;
+    if (p.combined) cols += 64 + p.s2_cols;
+    else if (want_dw) cols += p.K_pad;
     p.off_s2 = cols;
-    if (prev) cols += p.s2_cols;
+    if (prev && !p.combined) cols += p.s2_cols;
     p.off_s1 = cols;
     if (prev && p.ones_col < 0) cols += 16;
     int alloc = 32;
@@ -641,7 +717,8 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.ones_col = p.ones_col; a.s2_cols = p.s2_cols; a.o_coef = p.o_coef; a.coef_ld = p.coef_ld;
     a.o_w = p.o_w; a.o_da = p.o_da; a.o_z = p.o_z; a.o_x = p.o_x; a.o_act = p.o_act; a.o_stage = p.o_stage; a.o_ones = p.o_ones;
     a.stage_stride = p.stage_stride; a.bytes_a = p.bytes_a; a.bytes_b = p.bytes_b; a.stages = p.stages; a.acc_bufs = p.acc_bufs;
-    a.load_x = p.load_x; a.alias_act = p.alias_act;
+    a.load_x = p.load_x; a.alias_act = p.alias_act; a.combined = p.combined;
+    a.defer_store_wait = (want_dx && p.o_stage != p.o_da && p.stages >= 2) ? 1 : 0;
     { const char *e = getenv("PN2_BWD_DBG"); a.dbg = e ? atoi(e) : 0; }
     if ((a.dbg & 32) && L->scratch && L->K % 4 == 0) a.dbg_buf = (long long *)L->scratch;
     bwd_fused_kernel<<<(unsigned)grid, kBfThreads, p.dyn_smem, (cudaStream_t)stream>>>(a);

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned (SW128 atoms)
     const uint32_t b_bytes = (uint32_t)b_n_pad * 128u;
     const int z_slabs = (b_n_store + 63) >> 6;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
         // transform ownership: physical 16-byte unit q = tid + 128 i of a chunk: row r = q >> 3 (r & 7 is the same
         // for every i), logical column chunk cc = (q & 7) ^ (r & 7)
         const int t_cc = (tid & 7) ^ ((tid >> 3) & 7);
-        if (a.w_resident && tid == 0) mbar_wait(&bar_w, 0);
+        if (a.w_resident && warp == 0) mbar_wait(&bar_w, 0);
         uint32_t n = 0, acc_par = 0;
         for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
             const int64_t m0 = tile * kTcBM;
@@ -284,20 +284,24 @@ __global__ void __launch_bounds__(kLinTcThreads) linear_tc_kernel(const __grid_c
                     }
                     fence_proxy_async();
                     named_bar_sync(1, 128);
-                } else if (tid == 0) {
+                } else if (warp == 0) {
                     mbar_wait(&bar_full[s], par);
                 }
-                if (tid == 0) {
+                // warp 0, converged, one elected lane issues: descriptors stay on the uniform datapath (tc_common.cuh: elect_one_sync)
+                if (warp == 0) {
                     fence_after_sync();
                     const int k_left = a.K - kc * kTcBK;
                     const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
-                    const uint32_t a_base = smem_addr(slot);
-                    const uint32_t b_base = smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage);
-                    for (int j = 0; j < nk; ++j)
-                        umma_bf16(tmem, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024), idesc,
-                                  (uint32_t)((kc | j) != 0));
-                    umma_commit(&bar_empty[s]);
-                    if (kc == a.KC - 1) umma_commit(&bar_acc);
+                    const uint64_t ad = make_desc(smem_addr(slot), 0, 1024);
+                    const uint64_t bd = make_desc(smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage), 0, 1024);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nk) umma_bf16(tmem, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (uint32_t)((kc | j) != 0));
+                        umma_commit(&bar_empty[s]);
+                        if (kc == a.KC - 1) umma_commit(&bar_acc);
+                    }
+                    __syncwarp();
                 }
             }
             mbar_wait(&bar_acc, acc_par);
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     const uint32_t b_bytes = (uint32_t)b_n_pad * 128u;
     const int z_slabs = (b_n_store + 63) >> 6;
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
         const int ttid = tid - 128;
         const uint32_t idesc = make_idesc_bf16(kTcBM, b_n_pad, 0, 0);
         const int t_cc = (ttid & 7) ^ ((ttid >> 3) & 7);
-        if (a.w_resident && ttid == 0) mbar_wait(&bar_w, 0);
+        if (a.w_resident && warp == 4) mbar_wait(&bar_w, 0);
         uint32_t n = 0, t = 0;
         for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
             const uint32_t buf = t & 1u, buse = t >> 1;
@@ -518,21 +522,25 @@ __global__ void __launch_bounds__(kLinTc2Threads) linear_tc2_kernel(const __grid
                     }
                     fence_proxy_async();
                     named_bar_sync(2, 128);
-                } else if (ttid == 0) {
+                } else if (warp == 4) {
                     mbar_wait(&bar_full[s], par);
                 }
-                if (ttid == 0) {
+                if (warp == 4) {        // converged; one elected lane issues (tc_common.cuh: elect_one_sync)
                     if (kc == 0 && buse > 0) mbar_wait(&acc_empty[buf], (buse - 1) & 1u);   // the epilogue drained this buffer
                     fence_after_sync();
                     const int k_left = a.K - kc * kTcBK;
                     const int nk = k_left >= kTcBK ? 4 : (k_left + 15) / 16;
-                    const uint32_t a_base = smem_addr(slot);
-                    const uint32_t b_base = smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage);
-                    for (int j = 0; j < nk; ++j)
-                        umma_bf16(tmem + buf * (uint32_t)b_n_pad, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024),
-                                  idesc, (uint32_t)((kc | j) != 0));
-                    umma_commit(&bar_empty[s]);
-                    if (kc == a.KC - 1) umma_commit(&acc_full[buf]);
+                    const uint64_t ad = make_desc(smem_addr(slot), 0, 1024);
+                    const uint64_t bd = make_desc(smem_addr(a.w_resident ? w_res + (size_t)kc * b_bytes : slot + kTcAStage), 0, 1024);
+                    const uint32_t d_acc = tmem + buf * (uint32_t)b_n_pad;
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nk) umma_bf16(d_acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, (uint32_t)((kc | j) != 0));
+                        umma_commit(&bar_empty[s]);
+                        if (kc == a.KC - 1) umma_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -886,7 +894,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_scale[256], s_shift[256];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = uniform_warp_idx();
     const int n0 = ((int)blockIdx.y / a.nblk_k) * 128, k0 = ((int)blockIdx.y % a.nblk_k) * 256;
     const int nb = min(128, a.N - n0), kb = min(256, a.K - k0);
     const int kb_pad = (kb + 15) & ~15;
@@ -983,17 +991,20 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
                 }
                 fence_proxy_async();
                 named_bar_sync(1, 128);
-            } else if (tid == 0) {
+            } else if (warp == 0) {
                 mbar_wait(&bar_full[s], par);
             }
-            if (tid == 0) {
+            if (warp == 0) {            // converged; one elected lane issues (tc_common.cuh: elect_one_sync)
                 fence_after_sync();
-                const uint32_t a_base = smem_addr(stA), b_base = smem_addr(stB);
-                for (int j = 0; j < rows16 / 16; ++j)
-                    umma_bf16(tmem, make_desc(a_base + 2048 * j, slab_bytes, 1024), make_desc(b_base + 2048 * j, slab_bytes, 1024),
-                              idesc, (uint32_t)((it | j) != 0));
-                umma_commit(&bar_empty[s]);
-                if (it == n_it - 1) umma_commit(&bar_done);
+                const uint64_t ad = make_desc(smem_addr(stA), slab_bytes, 1024), bd = make_desc(smem_addr(stB), slab_bytes, 1024);
+                const int nj = rows16 / 16;
+                if (elect_one_sync()) {
+                    for (int j = 0; j < nj; ++j)
+                        umma_bf16(tmem, ad + (uint64_t)(128 * j), bd + (uint64_t)(128 * j), idesc, (uint32_t)((it | j) != 0));
+                    umma_commit(&bar_empty[s]);
+                    if (it == n_it - 1) umma_commit(&bar_done);
+                }
+                __syncwarp();
             }
         }
         if (n_it > 0) mbar_wait(&bar_done, 0);

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = uniform_warp_idx();
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t *const act = smem;
     uint8_t *const ring = act + (size_t)a.a_slabs * kSaSlab;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_
 
             int ss_base = 0;
             for (int l = 0; l < a.L; ++l) {
-                if (tid == 0) {
+                if (warp_u == 0) {      // warp 0, converged; one elected lane issues (tc_common.cuh: elect_one_sync)
                     fence_after_sync();
                     for (int c = a.chunk_begin[l]; c < a.chunk_begin[l + 1]; ++c, ++n) {
                         const SaChunk &ch = a.chunks[c];
@@ -251,14 +252,18 @@ __global__ void __launch_bounds__(kSaThreads) sa_fused_eval_kernel(const __grid_
                         const uint32_t par = a.resident ? 0u : (n / (uint32_t)a.stages) & 1u;
                         mbar_wait(&bar_full[s], par);
                         fence_after_sync();
-                        const uint32_t a_base = smem_addr(act + (size_t)ch.kc * kSaSlab);
-                        const uint32_t b_base = smem_addr(ring + (size_t)s * a.slot_bytes);
-                        for (int j = 0; j < ch.nk; ++j)
-                            umma_bf16(tmem + ch.tmem_col, make_desc(a_base + 32 * j, 0, 1024), make_desc(b_base + 32 * j, 0, 1024),
-                                      ch.idesc, (uint32_t)((ch.kc | j) != 0));
-                        if (!a.resident) umma_commit(&bar_empty[s]);
+                        const uint64_t ad = make_desc(smem_addr(act + (size_t)ch.kc * kSaSlab), 0, 1024);
+                        const uint64_t bd = make_desc(smem_addr(ring + (size_t)s * a.slot_bytes), 0, 1024);
+                        const int nk = ch.nk;
+                        const uint32_t d_acc = tmem + ch.tmem_col, idesc = ch.idesc, first = (uint32_t)(ch.kc != 0);
+                        if (elect_one_sync()) {
+                            for (int j = 0; j < nk; ++j) umma_bf16(d_acc, ad + (uint64_t)(2 * j), bd + (uint64_t)(2 * j), idesc, first | (uint32_t)(j != 0));
+                            if (!a.resident) umma_commit(&bar_empty[s]);
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&bar_acc);
+                    if (elect_one_sync()) umma_commit(&bar_acc);
+                    __syncwarp();
                 }
                 mbar_wait(&bar_acc, acc_par);
                 acc_par ^= 1u;

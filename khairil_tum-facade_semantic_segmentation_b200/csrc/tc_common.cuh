@@ -107,6 +107,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a CONVERGED warp (the lowest active one).  Single-thread work (tcgen05.mma / commit, TMA issue) belongs in
+//     if (warp_uniform_condition) { ...; if (elect_one_sync()) { issue } }
+// rather than `if (threadIdx.x == 0)`: the descriptors are then computed on the uniform datapath and the instruction is merely
+// predicated, whereas in a thread-divergent branch every tcgen05.mma is preceded by ELECT + 4-6 serialised R2UR moves of its
+// operands (~100-170 cycles per MMA measured with clock64 stamps in bwd_fused.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a warp-uniform value (the compiler cannot tell that threadIdx.x >> 5 is)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- UMMA descriptors ---------------------------------------------------------------------------
 // Shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
 // | layout type [61,64) (2 = 128-byte swizzle).
