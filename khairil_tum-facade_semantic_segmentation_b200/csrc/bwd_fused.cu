@@ -93,6 +93,12 @@ __device__ __forceinline__ void bf_mbar_arrive(uint64_t *bar) {
 //   nch == 4: only half of every 128-byte row is data.  A warp takes one 8-row swizzle atom per iteration; its four 8-thread
 //            phases take the row pairs (p, p + 4): logical chunks 0-3 of row p sit in the physical chunks {0..3} ^ p and those
 //            of row p + 4 in the complementary half, so a phase touches all 32 banks once (2 iterations per slab).
+// eight consecutive per-column coefficients (c0 % 8 == 0, tables 32-byte aligned): two LDS.128 instead of eight LDS
+__device__ __forceinline__ void ld_coef8(const float *tab, int c0, float (&v)[8]) {
+    const float4 lo = *reinterpret_cast<const float4 *>(tab + c0), hi = *reinterpret_cast<const float4 *>(tab + c0 + 4);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
 struct UnitMap {
     int chunk;        // logical 16-byte chunk (8 columns) inside the slab, constant per thread
     int row0, rstep;  // rows row0 + rstep * i
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], cb[8], cc[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { sc[e] = c_sc[c0 + e]; sh[e] = c_sh[c0 + e]; cb[e] = c_b[c0 + e]; cc[e] = c_c[c0 + e]; }
+                    ld_coef8(c_sc, c0, sc); ld_coef8(c_b, c0, cb); ld_coef8(c_c, c0, cc);
+                    if (a.da_mode == 0) ld_coef8(c_sh, c0, sh);
                     // (all of the thread's units are loaded before any arithmetic: 2 x <= 4 LDS.128 in flight instead of a
                     //  load -> compute -> store chain per unit; the loop bodies are fully unrolled and predicated on um.iters)
                     uint4 g4[4], z4[4];
@@ -273,8 +279,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], is[8], mi[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { sc[e] = p_sc[c0 + e]; sh[e] = p_sh[c0 + e]; is[e] = p_is[c0 + e]; mi[e] = p_mi[c0 + e]; }
+                    ld_coef8(p_sc, c0, sc); ld_coef8(p_sh, c0, sh); ld_coef8(p_is, c0, is); ld_coef8(p_mi, c0, mi);
                     uint4 x4[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
