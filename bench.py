@@ -91,6 +91,7 @@ def _esz(dtype_code):
 KERNEL_MODEL = {
     "pn2_farthest_point_sample": lambda a: (a[4] * (12 * a[5] + 20 * a[6]), 9.0 * a[4] * a[5] * a[6], "latency"),
     "pn2_query_ball_point": lambda a: (a[8] * (12 * a[9] + 12 * a[10] + 8 * a[10] * a[12]), 6.0 * a[8] * a[9] * a[10], "alu"),
+    "pn2_query_ball_point_grid": lambda a: (a[8] * (12 * a[9] + 12 * a[10] + 8 * a[10] * a[13]), 6.0 * a[8] * a[9] * a[10], "alu"),
     "pn2_three_nn": lambda a: (a[8] * (12 * a[9] + 12 * a[10] + 36 * a[9]), 6.0 * a[8] * a[9] * a[10], "alu"),
     "pn2_group_points": lambda a: (a[10] * a[12] * a[13] * (8 + (3 + a[14]) * 4 + a[16] * _esz(a[17])), 0.0, "hbm"),
     "pn2_group_points_bwd": lambda a: (a[4] * a[6] * a[7] * (8 + a[1] * _esz(a[2]) + a[8] * 4), 0.0, "hbm"),
@@ -495,7 +496,8 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
         return None
     pk, pk_kind = peaks()
     by = {n: (a, t) for n, a, t in calls}
-    fps_ms, ball_ms = by["pn2_farthest_point_sample"][1], by["pn2_query_ball_point"][1]
+    ball_entry = "pn2_query_ball_point_grid" if "pn2_query_ball_point_grid" in by else "pn2_query_ball_point"
+    fps_ms, ball_ms = by["pn2_farthest_point_sample"][1], by[ball_entry][1]
     b = hi - lo
     ball_bytes = b * (12 * N + 12 * S + 8 * S * 32)
     cpu = None
@@ -519,7 +521,7 @@ def run_fps_ball(args, rank, world, dev, pn2, lib_mod, barrier, sampler):
         "e2e": {"value": B_total * N / (e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": b * N * 12, "d2h_bytes_per_step": b * S * 32 * 8,
                 "ms_per_step": e2e},
         "gpu_launches": 2 * args.steps, "clocks": clocks,
-        "roofline": {"kernel": "ball_query_kernel", "bound": "hbm", "achieved": ball_bytes / (ball_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+        "roofline": {"kernel": ("bg_build_kernel + bg_query_kernel (cell grid)" if ball_entry.endswith("_grid") else "ball_query_kernel"), "bound": "hbm", "achieved": ball_bytes / (ball_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": ball_bytes / (ball_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
                      "peak_kind": pk_kind + " (burst copy bandwidth)", "avg_launch_ms": ball_ms,
                      "note": "the int64 index output dominates the bytes; fp32-ALU view: %.2f Tpair/s brute-force basis. "

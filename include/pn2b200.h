@@ -87,6 +87,19 @@ int pn2_query_ball_point(const float *xyz, int64_t sB, int64_t sN, int64_t sC,
                          int S, float r2, int nsample, int64_t *out_idx, int32_t *out_cnt,
                          void *stream);
 
+/* The same result through a uniform cell grid (csrc/ballgrid.cu): the cloud is counting-sorted into cells of edge >= 1.01 r,
+ * a query evaluates only the points of its 3 x 3 x 3 cells (~100 instead of N) and selects through an N-bit map, which
+ * reproduces "first nsample in index order, padded with the first" exactly.  `radius` is the reference's Python float,
+ * r2 = float32(radius ** 2) as above.  Clouds whose coordinates are so large that the fp32 rounding error of the
+ * reference's distance could reach the cell margin, or that hold NaN / Inf, are scanned in index order inside the same
+ * launch, so the output is always that of pn2_query_ball_point.  workspace: pn2_ball_grid_workspace_bytes(B, N) bytes,
+ * 16-byte aligned; N <= 409600 (per-query bitmaps in shared memory). */
+size_t pn2_ball_grid_workspace_bytes(int B, int N);
+int pn2_query_ball_point_grid(const float *xyz, int64_t sB, int64_t sN, int64_t sC,
+                              const float *new_xyz, int64_t qB, int64_t qN, int64_t qC, int B, int N,
+                              int S, float radius, float r2, int nsample, int64_t *out_idx, int32_t *out_cnt,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- a5 sample_and_group, gather half (:127-132) -----------------------------
  * rows[(b,s,k), 0:3]     = xyz[b, idx[b,s,k], :] - new_xyz[b,s,:]
  * rows[(b,s,k), 3:3+D]   = feats[b, idx[b,s,k], :]        (feats may be NULL, D = 0)

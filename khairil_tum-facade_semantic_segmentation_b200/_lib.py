@@ -33,6 +33,8 @@ _SIGNATURES = {
     "pn2_index_points_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
     "pn2_farthest_point_sample": (_i, [_p, _l, _l, _l, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_query_ball_point": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _f, _i, _p, _p, _p]),
+    "pn2_ball_grid_workspace_bytes": (_z, [_i, _i]),
+    "pn2_query_ball_point_grid": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _f, _f, _i, _p, _p, _p, _z, _p]),
     "pn2_group_points": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pn2_group_points_bwd": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pn2_linear_wpack_bytes": (_z, [_i, _i]),

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libpn2b200.so
-SRCS="api.cu fps.cu ballquery.cu group.cu threenn.cu linear_simt.cu bn.cu linear_tc.cu bwd_fused.cu sa_fused.cu head.cu vote.cu slicer.cu optim.cu"
+SRCS="api.cu fps.cu ballquery.cu ballgrid.cu group.cu threenn.cu linear_simt.cu bn.cu linear_tc.cu bwd_fused.cu sa_fused.cu head.cu vote.cu slicer.cu optim.cu"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include ${PN2_NVCC_EXTRA}"
 mkdir -p build

@@ -132,6 +132,78 @@ def test_ball_query_empty_ball_yields_N(pn2):
     assert np.array_equal(got, C.ball_query(0.1, 4, xyz.numpy(), far.numpy()))
 
 
+def _ball_both_paths(pn2, r, k, xyz, new_xyz):
+    """(cell-grid result, index-order-scan result) of query_ball_point, with counts"""
+    ops = __import__("importlib").import_module("khairil_tum-facade_semantic_segmentation_b200.ops")
+    saved, saved_max = ops.BALL_GRID, ops._BALL_GRID_MAX_N
+    try:
+        ops.BALL_GRID, ops._BALL_GRID_MAX_N = True, 409600
+        g = pn2.query_ball_point(r, k, xyz.to(DEV), new_xyz.to(DEV), return_count=True)
+        ops.BALL_GRID = False
+        s = pn2.query_ball_point(r, k, xyz.to(DEV), new_xyz.to(DEV), return_count=True)
+    finally:
+        ops.BALL_GRID, ops._BALL_GRID_MAX_N = saved, saved_max
+    return g, s
+
+
+@pytest.mark.parametrize("kind", ["facade", "cube", "lattice_at_r", "duplicates", "far_queries", "flat"])
+@pytest.mark.parametrize("r,k", [(0.1, 32), (0.2, 16), (0.4, 64)])
+def test_ball_query_cell_grid_equals_index_order_scan(pn2, kind, r, k):
+    """csrc/ballgrid.cu must reproduce the radius scan (= the reference's mask + sort, pointnet2_utils.py:96-106) bit for
+    bit, including the cases DESIGN.md named: a lattice with neighbours at EXACTLY the radius (the fp32 expanded-form
+    distance decides, not geometry), duplicated points, queries far outside the cloud (empty balls), degenerate boxes."""
+    g = torch.Generator().manual_seed(5)
+    B, N, S = 3, 3000, 700
+    if kind == "facade":
+        xyz = I.facade_xyz(B, N, 8)
+    elif kind == "cube":
+        xyz = I.cube_xyz(B, N, 3)
+    elif kind == "lattice_at_r":
+        xyz = torch.round(torch.rand(B, N, 3, generator=g) * 10) * r                  # spacing exactly r: ties at the radius
+    elif kind == "duplicates":
+        xyz = I.cube_xyz(B, N, 4)
+        xyz[:, N // 2:] = xyz[:, :N - N // 2]                                          # every point twice
+    elif kind == "far_queries":
+        xyz = I.cube_xyz(B, N, 6)
+    else:
+        xyz = I.cube_xyz(B, N, 7)
+        xyz[:, :, 1] = 0.25                                                            # a plane: one cell thick
+    new_xyz = xyz[:, torch.randperm(N, generator=torch.Generator().manual_seed(1))[:S]].contiguous()
+    if kind == "far_queries":
+        new_xyz = new_xyz.clone()
+        new_xyz[:, ::3] += 5.0
+    (gi, gc), (si, sc) = _ball_both_paths(pn2, r, k, xyz, new_xyz)
+    assert torch.equal(gi, si) and torch.equal(gc, sc)
+    want, wcnt = C.ball_query(r, k, xyz.numpy(), new_xyz.numpy(), return_count=True)
+    assert np.array_equal(gi.cpu().numpy(), want) and np.array_equal(gc.cpu().numpy(), wcnt)
+
+
+def test_ball_query_cell_grid_falls_back_where_rounding_could_reach_the_margin(pn2):
+    """un-centred coordinates (z ~ 512, as raw LAS heights would be): the reference's fp32 distance is mostly rounding
+    noise at r = 0.1 and accepts points far outside the ball; NaN coordinates count as inside (:102 compares false).
+    The grid path must hand such clouds to the index-order scan and still match it exactly."""
+    xyz = I.facade_xyz(2, 2048, 9)
+    xyz[0, :, 2] += 512.0
+    xyz[1, 7, 0] = float("nan")
+    new_xyz = xyz[:, ::8].contiguous()
+    (gi, gc), (si, sc) = _ball_both_paths(pn2, 0.1, 32, xyz, new_xyz)
+    assert torch.equal(gi, si) and torch.equal(gc, sc)
+    want = C.ball_query(0.1, 32, xyz[:1].numpy(), new_xyz[:1].numpy())
+    assert np.array_equal(gi[:1].cpu().numpy(), want)
+
+
+def test_ball_query_cell_grid_config3_shape(pn2, golden):
+    """BASELINE.json configs[2]: 65536 points, r = 0.1, nsample = 32 against the fixture of the unmodified reference"""
+    g = golden("ops_large")
+    xyz = I.cube_xyz(1, 65536, 0)
+    idx = torch.from_numpy(g["fps"].astype(np.int64))
+    new_xyz = torch.gather(xyz, 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    (gi, _), (si, _) = _ball_both_paths(pn2, 0.1, 32, xyz, new_xyz)
+    assert torch.equal(gi, si)
+    assert np.array_equal(gi[:, :256].cpu().numpy(), g["ball_head"].astype(np.int64))
+    assert np.array_equal(gi[:, -256:].cpu().numpy(), g["ball_tail"].astype(np.int64))
+
+
 @pytest.mark.parametrize("B,N,S", [(2, 300, 1), (2, 300, 2), (2, 300, 3), (4, 1024, 256), (1, 4096, 1024), (2, 100, 2500)])
 def test_three_nn_matches_c_oracle(pn2, B, N, S):
     fine, coarse = I.facade_xyz(B, N, 2), I.facade_xyz(B, S, 3, dup_frac=0.3 if S > 8 else 0.0)
