@@ -187,6 +187,8 @@ int pn2_linear_bwd_weight_accum(const void *dZ, int lddz, int dz_dtype, const vo
  *     dW       += dZ_l^T . act(X),  act = relu(prev_scale . X + prev_shift) or X itself (the MLP's input rows)
  *     dgamma_prev, dbeta_prev of layer l-1's BatchNorm from dX (when prev_* are given; "last CTA finalizes")
  * da_mode: 0 = dA dense, layer l's ReLU mask applied here; 1 = dA already masked by the call that produced it;
+ *          2 = pooled: the gradient is dOut [G, N] fp32 of the max over nsample = 32 with the arg-max map `arg` [G, N] int32
+ *              of pn2_bn_relu_max (row (g, k) receives dOut[g, c] where arg[g, c] == k; dA unused, M = 32 G);
  *          3 = `dA` IS dZ_l (Z / scale / ... unused).  mean == NULL: frozen statistics (dZ = scale . mask . dA).
  * dW is ADDED to (zero it first; L2 reductions, order varies run to run); K % 4 != 0 needs `scratch`
  * (pn2_mlp_bwd_layer_scratch_bytes) for a fixed-order partial sum instead.  dX / dW may be NULL (not wanted).
@@ -194,6 +196,7 @@ int pn2_linear_bwd_weight_accum(const void *dZ, int lddz, int dz_dtype, const vo
  * (N, ldx <= 128, row pitches % 8 == 0, shared / tensor memory) -- otherwise use the per-step entry points. */
 typedef struct pn2_bwd_layer {
     const void *dA; int ldda; int da_mode;
+    const float *dOut; const int32_t *arg; int nsample;
     const void *Z; int ldz;
     const float *scale, *shift, *mean, *invstd, *dgamma, *dbeta;
     const void *wpack_t;
@@ -230,6 +233,12 @@ int pn2_bn_eval_fold(const float *gamma, const float *beta, const float *running
  * G groups of nsample consecutive rows; out fp32 [G,C] contiguous. */
 int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
                     int64_t G, int nsample, int C, float *out, int32_t *arg, void *stream);
+/* ... and zmax[g,c] = Z[(g, arg[g,c]), c] (rows of Z's dtype, leading dimension ldzm): with it the pooled backward's
+ * BatchNorm gradients are a plain [G, C] column reduction -- pn2_bn_relu_bwd_reduce(dOut fp32, zmax) -- instead of a gather
+ * of one element per (group, channel) out of the [G * nsample, C] rows (5 % of HBM bandwidth, latency bound). */
+int pn2_bn_relu_max_keep(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                         int64_t G, int nsample, int C, float *out, int32_t *arg, void *zmax, int ldzm,
+                         void *stream);
 /* a8 tail: out[m,c] = relu(Z[m,c]*scale[c]+shift[c])  (fp32 [M,C] contiguous) */
 int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
                 int64_t M, int C, float *out, void *stream);

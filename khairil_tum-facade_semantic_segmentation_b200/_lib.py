@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pn2_bn_train_finalize": (_i, [_p, _l, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_bn_eval_fold": (_i, [_p, _p, _p, _p, _f, _i, _p, _p, _p]),
     "pn2_bn_relu_max": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p]),
+    "pn2_bn_relu_max_keep": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, _p, _p, _p, _i, _p]),
     "pn2_bn_relu": (_i, [_p, _i, _i, _p, _p, _l, _i, _p, _p]),
     "pn2_sa_fused_eval_workspace_bytes": (_z, [_i, _i, _p]),
     "pn2_sa_fused_eval": (_i, [_p, _l, _l, _l, _p, _p, _l, _l, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -92,7 +93,7 @@ class BnFinalize(ctypes.Structure):
 
 class BwdLayer(ctypes.Structure):
     """pn2_bwd_layer of include/pn2b200.h (a HOST struct of device pointers)."""
-    _fields_ = [("dA", _p), ("ldda", _i), ("da_mode", _i), ("Z", _p), ("ldz", _i),
+    _fields_ = [("dA", _p), ("ldda", _i), ("da_mode", _i), ("dOut", _p), ("arg", _p), ("nsample", _i), ("Z", _p), ("ldz", _i),
                 ("scale", _p), ("shift", _p), ("mean", _p), ("invstd", _p), ("dgamma", _p), ("dbeta", _p),
                 ("wpack_t", _p), ("X", _p), ("ldx", _i),
                 ("prev_scale", _p), ("prev_shift", _p), ("prev_mean", _p), ("prev_invstd", _p),

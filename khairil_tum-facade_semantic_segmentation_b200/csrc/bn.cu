@@ -82,21 +82,23 @@ __global__ void bn_eval_fold_kernel(const float *__restrict__ gamma, const float
 template <typename T>
 __global__ void bn_relu_max_kernel(const T *__restrict__ Z, int ldz, const float *__restrict__ scale,
                                    const float *__restrict__ shift, int64_t G, int nsample, int C,
-                                   float *__restrict__ out, int32_t *__restrict__ arg) {
+                                   float *__restrict__ out, int32_t *__restrict__ arg, T *__restrict__ zmax, int ldzm) {
     const int64_t total = G * C;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(e % C);
         int64_t g = e / C;
         const float sc = scale[c], sh = shift[c];
         const T *z = Z + g * nsample * (int64_t)ldz + c;
-        float best = -1.0f;
+        float best = -1.0f, bz = 0.0f;
         int bk = 0;
         for (int k = 0; k < nsample; ++k) {
-            float a = fmaxf(fmaf(ld_act<T>(z + (int64_t)k * ldz), sc, sh), 0.0f);
-            if (a > best) { best = a; bk = k; }
+            const float zz = ld_act<T>(z + (int64_t)k * ldz);
+            float a = fmaxf(fmaf(zz, sc, sh), 0.0f);
+            if (a > best) { best = a; bk = k; bz = zz; }
         }
         out[e] = best;
         if (arg) arg[e] = bk;
+        if (zmax) st_act<T>(zmax + g * ldzm + c, bz);
     }
 }
 
@@ -105,7 +107,7 @@ __global__ void bn_relu_max_kernel(const T *__restrict__ Z, int ldz, const float
 __global__ void __launch_bounds__(256)
 bn_relu_max_vec8_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const float *__restrict__ scale,
                         const float *__restrict__ shift, int64_t G, int nsample, int C, float *__restrict__ out,
-                        int32_t *__restrict__ arg) {
+                        int32_t *__restrict__ arg, __nv_bfloat16 *__restrict__ zmax, int ldzm) {
     const int cpr = C >> 3;
     const int64_t total = G * cpr;
     constexpr int U = 8;
@@ -114,13 +116,14 @@ bn_relu_max_vec8_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const floa
         int c8;
         fast_divmod(t, cpr, g, c8);
         const int c0 = c8 << 3;
-        float sc[8], sh[8], best[8];
+        float sc[8], sh[8], best[8], bz[8];
         int bk[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             sc[e] = scale[c0 + e];
             sh[e] = shift[c0 + e];
             best[e] = -1.0f;
+            bz[e] = 0.0f;
             bk[e] = 0;
         }
         const __nv_bfloat16 *z = Z + g * nsample * (int64_t)ldz + c0;
@@ -138,8 +141,8 @@ bn_relu_max_vec8_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const floa
                     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
                     const float a0 = fmaxf(fmaf(f.x, sc[2 * i], sh[2 * i]), 0.0f);
                     const float a1 = fmaxf(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]), 0.0f);
-                    if (a0 > best[2 * i]) { best[2 * i] = a0; bk[2 * i] = k0 + u; }
-                    if (a1 > best[2 * i + 1]) { best[2 * i + 1] = a1; bk[2 * i + 1] = k0 + u; }
+                    if (a0 > best[2 * i]) { best[2 * i] = a0; bk[2 * i] = k0 + u; bz[2 * i] = f.x; }
+                    if (a1 > best[2 * i + 1]) { best[2 * i + 1] = a1; bk[2 * i + 1] = k0 + u; bz[2 * i + 1] = f.y; }
                 }
             }
         }
@@ -150,6 +153,16 @@ bn_relu_max_vec8_kernel(const __nv_bfloat16 *__restrict__ Z, int ldz, const floa
             int32_t *a = arg + g * C + c0;
             *reinterpret_cast<int4 *>(a) = make_int4(bk[0], bk[1], bk[2], bk[3]);
             *reinterpret_cast<int4 *>(a + 4) = make_int4(bk[4], bk[5], bk[6], bk[7]);
+        }
+        if (zmax) {      // the pre-BatchNorm value that won (exactly the stored bf16): the pooled backward reduces over [G, C] rows
+            uint4 zo;
+            uint32_t *zw = reinterpret_cast<uint32_t *>(&zo);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(bz[2 * i], bz[2 * i + 1]);
+                zw[i] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            *reinterpret_cast<uint4 *>(zmax + g * ldzm + c0) = zo;
         }
     }
 }
@@ -471,23 +484,36 @@ extern "C" int pn2_bn_eval_fold(const float *gamma, const float *beta, const flo
     return check_launch("bn_eval_fold");
 }
 
-extern "C" int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
-                               int64_t G, int nsample, int C, float *out, int32_t *arg, void *stream) {
-    PN2_REQUIRE(Z && scale && shift && out, "bn_relu_max: null pointer");
-    PN2_REQUIRE(valid_dtype(z_dtype) && nsample >= 1 && C >= 1 && ldz >= C, "bn_relu_max: bad arguments");
+static int bn_relu_max_impl(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift, int64_t G, int nsample,
+                            int C, float *out, int32_t *arg, void *zmax, int ldzm, void *stream) {
     int64_t total = G * C;
     if (total == 0) return PN2_OK;
     if (z_dtype == PN2_BF16 && C % 8 == 0 && ldz % 8 == 0 && ((uintptr_t)Z & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
-        (!arg || ((uintptr_t)arg & 15) == 0)) {
+        (!arg || ((uintptr_t)arg & 15) == 0) && (!zmax || (((uintptr_t)zmax & 15) == 0 && ldzm % 8 == 0))) {
         bn_relu_max_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16 *)Z, ldz, scale, shift, G, nsample, C, out, arg);
+            (const __nv_bfloat16 *)Z, ldz, scale, shift, G, nsample, C, out, arg, (__nv_bfloat16 *)zmax, ldzm);
         count_launch();
         return check_launch("bn_relu_max_vec8");
     }
     PN2_DISPATCH_DTYPE(z_dtype, T, (bn_relu_max_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T *)Z, ldz, scale, shift, G, nsample, C, out, arg)));
+        (const T *)Z, ldz, scale, shift, G, nsample, C, out, arg, (T *)zmax, ldzm)));
     count_launch();
     return check_launch("bn_relu_max");
+}
+
+extern "C" int pn2_bn_relu_max(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                               int64_t G, int nsample, int C, float *out, int32_t *arg, void *stream) {
+    PN2_REQUIRE(Z && scale && shift && out, "bn_relu_max: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && nsample >= 1 && C >= 1 && ldz >= C, "bn_relu_max: bad arguments");
+    return bn_relu_max_impl(Z, ldz, z_dtype, scale, shift, G, nsample, C, out, arg, nullptr, 0, stream);
+}
+
+extern "C" int pn2_bn_relu_max_keep(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,
+                                    int64_t G, int nsample, int C, float *out, int32_t *arg, void *zmax, int ldzm,
+                                    void *stream) {
+    PN2_REQUIRE(Z && scale && shift && out && zmax, "bn_relu_max_keep: null pointer");
+    PN2_REQUIRE(valid_dtype(z_dtype) && nsample >= 1 && C >= 1 && ldz >= C && ldzm >= C, "bn_relu_max_keep: bad arguments");
+    return bn_relu_max_impl(Z, ldz, z_dtype, scale, shift, G, nsample, C, out, arg, zmax, ldzm, stream);
 }
 
 extern "C" int pn2_bn_relu(const void *Z, int ldz, int z_dtype, const float *scale, const float *shift,

@@ -48,7 +48,10 @@ struct BwdFusedArgs {
     int64_t M;
     int K, N, K_pad, k_store;    // K_pad = round_up(K, 16); k_store = columns of dX written (round_up(K, 8) <= lddx)
     int nS, kS;                  // 64-column slabs of the dA / Z tiles and of the X tile
-    int da_mode;                 // 0: dA dense, mask applied here; 1: dA already masked by its producer; 3: dZ_l given
+    int da_mode;                 // 0: dA dense, mask applied here; 1: dA already masked by its producer; 2: pooled (dOut, arg); 3: dZ_l given
+    const float *dOut;           // mode 2: [G, N] fp32 gradient of the max-pooled output, arg [G, N] int32 winners (32 samples per group)
+    const int32_t *arg;
+    uint32_t o_pool;             // per stage: [4][N] fp32 dOut rows then [4][N] int32 arg rows of the tile's four groups
     int want_dx, want_dw, want_stats, load_x;
     int ones_col;                // >= 0: the statistics' ones live in columns [ones_col, ones_col + 16) of the zhat tile; < 0: own tile
     int s2_cols;                 // N extent of the S2 product
@@ -196,11 +199,20 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 BF_STAMP(0);
                 if (u > 0) mbar_wait(&empty[s], (u - 1) & 1u);     // the whole stage is released at once (its buffers are re-used
                 uint32_t bytes = a.bytes_a;                        // inside a tile: staging over dZ, act over Z)
+                if (a.da_mode == 2) bytes += 2u * (uint32_t)min((int64_t)4, a.M / 32 - (int64_t)m0 / 32) * (uint32_t)a.N * 4u;
                 BF_STAMP(1);
                 if (t == 0 && a.want_dx) bytes += (uint32_t)a.nS * w_chunk_bytes;
                 mbar_expect_tx(&full_a[s], bytes);
                 if (t == 0 && a.want_dx)
                     for (int j = 0; j < a.nS; ++j) bulk_g2s(s_w + (size_t)j * w_chunk_bytes, a.Wimg + (size_t)j * w_chunk_bytes, w_chunk_bytes, &full_a[s]);
+                if (a.da_mode == 2) {
+                    // the four groups of the tile: their dOut / arg rows are contiguous in global memory
+                    const int64_t g0 = (int64_t)m0 / 32;
+                    const int64_t G = a.M / 32;
+                    const uint32_t ng = (uint32_t)min((int64_t)4, G - g0);
+                    bulk_g2s(st + a.o_pool, a.dOut + g0 * a.N, ng * (uint32_t)a.N * 4u, &full_a[s]);
+                    bulk_g2s(st + a.o_pool + 4u * (uint32_t)a.N * 4u, a.arg + g0 * a.N, ng * (uint32_t)a.N * 4u, &full_a[s]);
+                } else
                 for (int j = 0; j < a.nS; ++j) tma_load_2d(st + a.o_da + (size_t)j * kBfSlab, &a.tm_da, 64 * j, m0, &full_a[s]);
                 if (a.da_mode != 3)
                     for (int j = 0; j < a.nS; ++j) tma_load_2d(st + a.o_z + (size_t)j * kBfSlab, &a.tm_z, 64 * j, m0, &full_a[s]);
@@ -234,16 +246,30 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], cb[8], cc[8];
                     ld_coef8(c_sc, c0, sc); ld_coef8(c_b, c0, cb); ld_coef8(c_c, c0, cc);
-                    if (a.da_mode == 0) ld_coef8(c_sh, c0, sh);
+                    if (a.da_mode == 0 || a.da_mode == 2) ld_coef8(c_sh, c0, sh);
                     // (all of the thread's units are loaded before any arithmetic: 2 x <= 4 LDS.128 in flight instead of a
                     //  load -> compute -> store chain per unit; the loop bodies are fully unrolled and predicated on um.iters)
                     uint4 g4[4], z4[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (i < um.iters) {
-                            const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
-                            g4[i] = *reinterpret_cast<const uint4 *>(s_da + off);
+                            const int r = um.row0 + um.rstep * i;
+                            const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(r, um.chunk);
                             z4[i] = *reinterpret_cast<const uint4 *>(s_z + off);
+                            if (a.da_mode == 2) {
+                                // the pooled gradient reaches sample k of group (r >> 5) only where k won the max (:200)
+                                const float *dp = reinterpret_cast<const float *>(st + a.o_pool) + (r >> 5) * a.N + c0;
+                                const int *ap = reinterpret_cast<const int *>(st + a.o_pool + 4u * (uint32_t)a.N * 4u) + (r >> 5) * a.N + c0;
+                                const float4 d0 = *reinterpret_cast<const float4 *>(dp), d1 = *reinterpret_cast<const float4 *>(dp + 4);
+                                const int4 a0 = *reinterpret_cast<const int4 *>(ap), a1 = *reinterpret_cast<const int4 *>(ap + 4);
+                                const int k = r & 31;
+                                g4[i].x = pack_bf16x2(a0.x == k ? d0.x : 0.f, a0.y == k ? d0.y : 0.f);
+                                g4[i].y = pack_bf16x2(a0.z == k ? d0.z : 0.f, a0.w == k ? d0.w : 0.f);
+                                g4[i].z = pack_bf16x2(a1.x == k ? d1.x : 0.f, a1.y == k ? d1.y : 0.f);
+                                g4[i].w = pack_bf16x2(a1.z == k ? d1.z : 0.f, a1.w == k ? d1.w : 0.f);
+                            } else {
+                                g4[i] = *reinterpret_cast<const uint4 *>(s_da + off);
+                            }
                         }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -255,7 +281,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                             for (int e2 = 0; e2 < 4; ++e2) {
                                 float2 g = unpack_bf16x2(gw[e2]);
                                 const float2 z = unpack_bf16x2(zw[e2]);
-                                if (a.da_mode == 0) {
+                                if (a.da_mode == 0 || a.da_mode == 2) {
                                     if (!(fmaf(z.x, sc[2 * e2], sh[2 * e2]) > 0.0f)) g.x = 0.0f;
                                     if (!(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]) > 0.0f)) g.y = 0.0f;
                                 }
@@ -550,7 +576,7 @@ static int bf_round_up(int v, int m) { return (v + m - 1) / m * m; }
 struct BwdFusedPlan {
     bool ok;
     int nS, kS, K_pad, k_store, tmem_cols, acc_bufs, off_dw, off_s2, off_s1, ones_col, s2_cols, coef_ld, stages, load_x, alias_act, combined;
-    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
+    uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, o_pool, stage_stride, bytes_a, bytes_b;
     size_t dyn_smem;
 };
 
@@ -577,10 +603,10 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     p.o_da = o; o += (uint32_t)p.nS * kBfSlab;
     p.o_z = o;
     if (da_mode != 3) o += (uint32_t)p.nS * kBfSlab;
-    p.bytes_a = o;
+    p.bytes_a = da_mode == 2 ? (uint32_t)p.nS * kBfSlab : o;      // (pooled: only Z is a tile load; dOut / arg rows are added per tile)
     p.o_x = o;
     if (p.load_x) o += (uint32_t)p.kS * kBfSlab;
-    p.bytes_b = o - p.bytes_a;
+    p.bytes_b = p.load_x ? (uint32_t)p.kS * kBfSlab : 0u;
     // narrow layers: ONE product gives the weight gradient and the statistics (the tensor pipe takes ~170 cycles per
     // tcgen05.mma of these tiny shapes whatever it holds, so the MMA COUNT is what matters); it needs dZ alive next to the staged
     // tile and act next to zhat: [dZ][Z -> act][X -> zhat][staging]
@@ -596,6 +622,8 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     }
     if (want_dx && p.kS <= p.nS && !p.combined) p.o_stage = p.o_da;
     else { p.o_stage = o; if (want_dx) o += (uint32_t)p.kS * kBfSlab; }
+    p.o_pool = o;
+    if (da_mode == 2) o += (uint32_t)bf_round_up(8 * N * 4, 1024);
     p.stage_stride = o;
     const uint32_t w_bytes = want_dx ? (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024) : 0u;
     const uint32_t ones_bytes = (prev && p.ones_col < 0) ? 4096u : 0u;
@@ -661,8 +689,10 @@ extern "C" size_t pn2_mlp_bwd_layer_scratch_bytes(int64_t M, int K, int N) {
 
 extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     PN2_REQUIRE(L, "mlp_bwd_layer: null argument block");
-    PN2_REQUIRE(L->dA && L->M >= 1 && L->K >= 1 && L->N >= 1, "mlp_bwd_layer: bad sizes");
-    PN2_REQUIRE(L->da_mode == 0 || L->da_mode == 1 || L->da_mode == 3, "mlp_bwd_layer: da_mode must be 0, 1 or 3");
+    PN2_REQUIRE(L->M >= 1 && L->K >= 1 && L->N >= 1, "mlp_bwd_layer: bad sizes");
+    PN2_REQUIRE(L->da_mode >= 0 && L->da_mode <= 3, "mlp_bwd_layer: da_mode must be 0, 1, 2 or 3");
+    PN2_REQUIRE(L->da_mode == 2 ? (L->dOut && L->arg && L->nsample == 32 && L->M % 32 == 0) : L->dA != nullptr,
+                "mlp_bwd_layer: dA (or, pooled: dOut, arg, nsample == 32, M %% 32 == 0) is required");
     PN2_REQUIRE(L->da_mode == 3 || (L->Z && L->scale && L->shift), "mlp_bwd_layer: layer l's Z / scale / shift are required");
     PN2_REQUIRE(L->da_mode == 3 || !L->mean || (L->invstd && L->dgamma && L->dbeta), "mlp_bwd_layer: train-mode BatchNorm needs invstd, dgamma, dbeta");
     const bool prev = L->prev_scale != nullptr, want_dx = L->dX != nullptr, want_dw = L->dW != nullptr;
@@ -670,9 +700,9 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
                 "mlp_bwd_layer: the statistics of layer l-1 need shift, mean, invstd, accumulator, ticket, dgamma_prev, dbeta_prev");
     PN2_REQUIRE(!(want_dw || prev) || L->X, "mlp_bwd_layer: X is required");
     PN2_REQUIRE(!want_dx || L->wpack_t, "mlp_bwd_layer: the data gradient needs the transposed weight image");
-    PN2_REQUIRE(L->ldda >= L->N && (L->da_mode == 3 || L->ldz >= L->N) && (!L->X || L->ldx >= L->K) && (!want_dx || L->lddx >= L->K),
+    PN2_REQUIRE((L->da_mode == 2 || L->ldda >= L->N) && (L->da_mode == 3 || L->ldz >= L->N) && (!L->X || L->ldx >= L->K) && (!want_dx || L->lddx >= L->K),
                 "mlp_bwd_layer: leading dimensions");
-    PN2_REQUIRE(L->ldda % 8 == 0 && (L->da_mode == 3 || L->ldz % 8 == 0) && (!L->X || L->ldx % 8 == 0) && (!want_dx || L->lddx % 8 == 0),
+    PN2_REQUIRE((L->da_mode == 2 || L->ldda % 8 == 0) && (L->da_mode == 3 || L->ldz % 8 == 0) && (!L->X || L->ldx % 8 == 0) && (!want_dx || L->lddx % 8 == 0),
                 "mlp_bwd_layer: bf16 rows need a 16-byte row pitch");
     const BwdFusedPlan p = bwd_fused_plan(L->K, L->N, L->X ? L->ldx : bf_round_up(L->K, 8), want_dx ? L->lddx : 0, L->da_mode, prev, want_dx, want_dw);
     if (!p.ok || !bwd_fused_enabled()) {
@@ -691,9 +721,11 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     }
     BwdFusedArgs a;
     memset(&a, 0, sizeof(a));
-    bool ok = make_rows_tensor_map(&a.tm_da, L->dA, L->M, bf_round_up(L->N, 8) <= L->ldda ? bf_round_up(L->N, 8) : L->ldda, L->ldda, kBfBM);
+    bool ok = true;
+    if (L->da_mode != 2) ok = make_rows_tensor_map(&a.tm_da, L->dA, L->M, bf_round_up(L->N, 8) <= L->ldda ? bf_round_up(L->N, 8) : L->ldda, L->ldda, kBfBM);
     if (L->da_mode != 3) ok = ok && make_rows_tensor_map(&a.tm_z, L->Z, L->M, bf_round_up(L->N, 8) <= L->ldz ? bf_round_up(L->N, 8) : L->ldz, L->ldz, kBfBM);
     else a.tm_z = a.tm_da;
+    if (L->da_mode == 2) a.tm_da = a.tm_z;
     if (want_dw || prev) ok = ok && make_rows_tensor_map(&a.tm_x, L->X, L->M, L->ldx, L->ldx, kBfBM);
     else a.tm_x = a.tm_da;
     if (want_dx) ok = ok && make_rows_tensor_map(&a.tm_dx, L->dX, L->M, p.k_store, L->lddx, kBfBM);
@@ -723,6 +755,7 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.o_w = p.o_w; a.o_da = p.o_da; a.o_z = p.o_z; a.o_x = p.o_x; a.o_act = p.o_act; a.o_stage = p.o_stage; a.o_ones = p.o_ones;
     a.stage_stride = p.stage_stride; a.bytes_a = p.bytes_a; a.bytes_b = p.bytes_b; a.stages = p.stages; a.acc_bufs = p.acc_bufs;
     a.load_x = p.load_x; a.alias_act = p.alias_act; a.combined = p.combined;
+    a.o_pool = p.o_pool; a.dOut = L->dOut; a.arg = L->arg;
     a.defer_store_wait = (want_dx && p.o_stage != p.o_da && p.stages >= 2) ? 1 : 0;
     { const char *e = getenv("PN2_BWD_DBG"); a.dbg = e ? atoi(e) : 0; }
     if ((a.dbg & 32) && L->scratch && L->K % 4 == 0) a.dbg_buf = (long long *)L->scratch;

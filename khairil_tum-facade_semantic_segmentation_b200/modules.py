@@ -353,20 +353,25 @@ def _side_stream(dev):
 
 
 FUSED_BWD = True          # bf16 rows: one fused kernel per layer (csrc/bwd_fused.cu) wherever the library takes the layer
+FUSED_BWD_POOLED = False  # ... the pooled top layer too (da_mode 2).  Measured on B200 (config 2): the extra transform work costs more
+                          # (+0.13 ms in the fused kernels, whose transform group is the bottleneck) than the dense
+                          # pn2_pool_bn_relu_bwd_dz pass it replaces (0.12 ms at 4.3 TB/s): 2.66 vs 2.58 ms per step -- off
 
 
-def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dtype, keep):
+def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dtype, keep, pooled=None):
     """One launch of pn2_mlp_bwd_layer for layer `st` (see include/pn2b200.h), or None when the library does not take it.
-    cur / mode: the incoming gradient -- "dA" (dense, unmasked), "dA_masked" or "dZ".  Returns (dW, dA_prev, dgamma_prev,
-    dbeta_prev)."""
+    cur / mode: the incoming gradient -- "dA" (dense, unmasked), "dA_masked", "dZ", or "pooled" (cur None, pooled = (dOut
+    [G, N] fp32, arg [G, N] int32, nsample)).  Returns (dW, dA_prev, dgamma_prev, dbeta_prev)."""
     from ._lib import BwdLayer
     lib = load()
-    if not FUSED_BWD or dtype != torch.bfloat16 or cur.dtype != torch.bfloat16 or st.wpack_bwd is None and want_dx:
+    if not FUSED_BWD or dtype != torch.bfloat16 or (cur is not None and cur.dtype != torch.bfloat16) or st.wpack_bwd is None and want_dx:
+        return None
+    if mode == "pooled" and (pooled[2] != 32 or M % 32 != 0 or pooled[0].dtype != torch.float32 or not pooled[0].is_contiguous()):
         return None
     xin = x0 if prev is None else prev.Z
     ldx = xin.shape[1]
     ldd = (_row_ld(st.K, dtype) if prev is not None else x0.shape[1]) if want_dx else 0
-    da_mode = {"dA": 0, "dA_masked": 1, "dZ": 3}[mode]
+    da_mode = {"dA": 0, "dA_masked": 1, "pooled": 2, "dZ": 3}[mode]
     if xin.dtype != torch.bfloat16 or not lib.pn2_mlp_bwd_layer_supported(M, st.K, st.N, ldx, ldd, da_mode, int(prev is not None),
                                                                           int(want_dx), 1):
         return None
@@ -389,7 +394,9 @@ def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dt
             dgb = torch.empty(2, st.K, device=dev, dtype=torch.float32)
             dgamma_prev, dbeta_prev = dgb[0], dgb[1]
     L = BwdLayer()
-    L.dA, L.ldda, L.da_mode = ptr(cur), cur.shape[1], da_mode
+    L.dA, L.ldda, L.da_mode = ptr(cur), (0 if cur is None else cur.shape[1]), da_mode
+    if mode == "pooled":
+        L.dOut, L.arg, L.nsample = ptr(pooled[0]), ptr(pooled[1]), pooled[2]
     if da_mode != 3:
         L.Z, L.ldz = ptr(st.Z), st.Z.shape[1]
         L.scale, L.shift = ptr(st.scale), ptr(st.shift)
@@ -409,8 +416,8 @@ def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dt
     return dW, dA_prev, dgamma_prev, dbeta_prev
 
 
-def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bns=None):
-    """Backward of mlp_forward + tail.  dout: [G, C] fp32 pooled gradient with arg-max map `arg`
+def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bns=None, zmax=None):
+    """Backward of mlp_forward + tail.  zmax: [G, ld] pre-BatchNorm values of the pooled winners (pn2_bn_relu_max_keep).  dout: [G, C] fp32 pooled gradient with arg-max map `arg`
     (set abstraction) or [M, C] dense gradient (feature propagation: fp32; head: bf16), arg None.
     Returns (per-layer (dW, dbias, dgamma, dbeta), dX0 or None).
 
@@ -441,7 +448,12 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
         """dgamma / dbeta of layer l from the gradient w.r.t. its activation"""
         st = layers[l]
         st.dgamma, st.dbeta = bn_params(l)
-        if pooled:
+        if pooled and zmax is not None:
+            # the winners' pre-BatchNorm values were kept by the forward tail: a dense [G, C] column reduction
+            call("pn2_bn_relu_bwd_reduce_finalize", ptr(dout), dout.shape[1], dt(dout), ptr(zmax), zmax.shape[1], dt(zmax),
+                 ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M // nsample, st.N, ptr(_stat_accum(dev)),
+                 ptr(_ticket(dev)), ptr(st.dgamma), ptr(st.dbeta), stream())
+        elif pooled:
             call("pn2_pool_bn_relu_bwd_reduce_finalize", ptr(dout), ptr(arg), ptr(st.Z), st.Z.shape[1], dt(st.Z),
                  ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd), M // nsample, nsample, st.N, ptr(_stat_accum(dev)),
                  ptr(_ticket(dev)), ptr(st.dgamma), ptr(st.dbeta), stream())
@@ -474,8 +486,14 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
     top = L - 1
     pooled = arg is not None
     bn_reduce(top, dout, dout.shape[1], pooled)
+    pool_args = (dout, arg, nsample) if pooled else None
     if not pooled and dout.dtype == torch.bfloat16 and dtype == torch.bfloat16:
         cur, mode = dout, "dA"                        # (the head's bf16 gradient: dZ is formed inside the fused layer kernel)
+    elif pooled and FUSED_BWD and FUSED_BWD_POOLED and dtype == torch.bfloat16 and nsample == 32 and M % 32 == 0 and lib.pn2_mlp_bwd_layer_supported(
+            M, layers[top].K, layers[top].N, (layers[top - 1].Z.shape[1] if top > 0 else x0.shape[1]),
+            (_row_ld(layers[top].K, dtype) if top > 0 else x0.shape[1]) if (top > 0 or need_dx0) else 0, 2, int(top > 0),
+            int(top > 0 or need_dx0), 1):
+        cur, mode = None, "pooled"                    # dZ of the pooled layer is formed inside the fused kernel from (dOut, arg, Z)
     else:
         cur, mode = bn_dz(top, dout, dout.shape[1], pooled), "dZ"
     dx0 = None
@@ -485,7 +503,9 @@ def mlp_backward(layers, x0, K0, M, dout, arg, nsample, need_dx0, convs=None, bn
         conv = convs[l] if convs is not None else None
         want_dx = l > 0 or need_dx0
         fused = _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bns[l - 1] if (bns is not None and l > 0) else None,
-                                 want_dx, dev, dtype, keep)
+                                 want_dx, dev, dtype, keep, pooled=pool_args)
+        if fused is None and mode == "pooled":        # (the library declined after all: the per-step kernels)
+            cur, mode = bn_dz(l, dout, dout.shape[1], True), "dZ"
         if fused is not None:
             dW, dA, dgp, dbp = fused
             if prev is not None:
@@ -645,18 +665,24 @@ class _SetAbstractionFn(torch.autograd.Function):
         last = layers[-1]
         out = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.float32)
         arg = torch.empty(B, S, last.N, device=xyz_r.device, dtype=torch.int32)
-        call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B * S,
-             nsample, last.N, ptr(out), ptr(arg), stream())
-        ctx.state = (layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns)
+        zmax = None
+        if _want_backward(ctx):
+            zmax = torch.empty(B * S, last.Z.shape[1], device=xyz_r.device, dtype=dtype)
+            call("pn2_bn_relu_max_keep", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B * S,
+                 nsample, last.N, ptr(out), ptr(arg), ptr(zmax), zmax.shape[1], stream())
+        else:
+            call("pn2_bn_relu_max", ptr(last.Z), last.Z.shape[1], dt(last.Z), ptr(last.scale), ptr(last.shift), B * S,
+                 nsample, last.N, ptr(out), ptr(arg), stream())
+        ctx.state = (layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns, zmax)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns = ctx.state
+        layers, x0, K0, M, arg, idx, nsample, (B, N, S, D), convs, bns, zmax = ctx.state
         ctx.state = None
         need_pts = ctx.needs_input_grad[7] and D > 0
         dout = dout.contiguous().view(B * S, -1)
-        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, arg.view(B * S, -1), nsample, need_pts, convs, bns)
+        grads, dx0 = mlp_backward(layers, x0, K0, M, dout, arg.view(B * S, -1), nsample, need_pts, convs, bns, zmax=zmax)
         dpts = None
         if need_pts:
             dpts = torch.zeros(B, N, D, device=dout.device, dtype=torch.float32)

@@ -113,6 +113,33 @@ def test_feature_propagation_fused_backward_matches_per_step_kernels(pn2, with_s
         assert _rel(a, b) <= 6e-3, (n, _rel(a, b))
 
 
+def test_pooled_top_layer_inside_the_fused_kernel(pn2):
+    """da_mode 2 (modules.FUSED_BWD_POOLED, off by default: it measured slower): dZ of the max-pooled layer formed inside the
+    fused kernel from (dOut, arg-max map, Z) must agree with the dense pn2_pool_bn_relu_bwd_dz pass"""
+    M = _modules()
+    sa = I.randomize_module_(pn2.PointNetSetAbstraction(96, 0.4, 32, 3 + 9, [32, 32, 64], False), 44).to(DEV).train()
+    xyz = I.facade_xyz(2, 512, 3).to(DEV).permute(0, 2, 1).contiguous()
+    pts = torch.rand(2, 9, 512, generator=torch.Generator().manual_seed(1)).to(DEV).requires_grad_(True)
+    wsel = torch.rand(2, 64, 96, generator=torch.Generator().manual_seed(2)).to(DEV)
+
+    def run():
+        torch.manual_seed(5)
+        _, out = sa(xyz, pts)
+        (out * wsel).sum().backward()
+
+    params = list(sa.parameters()) + [pts]
+    try:
+        M.FUSED_BWD_POOLED = True
+        g_pool, _ = _grads(sa, params, run)
+    finally:
+        M.FUSED_BWD_POOLED = False
+    g_dense, _ = _grads(sa, params, run)
+    for (n, _), a, b in zip(list(sa.named_parameters()) + [("dpoints", None)], g_pool, g_dense):
+        if n.endswith("bias") and "convs" in n:
+            continue
+        assert _rel(a, b) <= 6e-3, (n, _rel(a, b))
+
+
 def test_fused_backward_with_frozen_batchnorm_statistics(pn2):
     """eval-mode BatchNorm inside a differentiated forward: dZ = scale . mask . dA (no mean / zhat terms)"""
     fp = I.randomize_module_(pn2.PointNetFeaturePropagation(32 + 32, [64, 64]), 43).to(DEV).eval()
