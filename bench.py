@@ -98,6 +98,10 @@ KERNEL_MODEL = {
     "pn2_linear_fwd": lambda a: (a[7] * (a[1] * _esz(a[2]) + a[11] * _esz(a[12])), 2.0 * a[7] * a[8] * a[9], "hbm"),
     "pn2_linear_bwd_data": lambda a: (a[4] * (a[1] * _esz(a[2]) + a[8] * _esz(a[9])), 2.0 * a[4] * a[5] * a[6], "hbm"),
     "pn2_linear_bwd_weight": lambda a: (a[8] * (a[1] * _esz(a[2]) + a[4] * _esz(a[5])), 2.0 * a[8] * a[9] * a[10], "hbm"),
+    # fused backward layer (csrc/bwd_fused.cu): dA_l (or dZ_l) + Z_l + X read, dA_{l-1} written, bf16 rows, each once
+    # (args: M, K, N, da_mode, ldda, ldz, ldx, lddx, has dX, has X -- recorded by _lib.call from the host struct)
+    "pn2_mlp_bwd_layer": lambda a: (a[0] * 2 * ((a[4] if a[3] != 2 else 0) + (a[5] if a[3] != 3 else 0) + (a[6] if a[9] else 0) + (a[7] if a[8] else 0)),
+                                    2.0 * a[0] * a[1] * a[2] * (2 if a[8] else 1), "hbm"),
     "pn2_bn_relu_max": lambda a: (a[5] * a[6] * a[7] * _esz(a[2]) + a[5] * a[7] * 8, 0.0, "hbm"),
     "pn2_bn_relu": lambda a: (a[5] * a[6] * (_esz(a[2]) + 4), 0.0, "hbm"),
     "pn2_bn_relu_bwd_reduce": lambda a: (a[10] * a[11] * (_esz(a[2]) + _esz(a[5])), 0.0, "hbm"),
@@ -118,7 +122,7 @@ KERNEL_MODEL = {
     "pn2_adam_step": lambda a: (a[4] * a[5] * 28, 0.0, "hbm"),
 }
 # the launch-saving variants move the same bytes as the entry points they replace (same leading argument layout)
-for _alias, _base in (("pn2_linear_fwd_prepacked", "pn2_linear_fwd"), ("pn2_linear_bwd_data_prepacked", "pn2_linear_bwd_data"),
+for _alias, _base in (("pn2_bn_relu_max_keep", "pn2_bn_relu_max"), ("pn2_linear_fwd_prepacked", "pn2_linear_fwd"), ("pn2_linear_bwd_data_prepacked", "pn2_linear_bwd_data"),
                       ("pn2_linear_bwd_weight_accum", "pn2_linear_bwd_weight"),
                       ("pn2_bn_relu_bwd_reduce_finalize", "pn2_bn_relu_bwd_reduce"),
                       ("pn2_pool_bn_relu_bwd_reduce_finalize", "pn2_pool_bn_relu_bwd_reduce")):

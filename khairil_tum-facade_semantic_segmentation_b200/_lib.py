@@ -153,6 +153,9 @@ def call(name, *args):
         rc = getattr(lib, name)(*args)
         e.record(st)
         _TIMED["events"].append((s, e))
+        if name == "pn2_mlp_bwd_layer":      # (its arguments travel in a host struct: keep what the byte model needs)
+            L = ctypes.cast(args[0], ctypes.POINTER(BwdLayer)).contents
+            args = (int(L.M), int(L.K), int(L.N), int(L.da_mode), int(L.ldda), int(L.ldz), int(L.ldx), int(L.lddx), bool(L.dX), bool(L.X))
         _TIMED["calls"].append((name, args))
     else:
         rc = getattr(lib, name)(*args)

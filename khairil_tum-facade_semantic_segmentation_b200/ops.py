@@ -223,6 +223,8 @@ def farthest_point_sample(xyz, npoint, start=None, return_xyz=False, staging=Non
             start = torch.randint(0, N, (B,), dtype=torch.long)
         if start.shape != (B,) or start.dtype != torch.int64:
             raise ValueError("start must be int64 [B]")
+        if not start.is_cuda and B and (int(start.min()) < 0 or int(start.max()) >= N):
+            raise ValueError("start indices must lie in [0, %d)" % N)      # (the kernel reads xyz[start] unchecked)
         start = start.to(xyz.device, non_blocking=True)
     out = _out((B, npoint), torch.int64, xyz.device)
     new_xyz = _out((B, npoint, 3), torch.float32, xyz.device) if return_xyz else None

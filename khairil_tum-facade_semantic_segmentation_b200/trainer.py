@@ -611,9 +611,20 @@ class SemSegTrainer:
         self._graph.replay()
         return self._g_loss
 
+    def _check_labels(self, target_host):
+        """F.nll_loss (the reference's criterion, pointnet2_sem_seg.py:47-48) raises on a label outside [0, classes) other
+        than ignore_index = -100; the fused loss kernel would silently give such points weight 0 -- e.g. a wrong class
+        mapping (class8 remap vs NUM_CLASSES) would train on a subset.  Host labels are checked here (two reductions over
+        ~130 k int64, well inside the pipelined step's host slack)."""
+        if not target_host.is_cuda and target_host.numel():
+            lo, hi = int(target_host.min()), int(target_host.max())
+            if hi >= self.num_classes or (lo < 0 and bool(((target_host < 0) & (target_host != -100)).any())):
+                raise ValueError("labels must lie in [0, %d) or be -100 (ignored); got range [%d, %d]" % (self.num_classes, lo, hi))
+
     def step(self, points_host, target_host):
         """One training step from HOST buffers (pinned memory recommended); returns the loss as a float
         (a device->host read, like the reference's per-batch `seg_pred.cpu()`)."""
+        self._check_labels(target_host)
         if self._graph is not None and self._pipeline:
             self.model.train()
             st = self._stager

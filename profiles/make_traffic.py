@@ -12,6 +12,8 @@ import sys
 # kernel-name pattern -> C-ABI entry point whose launches it implements in the TRAINING step
 # (linear_tc*: the statistics epilogue <1>/<true> is the forward layer, <0>/<false> the data gradient)
 ENTRY = [
+    (r"bwd_fused_kernel", "pn2_mlp_bwd_layer"),
+    (r"bg_(build|query)_kernel", "pn2_query_ball_point_grid"),
     (r"wgrad_tc_kernel", "pn2_linear_bwd_weight_accum"),
     (r"linear_tc2?_kernel<(1|true)>", "pn2_linear_fwd_prepacked"),
     (r"linear_tc2?_kernel<(0|false)>", "pn2_linear_bwd_data_prepacked"),
@@ -19,7 +21,7 @@ ENTRY = [
     (r"bn_bwd_dz", "pn2_bn_relu_bwd_dz"),
     (r"bn_bwd_reduce_vec8_kernel<2>", "pn2_pool_bn_relu_bwd_reduce_finalize"),
     (r"bn_bwd_reduce", "pn2_bn_relu_bwd_reduce_finalize"),
-    (r"bn_relu_max", "pn2_bn_relu_max"),
+    (r"bn_relu_max", "pn2_bn_relu_max_keep"),
     (r"bn_relu_kernel", "pn2_bn_relu"),
     (r"fps_kernel", "pn2_farthest_point_sample"),
     (r"ball_query_kernel", "pn2_query_ball_point"),

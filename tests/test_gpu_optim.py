@@ -153,3 +153,21 @@ def test_trainer_with_flat_adam_tracks_torch_adam(pn2):
         assert moved < 1.5e-3
     finally:
         pn2.set_precision("fp32")
+
+
+def test_trainer_rejects_labels_outside_the_class_range(pn2):
+    """F.nll_loss raises on such labels; the fused loss would silently ignore them"""
+    import _inputs as I
+    pn2.set_precision("bf16")
+    t = pn2.SemSegTrainer(18, 3, device="cuda")
+    pts = I.facade_batch(2, 1024, 9, 1)
+    bad = I.labels(2, 1024, 18, 2).clone()
+    bad[5] = 18
+    with pytest.raises(ValueError, match="labels"):
+        t.step(pts, bad)
+    ok = I.labels(2, 1024, 18, 2).clone()
+    ok[7] = -100                                   # ignore_index is fine
+    assert isinstance(t.step(pts, ok), float)
+    with pytest.raises(ValueError, match="start"):
+        pn2.farthest_point_sample(pts[:, :, :3].cuda(), 16, start=torch.tensor([0, 1024]))
+    pn2.set_precision("fp32")
