@@ -41,7 +41,7 @@ enum { PN2_F32 = 0, PN2_BF16 = 1 };
  * [2][C] doubles: CTA i adds into copy i % PN2_STAT_REPLICAS (spreads same-address atomics),
  * the *_finalize entry points add the copies in a fixed order and zero them. */
 #ifndef PN2_STAT_REPLICAS
-#define PN2_STAT_REPLICAS 8
+#define PN2_STAT_REPLICAS 4
 #endif
 
 /* ---- library ---------------------------------------------------------------- */

@@ -112,6 +112,80 @@ interp_concat_kernel(const float *__restrict__ points1, int64_t pB, int64_t pN, 
     }
 }
 
+// bf16 rows, unit channel strides, D1 % 4 == D2 % 4 == 0: a lane owns FOUR channels (float4 loads of the three neighbours,
+// one 8-byte store of four bf16) -- a 128-wide level is one pass of the warp instead of four with 2-byte stores
+__global__ void __launch_bounds__(256)
+interp_concat_vec4_kernel(const float *__restrict__ points1, int64_t pB, int64_t pN, const float *__restrict__ points2,
+                          int64_t qB, int64_t qN, const int64_t *__restrict__ idx3, const float *__restrict__ w3, int N, int S,
+                          int D1, int D2, __nv_bfloat16 *__restrict__ rows, int ld, int64_t M) {
+    const int lane = threadIdx.x & 31;
+    const int K3 = S < 3 ? S : 3;
+    for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M;
+         m += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t b = m / N, n = m % N;
+        __nv_bfloat16 *row = rows + m * ld;
+        const int64_t j0 = idx3[m * 3 + 0], j1 = K3 > 1 ? idx3[m * 3 + 1] : 0, j2 = K3 > 2 ? idx3[m * 3 + 2] : 0;
+        const float w0 = w3[m * 3 + 0], w1 = K3 > 1 ? w3[m * 3 + 1] : 0.0f, w2 = K3 > 2 ? w3[m * 3 + 2] : 0.0f;
+        const float *a0 = points2 + b * qB + j0 * qN, *a1 = points2 + b * qB + j1 * qN, *a2 = points2 + b * qB + j2 * qN;
+        for (int c = 4 * lane; c < D2; c += 128) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(a0 + c);
+            float4 v = make_float4(__fmul_rn(x0.x, w0), __fmul_rn(x0.y, w0), __fmul_rn(x0.z, w0), __fmul_rn(x0.w, w0));
+            if (K3 > 1) {
+                const float4 x1 = *reinterpret_cast<const float4 *>(a1 + c);
+                v.x = __fadd_rn(v.x, __fmul_rn(x1.x, w1)); v.y = __fadd_rn(v.y, __fmul_rn(x1.y, w1));
+                v.z = __fadd_rn(v.z, __fmul_rn(x1.z, w1)); v.w = __fadd_rn(v.w, __fmul_rn(x1.w, w1));
+            }
+            if (K3 > 2) {
+                const float4 x2 = *reinterpret_cast<const float4 *>(a2 + c);
+                v.x = __fadd_rn(v.x, __fmul_rn(x2.x, w2)); v.y = __fadd_rn(v.y, __fmul_rn(x2.y, w2));
+                v.z = __fadd_rn(v.z, __fmul_rn(x2.z, w2)); v.w = __fadd_rn(v.w, __fmul_rn(x2.w, w2));
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t *>(&lo);
+            o.y = *reinterpret_cast<uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(row + D1 + c) = o;
+        }
+        if (D1 > 0) {
+            const float *p1 = points1 + b * pB + n * pN;
+            for (int c = 4 * lane; c < D1; c += 128) {
+                const float4 x = *reinterpret_cast<const float4 *>(p1 + c);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t *>(&lo);
+                o.y = *reinterpret_cast<uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(row + c) = o;
+            }
+        }
+        for (int c = D1 + D2 + lane; c < ld; c += 32) row[c] = __float2bfloat16_rn(0.0f);
+    }
+}
+
+// bf16 gradient rows, D2 % 4 == 0, 16-byte aligned targets: one red.global.add.v4.f32 per four channels
+__global__ void __launch_bounds__(256)
+interp_bwd_vec4_kernel(const __nv_bfloat16 *__restrict__ drows, int ld, const int64_t *__restrict__ idx3,
+                       const float *__restrict__ w3, int N, int S, int D1, int D2, float *__restrict__ dpoints2, int64_t M) {
+    const int lane = threadIdx.x & 31;
+    const int K3 = S < 3 ? S : 3;
+    for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M;
+         m += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t b = m / N;
+        const __nv_bfloat16 *row = drows + m * ld + D1;
+        for (int c = 4 * lane; c < D2; c += 128) {
+            const uint2 g = *reinterpret_cast<const uint2 *>(row + c);
+            const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&g.x));
+            const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&g.y));
+            for (int k = 0; k < K3; ++k) {
+                const float w = w3[m * 3 + k];
+                float *dst = dpoints2 + (b * S + idx3[m * 3 + k]) * D2 + c;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w * g01.x), "f"(w * g01.y), "f"(w * g23.x),
+                             "f"(w * g23.y)
+                             : "memory");
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 interp_bwd_kernel(const T *__restrict__ drows, int ld, const int64_t *__restrict__ idx3,
@@ -158,6 +232,14 @@ extern "C" int pn2_interp_concat(const float *points1, int64_t pB, int64_t pN, i
     int64_t M = (int64_t)B * N;
     if (M == 0) return PN2_OK;
     int grid = grid_for(M, 8);
+    if (dtype == PN2_BF16 && qD == 1 && (D1 == 0 || pD == 1) && D1 % 4 == 0 && D2 % 4 == 0 && ld % 4 == 0 && qN % 4 == 0 && qB % 4 == 0 &&
+        (D1 == 0 || (pN % 4 == 0 && pB % 4 == 0 && ((uintptr_t)points1 & 15) == 0)) && ((uintptr_t)points2 & 15) == 0 &&
+        ((uintptr_t)rows & 7) == 0) {
+        interp_concat_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points1, pB, pN, points2, qB, qN, idx3, w3, N, S, D1, D2,
+                                                                         (__nv_bfloat16 *)rows, ld, M);
+        count_launch();
+        return check_launch("interp_concat_vec4");
+    }
     PN2_DISPATCH_DTYPE(dtype, T, (interp_concat_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
         points1, pB, pN, pD, points2, qB, qN, qD, idx3, w3, N, S, D1, D2, (T *)rows, ld, M)));
     count_launch();
@@ -171,6 +253,11 @@ extern "C" int pn2_interp_bwd(const void *drows, int ld, int dtype, const int64_
     int64_t M = (int64_t)B * N;
     if (M == 0 || D2 == 0) return PN2_OK;
     int grid = grid_for(M, 8);
+    if (dtype == PN2_BF16 && D1 % 4 == 0 && D2 % 4 == 0 && ld % 4 == 0 && ((uintptr_t)drows & 7) == 0 && ((uintptr_t)dpoints2 & 15) == 0) {
+        interp_bwd_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)drows, ld, idx3, w3, N, S, D1, D2, dpoints2, M);
+        count_launch();
+        return check_launch("interp_bwd_vec4");
+    }
     PN2_DISPATCH_DTYPE(dtype, T, (interp_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const T *)drows, ld, idx3, w3, N, S, D1, D2, dpoints2, M)));
     count_launch();

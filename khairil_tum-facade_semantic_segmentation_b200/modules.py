@@ -97,7 +97,7 @@ def _bn_trains(bn):
 
 _ACCUM = {}
 _ACCUM_COLS = 4096
-_ACCUM_REPLICAS = 8          # PN2_STAT_REPLICAS of include/pn2b200.h
+_ACCUM_REPLICAS = 4          # PN2_STAT_REPLICAS of include/pn2b200.h
 
 
 def _scratch(table, dev, make):

@@ -63,7 +63,7 @@ def main():
         nbytes = lib.pn2_mlp_bwd_layer_scratch_bytes(M, K, N)
         dbg = int(os.environ.get("PN2_BWD_DBG", "0"))
         scratch = torch.zeros(max(nbytes, 24 * 16 * 8), device=DEV, dtype=torch.uint8)
-        accum = torch.zeros(8 * 2 * 4096, device=DEV, dtype=torch.float64)
+        accum = torch.zeros(4 * 2 * 4096, device=DEV, dtype=torch.float64)
         ticket = torch.zeros(4, device=DEV, dtype=torch.int32)
         dgb = torch.zeros(2, 128, device=DEV)
         a = L.BwdLayer()

@@ -82,7 +82,7 @@ def main():
             scn, shn = torch.rand(N, device=DEV) + 0.5, torch.randn(N, device=DEV) * 0.1
             mean, invstd = torch.randn(N, device=DEV) * 0.1, torch.rand(N, device=DEV) + 0.5
             dgb = torch.randn(2, N, device=DEV)
-            accum = torch.zeros(8 * 2 * 4096, device=DEV, dtype=torch.float64)
+            accum = torch.zeros(4 * 2 * 4096, device=DEV, dtype=torch.float64)
             wp1 = torch.empty(lib.pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8)
             wp2 = torch.empty(lib.pn2_linear_wpack_bytes(N, K), device=DEV, dtype=torch.uint8)
             scratch = torch.empty(lib.pn2_linear_wgrad_scratch_bytes(M, K, N), device=DEV, dtype=torch.uint8)

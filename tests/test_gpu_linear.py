@@ -37,7 +37,7 @@ def _forward(lib, x, K, W, bias, scale, shift, stats, use_tc):
     M, N = x.shape[0], W.shape[0]
     ldz = _ld(N) if x.dtype == torch.bfloat16 else N
     z = torch.full((M, ldz), float("nan"), device=DEV, dtype=x.dtype)
-    partials = torch.zeros(8, 2, N, device=DEV, dtype=torch.float64) if stats else None   # PN2_STAT_REPLICAS fp64 column-sum accumulators
+    partials = torch.zeros(4, 2, N, device=DEV, dtype=torch.float64) if stats else None   # PN2_STAT_REPLICAS fp64 column-sum accumulators
     wpack = torch.empty(lib.load().pn2_linear_wpack_bytes(K, N), device=DEV, dtype=torch.uint8) if use_tc else None
     lib.call("pn2_linear_fwd", lib.ptr(x), x.shape[1], lib.dt(x), lib.ptr(scale), lib.ptr(shift), lib.ptr(W), lib.ptr(bias),
              M, K, N, lib.ptr(z), ldz, lib.dt(z), lib.ptr(partials), lib.ptr(wpack), lib.stream())
@@ -191,7 +191,7 @@ def test_bn_relu_backward_kernels(lib, M, C, mode, train, ns):
     shift = (torch.randn(C, generator=g) * 0.2).to(DEV)
     mean = (torch.randn(C, generator=g) * 0.1).to(DEV)
     invstd = (0.5 + torch.rand(C, generator=g)).to(DEV)
-    accum = torch.zeros(8, 2, C, dtype=torch.float64, device=DEV)
+    accum = torch.zeros(4, 2, C, dtype=torch.float64, device=DEV)
     zf = Z[:, :C].float()
     mask = (zf * scale + shift) > 0
     if mode == "pool":
@@ -266,7 +266,7 @@ def test_prepacked_forward_with_fused_finalize_matches_two_step_path(lib, M, K, 
 
     def buffers():
         return dict(z=torch.full((M, ldz), float("nan"), device=DEV, dtype=torch.bfloat16),
-                    accum=torch.zeros(8, 2, N, device=DEV, dtype=torch.float64), out=torch.zeros(4, N, device=DEV),
+                    accum=torch.zeros(4, 2, N, device=DEV, dtype=torch.float64), out=torch.zeros(4, N, device=DEV),
                     rm=torch.full((N,), 0.25, device=DEV), rv=torch.full((N,), 2.0, device=DEV),
                     nbt=torch.tensor(3, device=DEV, dtype=torch.int64))
 
@@ -321,7 +321,7 @@ def test_bn_backward_reduce_with_fused_finalize(lib, M, C, da):
     dA = _rows(M, C, da, 9) if da == torch.bfloat16 else torch.randn(M, C, generator=g).to(DEV)
     scale, shift = (0.5 + torch.rand(C, generator=g)).to(DEV), (torch.randn(C, generator=g) * 0.2).to(DEV)
     mean, invstd = (torch.randn(C, generator=g) * 0.1).to(DEV), (0.5 + torch.rand(C, generator=g)).to(DEV)
-    acc1, acc2 = (torch.zeros(8, 2, C, device=DEV, dtype=torch.float64) for _ in range(2))
+    acc1, acc2 = (torch.zeros(4, 2, C, device=DEV, dtype=torch.float64) for _ in range(2))
     want, got = torch.zeros(2, C, device=DEV), torch.zeros(2, C, device=DEV)
     lib.call("pn2_bn_relu_bwd_reduce", lib.ptr(dA), dA.shape[1], lib.dt(dA), lib.ptr(z), ld, 1, lib.ptr(scale), lib.ptr(shift),
              lib.ptr(mean), lib.ptr(invstd), M, C, lib.ptr(acc1), lib.stream())
