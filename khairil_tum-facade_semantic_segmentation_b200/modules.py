@@ -364,8 +364,9 @@ def _fused_bwd_layer(st, prev, x0, M, cur, mode, conv, bn_prev, want_dx, dev, dt
     [G, N] fp32, arg [G, N] int32, nsample)).  Returns (dW, dA_prev, dgamma_prev, dbeta_prev)."""
     from ._lib import BwdLayer
     lib = load()
-    if not FUSED_BWD or dtype != torch.bfloat16 or (cur is not None and cur.dtype != torch.bfloat16) or st.wpack_bwd is None and want_dx:
-        return None
+    if not FUSED_BWD or not WGRAD_ACCUMULATE or dtype != torch.bfloat16 or (cur is not None and cur.dtype != torch.bfloat16) or (
+            st.wpack_bwd is None and want_dx):
+        return None          # (PN2_WGRAD_DETERMINISTIC=1 keeps the fixed-order per-step kernels: the fused kernel adds dW with L2 reductions)
     if mode == "pooled" and (pooled[2] != 32 or M % 32 != 0 or pooled[0].dtype != torch.float32 or not pooled[0].is_contiguous()):
         return None
     xin = x0 if prev is None else prev.Z
