@@ -35,8 +35,8 @@ int tc_wgrad_reduce(const float *scratch, int splits, int N, int K, int K_ld, fl
 constexpr int kBfBM = 128;
 constexpr int kBfSlab = kBfBM * 128;          // one 64-column slab of a 128-row tile: 16 KB (SW128 box layout)
 constexpr int kBfEpi = 128;                   // warps 0-3 : epilogue group (tensor-memory lane quarters), statistics MMAs
-constexpr int kBfXf = 256;                    // warps 4-11: transform group; its thread 0 issues the data / weight-gradient MMAs
-constexpr int kBfThreads = kBfEpi + kBfXf + 32;   // warp 12: TMA producer
+constexpr int kBfXf = 256;                    // warps 4-11: transform group
+constexpr int kBfThreads = kBfEpi + kBfXf + 64;   // warp 12: TMA producer, warp 13: MMA issue (every product of the kernel)
 constexpr int kBfMaxC = 128;                  // widest layer (N) / input (K_ld) this kernel takes
 constexpr int kBfMaxStages = 4;
 
@@ -133,7 +133,7 @@ __device__ __forceinline__ UnitMap unit_map(int tid, int nch) {
 __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_constant__ BwdFusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[kBfMaxStages], full_b[kBfMaxStages], empty[kBfMaxStages], act_rdy[kBfMaxStages],
-        acc_full[2], acc_empty[2], bar_done;
+        acc_full[2], acc_empty[2], e_rdy[kBfMaxStages], bar_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < kBfMaxStages; ++i) {
-            mbar_init(&full_a[i], 1); mbar_init(&full_b[i], 1); mbar_init(&empty[i], 1); mbar_init(&act_rdy[i], 1);
+            mbar_init(&full_a[i], 1); mbar_init(&full_b[i], 1); mbar_init(&empty[i], 1); mbar_init(&act_rdy[i], 1); mbar_init(&e_rdy[i], 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1); }
-        mbar_init(&bar_done, 2);
+        mbar_init(&bar_done, 1);
         mbar_init_fence();
     }
     for (int c = tid; c < cl; c += kBfThreads) {
@@ -223,13 +223,11 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             }
         }
         __syncwarp();
-    } else if (warp >= kBfEpi / 32) {
-        // ================= transform group (+ data / weight-gradient MMA issue) =================
+    } else if (warp >= kBfEpi / 32 && warp < (kBfEpi + kBfXf) / 32) {
+        // ================= transform group =================
         const int ttid = tid - kBfEpi;
-        const uint32_t idesc_dx = make_idesc_bf16(kBfBM, a.K_pad, 0, 0);      // dA = dZ . W      (A, B K-major)
-        const uint32_t idesc_dw = make_idesc_bf16(kBfBM, a.K_pad, 1, 1);      // dW = dZ^T . act  (A, B MN-major)
         for (uint32_t t = 0; t < n_my; ++t) {
-            const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S, b = t % (uint32_t)AB;
+            const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S;
             const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
             const int rows_valid = (int)min((int64_t)kBfBM, a.M - m0);
             uint8_t *st = smem + (size_t)s * a.stage_stride;
@@ -338,12 +336,27 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             fence_proxy_async();
             named_bar_sync(1, kBfXf);
             if (ttid == 0) BF_STAMP(6);
-            // ---- MMAs of the tile: data gradient (accumulator buffer b) and weight gradient (lives across all tiles) ----
-            if (warp == kBfEpi / 32) {          // the group's first warp, converged: one elected lane issues (see elect_one_sync)
-                if (a.want_dx && t >= (uint32_t)AB) mbar_wait(&acc_empty[b], ((t / (uint32_t)AB) - 1) & 1u);
-                fence_after_sync();
-              if (elect_one_sync()) {
-                if (a.want_dx) bf_mbar_arrive(&act_rdy[s]);      // (release: the epilogue group may read act[s])
+            // the tile's operands are in place: the MMA warp issues its products, the epilogue group may read act[s]
+            if (warp == kBfEpi / 32 && elect_one_sync()) bf_mbar_arrive(&act_rdy[s]);
+        }
+    } else if (warp == (kBfEpi + kBfXf) / 32 + 1) {
+        // ================= MMA warp: one elected lane issues every product =================
+        // (in a warp of its own the issue -- ~400 cycles for the data/weight gradient, ~800 for the statistics, waits on the
+        //  accumulator buffers included -- is off the transform and epilogue groups' critical paths)
+        const uint32_t idesc_dx = make_idesc_bf16(kBfBM, a.K_pad, 0, 0);      // dA = dZ . W      (A, B K-major)
+        const uint32_t idesc_dw = make_idesc_bf16(kBfBM, a.K_pad, 1, 1);      // dW = dZ^T . act  (A, B MN-major)
+        const uint32_t idesc_s2 = make_idesc_bf16(kBfBM, a.s2_cols, 1, 1);    // S2 = dA'^T . [zhat | ones]
+        const uint32_t idesc_s1 = make_idesc_bf16(kBfBM, 16, 1, 0);           // S1 = dA'^T . ones (B K-major, own tile)
+        const uint32_t idesc_c = make_idesc_bf16(kBfBM, 64 + a.s2_cols, 1, 1);
+        // Two kinds of work per tile, taken in whichever order their inputs arrive (a blocking tile-by-tile loop made the data
+        // gradient of tile t + 1 wait for the epilogue of tile t): "front" = data + weight gradient once the transform group
+        // is done, "back" = the statistics (+ combined weight gradient) once the epilogue staged dA'.
+        auto front = [&](const uint32_t t) {
+            const uint32_t s = t % (uint32_t)S, b = t % (uint32_t)AB;
+            uint8_t *st = smem + (size_t)s * a.stage_stride;
+            uint8_t *const s_da = st + a.o_da, *const s_x = st + a.o_x, *const s_act = st + a.o_act;
+            fence_after_sync();
+            if (elect_one_sync()) {
                 BF_STAMP(7);
                 // (descriptors: the start address sits in the low 14 bits in 16-byte units -- stepping through a tile is an
                 //  integer add on a descriptor built once; building each one from scratch cost ~170 cycles per MMA of dependent
@@ -369,23 +382,72 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 }
                 if (a.want_dx) umma_commit(&acc_full[b]);
                 else umma_commit(&empty[s]);                      // no epilogue: the stage may be refilled
-                if (t == n_my - 1) umma_commit(&bar_done);
                 BF_STAMP(8);
-              }
-              __syncwarp();
+            }
+            __syncwarp();
+        };
+        auto back = [&](const uint32_t t) {
+            const uint32_t s = t % (uint32_t)S;
+            uint8_t *st = smem + (size_t)s * a.stage_stride;
+            uint8_t *const s_da = st + a.o_da, *const s_x = st + a.o_x, *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
+            fence_after_sync();
+            if (elect_one_sync()) {
+                if (a.combined) {
+                    // A = [dZ slab | staged dA' slab] (M = 128 through LBO), B = [act slab | zhat (+ ones) slab] (N through LBO):
+                    // D[0:64, 0:64] = dZ^T.act = dW, D[64:128, 64:] = dA'^T.[zhat | ones] = the statistics; 8 MMAs instead of 16
+                    const uint64_t ad = make_desc(smem_addr(s_da), a.o_stage - a.o_da, 1024);
+                    const uint64_t bd = make_desc(smem_addr(s_act), a.o_x - a.o_act, 1024);
+                    const uint32_t d_c = tmem + (uint32_t)a.off_dw;
+#pragma unroll
+                    for (int r = 0; r < kBfBM / 16; ++r)
+                        umma_bf16(d_c, ad + (uint64_t)(128 * r), bd + (uint64_t)(128 * r), idesc_c, r ? 1u : (uint32_t)(t != 0));
+                    if (a.ones_col < 0) {
+                        const uint64_t as = make_desc(smem_addr(s_stage), 0, 1024), b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                        const uint32_t d1 = tmem + (uint32_t)a.off_s1;
+#pragma unroll
+                        for (int r = 0; r < kBfBM / 16; ++r)
+                            umma_bf16(d1, as + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, r ? 1u : (uint32_t)(t != 0));
+                    }
+                } else if (a.want_stats && !(a.dbg & 2)) {
+                    const uint64_t ad = make_desc(smem_addr(s_stage), lbo_k, 1024), b2 = make_desc(smem_addr(s_x), lbo_k, 1024);
+                    const uint64_t b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                    const uint32_t d2 = tmem + (uint32_t)a.off_s2, d1 = tmem + (uint32_t)a.off_s1;
+                    const bool own_ones = a.ones_col < 0;
+#pragma unroll
+                    for (int r = 0; r < kBfBM / 16; ++r) {
+                        const uint32_t acc = r ? 1u : (uint32_t)(t != 0);
+                        umma_bf16(d2, ad + (uint64_t)(128 * r), b2 + (uint64_t)(128 * r), idesc_s2, acc);
+                        if (own_ones) umma_bf16(d1, ad + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, acc);
+                    }
+                }
+                BF_STAMP(13);
+                umma_commit(&empty[s]);       // every MMA that reads the stage is done (and the store has read its staging) -> refill
+            }
+            __syncwarp();
+        };
+        const uint32_t n_back = a.want_dx ? n_my : 0u;
+        for (uint32_t td = 0, ts = 0; td < n_my || ts < n_back;) {
+            if (td < n_my) {
+                const uint32_t s = td % (uint32_t)S, u = td / (uint32_t)S, b = td % (uint32_t)AB;
+                bool ok = mbar_test(&act_rdy[s], u & 1u);
+                if (ok && a.want_dx && td >= (uint32_t)AB) ok = mbar_test(&acc_empty[b], ((td / (uint32_t)AB) - 1) & 1u);
+                if (__all_sync(0xffffffffu, ok)) { front(td); ++td; }
+            }
+            if (ts < td && ts < n_back) {
+                if (__all_sync(0xffffffffu, mbar_test(&e_rdy[ts % (uint32_t)S], (ts / (uint32_t)S) & 1u))) { back(ts); ++ts; }
             }
         }
+        if (elect_one_sync()) umma_commit(&bar_done);     // every product of this CTA has landed in tensor memory
+        __syncwarp();
     } else {
-        // ================= epilogue group (+ statistics MMA issue) =================
-        const uint32_t idesc_s2 = make_idesc_bf16(kBfBM, a.s2_cols, 1, 1);    // S2 = dA'^T . [zhat | ones]
-        const uint32_t idesc_s1 = make_idesc_bf16(kBfBM, 16, 1, 0);           // S1 = dA'^T . ones (B K-major, own tile)
+        // ================= epilogue group =================
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         if (a.want_dx) {
             for (uint32_t t = 0; t < n_my; ++t) {
                 const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S, b = t % (uint32_t)AB;
                 const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
                 uint8_t *st = smem + (size_t)s * a.stage_stride;
-                uint8_t *const s_x = st + a.o_x, *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
+                uint8_t *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
                 if (tid == 0) BF_STAMP(9);
                 mbar_wait(&acc_full[b], (t / (uint32_t)AB) & 1u);
                 mbar_wait(&act_rdy[s], u & 1u);
@@ -433,49 +495,14 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     bf_mbar_arrive(&acc_empty[b]);       // the data-gradient MMAs of tile t + AB may overwrite this buffer
                     for (int j = 0; j < a.kS; ++j)
                         if (64 * j < a.k_store) tma_store_2d(&a.tm_dx, 64 * j, (int)m0, s_stage + (size_t)j * kBfSlab);
-                    if (a.combined) {
-                        // A = [dZ slab | staged dA' slab] (M = 128 through LBO), B = [act slab | zhat (+ ones) slab] (N through LBO):
-                        // D[0:64, 0:64] = dZ^T.act = dW, D[64:128, 64:] = dA'^T.[zhat | ones] = the statistics; 8 MMAs instead of 16
-                        fence_after_sync();
-                        const uint64_t ad = make_desc(smem_addr(st + a.o_da), a.o_stage - a.o_da, 1024);
-                        const uint64_t bd = make_desc(smem_addr(s_act), a.o_x - a.o_act, 1024);
-                        const uint32_t idesc_c = make_idesc_bf16(kBfBM, 64 + a.s2_cols, 1, 1);
-                        const uint32_t d_c = tmem + (uint32_t)a.off_dw;
-#pragma unroll
-                        for (int r = 0; r < kBfBM / 16; ++r)
-                            umma_bf16(d_c, ad + (uint64_t)(128 * r), bd + (uint64_t)(128 * r), idesc_c, r ? 1u : (uint32_t)(t != 0));
-                        if (a.ones_col < 0) {
-                            const uint64_t as = make_desc(smem_addr(s_stage), 0, 1024), b1 = make_desc(smem_addr(s_ones), 0, 1024);
-                            const uint32_t d1 = tmem + (uint32_t)a.off_s1;
-#pragma unroll
-                            for (int r = 0; r < kBfBM / 16; ++r)
-                                umma_bf16(d1, as + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, r ? 1u : (uint32_t)(t != 0));
-                        }
-                    } else if (a.want_stats && !(a.dbg & 2)) {
-                        fence_after_sync();
-                        const uint64_t ad = make_desc(smem_addr(s_stage), lbo_k, 1024), b2 = make_desc(smem_addr(s_x), lbo_k, 1024);
-                        const uint64_t b1 = make_desc(smem_addr(s_ones), 0, 1024);
-                        const uint32_t d2 = tmem + (uint32_t)a.off_s2, d1 = tmem + (uint32_t)a.off_s1;
-                        const bool own_ones = a.ones_col < 0;
-#pragma unroll
-                        for (int r = 0; r < kBfBM / 16; ++r) {
-                            const uint32_t acc = r ? 1u : (uint32_t)(t != 0);
-                            umma_bf16(d2, ad + (uint64_t)(128 * r), b2 + (uint64_t)(128 * r), idesc_s2, acc);
-                            if (own_ones) umma_bf16(d1, ad + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, acc);
-                        }
-                    }
-                    BF_STAMP(13);
                     if (!a.defer_store_wait) tma_store_wait_read();   // (staging sits in this stage's dA buffer: the refill must wait)
                     BF_STAMP(14);
-                    umma_commit(&empty[s]);       // every MMA that reads the stage is done -> refill
-                    if (t == n_my - 1) umma_commit(&bar_done);
+                    bf_mbar_arrive(&e_rdy[s]);           // MMA warp: the statistics products, then the stage is released
                   }
                   __syncwarp();
                 }
             }
             if (warp == 0 && elect_one_sync()) tma_store_wait_all();
-        } else if (tid == 0) {
-            bf_mbar_arrive(&bar_done);
         }
         // ---- end of the CTA: drain the accumulators that lived in tensor memory across all its tiles ----
         mbar_wait(&bar_done, 0);
