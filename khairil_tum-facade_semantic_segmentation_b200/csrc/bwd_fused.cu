@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
         if (lane == 0) {
             tma_prefetch_desc(&a.tm_da);
             tma_prefetch_desc(&a.tm_x);
-            for (uint32_t t = 0; t < n_my; ++t) {
-                const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S;
+            // (stage index / use count kept incrementally: S is a run-time value, t % S and t / S are ~100-cycle divisions)
+            for (uint32_t t = 0, s = 0, u = 0; t < n_my; ++t, s = (s + 1 == (uint32_t)S ? 0u : s + 1), u += (s == 0)) {
                 const int m0 = (int)(((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM);
                 uint8_t *st = smem + (size_t)s * a.stage_stride;
                 BF_STAMP(0);
@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
     } else if (warp >= kBfEpi / 32 && warp < (kBfEpi + kBfXf) / 32) {
         // ================= transform group =================
         const int ttid = tid - kBfEpi;
-        for (uint32_t t = 0; t < n_my; ++t) {
-            const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S;
+        for (uint32_t t = 0, s = 0, u = 0; t < n_my; ++t, s = (s + 1 == (uint32_t)S ? 0u : s + 1), u += (s == 0)) {
             const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
             const int rows_valid = (int)min((int64_t)kBfBM, a.M - m0);
             uint8_t *st = smem + (size_t)s * a.stage_stride;
@@ -351,8 +350,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
         // Two kinds of work per tile, taken in whichever order their inputs arrive (a blocking tile-by-tile loop made the data
         // gradient of tile t + 1 wait for the epilogue of tile t): "front" = data + weight gradient once the transform group
         // is done, "back" = the statistics (+ combined weight gradient) once the epilogue staged dA'.
-        auto front = [&](const uint32_t t) {
-            const uint32_t s = t % (uint32_t)S, b = t % (uint32_t)AB;
+        auto front = [&](const uint32_t t, const uint32_t s, const uint32_t b) {
             uint8_t *st = smem + (size_t)s * a.stage_stride;
             uint8_t *const s_da = st + a.o_da, *const s_x = st + a.o_x, *const s_act = st + a.o_act;
             fence_after_sync();
@@ -386,8 +384,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             }
             __syncwarp();
         };
-        auto back = [&](const uint32_t t) {
-            const uint32_t s = t % (uint32_t)S;
+        auto back = [&](const uint32_t t, const uint32_t s) {
             uint8_t *st = smem + (size_t)s * a.stage_stride;
             uint8_t *const s_da = st + a.o_da, *const s_x = st + a.o_x, *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
             fence_after_sync();
@@ -426,15 +423,24 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             __syncwarp();
         };
         const uint32_t n_back = a.want_dx ? n_my : 0u;
+        uint32_t sd = 0, ud = 0, ss = 0, us = 0;      // stage / use count of the next front (td) and back (ts) tile
         for (uint32_t td = 0, ts = 0; td < n_my || ts < n_back;) {
             if (td < n_my) {
-                const uint32_t s = td % (uint32_t)S, u = td / (uint32_t)S, b = td % (uint32_t)AB;
-                bool ok = mbar_test(&act_rdy[s], u & 1u);
-                if (ok && a.want_dx && td >= (uint32_t)AB) ok = mbar_test(&acc_empty[b], ((td / (uint32_t)AB) - 1) & 1u);
-                if (__all_sync(0xffffffffu, ok)) { front(td); ++td; }
+                const uint32_t b = AB == 2 ? (td & 1u) : 0u, ub = AB == 2 ? (td >> 1) : td;
+                bool ok = mbar_test(&act_rdy[sd], ud & 1u);
+                if (ok && a.want_dx && td >= (uint32_t)AB) ok = mbar_test(&acc_empty[b], (ub - 1) & 1u);
+                if (__all_sync(0xffffffffu, ok)) {
+                    front(td, sd, b);
+                    ++td;
+                    if (++sd == (uint32_t)S) { sd = 0; ++ud; }
+                }
             }
             if (ts < td && ts < n_back) {
-                if (__all_sync(0xffffffffu, mbar_test(&e_rdy[ts % (uint32_t)S], (ts / (uint32_t)S) & 1u))) { back(ts); ++ts; }
+                if (__all_sync(0xffffffffu, mbar_test(&e_rdy[ss], us & 1u))) {
+                    back(ts, ss);
+                    ++ts;
+                    if (++ss == (uint32_t)S) { ss = 0; ++us; }
+                }
             }
         }
         if (elect_one_sync()) umma_commit(&bar_done);     // every product of this CTA has landed in tensor memory
@@ -443,13 +449,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
         // ================= epilogue group =================
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         if (a.want_dx) {
-            for (uint32_t t = 0; t < n_my; ++t) {
-                const uint32_t s = t % (uint32_t)S, u = t / (uint32_t)S, b = t % (uint32_t)AB;
+            for (uint32_t t = 0, s = 0, u = 0; t < n_my; ++t, s = (s + 1 == (uint32_t)S ? 0u : s + 1), u += (s == 0)) {
+                const uint32_t b = AB == 2 ? (t & 1u) : 0u, ub = AB == 2 ? (t >> 1) : t;      // t % AB, t / AB (AB is 1 or 2)
                 const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * kBfBM;
                 uint8_t *st = smem + (size_t)s * a.stage_stride;
                 uint8_t *const s_act = st + a.o_act, *const s_stage = st + a.o_stage;
                 if (tid == 0) BF_STAMP(9);
-                mbar_wait(&acc_full[b], (t / (uint32_t)AB) & 1u);
+                mbar_wait(&acc_full[b], ub & 1u);
                 mbar_wait(&act_rdy[s], u & 1u);
                 if (tid == 0) BF_STAMP(10);
                 fence_after_sync();
