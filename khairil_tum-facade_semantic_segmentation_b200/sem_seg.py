@@ -198,6 +198,9 @@ class get_model(nn.Module):
             hook = self.feature_grad_hooks.get(i + 1) if self.feature_grad_hooks else None
             if hook is not None and f.requires_grad:
                 f.register_hook(hook)
+            issued = self.feature_grad_hooks.get("sa%d_issued" % (i + 1)) if self.feature_grad_hooks else None
+            if issued is not None:
+                issued()           # (forward position: that level's kernels have just been issued on the current stream)
             feats.append(f)
         l4_points = feats[4]
         up = feats[4]
@@ -225,10 +228,16 @@ class get_model(nn.Module):
                 up = fp(coords[fine], coords[fine + 1], skip, up, neighbours=nn3[i])
             else:
                 up = fp(coords[fine], coords[fine + 1], skip, up)
+            hook = self.feature_grad_hooks.get("fp%d" % (4 - i)) if self.feature_grad_hooks else None
+            if hook is not None and up.requires_grad:
+                up.register_hook(hook)
         return self._head(up), l4_points
 
     feature_grad_hooks = None    # {level 1..4: hook}: registered on that set-abstraction level's output features when they
-                                 # carry a gradient (trainer.SemSegTrainer: early all-reduce of finished gradient buckets)
+                                 # carry a gradient (trainer.SemSegTrainer: early all-reduce of finished gradient buckets);
+                                 # {"fp4" | "fp3" | "fp2": hook}: on that feature-propagation level's output (its gradient is
+                                 # complete when the next finer level's backward is done: the trainer's anchor for the index
+                                 # pipeline of the next batch)
     fused_head = True     # bf16 mode: fp1 + head as one chain of rows on this library's kernels
     rows_head = True      # otherwise: the PyTorch head on point-major rows (no layout copies)
 

@@ -309,6 +309,9 @@ class SemSegTrainer:
         /root/reference/localfunctions.py:205) to every batch ON THE DEVICE, with the reference's numpy angle draws."""
         self.augment_rotate_z = bool(augment_rotate_z)
         self.overlap_allreduce = os.environ.get("PN2_OVERLAP_ALLREDUCE", "1") != "0"
+        # where the pipelined graph forks the next batch's index pipeline: "start" (top of the step), "sa<l>_issued" (after that
+        # level's forward kernels) or "fp<l>" (when the gradient of that level's output is complete); see enable_cuda_graph
+        self.index_anchor = os.environ.get("PN2_INDEX_ANCHOR", "start")
         self.fused_loss = bool(fused_loss)
         self.prepack = True                  # every MLP's weight images in one launch per step (modules.prepack_mlps)
         self._rot_staging = None
@@ -396,6 +399,9 @@ class SemSegTrainer:
                 return hook
 
             self.model.feature_grad_hooks = {4: reduce_when_ready(4), 2: reduce_when_ready(2)}
+        index_hook, self._index_hook = getattr(self, "_index_hook", None), None
+        if index_hook is not None and hasattr(self.model, "feature_grad_hooks"):
+            self.model.feature_grad_hooks = dict(self.model.feature_grad_hooks or {}, **{self.index_anchor: index_hook})
         try:
             if self.fused_loss and hasattr(self.model, "forward_loss"):
                 # forward + weighted NLL in one pass (the loss and its gradient come out of the head kernels when they apply)
@@ -407,7 +413,7 @@ class SemSegTrainer:
                     pred, feat = self.model(points.transpose(2, 1), geometry=geometry)
                 loss = self.criterion(pred.contiguous().view(-1, self.num_classes), target, feat, self.class_weights)
         finally:
-            if buckets is not None:
+            if buckets is not None or index_hook is not None:
                 self.model.feature_grad_hooks = None
         modules._STEP_IMAGES.clear()          # images a forward did not pick up must not outlive the parameters they were packed from
         loss.backward()
@@ -510,11 +516,30 @@ class SemSegTrainer:
             with _no_gc(), torch.cuda.graph(graph, stream=_capture_stream(dev), **pool):
                 if pipeline:
                     main = torch.cuda.current_stream(dev)
-                    self._geo_stream.wait_stream(main)
-                    with torch.cuda.stream(self._geo_stream), torch.no_grad():
-                        with ops.reuse_outputs(self._slots[1 - k][1]):
-                            self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :], fork=self._fork)
+                    forked = []
+
+                    def index_branch(grad=None, k=k, main=main, forked=forked):
+                        # the index pipeline of the batch waiting in the other slot, forked off the main stream HERE
+                        if not forked:
+                            forked.append(True)
+                            self._geo_stream.wait_stream(main)
+                            with torch.cuda.stream(self._geo_stream), torch.no_grad():
+                                with ops.reuse_outputs(self._slots[1 - k][1]):
+                                    self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :], fork=self._fork)
+                        return grad
+
+                    # Where the branch forks.  Its two long FPS kernels pin one CTA per cloud to 32 SMs for ~0.45 ms, and a
+                    # persistent 148-CTA kernel of the feature path that meets them runs as two waves (sa1's three forward
+                    # layers: 192 us next to FPS, 129 us alone).  Forking later -- next to the few-CTA layers of fp2..fp4 /
+                    # sa4 / sa3 -- was measured (B200, 32 x 4096, ms/step): start 2.570, sa1_issued 2.598, sa2_issued 2.563,
+                    # sa3_issued 2.628, fp4 2.604, fp2 2.594: the 32 SM x 0.45 ms the branch takes cost the same wherever they
+                    # land, so the default stays at the top of the step.
+                    if self.index_anchor != "start" and hasattr(self.model, "feature_grad_hooks"):
+                        self._index_hook = index_branch
+                    else:
+                        index_branch()
                     loss = self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])
+                    index_branch()          # (an anchor that never fired: fork here, the join below still orders it)
                     main.wait_stream(self._geo_stream)
                 else:
                     loss = self._step_impl(self._pts[0], self._tgt[0])
