@@ -49,6 +49,12 @@ int pn2_version(void);
 const char *pn2_last_error(void);
 /* kernels launched by this library since load (bench.py's "gpu_launches") */
 unsigned long long pn2_launch_count(void);
+/* SM budget of the persistent kernels (linear layers, fused set abstraction, fused backward layer): their grids are sized
+ * for `sms` SMs instead of all 148 until changed again; 0 restores the default.  Returns the previous value.  A caller that
+ * knows other work pins SMs at the same time (the pipelined trainer / predictor: the FPS chain of the next batch holds one
+ * CTA per cloud) sizes the grid to the SMs that are really free, so that every CTA is resident at once instead of a
+ * second partial wave.  Process-global; takes effect at launch (so at capture time for CUDA graphs). */
+int pn2_set_sm_budget(int sms);
 
 /* ---- a1 square_distance (:19-40) ---------------------------------------------
  * out[b,i,j] = ((-2*<src_i,dst_j>) + |src_i|^2) + |dst_j|^2 in the reference's

@@ -5,6 +5,7 @@ PyTorch fallback: if the library is missing or a call fails, an exception is
 raised.  PyTorch is used by the callers of this module for device memory and
 streams only; every pointer handed to the library is a raw ``data_ptr()``.
 """
+import contextlib
 import ctypes
 import os
 
@@ -28,6 +29,7 @@ _SIGNATURES = {
     "pn2_version": (_i, []),
     "pn2_last_error": (ctypes.c_char_p, []),
     "pn2_launch_count": (ctypes.c_ulonglong, []),
+    "pn2_set_sm_budget": (ctypes.c_int, [ctypes.c_int]),
     "pn2_square_distance": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "pn2_index_points": (_i, [_p, _l, _l, _l, _i, _i, _i, _p, _l, _p, _p]),
     "pn2_index_points_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p, _p]),
@@ -188,3 +190,17 @@ def require_cuda(t, name, dtype=torch.float32):
     if dtype is not None and t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
     return t
+
+
+@contextlib.contextmanager
+def sm_budget(sms):
+    """Inside: the persistent kernels size their grids for `sms` SMs (pn2_set_sm_budget); None / 0: no change."""
+    if not sms:
+        yield
+        return
+    lib = load()
+    prev = lib.pn2_set_sm_budget(int(sms))
+    try:
+        yield
+    finally:
+        lib.pn2_set_sm_budget(prev)

@@ -20,6 +20,11 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<int> g_sm_budget{0};
+int sm_budget() {
+    const int b = g_sm_budget.load(std::memory_order_relaxed);
+    return b > 0 && b < kNumSMs ? b : kNumSMs;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -68,6 +73,7 @@ using namespace pn2;
 extern "C" int pn2_version(void) { return PN2_VERSION; }
 extern "C" const char *pn2_last_error(void) { return g_err; }
 extern "C" unsigned long long pn2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int pn2_set_sm_budget(int sms) { return g_sm_budget.exchange(sms < 0 ? 0 : sms, std::memory_order_relaxed); }
 
 extern "C" int pn2_linear_fwd(const void *X, int ldx, int x_dtype, const float *in_scale, const float *in_shift,
                               const float *W, const float *bias, int64_t M, int K, int N, void *Z, int ldz,

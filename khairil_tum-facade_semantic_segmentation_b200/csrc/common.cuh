@@ -23,6 +23,7 @@ int check_launch(const char *what);   // cudaGetLastError -> PN2_OK / PN2_ERR_CU
     } while (0)
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+int sm_budget();               // SMs the persistent kernels size their grids for (pn2_set_sm_budget), default kNumSMs
 constexpr int kStatReplicas = PN2_STAT_REPLICAS;   // copies of every fp64 column-sum accumulator (atomic contention)
 
 // ---- exact fp32 arithmetic of the reference (never contracted by the compiler) -

@@ -801,7 +801,7 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
                 if (stages2 > kTc2MaxStages) stages2 = kTc2MaxStages;
                 a.stages = stages2;
                 const size_t dyn2 = fixed + slot * stages2;
-                int64_t grid2 = ((int64_t)per_sm2 * kNumSMs + ng - 1) / ng;
+                int64_t grid2 = ((int64_t)per_sm2 * sm_budget() + ng - 1) / ng;
                 if (grid2 > m_tiles) grid2 = m_tiles;
                 const dim3 grid((unsigned)grid2, (unsigned)ng);
                 if (stat_accum)
@@ -834,7 +834,7 @@ int tc_linear_nt(const void *X, int ldx, const float *in_scale, const float *in_
             if (stages > 8) stages = 8;
             a.stages = stages;
             const size_t dyn = fixed + slot * stages;
-            int64_t gx = ((int64_t)per_sm * kNumSMs + ng - 1) / ng;
+            int64_t gx = ((int64_t)per_sm * sm_budget() + ng - 1) / ng;
             if (gx > m_tiles) gx = m_tiles;
             const dim3 grid((unsigned)gx, (unsigned)ng);
             if (stat_accum)

@@ -487,7 +487,7 @@ extern "C" int pn2_sa_fused_eval(const float *xyz, int64_t sB, int64_t sN, int64
     a.Wimg = img;
     a.out = out;
     const int64_t n_tiles = (a.G * 32 + kSaTile - 1) / kSaTile;
-    int64_t grid = (int64_t)p.per_sm * kNumSMs;
+    int64_t grid = (int64_t)p.per_sm * sm_budget();
     if (grid > n_tiles) grid = n_tiles;
     // rows in flight per thread during the gather: 8 when shared memory allows at most two CTAs per SM (registers are
     // plentiful then and nothing else hides the L2 latency), 4 otherwise

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .modules import PointNetFeaturePropagation, PointNetSetAbstraction
 
 # (npoint, radius, nsample, mlp) -- pointnet2_sem_seg.py:9-12
@@ -189,11 +190,12 @@ class get_model(nn.Module):
         elif ahead:
             geo, nn3, events, main = self._geometry_ahead(coords[0])
         for i, sa in enumerate(sas):
-            if ahead:
-                main.wait_event(events[i])
-                c, f = sa(coords[-1], feats[-1], geometry=geo[i])
-            else:
-                c, f = sa(coords[-1], feats[-1])
+            with _lib.sm_budget(self.sa_sm_budget.get(i) if self.sa_sm_budget else None):
+                if ahead:
+                    main.wait_event(events[i])
+                    c, f = sa(coords[-1], feats[-1], geometry=geo[i])
+                else:
+                    c, f = sa(coords[-1], feats[-1])
             coords.append(c)
             hook = self.feature_grad_hooks.get(i + 1) if self.feature_grad_hooks else None
             if hook is not None and f.requires_grad:
@@ -233,6 +235,9 @@ class get_model(nn.Module):
                 up.register_hook(hook)
         return self._head(up), l4_points
 
+    sa_sm_budget = None          # {set-abstraction index 0..3: SMs}: grid budget of that level's persistent forward kernels
+                                 # (pn2_set_sm_budget); the pipelined trainer / predictor set it while they capture, for the
+                                 # levels that run next to the FPS chain of the following batch
     feature_grad_hooks = None    # {level 1..4: hook}: registered on that set-abstraction level's output features when they
                                  # carry a gradient (trainer.SemSegTrainer: early all-reduce of finished gradient buckets);
                                  # {"fp4" | "fp3" | "fp2": hook}: on that feature-propagation level's output (its gradient is

@@ -33,6 +33,19 @@ def _no_gc():
             gc.enable()
 
 
+def _fps_sm_budget(batch_clouds):
+    """{set-abstraction index: SMs} for the levels whose forward kernels run next to the FPS kernels of the NEXT batch in a
+    pipelined graph.  FPS holds one CTA per cloud for ~0.45 ms (levels 1 and 2 of the index pipeline) and that CTA's shared
+    memory keeps the SM from taking its full share of a persistent feature-path kernel, whose grid (sized for 148 SMs) then
+    ends in a partial second wave: sa1's three forward layers took 192 us next to FPS, 129 us alone.  Sizing those grids for
+    148 - clouds SMs keeps every CTA resident at once.  PN2_SA_SM_BUDGET=0 disables, =a,b,.. picks the levels."""
+    env = os.environ.get("PN2_SA_SM_BUDGET", "0,1")
+    if env in ("", "0") or not (0 < batch_clouds <= 74):
+        return None
+    sms = int(os.environ.get("PN2_SA_SM_BUDGET_SMS", "0")) or 148 - int(batch_clouds)
+    return {int(v): sms for v in env.split(",")}
+
+
 def _capture_stream(dev):
     """The stream a step / forward graph is captured on: HIGH priority, so its kernel nodes win the block scheduler
     against the index-pipeline branch (captured from default-priority streams).  Without it the big-grid ball-query and
@@ -538,7 +551,14 @@ class SemSegTrainer:
                         self._index_hook = index_branch
                     else:
                         index_branch()
-                    loss = self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])
+                    budget = _fps_sm_budget(batch_clouds) if self.index_anchor == "start" else None
+                    if budget and hasattr(self.model, "sa_sm_budget"):
+                        self.model.sa_sm_budget = budget
+                    try:
+                        loss = self._step_impl(self._pts[k], self._tgt[k], self._slots[k][0])
+                    finally:
+                        if budget and hasattr(self.model, "sa_sm_budget"):
+                            self.model.sa_sm_budget = None
                     index_branch()          # (an anchor that never fired: fork here, the join below still orders it)
                     main.wait_stream(self._geo_stream)
                 else:
@@ -757,7 +777,14 @@ class SemSegPredictor:
                 self._geo_stream.wait_stream(main)
                 with torch.cuda.stream(self._geo_stream), ops.reuse_outputs(self._slots[1 - k][1]):
                     self.model.geometry_all(self._pts[1 - k].transpose(2, 1)[:, :3, :])
-            labels, log_probs, _ = self._forward(k)                            # [B, npoint], [B, npoint, classes]
+            budget = _fps_sm_budget(self._pts[k].shape[0]) if self.pipeline else None
+            if budget and hasattr(self.model, "sa_sm_budget"):
+                self.model.sa_sm_budget = budget
+            try:
+                labels, log_probs, _ = self._forward(k)                        # [B, npoint], [B, npoint, classes]
+            finally:
+                if budget and hasattr(self.model, "sa_sm_budget"):
+                    self.model.sa_sm_budget = None
             if self.pipeline:
                 main.wait_stream(self._geo_stream)
         self._graphs.append(graph)

@@ -30,7 +30,14 @@ def _trainer(pn2, pipeline, lr=0.0):
     return t
 
 
-def test_pipelined_train_steps_match_unpipelined(pn2):
+@pytest.mark.parametrize("sm_budget,tol", [("0", 1e-5), (None, 1e-3)])
+def test_pipelined_train_steps_match_unpipelined(pn2, monkeypatch, sm_budget, tol):
+    """sm_budget "0": the pipelined graph launches exactly the un-pipelined graph's kernels (same grids), so the losses agree
+    to rounding.  Default: the pipelined graph sizes the grids of sa1 / sa2's forward layers for the SMs FPS leaves free
+    (trainer._fps_sm_budget); fewer CTAs -> other fp32 partial sums of the BatchNorm statistics -> ReLU decisions of
+    near-zero activations flip: the same 1e-4-level noise two runs with different atomic order show."""
+    if sm_budget is not None:
+        monkeypatch.setenv("PN2_SA_SM_BUDGET", sm_budget)
     data = _batches(5, 300)
     plain = _trainer(pn2, False)
     torch.manual_seed(99)                       # FPS start draws: 4 per batch, in batch order, in both modes
@@ -47,11 +54,11 @@ def test_pipelined_train_steps_match_unpipelined(pn2):
     assert len(rest) == 1 and piped.flush() == []
     got += rest
     for a, b in zip(got, want):
-        assert abs(a - b) <= 1e-5 * abs(b), (got, want)      # same batch, same indices, same kernels, same parameters
+        assert abs(a - b) <= tol * abs(b), (got, want)      # same batch, same indices, same parameters
     # running statistics after the same five batches (a skipped or repeated batch would show here)
     for (k, a), b in zip(piped.model.state_dict().items(), plain.model.state_dict().values()):
         if a.dtype.is_floating_point:
-            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), k
+            assert torch.allclose(a, b, rtol=1e-4 if tol < 1e-4 else 1e-2, atol=1e-5 if tol < 1e-4 else 2e-3), k
         else:
             assert torch.equal(a, b), k          # num_batches_tracked
     pn2.set_precision("fp32")
