@@ -325,22 +325,41 @@ def _weight_grad(dZ, xin, ldx, sc, sh, M, K, N, param, dev, cuda_stream, keep):
 
 OVERLAP_WGRAD = True      # weight gradients on a side stream, concurrently with the data-gradient / BatchNorm chain
 _SIDE = {}
-_GRAD_SINK = {}           # id(parameter) -> flat fp32 view the parameter's gradient is written into (trainer.FlatGradients)
+_GRAD_SINK = {}           # id(parameter) -> (weak reference to it, flat fp32 view its gradient is written into)
 
 
-def set_grad_sink(mapping):
-    """mapping: {id(parameter): preallocated fp32 tensor of the parameter's shape} or None.  Backward passes write
-    weight / BatchNorm gradients straight into these buffers and hand autograd views of them (no accumulate kernels)."""
-    _GRAD_SINK.clear()
-    if mapping:
-        _GRAD_SINK.update(mapping)
+def set_grad_sink(params, views):
+    """The gradient sink of the hot path (trainer.FlatGradients): backward passes write the weight / BatchNorm gradients of
+    `params` straight into `views` (preallocated fp32 tensors of the parameters' shapes, zeroed once per step by their
+    owner) and hand autograd views of them -- no accumulate kernels.  The latest owner of a parameter wins; entries of
+    parameters that no longer exist are dropped here and can never be hit: a sink is looked up by id() AND checked
+    against a weak reference, because Python hands the id of a dead parameter to the next object allocated there -- a
+    new model would otherwise write its gradients into a finished trainer's buffer, on top of that trainer's last step."""
+    for k in [k for k, (ref, _) in _GRAD_SINK.items() if ref() is None]:
+        del _GRAD_SINK[k]
+    for p, v in zip(params, views):
+        _GRAD_SINK[id(p)] = (weakref.ref(p), v)
+
+
+def clear_grad_sink(params=None):
+    """Forget the sink of `params` (None: every sink): their gradients go the ordinary autograd way again."""
+    if params is None:
+        _GRAD_SINK.clear()
+        return
+    for p in params:
+        ent = _GRAD_SINK.get(id(p))
+        if ent is not None and ent[0]() is p:
+            del _GRAD_SINK[id(p)]
 
 
 def _sink(param, shape=None):
     if param is None or not isinstance(param, nn.Parameter):
         return None
-    v = _GRAD_SINK.get(id(param))
-    if v is None or not v.is_cuda or v.dtype != torch.float32 or v.numel() != param.numel() or not v.is_contiguous():
+    ent = _GRAD_SINK.get(id(param))
+    if ent is None or ent[0]() is not param:
+        return None
+    v = ent[1]
+    if not v.is_cuda or v.dtype != torch.float32 or v.numel() != param.numel() or not v.is_contiguous():
         return None
     return v.view(shape if shape is not None else param.shape)      # a fresh tensor object every time
 

@@ -155,7 +155,7 @@ class FlatGradients:
         self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
         self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, offsets)]
         if self.flat.is_cuda:
-            modules.set_grad_sink({id(p): v for p, v in zip(self.params, self.views)})
+            modules.set_grad_sink(self.params, self.views)
 
     def zero(self):
         for p in self.params:
