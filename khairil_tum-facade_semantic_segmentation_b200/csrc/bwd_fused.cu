@@ -69,6 +69,8 @@ struct BwdFusedArgs {
     // shared-memory byte offsets from the 1024-aligned base; per-stage buffers are stage_stride apart
     uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, stage_stride, bytes_a, bytes_b;
     int coef_ld;
+    int coef_global;             // 1: every per-column coefficient is formed from the layers' arrays on the fly (no shared tables);
+                                 // 2: only layer l-1's (the T2 phase) -- layer l's three tables (sc, cb, cc) stay in shared memory
     long long *dbg_buf;
     int dbg;                     // PN2_BWD_DBG bit mask (profiling experiments): 1 skip wgrad MMAs, 2 skip statistics MMAs, 4 skip T1/T2
 };
@@ -79,6 +81,8 @@ __device__ __forceinline__ void bf_red_add_f32(float *p, float v) {
 __device__ __forceinline__ void bf_red_add_v4_f32(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// un-swizzled K-major descriptor with zero strides: every core matrix of the operand is the 128 bytes at saddr
+__device__ __forceinline__ uint64_t make_desc_ones(uint32_t saddr) { return (1ull << 46) | (uint64_t)((saddr >> 4) & 0x3fff); }
 __device__ __forceinline__ void bf_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -99,6 +103,11 @@ __device__ __forceinline__ void bf_mbar_arrive(uint64_t *bar) {
 // eight consecutive per-column coefficients (c0 % 8 == 0, tables 32-byte aligned): two LDS.128 instead of eight LDS
 __device__ __forceinline__ void ld_coef8(const float *tab, int c0, float (&v)[8]) {
     const float4 lo = *reinterpret_cast<const float4 *>(tab + c0), hi = *reinterpret_cast<const float4 *>(tab + c0 + 4);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+__device__ __forceinline__ void ldg_coef8(const float *tab, int c0, float (&v)[8]) {
+    const float4 lo = __ldg(reinterpret_cast<const float4 *>(tab + c0)), hi = __ldg(reinterpret_cast<const float4 *>(tab + c0 + 4));
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 }
 
@@ -144,7 +153,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
     // zhat = pis.z + pmi (pmi = -mean.invstd)
     float *const coef = reinterpret_cast<float *>(smem + a.o_coef);
     const int cl = a.coef_ld;
-    float *const c_sc = coef, *const c_sh = coef + cl, *const c_b = coef + 2 * cl, *const c_c = coef + 3 * cl;
+    // (coef_global 2 keeps three tables only: sc, cb, cc at 0, 1, 2 -- the shift table is not needed by da_mode 1)
+    float *const c_sc = coef, *const c_sh = coef + (a.coef_global == 2 ? 0 : cl), *const c_b = coef + (a.coef_global == 2 ? 1 : 2) * cl,
+                 *const c_c = coef + (a.coef_global == 2 ? 2 : 3) * cl;
     float *const p_sc = coef + 4 * cl, *const p_sh = coef + 5 * cl, *const p_is = coef + 6 * cl, *const p_mi = coef + 7 * cl;
     const bool prev = a.p_scale != nullptr;
     const int S = a.stages, AB = a.acc_bufs;
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
         mbar_init(&bar_done, 1);
         mbar_init_fence();
     }
-    for (int c = tid; c < cl; c += kBfThreads) {
+    for (int c = a.coef_global == 1 ? cl : tid; c < cl; c += kBfThreads) {
         float sc = 0.f, sh = 0.f, cb = 0.f, cc = 0.f;
         if (c < a.N && a.da_mode != 3) {
             sc = a.scale[c];
@@ -168,13 +179,17 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                 cc = -sc * a.dbeta[c] * a.inv_m - cb * a.mean[c];
             }
         }
-        c_sc[c] = sc; c_sh[c] = sh; c_b[c] = cb; c_c[c] = cc;
+        if (a.coef_global != 2) c_sh[c] = sh;
+        c_sc[c] = sc; c_b[c] = cb; c_c[c] = cc;
+        if (a.coef_global) continue;
         float ps = 0.f, ph = 0.f, pi = 0.f, pm = 0.f;
         if (prev && c < a.K) { ps = a.p_scale[c]; ph = a.p_shift[c]; pi = a.p_invstd[c]; pm = -a.p_mean[c] * pi; }
         p_sc[c] = ps; p_sh[c] = ph; p_is[c] = pi; p_mi[c] = pm;
     }
-    if (a.want_stats && a.ones_col < 0)     // the all-ones K-major B operand of the S1 product: [16 n-rows x 128 k] bf16 = 4 KB
-        for (int i = tid; i < 4096 / 4; i += kBfThreads) reinterpret_cast<uint32_t *>(s_ones)[i] = 0x3f803f80u;
+    // the all-ones K-major B operand of the S1 product: ONE 128-byte core matrix (8 n-rows x 8 k) in the un-swizzled layout,
+    // read for every (n group, k step) through a descriptor whose strides are 0 -- every element is 1.0, so 128 bytes stand in
+    // for the [16 x 128] tile (it used to be a 4 KB swizzled tile: the bytes that kept the 128-wide layers at one stage)
+    if (a.want_stats && a.ones_col < 0 && tid < 32) reinterpret_cast<uint32_t *>(s_ones)[tid] = 0x3f803f80u;
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -242,8 +257,26 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], cb[8], cc[8];
-                    ld_coef8(c_sc, c0, sc); ld_coef8(c_b, c0, cb); ld_coef8(c_c, c0, cc);
-                    if (a.da_mode == 0 || a.da_mode == 2) ld_coef8(c_sh, c0, sh);
+                    if (a.coef_global == 1) {
+                        // (same expressions as the shared tables of the prologue)
+                        ldg_coef8(a.scale, c0, sc);
+                        if (a.da_mode == 0 || a.da_mode == 2) ldg_coef8(a.shift, c0, sh);
+                        if (a.mean) {
+                            float dg[8], is[8], db[8], mu[8];
+                            ldg_coef8(a.dgamma, c0, dg); ldg_coef8(a.invstd, c0, is); ldg_coef8(a.dbeta, c0, db); ldg_coef8(a.mean, c0, mu);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                cb[e] = -sc[e] * dg[e] * is[e] * a.inv_m;
+                                cc[e] = -sc[e] * db[e] * a.inv_m - cb[e] * mu[e];
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) cb[e] = cc[e] = 0.0f;
+                        }
+                    } else {
+                        ld_coef8(c_sc, c0, sc); ld_coef8(c_b, c0, cb); ld_coef8(c_c, c0, cc);
+                        if (a.da_mode == 0 || a.da_mode == 2) ld_coef8(c_sh, c0, sh);
+                    }
                     // (all of the thread's units are loaded before any arithmetic: 2 x <= 4 LDS.128 in flight instead of a
                     //  load -> compute -> store chain per unit; the loop bodies are fully unrolled and predicated on um.iters)
                     uint4 g4[4], z4[4];
@@ -302,7 +335,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
                     float sc[8], sh[8], is[8], mi[8];
-                    ld_coef8(p_sc, c0, sc); ld_coef8(p_sh, c0, sh); ld_coef8(p_is, c0, is); ld_coef8(p_mi, c0, mi);
+                    if (a.coef_global) {
+                        ldg_coef8(a.p_scale, c0, sc); ldg_coef8(a.p_shift, c0, sh); ldg_coef8(a.p_invstd, c0, is); ldg_coef8(a.p_mean, c0, mi);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) mi[e] = -mi[e] * is[e];
+                    } else {
+                        ld_coef8(p_sc, c0, sc); ld_coef8(p_sh, c0, sh); ld_coef8(p_is, c0, is); ld_coef8(p_mi, c0, mi);
+                    }
                     uint4 x4[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -399,22 +438,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                     for (int r = 0; r < kBfBM / 16; ++r)
                         umma_bf16(d_c, ad + (uint64_t)(128 * r), bd + (uint64_t)(128 * r), idesc_c, r ? 1u : (uint32_t)(t != 0));
                     if (a.ones_col < 0) {
-                        const uint64_t as = make_desc(smem_addr(s_stage), 0, 1024), b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                        const uint64_t as = make_desc(smem_addr(s_stage), 0, 1024), b1 = make_desc_ones(smem_addr(s_ones));
                         const uint32_t d1 = tmem + (uint32_t)a.off_s1;
 #pragma unroll
                         for (int r = 0; r < kBfBM / 16; ++r)
-                            umma_bf16(d1, as + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, r ? 1u : (uint32_t)(t != 0));
+                            umma_bf16(d1, as + (uint64_t)(128 * r), b1, idesc_s1, r ? 1u : (uint32_t)(t != 0));
                     }
                 } else if (a.want_stats && !(a.dbg & 2)) {
                     const uint64_t ad = make_desc(smem_addr(s_stage), lbo_k, 1024), b2 = make_desc(smem_addr(s_x), lbo_k, 1024);
-                    const uint64_t b1 = make_desc(smem_addr(s_ones), 0, 1024);
+                    const uint64_t b1 = make_desc_ones(smem_addr(s_ones));
                     const uint32_t d2 = tmem + (uint32_t)a.off_s2, d1 = tmem + (uint32_t)a.off_s1;
                     const bool own_ones = a.ones_col < 0;
 #pragma unroll
                     for (int r = 0; r < kBfBM / 16; ++r) {
                         const uint32_t acc = r ? 1u : (uint32_t)(t != 0);
                         umma_bf16(d2, ad + (uint64_t)(128 * r), b2 + (uint64_t)(128 * r), idesc_s2, acc);
-                        if (own_ones) umma_bf16(d1, ad + (uint64_t)(128 * r), b1 + (uint64_t)((r >> 2) * 128 + (r & 3) * 2), idesc_s1, acc);
+                        if (own_ones) umma_bf16(d1, ad + (uint64_t)(128 * r), b1, idesc_s1, acc);
                     }
                 }
                 BF_STAMP(13);
@@ -609,11 +648,13 @@ static int bf_round_up(int v, int m) { return (v + m - 1) / m * m; }
 struct BwdFusedPlan {
     bool ok;
     int nS, kS, K_pad, k_store, tmem_cols, acc_bufs, off_dw, off_s2, off_s1, ones_col, s2_cols, coef_ld, stages, load_x, alias_act, combined;
+    int coef_global;
     uint32_t o_w, o_da, o_z, o_x, o_act, o_stage, o_ones, o_coef, o_pool, stage_stride, bytes_a, bytes_b;
     size_t dyn_smem;
 };
 
-static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode, bool prev, bool want_dx, bool want_dw) {
+static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode, bool prev, bool want_dx, bool want_dw,
+                                   bool allow_coef_global = true) {
     BwdFusedPlan p;
     memset(&p, 0, sizeof(p));
     if (N < 8 || N > kBfMaxC || N % 8 != 0 || K < 1 || ldx > kBfMaxC || ldx % 8 != 0 || bf_round_up(K, 16) > kBfMaxC) return p;
@@ -659,12 +700,29 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     if (da_mode == 2) o += (uint32_t)bf_round_up(8 * N * 4, 1024);
     p.stage_stride = o;
     const uint32_t w_bytes = want_dx ? (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024) : 0u;
-    const uint32_t ones_bytes = (prev && p.ones_col < 0) ? 4096u : 0u;
+    const uint32_t ones_bytes = (prev && p.ones_col < 0) ? 128u : 0u;       // one core matrix (see the kernel's prologue)
     p.coef_ld = bf_round_up(N > p.kS * 64 ? N : p.kS * 64, 64);
-    const uint32_t coef_bytes = (uint32_t)(8 * p.coef_ld * sizeof(float));
-    const uint32_t budget = 227 * 1024 - 2048;                 // (static shared: barriers; 1 KB alignment slack)
-    p.stages = kBfMaxStages;
-    while (p.stages > 1 && (size_t)p.stages * p.stage_stride + w_bytes + ones_bytes + coef_bytes + 1024 > budget) --p.stages;
+    uint32_t coef_bytes = (uint32_t)(8 * p.coef_ld * sizeof(float));
+    // dynamic + static shared memory <= 227 KB: the kernel's static part is 208 bytes (barriers), 256 reserved; the 1 KB
+    // alignment slack is added below
+    const uint32_t budget = 227 * 1024 - 256;
+    auto stages_with = [&](uint32_t cb) {
+        int st = kBfMaxStages;
+        while (st > 1 && (size_t)st * p.stage_stride + w_bytes + ones_bytes + cb + 1024 > budget) --st;
+        return st;
+    };
+    p.stages = stages_with(coef_bytes);
+    // The 128-wide layers: two 96 KB stages + the 32 KB weight image leave < 2 KB.  With 4 KB of coefficient tables (and a
+    // 4 KB ones tile) they ran ONE stage -- load -> transform -> MMA -> epilogue -> store strictly in turn, 15.5 k cycles per
+    // tile.  Then: layer l-1's coefficients (T2) straight from its arrays (__ldg, L1-resident), and layer l's three derived
+    // tables (1.5 KB) in shared memory when the shift is not needed (da_mode 1), else from the arrays as well.
+    static const bool coef_global_on = !(getenv("PN2_BWD_COEF_SMEM") && atoi(getenv("PN2_BWD_COEF_SMEM")) == 1);
+    if (allow_coef_global && coef_global_on && p.stages < 2) {
+        const uint32_t three = (uint32_t)(3 * p.coef_ld * sizeof(float));
+        if ((da_mode == 1 || da_mode == 3) && stages_with(three) >= 2) { p.coef_global = 2; coef_bytes = three; }
+        else if (stages_with(0) >= 2) { p.coef_global = 1; coef_bytes = 0; }
+        p.stages = stages_with(coef_bytes);
+    }
     if ((size_t)p.stage_stride + w_bytes + ones_bytes + coef_bytes + 1024 > budget) return p;
     o = (uint32_t)p.stages * p.stage_stride;
     p.o_w = o; o += w_bytes;
@@ -737,14 +795,19 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
                 "mlp_bwd_layer: leading dimensions");
     PN2_REQUIRE((L->da_mode == 2 || L->ldda % 8 == 0) && (L->da_mode == 3 || L->ldz % 8 == 0) && (!L->X || L->ldx % 8 == 0) && (!want_dx || L->lddx % 8 == 0),
                 "mlp_bwd_layer: bf16 rows need a 16-byte row pitch");
-    const BwdFusedPlan p = bwd_fused_plan(L->K, L->N, L->X ? L->ldx : bf_round_up(L->K, 8), want_dx ? L->lddx : 0, L->da_mode, prev, want_dx, want_dw);
+    // (coefficients straight from the arrays need 16-byte aligned arrays: float4 loads)
+    auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    const bool arrays_aligned = al16(L->scale) && al16(L->shift) && al16(L->mean) && al16(L->invstd) && al16(L->dgamma) && al16(L->dbeta) &&
+                                al16(L->prev_scale) && al16(L->prev_shift) && al16(L->prev_mean) && al16(L->prev_invstd);
+    const BwdFusedPlan p = bwd_fused_plan(L->K, L->N, L->X ? L->ldx : bf_round_up(L->K, 8), want_dx ? L->lddx : 0, L->da_mode, prev, want_dx, want_dw,
+                                          arrays_aligned);
     if (!p.ok || !bwd_fused_enabled()) {
         set_error("mlp_bwd_layer: layer K=%d N=%d is not supported by the fused kernel (see pn2_mlp_bwd_layer_supported)", L->K, L->N);
         return PN2_ERR_UNSUPPORTED;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+        cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
         if (e != cudaSuccess) {
             set_error("mlp_bwd_layer: shared-memory opt-in failed: %s", cudaGetErrorString(e));
             cudaGetLastError();
@@ -787,7 +850,7 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.ones_col = p.ones_col; a.s2_cols = p.s2_cols; a.o_coef = p.o_coef; a.coef_ld = p.coef_ld;
     a.o_w = p.o_w; a.o_da = p.o_da; a.o_z = p.o_z; a.o_x = p.o_x; a.o_act = p.o_act; a.o_stage = p.o_stage; a.o_ones = p.o_ones;
     a.stage_stride = p.stage_stride; a.bytes_a = p.bytes_a; a.bytes_b = p.bytes_b; a.stages = p.stages; a.acc_bufs = p.acc_bufs;
-    a.load_x = p.load_x; a.alias_act = p.alias_act; a.combined = p.combined;
+    a.load_x = p.load_x; a.alias_act = p.alias_act; a.combined = p.combined; a.coef_global = p.coef_global;
     a.o_pool = p.o_pool; a.dOut = L->dOut; a.arg = L->arg;
     a.defer_store_wait = (want_dx && p.o_stage != p.o_da && p.stages >= 2) ? 1 : 0;
     { const char *e = getenv("PN2_BWD_DBG"); a.dbg = e ? atoi(e) : 0; }
