@@ -836,7 +836,7 @@ extern "C" int pn2_mlp_bwd_layer(const pn2_bwd_layer *L, void *stream) {
     a.M = L->M; a.K = L->K; a.N = L->N; a.K_pad = p.K_pad; a.k_store = p.k_store; a.nS = p.nS; a.kS = p.kS;
     a.da_mode = L->da_mode; a.want_dx = want_dx; a.want_dw = want_dw; a.want_stats = prev;
     const int64_t m_tiles = (L->M + kBfBM - 1) / kBfBM;
-    int64_t grid = kNumSMs;                                  // one CTA per SM, pipelined over its tiles
+    int64_t grid = sm_budget();                              // one CTA per SM, pipelined over its tiles (pn2_set_sm_budget: fewer)
     if (grid > m_tiles) grid = m_tiles;
     a.K_ld4 = bf_round_up(L->K, 4);
     if (want_dw) {
