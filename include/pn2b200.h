@@ -318,6 +318,15 @@ int pn2_pool_bn_relu_bwd_dz(const float *dOut, const int32_t *arg, const void *Z
 int pn2_three_nn(const float *xyz1, int64_t aB, int64_t aN, int64_t aC, const float *xyz2,
                  int64_t cB, int64_t cN, int64_t cC, int B, int N, int S, int64_t *idx3, float *w3,
                  void *stream);
+/* The same result through a cell grid over the coarse cloud (csrc/ballgrid.cu: the ball query's build kernel with cells
+ * sized from the cloud's density, one thread per fine point over the 27 cells around it).  A query whose third neighbour
+ * is not provably inside its 27 cells -- and every query of a cloud the grid refuses (NaN/Inf, coordinates so large that
+ * fp32 rounding of the a1-order distance reaches the cell size) -- takes the full index-order scan inside the same launch;
+ * fallback_count (may be NULL) is incremented once per such query.  workspace: pn2_ball_grid_workspace_bytes(B, S) bytes,
+ * 16-byte aligned. */
+int pn2_three_nn_grid(const float *xyz1, int64_t aB, int64_t aN, int64_t aC, const float *xyz2,
+                      int64_t cB, int64_t cN, int64_t cC, int B, int N, int S, int64_t *idx3, float *w3,
+                      void *workspace, size_t workspace_bytes, unsigned *fallback_count, void *stream);
 /* rows[(b,n), 0:D1]      = points1[b,n,:]                 (may be NULL, D1 = 0)
  * rows[(b,n), D1:D1+D2]  = (p2[i0]*w0 + p2[i1]*w1) + p2[i2]*w2   (products rounded, :303)
  * rows[(b,n), D1+D2:ld]  = 0.   points1 [B,N,D1] strides (pB,pN,pD); points2 [B,S,D2] strides (qB,qN,qD). */

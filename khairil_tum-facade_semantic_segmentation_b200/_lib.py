@@ -73,6 +73,7 @@ _SIGNATURES = {
     "pn2_bn_relu_bwd_dz": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _p, _i, _i, _p]),
     "pn2_pool_bn_relu_bwd_dz": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _i, _i, _p]),
     "pn2_three_nn": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p, _p, _p]),
+    "pn2_three_nn_grid": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p, _p, _p, _z, _p, _p]),
     "pn2_interp_concat": (_i, [_p, _l, _l, _l, _p, _l, _l, _l, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pn2_interp_bwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pn2_head_tail_fwd": (_i, [_p, _i, _p, _p, _p, _p, _l, _i, _i, _f, _p, _p, _p, _i, _p, _p]),

@@ -18,6 +18,8 @@
 // at most one cell away.  Clouds that fail the check (huge un-centred coordinates, where the reference's own test is
 // mostly rounding noise) or contain NaN (which the reference counts as inside) take the index-order scan instead, inside
 // the same launch.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace pn2 {
@@ -100,9 +102,22 @@ bg_build_kernel(const float *__restrict__ xyz, int64_t sB, int64_t sN, int64_t s
         // R^2 bound from the box, the rounding-error budget of the fp32 expanded-form distance against the cell margin
         double R2 = 0.0;
         for (int d = 0; d < 3; ++d) { const double m = fmax(fabs((double)l[d]), fabs((double)h[d])); R2 += m * m; }
-        const double rr = (double)radius * (double)radius;
-        const bool margin_ok = !any_bad && radius > 0.0f && ((double)r2 + ldexp(R2, -18) <= rr * 1.010025) && ((double)r2 <= rr * 1.0001);
-        double cell = 1.01 * (double)radius;
+        // radius <= 0 (3-NN search, no radius given): cells of about two point spacings, the spacing estimated from the box both
+        // as a volume and as a surface (facade clouds are surfaces inside a tall box) -- any cell size is correct (the search
+        // falls back to the full scan for a query whose third neighbour is not provably inside its 27 cells), this only sets
+        // how many candidates a query looks at
+        double rad = (double)radius, r2d = (double)r2;
+        if (!(radius > 0.0f) && !any_bad && N > 0) {
+            double e[3];
+            for (int d = 0; d < 3; ++d) e[d] = (double)h[d] - (double)l[d];
+            const double vol = e[0] * e[1] * e[2];
+            const double area = fmax(e[0] * e[1], fmax(e[1] * e[2], e[0] * e[2]));
+            rad = fmax(2.0 * cbrt(vol / (double)N), 2.5 * sqrt(area / (double)N)) / 1.01;
+            r2d = rad * rad;
+        }
+        const double rr = rad * rad;
+        const bool margin_ok = !any_bad && rad > 0.0 && (r2d + ldexp(R2, -18) <= rr * 1.010025) && (r2d <= rr * 1.0001);
+        double cell = 1.01 * rad;
         int gx = 1, gy = 1, gz = 1;
         if (margin_ok) {
             for (int it = 0; it < 64; ++it) {
@@ -303,6 +318,116 @@ bg_query_kernel(const float *__restrict__ xyz, int64_t sB, int64_t sN, int64_t s
     if (out_cnt && lane == 0) out_cnt[(int64_t)b * S + s] = c;
 }
 
+// ---- 3-NN through the same grid (pointnet2_utils.py:296-302) -----------------------------------------------------
+// One thread per fine point.  The coarse cloud is the gridded one; the candidates are the points of the 27 cells around
+// the query's (clamped) cell, the list keeps the three smallest (distance, index) pairs -- what three_nn_kernel's
+// index-order scan with its strict '<' keeps, whatever order the candidates come in.  The list is final when no point
+// OUTSIDE the 27 cells can enter it: such a point is at least D away from the query along one axis (D = the query's
+// distance to the nearest face of its block that has cells beyond it), its fp32 expanded-form distance is therefore
+// >= D^2 - err with err < 2^-18 R^2 (R^2 bounds |q|^2 and every |p|^2), and the test is
+// d_third < (0.995 D)^2 - 2^-17 R^2 (the 0.995 absorbs the fp32 rounding of the face coordinates: R / h < 60 by the build
+// kernel's margin check).  Queries that fail it (third neighbour farther than the block, fewer than three candidates,
+// NaN) and clouds without a grid take the full index-order scan -- same arithmetic, same result as three_nn_kernel.
+constexpr int kNn3Threads = 128;
+
+__device__ __forceinline__ void nn3_insert(float d, int j, float &d0, float &d1, float &d2, int &i0, int &i1, int &i2) {
+    if (d < d2 || (d == d2 && j < i2)) {
+        if (d < d1 || (d == d1 && j < i1)) {
+            d2 = d1; i2 = i1;
+            if (d < d0 || (d == d0 && j < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+            else { d1 = d; i1 = j; }
+        } else { d2 = d; i2 = j; }
+    }
+}
+
+__global__ void __launch_bounds__(kNn3Threads)
+nn3_grid_kernel(const float *__restrict__ xyz1, int64_t aB, int64_t aN, int64_t aC, const float *__restrict__ xyz2, int64_t cB,
+                int64_t cN, int64_t cC, int N, int S, const uint8_t *__restrict__ ws, int64_t *__restrict__ idx3,
+                float *__restrict__ w3, unsigned *__restrict__ fallbacks) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * kNn3Threads + threadIdx.x;
+    if (n >= N) return;
+    const uint8_t *base = ws + (size_t)b * bg_cloud_bytes(S);
+    const BgHeader hd = *reinterpret_cast<const BgHeader *>(base);
+    const int *cell_start = reinterpret_cast<const int *>(base + 32);
+    const float4 *sorted = reinterpret_cast<const float4 *>(base + 32 + (((size_t)(kBgMaxCells + 1) * 4 + 15) & ~(size_t)15));
+    const int *sidx = reinterpret_cast<const int *>(reinterpret_cast<const uint8_t *>(sorted) + (size_t)S * 16);
+    const float *qp = xyz1 + (int64_t)b * aB + (int64_t)n * aN;
+    const float qx = qp[0], qy = qp[aC], qz = qp[2 * aC];
+    const float qn = sq_norm3(qx, qy, qz);
+    float d0 = CUDART_INF_F, d1 = CUDART_INF_F, d2 = CUDART_INF_F;
+    int i0 = 0, i1 = 0, i2 = 0;
+    bool final_list = false;
+    if (hd.use_grid) {
+        const float h = 1.0f / hd.inv_h;
+        const int cx = bg_cell1(qx, hd.minx, hd.inv_h, hd.gx), cy = bg_cell1(qy, hd.miny, hd.inv_h, hd.gy),
+                  cz = bg_cell1(qz, hd.minz, hd.inv_h, hd.gz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, hd.gx - 1);
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= hd.gz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= hd.gy) continue;
+                const int row = (z * hd.gy + y) * hd.gx;
+                const int beg = cell_start[row + x0], end = cell_start[row + x1 + 1];
+                for (int src = beg; src < end; ++src) {
+                    const float4 p = sorted[src];
+                    nn3_insert(expanded_sqdist(qx, qy, qz, qn, p.x, p.y, p.z, p.w), sidx[src], d0, d1, d2, i0, i1, i2);
+                }
+            }
+        }
+        // distance to the nearest face of the block with cells beyond it, per axis (see the header comment)
+        float D = CUDART_INF_F;
+        const float q[3] = {qx, qy, qz}, lo[3] = {hd.minx, hd.miny, hd.minz};
+        const int c[3] = {cx, cy, cz}, g[3] = {hd.gx, hd.gy, hd.gz};
+        float R2 = qn;
+        float m2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (c[a] >= 2) D = fminf(D, q[a] - (lo[a] + (float)(c[a] - 1) * h));
+            if (c[a] <= g[a] - 3) D = fminf(D, (lo[a] + (float)(c[a] + 2) * h) - q[a]);
+            const float m = fmaxf(fabsf(lo[a]), fabsf(lo[a] + (float)g[a] * h));
+            m2 += m * m;
+        }
+        R2 = fmaxf(R2, m2 * 1.0001f);
+        const float lim = D == CUDART_INF_F ? CUDART_INF_F : (0.995f * D) * (0.995f * D) - R2 * 7.62939453125e-6f;   // 2^-17
+        final_list = D > 0.0f && d2 < lim;       // (d2 == inf or NaN, a negative D: not final)
+    }
+    if (!final_list) {
+        if (fallbacks) atomicAdd(fallbacks, 1u);
+        d0 = d1 = d2 = CUDART_INF_F;
+        i0 = i1 = i2 = 0;
+        const float *coarse = xyz2 + (int64_t)b * cB;
+        for (int j = 0; j < S; ++j) {
+            const float *p = coarse + (int64_t)j * cN;
+            const float x = p[0], y = p[cC], z = p[2 * cC];
+            const float d = expanded_sqdist(qx, qy, qz, qn, x, y, z, sq_norm3(x, y, z));
+            if (d < d2) {
+                if (d < d1) {
+                    d2 = d1; i2 = i1;
+                    if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+                    else { d1 = d; i1 = j; }
+                } else { d2 = d; i2 = j; }
+            }
+        }
+    }
+    const int K3 = S < 3 ? S : 3;
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(d0, 1e-8f));
+    const float r1 = K3 > 1 ? __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f)) : 0.0f;
+    const float r2 = K3 > 2 ? __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f)) : 0.0f;
+    float norm = r0;
+    if (K3 > 1) norm = __fadd_rn(norm, r1);
+    if (K3 > 2) norm = __fadd_rn(norm, r2);
+    const int64_t o = ((int64_t)b * N + n) * 3;
+    idx3[o + 0] = i0;
+    idx3[o + 1] = K3 > 1 ? i1 : 0;
+    idx3[o + 2] = K3 > 2 ? i2 : 0;
+    w3[o + 0] = __fdiv_rn(r0, norm);
+    w3[o + 1] = K3 > 1 ? __fdiv_rn(r1, norm) : 0.0f;
+    w3[o + 2] = K3 > 2 ? __fdiv_rn(r2, norm) : 0.0f;
+}
+
 }  // namespace pn2
 
 using namespace pn2;
@@ -343,4 +468,25 @@ extern "C" int pn2_query_ball_point_grid(const float *xyz, int64_t sB, int64_t s
                                                                               (const uint8_t *)workspace, out_idx, out_cnt);
     count_launch();
     return check_launch("ball_grid_query");
+}
+
+extern "C" int pn2_three_nn_grid(const float *xyz1, int64_t aB, int64_t aN, int64_t aC, const float *xyz2, int64_t cB, int64_t cN,
+                                 int64_t cC, int B, int N, int S, int64_t *idx3, float *w3, void *workspace, size_t workspace_bytes,
+                                 unsigned *fallback_count, void *stream) {
+    PN2_REQUIRE(xyz1 && xyz2 && idx3 && w3 && workspace, "three_nn (grid): null pointer");
+    PN2_REQUIRE(B >= 0 && N >= 0 && S >= 1, "three_nn (grid): bad sizes B=%d N=%d S=%d", B, N, S);
+    PN2_REQUIRE(B <= 65535, "three_nn (grid): B too large");
+    PN2_REQUIRE(workspace_bytes >= pn2_ball_grid_workspace_bytes(B, S), "three_nn (grid): workspace too small");
+    PN2_REQUIRE(((uintptr_t)workspace & 15) == 0, "three_nn (grid): workspace must be 16-byte aligned");
+    if (B == 0 || N == 0) return PN2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bg_build_kernel<<<B, kBgBuildThreads, 0, st>>>(xyz2, cB, cN, cC, S, 0.0f, 0.0f, (uint8_t *)workspace);      // radius 0: cells from the density
+    count_launch();
+    int rc = check_launch("three_nn (grid) build");
+    if (rc != PN2_OK) return rc;
+    dim3 grid((N + kNn3Threads - 1) / kNn3Threads, B);
+    nn3_grid_kernel<<<grid, kNn3Threads, 0, st>>>(xyz1, aB, aN, aC, xyz2, cB, cN, cC, N, S, (const uint8_t *)workspace, idx3, w3,
+                                                  fallback_count);
+    count_launch();
+    return check_launch("three_nn (grid)");
 }

@@ -267,8 +267,18 @@ def query_ball_point(radius, nsample, xyz, new_xyz, return_count=False):
     return (out, cnt) if return_count else out
 
 
-def three_nn(xyz1, xyz2):
-    """pointnet2_utils.py:296-302 -- (idx [B,N,3] int64, weight [B,N,3]) of the three nearest xyz2 points."""
+# three_nn through the cell grid of csrc/ballgrid.cu (pn2_three_nn_grid): identical output (tests/test_gpu_ops.py), OFF by default --
+# measured on B200, 32 facade clouds: 4096 fine / 1024 coarse 96.6 us vs 108.8 us for the index-order scan, 1024 / 256 60.8 vs 38.5 us;
+# with smaller cells (43 instead of 92 candidates per query) 142.6 / 67.8 us: one thread per query reads its candidates with
+# divergent 16-byte loads, which costs what the scan's one shared-memory broadcast per candidate saves, and a single query that
+# falls back to the full scan holds its whole warp.  It needs queries processed in cell order to pay.
+THREE_NN_GRID = False
+_NN_GRID_MIN_S = 256
+
+
+def three_nn(xyz1, xyz2, fallback_count=None):
+    """pointnet2_utils.py:296-302 -- (idx [B,N,3] int64, weight [B,N,3]) of the three nearest xyz2 points.
+    fallback_count: optional 1-element int32 CUDA tensor; the grid search adds the number of queries that took the full scan."""
     _xyz3(xyz1, "xyz1"), _xyz3(xyz2, "xyz2")
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
@@ -276,6 +286,12 @@ def three_nn(xyz1, xyz2):
     w = _out((B, N, 3), torch.float32, xyz1.device)
     aB, aN, aC = xyz1.stride()
     cB, cN, cC = xyz2.stride()
+    if THREE_NN_GRID and _NN_GRID_MIN_S <= S <= _BALL_GRID_MAX_N:
+        nbytes = _lib.load().pn2_ball_grid_workspace_bytes(B, S)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz1.device)
+        call("pn2_three_nn_grid", ptr(xyz1), aB, aN, aC, ptr(xyz2), cB, cN, cC, B, N, S, ptr(idx), ptr(w), ptr(ws), nbytes,
+             ptr(fallback_count), stream())
+        return idx, w
     call("pn2_three_nn", ptr(xyz1), aB, aN, aC, ptr(xyz2), cB, cN, cC, B, N, S, ptr(idx), ptr(w), stream())
     return idx, w
 

@@ -4,6 +4,8 @@ features are bit-exact too (same fp32 operation order)."""
 import hashlib
 
 import numpy as np
+import importlib
+
 import pytest
 import torch
 
@@ -226,6 +228,61 @@ def test_three_nn_exact_ties_take_the_lower_index(pn2):
     np.testing.assert_allclose(w.cpu().numpy(), 1.0 / 3.0, rtol=1e-6)
     widx, _, ww = C.three_nn(fine.numpy(), coarse.numpy())
     assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(w.cpu().numpy(), ww)
+
+
+def _nn3_both_paths(pn2, fine, coarse):
+    ops = importlib.import_module("khairil_tum-facade_semantic_segmentation_b200.ops")
+    count = torch.zeros(1, dtype=torch.int32, device=DEV)
+    try:
+        ops.THREE_NN_GRID = True
+        gi, gw = ops.three_nn(fine, coarse, fallback_count=count)
+    finally:
+        ops.THREE_NN_GRID = False
+    si, sw = ops.three_nn(fine, coarse)
+    return (gi, gw), (si, sw), int(count.item())
+
+
+@pytest.mark.parametrize("case", ["facade_levels", "cube", "plane", "queries_outside", "lattice_ties", "duplicates", "offset_512", "nan"])
+def test_three_nn_grid_equals_the_index_order_scan(pn2, case):
+    """csrc/ballgrid.cu nn3_grid_kernel vs three_nn_kernel: indices AND weights identical, bit for bit, whatever the cloud --
+    the grid search only accepts a list it can prove final and scans everything otherwise"""
+    g = torch.Generator().manual_seed(5)
+    B = 3
+    if case == "facade_levels":            # the network's own pairs: coarse = FPS samples of fine (fp1: 4096 / 1024, fp2: 1024 / 256)
+        fine = I.facade_xyz(B, 4096, 7).to(DEV)
+        idx = pn2.farthest_point_sample(fine, 1024, start=I.start_indices(B, 4096, 1).to(DEV))
+        coarse = torch.gather(fine, 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    elif case == "cube":
+        fine, coarse = I.cube_xyz(B, 3000, 1).to(DEV), I.cube_xyz(B, 700, 2).to(DEV)
+    elif case == "plane":                  # a degenerate box: the density estimate must not break anything
+        fine, coarse = torch.rand(B, 2000, 3, generator=g), torch.rand(B, 512, 3, generator=g)
+        fine[:, :, 2] = 0.25
+        coarse[:, :, 2] = 0.25
+        fine, coarse = fine.to(DEV), coarse.to(DEV)
+    elif case == "queries_outside":        # fine points far outside the coarse cloud's box (clamped cells)
+        coarse = (torch.rand(B, 600, 3, generator=g) * 0.2 + 0.4).to(DEV)
+        fine = (torch.rand(B, 2000, 3, generator=g) * 3.0 - 1.0).to(DEV)
+    elif case == "lattice_ties":           # a regular lattice: many exactly equal distances, the lower index must win
+        ax = torch.arange(8, dtype=torch.float32) * 0.125
+        lat = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, 512, 3)
+        coarse = lat[:, torch.randperm(512, generator=g)].expand(B, -1, -1).contiguous().to(DEV)
+        fine = (lat + 0.0625).expand(B, -1, -1).contiguous().to(DEV)          # cell centres: 8 equidistant corners each
+    elif case == "duplicates":
+        fine, coarse = I.facade_xyz(B, 1500, 2).to(DEV), I.facade_xyz(B, 400, 3, dup_frac=0.5).to(DEV)
+    elif case == "offset_512":             # un-centred coordinates: the build refuses the grid (rounding error > cell margin)
+        fine, coarse = I.facade_xyz(B, 1024, 2).to(DEV) + 512.0, I.facade_xyz(B, 300, 3).to(DEV) + 512.0
+    else:                                   # NaN in the coarse cloud of one batch element
+        fine, coarse = I.facade_xyz(B, 1024, 2).to(DEV), I.facade_xyz(B, 300, 3).to(DEV)
+        coarse[1, 17, 1] = float("nan")
+    (gi, gw), (si, sw), fallbacks = _nn3_both_paths(pn2, fine, coarse)
+    assert torch.equal(gi, si), case
+    assert torch.equal(torch.nan_to_num(gw, nan=-7.0), torch.nan_to_num(sw, nan=-7.0)), case
+    total = fine.shape[0] * fine.shape[1]
+    if case in ("facade_levels", "cube", "duplicates"):
+        assert fallbacks < 0.25 * total, (case, fallbacks, total)       # the grid is doing the work
+    if case == "offset_512":
+        assert fallbacks == total
+    print("three_nn grid [%s]: %d of %d queries took the full scan" % (case, fallbacks, total))
 
 
 def test_index_points_forward_backward(pn2):
