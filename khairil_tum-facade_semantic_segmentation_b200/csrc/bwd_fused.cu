@@ -327,20 +327,21 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
             if (ttid == 0) BF_STAMP(4);
             if (a.load_x) mbar_wait(&full_b[s], u & 1u);
             if (a.alias_act) named_bar_sync(1, kBfXf);       // every thread is done reading Z before act overwrites it
-            // ---- T2: X tile -> act (weight-gradient operand) and zhat in place (statistics operand) ----
+            // ---- T2: X tile -> act (weight-gradient operand).  The statistics product reads the X tile AS LOADED: S2 = sum dA'.z, and
+            //      the finalize forms dgamma = invstd . (S2 - mean . S1) -- sum dA'.zhat without a zhat tile (it used to be computed and
+            //      written back in place here: 8 FMAs, 4 packs and a 16-byte store per unit of the pipeline's longest stage; the
+            //      operand is now the stored bf16 z itself instead of a second rounding of it) ----
             if (prev && !(a.dbg & 4)) {
                 for (int j = 0; j < a.kS; ++j) {
                     const int nch = min(8, (a.K - 64 * j) >> 3);
                     const UnitMap um = unit_map(ttid, nch);
                     const int c0 = 64 * j + 8 * um.chunk;
                     if (um.chunk >= nch) continue;
-                    float sc[8], sh[8], is[8], mi[8];
+                    float sc[8], sh[8];
                     if (a.coef_global) {
-                        ldg_coef8(a.p_scale, c0, sc); ldg_coef8(a.p_shift, c0, sh); ldg_coef8(a.p_invstd, c0, is); ldg_coef8(a.p_mean, c0, mi);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) mi[e] = -mi[e] * is[e];
+                        ldg_coef8(a.p_scale, c0, sc); ldg_coef8(a.p_shift, c0, sh);
                     } else {
-                        ld_coef8(p_sc, c0, sc); ld_coef8(p_sh, c0, sh); ld_coef8(p_is, c0, is); ld_coef8(p_mi, c0, mi);
+                        ld_coef8(p_sc, c0, sc); ld_coef8(p_sh, c0, sh);
                     }
                     uint4 x4[4];
 #pragma unroll
@@ -352,15 +353,14 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                         if (i < um.iters) {
                             const uint32_t off = (uint32_t)j * kBfSlab + sw128_offset(um.row0 + um.rstep * i, um.chunk);
                             uint4 a4;
-                            uint32_t *zw = reinterpret_cast<uint32_t *>(&x4[i]), *aw = reinterpret_cast<uint32_t *>(&a4);
+                            const uint32_t *zw = reinterpret_cast<const uint32_t *>(&x4[i]);
+                            uint32_t *aw = reinterpret_cast<uint32_t *>(&a4);
 #pragma unroll
                             for (int e2 = 0; e2 < 4; ++e2) {
                                 const float2 z = unpack_bf16x2(zw[e2]);
                                 aw[e2] = pack_bf16x2(fmaxf(fmaf(z.x, sc[2 * e2], sh[2 * e2]), 0.0f), fmaxf(fmaf(z.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.0f));
-                                zw[e2] = pack_bf16x2(fmaf(z.x, is[2 * e2], mi[2 * e2]), fmaf(z.y, is[2 * e2 + 1], mi[2 * e2 + 1]));
                             }
                             *reinterpret_cast<uint4 *>(s_act + off) = a4;
-                            *reinterpret_cast<uint4 *>(s_x + off) = x4[i];
                         }
                 }
                 if (a.ones_col >= 0) {
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
                         acc[a.K + c] = 0.0;
                     }
                     a.dbeta_prev[c] = (float)t1;
-                    a.dgamma_prev[c] = (float)t2;
+                    a.dgamma_prev[c] = (float)((t2 - (double)a.p_mean[c] * t1) * (double)a.p_invstd[c]);      // t2 = sum dA'.z (see T2)
                 }
                 if (tid == 0) *a.ticket = 0u;
             }

@@ -3,8 +3,9 @@
 Checked two ways:
 * against the per-step kernels it replaces (reduce / dz / data gradient / weight gradient: modules.FUSED_BWD off) on the
   same module, input and upstream gradient -- the two paths round the SAME quantities to bf16 (dZ, the masked
-  dA_{l-1}), so they agree to fp32 summation order -- except that the statistics' zhat operand is a bf16 tile here (an
-  fp32 value there): relative L2 error <= 6e-3 on every gradient (measured <= 2.3e-3);
+  dA_{l-1}), so they agree to fp32 summation order -- except that dgamma is formed here as invstd . (sum dA'.z - mean . sum dA')
+  from tensor-core products on the stored bf16 z (sum dA'.zhat with zhat in fp32 there): relative L2 error <= 6e-3 on
+  every gradient (measured <= 2.3e-3);
 * against the fp32 torch-CPU port of the reference modules (pointnet2_utils.py:161-202, :265-315): module-level
   gradient cosine >= 0.98, the repo's bf16 bar.
 Shapes cover: nsample-pooled set abstraction with a 3 + D wide first layer whose width is not a multiple of 4 (fixed-order
