@@ -149,14 +149,13 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
     uint8_t *const s_w = smem + a.o_w, *const s_ones = smem + a.o_ones;
-    // per-column coefficients: layer l  dz = sc.g + cb.z + cc (mask test sc.z + sh > 0), layer l-1  act = relu(psc.z + psh),
-    // zhat = pis.z + pmi (pmi = -mean.invstd)
+    // per-column coefficients: layer l  dz = sc.g + cb.z + cc (mask test sc.z + sh > 0), layer l-1  act = relu(psc.z + psh)
     float *const coef = reinterpret_cast<float *>(smem + a.o_coef);
     const int cl = a.coef_ld;
     // (coef_global 2 keeps three tables only: sc, cb, cc at 0, 1, 2 -- the shift table is not needed by da_mode 1)
     float *const c_sc = coef, *const c_sh = coef + (a.coef_global == 2 ? 0 : cl), *const c_b = coef + (a.coef_global == 2 ? 1 : 2) * cl,
                  *const c_c = coef + (a.coef_global == 2 ? 2 : 3) * cl;
-    float *const p_sc = coef + 4 * cl, *const p_sh = coef + 5 * cl, *const p_is = coef + 6 * cl, *const p_mi = coef + 7 * cl;
+    float *const p_sc = coef + 4 * cl, *const p_sh = coef + 5 * cl;
     const bool prev = a.p_scale != nullptr;
     const int S = a.stages, AB = a.acc_bufs;
 
@@ -182,9 +181,9 @@ __global__ void __launch_bounds__(kBfThreads, 1) bwd_fused_kernel(const __grid_c
         if (a.coef_global != 2) c_sh[c] = sh;
         c_sc[c] = sc; c_b[c] = cb; c_c[c] = cc;
         if (a.coef_global) continue;
-        float ps = 0.f, ph = 0.f, pi = 0.f, pm = 0.f;
-        if (prev && c < a.K) { ps = a.p_scale[c]; ph = a.p_shift[c]; pi = a.p_invstd[c]; pm = -a.p_mean[c] * pi; }
-        p_sc[c] = ps; p_sh[c] = ph; p_is[c] = pi; p_mi[c] = pm;
+        float ps = 0.f, ph = 0.f;
+        if (prev && c < a.K) { ps = a.p_scale[c]; ph = a.p_shift[c]; }
+        p_sc[c] = ps; p_sh[c] = ph;
     }
     // the all-ones K-major B operand of the S1 product: ONE 128-byte core matrix (8 n-rows x 8 k) in the un-swizzled layout,
     // read for every (n group, k step) through a descriptor whose strides are 0 -- every element is 1.0, so 128 bytes stand in
@@ -702,7 +701,7 @@ static BwdFusedPlan bwd_fused_plan(int K, int N, int ldx, int lddx, int da_mode,
     const uint32_t w_bytes = want_dx ? (uint32_t)bf_round_up(p.nS * p.K_pad * 128, 1024) : 0u;
     const uint32_t ones_bytes = (prev && p.ones_col < 0) ? 128u : 0u;       // one core matrix (see the kernel's prologue)
     p.coef_ld = bf_round_up(N > p.kS * 64 ? N : p.kS * 64, 64);
-    uint32_t coef_bytes = (uint32_t)(8 * p.coef_ld * sizeof(float));
+    uint32_t coef_bytes = (uint32_t)(6 * p.coef_ld * sizeof(float));      // sc, sh, cb, cc of layer l; scale, shift of layer l-1
     // dynamic + static shared memory <= 227 KB: the kernel's static part is 208 bytes (barriers), 256 reserved; the 1 KB
     // alignment slack is added below
     const uint32_t budget = 227 * 1024 - 256;
