@@ -44,6 +44,27 @@ def test_library_exports_every_declared_symbol(pn2):
     assert lib.pn2_linear_wgrad_scratch_bytes(1 << 20, 12, 32) > 0
 
 
+def test_sm_budget_is_plain_library_state(pn2):
+    """pn2_set_sm_budget: returns the previous value, 0 restores the default, negative values count as 0; fused-backward planning
+    and the grid workspace sizes answer without a GPU"""
+    lib = pn2.load()
+    assert lib.pn2_set_sm_budget(0) in (0,)                       # default: no budget
+    assert lib.pn2_set_sm_budget(116) == 0
+    assert lib.pn2_set_sm_budget(-5) == 116
+    assert lib.pn2_set_sm_budget(0) == 0
+    from importlib import import_module
+    lib_mod = import_module(pn2.__name__ + "._lib")
+    with lib_mod.sm_budget(100):
+        assert lib.pn2_set_sm_budget(100) == 100                   # inside: the budget is set
+    assert lib.pn2_set_sm_budget(0) == 0                           # ... and restored on exit
+    # the layers the fused backward takes (M, K, N, ldx, lddx, da_mode, has_prev, want_dx, want_dw)
+    assert lib.pn2_mlp_bwd_layer_supported(1 << 20, 32, 32, 32, 32, 1, 1, 1, 1) == 1
+    assert lib.pn2_mlp_bwd_layer_supported(131072, 128, 128, 128, 128, 1, 1, 1, 1) == 1
+    assert lib.pn2_mlp_bwd_layer_supported(65536, 131, 128, 136, 136, 1, 0, 1, 1) == 0      # K_ld > 128
+    assert lib.pn2_mlp_bwd_layer_supported(16384, 256, 256, 256, 256, 1, 1, 1, 1) == 0
+    assert lib.pn2_ball_grid_workspace_bytes(32, 1024) > 32 * 1024 * 20
+
+
 def test_argument_errors_do_not_need_a_gpu(pn2):
     from importlib import import_module
     lib_mod = import_module(pn2.__name__ + "._lib")
